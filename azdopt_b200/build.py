@@ -1,0 +1,53 @@
+"""Builds lib/libazb.so with nvcc for sm_100a (cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIB = os.path.join(_HERE, "lib", "libazb.so")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-fmad=false",  # every contraction in the search kernels is written out (bit parity with the reference's f32)
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def lib_path() -> str:
+    return _LIB
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; azdopt_b200 has no CPU fallback")
+
+
+def _stale() -> bool:
+    if not os.path.exists(_LIB):
+        return True
+    t = os.path.getmtime(_LIB)
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)]
+    srcs.append(os.path.join(_HERE, "..", "include", "azb.h"))
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree; returns its path."""
+    if not force and not _stale():
+        return _LIB
+    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", _LIB, os.path.join(_CSRC, "azb.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd)
+    return _LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

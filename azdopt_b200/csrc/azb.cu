@@ -1,0 +1,896 @@
+// azb.cu — host side of libazb.so: the C ABI of include/azb.h over the sm_100a kernels in this directory.
+//
+// Replaces the data-parallel part of NablaOptimizer (az-discrete-opt/src/nabla/optimizer/mod.rs:39-281) for the
+// c21 space.  All search state lives in HBM between calls; a step is one launch of the tree kernel plus the MLP
+// forward, enqueued on the handle's stream with no host round trip.
+//
+// This file never includes, links or loads anything under oracle/.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/azb.h"
+#include "azb_common.cuh"
+#include "azb_cost.cuh"
+#include "azb_mlp.cuh"
+#include "azb_mlp_tc.cuh"
+#include "azb_tree.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+struct azb_handle {
+    azb_config cfg;
+    AzbLayout L;
+    uint32_t N, A, W, PW, WS, S;
+    uint32_t dims[5];
+    size_t n_params;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    // model
+    float *params;      // dfdx order, f32
+    float *act[3];      // hidden activations of the fp32 path
+    float *mlp_x, *mlp_y;
+    uint32_t mlp_rows;  // rows the staging buffers hold
+    AzbMlpTc tc;        // tensor-core path state (bf16 weights, activations)
+    // stand-alone cost kernel scratch
+    uint8_t *cost_par;
+    double *cost_l1;
+    uint32_t *cost_mu;
+    float *cost_c;
+    uint32_t *cost_err;
+    uint32_t cost_cap;
+    // observations scratch
+    float *obs, *obs_w;
+    void *flush_buf;
+    size_t flush_bytes;
+    uint64_t launches, dev_bytes;
+    bool roots_set, trees_init, pending_add, first_init_done, params_set;
+    int improved_last_rollout;
+    uint32_t lcap, smem_words_per_warp;
+    size_t smem_bytes;
+    bool graph_ok;
+    cudaGraphExec_t step_graph;
+    char err[512];
+};
+
+static const char *k_empty = "";
+
+static int fail(azb_handle *h, int code, const char *fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(h, AZB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+static cudaError_t dmalloc(azb_handle *h, T **p, size_t count) {
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e == cudaSuccess) h->dev_bytes += bytes;
+    return e;
+}
+
+static uint32_t isqrt_ceil(uint32_t x) {
+    uint32_t s = 0;
+    while ((s + 1) * (s + 1) <= x) ++s;
+    return s * s == x ? s : s + 1;
+}
+static uint32_t next_pow2(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+static uint32_t action_dim(uint32_t n) { return (n - 1) * (n - 2) / 2 - 1; }  // rooted_tree/space.rs:48
+
+extern "C" {
+
+int azb_version(void) { return AZB_VERSION; }
+
+const char *azb_strerror(int code) {
+    switch (code) {
+        case AZB_OK: return "ok";
+        case AZB_ERR_INVALID: return "invalid argument";
+        case AZB_ERR_CUDA: return "CUDA error";
+        case AZB_ERR_CAPACITY: return "per-tree arena capacity exceeded";
+        case AZB_ERR_NAN: return "NaN reached a comparison";
+        case AZB_ERR_LAMBDA: return "lambda_1 < 1.4";
+        case AZB_ERR_UNREACHABLE: return "inactive non-root walker";
+        case AZB_ERR_STATE: return "call order violated";
+        default: return "unknown";
+    }
+}
+
+const char *azb_last_error(const azb_handle *h) { return h ? h->err : k_empty; }
+
+// NablaOptimizer's constants for the c21 example (graph-state/examples/04-c21-tree.rs:33-68,133-138)
+int azb_config_default(azb_config *cfg, uint32_t n_vertices, uint32_t n_roots) {
+    if (!cfg || n_vertices < 5 || n_vertices > AZB_MAX_VERTICES || n_roots == 0) return AZB_ERR_INVALID;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(*cfg);
+    cfg->n_vertices = n_vertices;
+    cfg->n_roots = n_roots;
+    cfg->device = 0;
+    cfg->first_root = 0;
+    cfg->c_lower = 2.0f;
+    cfg->c_upper = 0.0f;
+    cfg->n_as_tol[0] = 200;
+    cfg->n_as_tol[1] = 50;
+    cfg->n_as_tol[2] = 50;
+    cfg->n_as_tol_len = 3;
+    cfg->n_as_tol_default = 25;
+    cfg->mlp_hidden[0] = 512;
+    cfg->mlp_hidden[1] = 1024;
+    cfg->mlp_hidden[2] = 512;
+    cfg->mlp_mode = AZB_MLP_FP32;
+    cfg->prior_mode = AZB_PRIOR_MLP;
+    cfg->prior_seed = 0;
+    cfg->max_steps = 800;
+    return AZB_OK;
+}
+
+int azb_destroy(azb_handle *h) {
+    if (!h) return AZB_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    void *ptrs[] = {h->L.walker, h->L.node, h->L.pred, h->L.kid, h->L.arcseq, h->L.inl, h->L.key, h->L.hash, h->L.sv,
+                    h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
+                    h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    azb_mlp_tc_destroy(h->tc);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return AZB_OK;
+}
+
+int azb_create(const azb_config *cfg_in, azb_handle **out) {
+    if (!cfg_in || !out) return AZB_ERR_INVALID;
+    *out = nullptr;
+    if (cfg_in->struct_size != sizeof(azb_config)) return AZB_ERR_INVALID;
+    azb_config cfg = *cfg_in;
+    if (cfg.n_vertices < 5 || cfg.n_vertices > AZB_MAX_VERTICES || cfg.n_roots == 0) return AZB_ERR_INVALID;
+    if (cfg.n_as_tol_len > AZB_MAX_TOL) return AZB_ERR_INVALID;
+    if (cfg.prior_mode > AZB_PRIOR_INJECTED || cfg.mlp_mode > AZB_MLP_TC) return AZB_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg.device < 0 || cfg.device >= ndev) return AZB_ERR_CUDA;
+    azb_handle *h = new azb_handle();
+    memset((void *)h, 0, sizeof(*h));
+    h->err[0] = 0;
+    *out = h;  // returned even on failure so that azb_last_error can be read; the caller destroys it
+    const uint32_t N = cfg.n_vertices, A = action_dim(N), W = (A + 31) / 32, PW = (N + 3) / 4, B = cfg.n_roots;
+    if (cfg.c_upper == 0.0f) cfg.c_upper = (float)(isqrt_ceil(N - 1) + (N + 1) / 2);  // 04-c21-tree.rs:59-68
+    if (!(cfg.c_upper > cfg.c_lower)) return fail(h, AZB_ERR_INVALID, "c_upper must exceed c_lower");
+    if (cfg.max_steps == 0) cfg.max_steps = 800;
+    for (int i = 0; i < 3; ++i)
+        if (cfg.mlp_hidden[i] == 0) cfg.mlp_hidden[i] = i == 1 ? 1024 : 512;
+    if (cfg.cap_nodes == 0) cfg.cap_nodes = cfg.max_steps + cfg.max_steps / 2 + 64;
+    if (cfg.cap_preds == 0) {
+        uint32_t per = std::min<uint32_t>(std::max<uint32_t>(A / 12, 8), 256);
+        cfg.cap_preds = A + cfg.cap_nodes * per;
+    }
+    if (cfg.cap_parents == 0) cfg.cap_parents = cfg.cap_nodes * (N - 3);
+    if (cfg.cap_nodes > 0x3fffffffu / 8) return fail(h, AZB_ERR_INVALID, "cap_nodes too large");
+    h->cfg = cfg;
+    h->N = N;
+    h->A = A;
+    h->W = W;
+    h->PW = PW;
+    h->WS = WK_HDR + 2 * PW + 3 * W;
+    h->S = 2 * A;
+    h->dims[0] = h->S;
+    h->dims[1] = cfg.mlp_hidden[0];
+    h->dims[2] = cfg.mlp_hidden[1];
+    h->dims[3] = cfg.mlp_hidden[2];
+    h->dims[4] = A;
+    h->n_params = 0;
+    for (int l = 0; l < 4; ++l) h->n_params += (size_t)h->dims[l] * h->dims[l + 1] + h->dims[l + 1];
+
+    CK(cudaSetDevice(cfg.device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+
+    AzbLayout &L = h->L;
+    L.N = N;
+    L.A = A;
+    L.W = W;
+    L.B = B;
+    L.PW = PW;
+    L.WS = h->WS;
+    L.cap_nodes = cfg.cap_nodes;
+    L.cap_preds = cfg.cap_preds;
+    L.cap_in = cfg.cap_parents;
+    L.cap_hash = next_pow2(2 * cfg.cap_nodes);
+    L.sv_ld = h->S;
+    L.h_ld = A;
+    L.c_lower = cfg.c_lower;
+    L.slope = 1.0f / (cfg.c_upper - cfg.c_lower);  // 04-c21-tree.rs:71
+    for (uint32_t i = 0; i < 8; ++i) L.tol[i] = cfg.n_as_tol[i];
+    L.tol_len = cfg.n_as_tol_len;
+    L.tol_default = cfg.n_as_tol_default;
+    L.prior_mode = cfg.prior_mode;
+    L.log_cap = 4096;
+    L.first_root = cfg.first_root;
+    L.prior_seed = cfg.prior_seed;
+    CK(dmalloc(h, &L.walker, (size_t)B * L.WS));
+    CK(dmalloc(h, &L.node, (size_t)B * L.cap_nodes * 2));
+    CK(dmalloc(h, &L.pred, (size_t)B * L.cap_preds));
+    CK(dmalloc(h, &L.kid, (size_t)B * L.cap_preds));
+    CK(dmalloc(h, &L.arcseq, (size_t)B * L.cap_preds));
+    CK(dmalloc(h, &L.inl, (size_t)B * L.cap_in));
+    CK(dmalloc(h, &L.key, (size_t)B * L.cap_nodes * W));
+    CK(dmalloc(h, &L.hash, (size_t)B * L.cap_hash));
+    CK(dmalloc(h, &L.sv, (size_t)B * L.sv_ld));
+    CK(dmalloc(h, &L.h, (size_t)B * L.h_ld));
+    CK(dmalloc(h, &L.g, 1));
+    CK(dmalloc(h, &L.log, L.log_cap));
+    CK(cudaMemsetAsync(L.walker, 0, (size_t)B * L.WS * 4, h->stream));
+    CK(cudaMemsetAsync(L.sv, 0, (size_t)B * L.sv_ld * 4, h->stream));
+    CK(cudaMemsetAsync(L.h, 0, (size_t)B * L.h_ld * 4, h->stream));
+    AzbGlobals g0;
+    memset(&g0, 0, sizeof(g0));
+    g0.step_best = ~0ull;
+    g0.best_c = 0xffffffffu;
+    CK(cudaMemcpyAsync(L.g, &g0, sizeof(g0), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+
+    CK(dmalloc(h, &h->params, h->n_params));
+    for (int i = 0; i < 3; ++i) CK(dmalloc(h, &h->act[i], (size_t)B * h->dims[i + 1]));
+    if (cfg.mlp_mode == AZB_MLP_TC) {
+        const char *why = azb_mlp_tc_create(h->tc, B, h->dims, &h->dev_bytes);
+        if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
+    }
+
+    // shared memory per warp of the tree kernel: walker block + masks + children's c* + cascade frontiers
+    h->lcap = (std::max<uint32_t>(A, 64) + 31) & ~31u;
+    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + h->lcap + 4 * AZB_FRONTIER_CAP;
+    h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4;
+    if (N <= 32)
+        CK(cudaFuncSetAttribute(azb_tree_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    else
+        CK(cudaFuncSetAttribute(azb_tree_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    return AZB_OK;
+}
+
+int azb_get_config(const azb_handle *h, azb_config *out) {
+    if (!h || !out) return AZB_ERR_INVALID;
+    *out = h->cfg;
+    return AZB_OK;
+}
+
+// ---- synthetic roots: the example's distribution (04-c21-tree.rs:85,108-112; rooted_tree/mod.rs:14-20;
+//      modify_parent_once.rs:14-25) driven by a counter hash of (seed, global root index) ----
+static inline uint32_t bounded(unsigned long long r, uint32_t n) {
+    return (uint32_t)(((r >> 32) * (unsigned long long)n) >> 32);
+}
+
+int azb_generate_roots(uint64_t seed, uint64_t first_root, uint32_t count, uint32_t n, uint32_t k_min, uint32_t k_max,
+                       uint8_t *parents, uint32_t *permitted) {
+    if (!parents || !permitted || n < 5 || n > AZB_MAX_VERTICES) return AZB_ERR_INVALID;
+    const uint32_t a_dim = action_dim(n), words = (a_dim + 31) / 32;
+    if (k_max == 0) k_max = a_dim / 2;
+    if (k_min > k_max || k_max > a_dim) return AZB_ERR_INVALID;
+    std::vector<uint32_t> perm(a_dim);
+    for (uint32_t r = 0; r < count; ++r) {
+        uint8_t *par = parents + (size_t)r * n;
+        uint32_t *msk = permitted + (size_t)r * words;
+        unsigned long long s = azb_mix64(seed ^ azb_mix64(first_root + r + 0x5851F42D4C957F2Dull));
+        unsigned long long ctr = 0;
+        auto next = [&]() { return azb_mix64(s + (ctr++) * 0xD1342543DE82EF95ull); };
+        for (uint32_t i = 0; i < n; ++i) par[i] = 0;
+        for (uint32_t i = 2; i + 1 < n; ++i) par[i] = (uint8_t)bounded(next(), i);
+        uint32_t kk = k_min + bounded(next(), k_max - k_min + 1);
+        for (uint32_t i = 0; i < a_dim; ++i) perm[i] = i;
+        for (uint32_t i = 0; i < words; ++i) msk[i] = 0;
+        for (uint32_t t = 0; t < kk; ++t) {
+            uint32_t j = t + bounded(next(), a_dim - t);
+            std::swap(perm[t], perm[j]);
+            msk[perm[t] >> 5] |= 1u << (perm[t] & 31);
+        }
+    }
+    return AZB_OK;
+}
+
+static int check_roots(azb_handle *h, const uint8_t *parents, const uint32_t *permitted) {
+    const uint32_t N = h->N, A = h->A, W = h->W, B = h->L.B;
+    for (uint32_t i = 0; i < B; ++i) {
+        const uint8_t *p = parents + (size_t)i * N;
+        for (uint32_t v = 1; v < N; ++v)
+            if (p[v] >= v) return fail(h, AZB_ERR_INVALID, "root %u: parents[%u] = %u is not < %u", i, v, p[v], v);
+        const uint32_t *m = permitted + (size_t)i * W;
+        if (A % 32 && (m[W - 1] >> (A % 32))) return fail(h, AZB_ERR_INVALID, "root %u: permitted bit >= ACTION_DIM", i);
+    }
+    return AZB_OK;
+}
+
+int azb_set_roots(azb_handle *h, const uint8_t *parents, const uint32_t *permitted) {
+    if (!h || !parents || !permitted) return AZB_ERR_INVALID;
+    int rc = check_roots(h, parents, permitted);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->cfg.device));
+    const uint32_t N = h->N, W = h->W, PW = h->PW, WS = h->WS, B = h->L.B;
+    // the root part of each walker block: [hdr | state parents, permitted, path | ROOT parents, permitted]
+    std::vector<uint32_t> blk((size_t)B * (PW + W), 0u);
+    for (uint32_t i = 0; i < B; ++i) {
+        uint32_t *dst = blk.data() + (size_t)i * (PW + W);
+        memcpy(dst, parents + (size_t)i * N, N);
+        memcpy(dst + PW, permitted + (size_t)i * W, (size_t)W * 4);
+    }
+    CK(cudaMemcpy2DAsync(h->L.walker + WK_HDR + PW + 2 * W, (size_t)WS * 4, blk.data(), (size_t)(PW + W) * 4,
+                         (size_t)(PW + W) * 4, B, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->roots_set = true;
+    h->trees_init = false;
+    return AZB_OK;
+}
+
+int azb_get_roots(azb_handle *h, uint8_t *parents, uint32_t *permitted) {
+    if (!h || !parents || !permitted) return AZB_ERR_INVALID;
+    if (!h->roots_set) return fail(h, AZB_ERR_STATE, "roots not set");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint32_t N = h->N, W = h->W, PW = h->PW, WS = h->WS, B = h->L.B;
+    std::vector<uint32_t> blk((size_t)B * (PW + W));
+    CK(cudaMemcpy2DAsync(blk.data(), (size_t)(PW + W) * 4, h->L.walker + WK_HDR + PW + 2 * W, (size_t)WS * 4,
+                         (size_t)(PW + W) * 4, B, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (uint32_t i = 0; i < B; ++i) {
+        const uint32_t *src = blk.data() + (size_t)i * (PW + W);
+        memcpy(parents + (size_t)i * N, src, N);
+        memcpy(permitted + (size_t)i * W, src + PW, (size_t)W * 4);
+    }
+    return AZB_OK;
+}
+
+// ---- model ----
+size_t azb_mlp_num_params(const azb_handle *h) { return h ? h->n_params : 0; }
+
+int azb_mlp_set_params(azb_handle *h, const float *params) {
+    if (!h || !params) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(h->params, params, h->n_params * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->cfg.mlp_mode == AZB_MLP_TC) {
+        const char *why = azb_mlp_tc_load(h->tc, h->params, h->stream, &h->launches);
+        if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->params_set = true;
+    return AZB_OK;
+}
+
+// dfdx Linear default init: weight and bias ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+int azb_mlp_init(azb_handle *h, uint64_t seed) {
+    if (!h) return AZB_ERR_INVALID;
+    std::vector<float> p(h->n_params);
+    size_t off = 0;
+    for (int l = 0; l < 4; ++l) {
+        const size_t cnt = (size_t)h->dims[l] * h->dims[l + 1] + h->dims[l + 1];
+        const float bound = 1.0f / sqrtf((float)h->dims[l]);
+        for (size_t i = 0; i < cnt; ++i) {
+            unsigned long long r = azb_mix64(azb_mix64(seed + 0x1234567ull * (l + 1)) + (off + i) * 0x9E3779B97F4A7C15ull);
+            float u = (float)(r >> 40) * 5.9604644775390625e-08f;
+            p[off + i] = (2.0f * u - 1.0f) * bound;
+        }
+        off += cnt;
+    }
+    return azb_mlp_set_params(h, p.data());
+}
+
+int azb_mlp_get_params(azb_handle *h, float *params) {
+    if (!h || !params) return AZB_ERR_INVALID;
+    if (!h->params_set) return fail(h, AZB_ERR_STATE, "model parameters not set");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(params, h->params, h->n_params * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+// ActionModel::forward (nabla/model/dfdx.rs:81-83) on device rows
+static int mlp_forward(azb_handle *h, const float *x, uint32_t ldx, float *y, uint32_t ldy, uint32_t rows) {
+    if (h->cfg.mlp_mode == AZB_MLP_TC) {
+        const char *why = azb_mlp_tc_forward(h->tc, x, ldx, y, ldy, rows, h->stream, &h->launches);
+        if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
+        return AZB_OK;
+    }
+    const float *in = x;
+    uint32_t ld_in = ldx;
+    const float *p = h->params;
+    for (int l = 0; l < 4; ++l) {
+        const uint32_t K = h->dims[l], Nout = h->dims[l + 1];
+        float *outp = l < 3 ? h->act[l] : y;
+        const uint32_t ld_out = l < 3 ? Nout : ldy;
+        dim3 grid((Nout + 63) / 64, (rows + 63) / 64);
+        if (l < 3)
+            azb_linear_fp32_kernel<AZB_ACT_RELU><<<grid, 256, 0, h->stream>>>(in, ld_in, p, p + (size_t)K * Nout, outp,
+                                                                              ld_out, rows, K, Nout);
+        else
+            azb_linear_fp32_kernel<AZB_ACT_SIGMOID><<<grid, 256, 0, h->stream>>>(in, ld_in, p, p + (size_t)K * Nout,
+                                                                                 outp, ld_out, rows, K, Nout);
+        h->launches += 1;
+        in = outp;
+        ld_in = ld_out;
+        p += (size_t)K * Nout + Nout;
+    }
+    CK(cudaGetLastError());
+    return AZB_OK;
+}
+
+int azb_model_write_predictions(azb_handle *h, const float *states, float *predictions, uint32_t rows) {
+    if (!h || !states || !predictions || rows == 0 || rows > h->L.B) return AZB_ERR_INVALID;
+    if (!h->params_set) return fail(h, AZB_ERR_STATE, "model parameters not set");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->mlp_x) {
+        CK(dmalloc(h, &h->mlp_x, (size_t)h->L.B * h->S));
+        CK(dmalloc(h, &h->mlp_y, (size_t)h->L.B * h->A));
+    }
+    CK(cudaMemcpyAsync(h->mlp_x, states, (size_t)rows * h->S * 4, cudaMemcpyHostToDevice, h->stream));
+    int rc = mlp_forward(h, h->mlp_x, h->S, h->mlp_y, h->A, rows);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(predictions, h->mlp_y, (size_t)rows * h->A * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+// ---- tree kernel launches ----
+static int launch_tree(azb_handle *h, uint32_t flags, int prior_mode_override = -1) {
+    AzbLayout L = h->L;
+    if (prior_mode_override >= 0) L.prior_mode = (uint32_t)prior_mode_override;
+    const uint32_t blocks = (L.B + AZB_WARPS_PER_BLOCK - 1) / AZB_WARPS_PER_BLOCK;
+    if (h->N <= 32)
+        azb_tree_kernel<32><<<blocks, AZB_WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(L, flags,
+                                                                                           h->smem_words_per_warp, h->lcap);
+    else
+        azb_tree_kernel<64><<<blocks, AZB_WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(L, flags,
+                                                                                           h->smem_words_per_warp, h->lcap);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return AZB_OK;
+}
+
+// read the device error word; translate it
+static int check_device_error(azb_handle *h) {
+    AzbGlobals g;
+    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    return AZB_OK;
+}
+
+// the add_actions of the last rollout is fused into the NEXT step's launch; anything that reads the trees first
+// runs it on its own
+static int flush_pending(azb_handle *h) {
+    if (!h->pending_add) return AZB_OK;
+    int rc = launch_tree(h, AZB_F_ADD);
+    if (rc) return rc;
+    h->pending_add = false;
+    return AZB_OK;
+}
+
+int azb_set_priors(azb_handle *h, const float *priors) {
+    if (!h || !priors) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy2DAsync(h->L.h, (size_t)h->L.h_ld * 4, priors, (size_t)h->A * 4, (size_t)h->A * 4, h->L.B,
+                         cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+int azb_init_trees(azb_handle *h) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->roots_set) return fail(h, AZB_ERR_STATE, "azb_set_roots has not been called");
+    if (h->cfg.prior_mode == AZB_PRIOR_MLP && !h->params_set) return fail(h, AZB_ERR_STATE, "model parameters not set");
+    CK(cudaSetDevice(h->cfg.device));
+    // SearchTree::clear (tree/mod.rs:45-49): only the transposition table needs wiping, the arenas are bump-allocated
+    CK(cudaMemsetAsync(h->L.hash, 0, (size_t)h->L.B * h->L.cap_hash * 4, h->stream));
+    CK(cudaMemsetAsync(&h->L.g->step, 0, 4, h->stream));
+    CK(cudaMemsetAsync(&h->L.g->err, 0, 8, h->stream));
+    int rc = launch_tree(h, AZB_F_INIT | (h->first_init_done ? 0u : (uint32_t)AZB_F_FIRST));
+    if (rc) return rc;
+    if (h->cfg.prior_mode == AZB_PRIOR_MLP) {
+        rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+        if (rc) return rc;
+    }
+    rc = launch_tree(h, AZB_F_ADD);
+    if (rc) return rc;
+    h->pending_add = false;
+    rc = check_device_error(h);
+    if (rc) return rc;
+    h->first_init_done = true;
+    h->trees_init = true;
+    return AZB_OK;
+}
+
+static int enqueue_steps(azb_handle *h, uint32_t n_steps) {
+    for (uint32_t s = 0; s < n_steps; ++s) {
+        int rc = launch_tree(h, AZB_F_ADD | AZB_F_ROLLOUT);
+        if (rc) return rc;
+        if (h->cfg.prior_mode == AZB_PRIOR_MLP) {
+            rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+            if (rc) return rc;
+        }
+        h->pending_add = true;
+    }
+    return AZB_OK;
+}
+
+int azb_step(azb_handle *h, uint32_t n_steps, azb_improvement *improvements, uint32_t cap, uint32_t *n_improved) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemsetAsync(&h->L.g->n_improved, 0, 4, h->stream));
+    int rc = enqueue_steps(h, n_steps);
+    if (rc) return rc;
+    AzbGlobals g;
+    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    if (n_improved) *n_improved = g.n_improved;
+    const uint32_t take = std::min(std::min(g.n_improved, cap), h->L.log_cap);
+    if (improvements && take) {
+        static_assert(sizeof(AzbImprovementDev) == sizeof(azb_improvement), "log record layout");
+        CK(cudaMemcpyAsync(improvements, h->L.log, (size_t)take * sizeof(azb_improvement), cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->improved_last_rollout = (int)g.improved_last;
+    return AZB_OK;
+}
+
+int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_improved) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemsetAsync(&h->L.g->n_improved, 0, 4, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    int rc = enqueue_steps(h, n_steps);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    if (ms) CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    AzbGlobals g;
+    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    if (n_improved) *n_improved = g.n_improved;
+    return AZB_OK;
+}
+
+int azb_step_profile(azb_handle *h, uint32_t n_steps, float *tree_ms, float *mlp_ms) {
+    if (!h || n_steps == 0) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    std::vector<cudaEvent_t> ev((size_t)n_steps * 2 + 1);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    const bool mlp = h->cfg.prior_mode == AZB_PRIOR_MLP;
+    int rc = AZB_OK;
+    CK(cudaEventRecord(ev[0], h->stream));
+    for (uint32_t s = 0; s < n_steps && rc == AZB_OK; ++s) {
+        rc = launch_tree(h, AZB_F_ADD | AZB_F_ROLLOUT);
+        cudaEventRecord(ev[2 * s + 1], h->stream);
+        if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+        cudaEventRecord(ev[2 * s + 2], h->stream);
+        h->pending_add = true;
+    }
+    cudaStreamSynchronize(h->stream);
+    double t_tree = 0, t_mlp = 0;
+    if (rc == AZB_OK)
+        for (uint32_t s = 0; s < n_steps; ++s) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ev[2 * s], ev[2 * s + 1]);
+            cudaEventElapsedTime(&b, ev[2 * s + 1], ev[2 * s + 2]);
+            t_tree += a;
+            t_mlp += b;
+        }
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    if (tree_ms) *tree_ms = (float)t_tree;
+    if (mlp_ms) *mlp_ms = (float)t_mlp;
+    return check_device_error(h);
+}
+
+int azb_rollout_host(azb_handle *h, float *state_vecs) {
+    if (!h || !state_vecs) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    if (h->pending_add) return fail(h, AZB_ERR_STATE, "azb_add_actions_host must follow azb_rollout_host");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = launch_tree(h, AZB_F_ROLLOUT);
+    if (rc) return rc;
+    h->pending_add = true;
+    CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, h->L.B,
+                         cudaMemcpyDeviceToHost, h->stream));
+    AzbGlobals g;
+    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    h->improved_last_rollout = (int)g.improved_last;
+    return AZB_OK;
+}
+
+int azb_add_actions_host(azb_handle *h, const float *h_theta, int *improved) {
+    if (!h || !h_theta) return AZB_ERR_INVALID;
+    if (!h->pending_add) return fail(h, AZB_ERR_STATE, "azb_rollout_host has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy2DAsync(h->L.h, (size_t)h->L.h_ld * 4, h_theta, (size_t)h->A * 4, (size_t)h->A * 4, h->L.B,
+                         cudaMemcpyHostToDevice, h->stream));
+    int rc = launch_tree(h, AZB_F_ADD, AZB_PRIOR_INJECTED);
+    if (rc) return rc;
+    h->pending_add = false;
+    rc = check_device_error(h);
+    if (rc) return rc;
+    if (improved) *improved = h->improved_last_rollout;
+    return AZB_OK;
+}
+
+// ---- stand-alone cost kernel ----
+static int eval_costs_dev(azb_handle *h, const uint8_t *parents, uint32_t m, double *lambda1, uint32_t *mu, float *c,
+                          float *ms) {
+    if (m > h->cost_cap) {
+        void *old[] = {h->cost_par, h->cost_l1, h->cost_mu, h->cost_c};
+        for (void *p : old)
+            if (p) cudaFree(p);
+        h->cost_par = nullptr;
+        h->cost_l1 = nullptr;
+        h->cost_mu = nullptr;
+        h->cost_c = nullptr;
+        CK(dmalloc(h, &h->cost_par, (size_t)m * h->N));
+        CK(dmalloc(h, &h->cost_l1, m));
+        CK(dmalloc(h, &h->cost_mu, m));
+        CK(dmalloc(h, &h->cost_c, m));
+        h->cost_cap = m;
+    }
+    if (!h->cost_err) CK(dmalloc(h, &h->cost_err, 1));
+    CK(cudaMemcpyAsync(h->cost_par, parents, (size_t)m * h->N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->cost_err, 0, 4, h->stream));
+    const uint32_t threads = 128, blocks = (m + threads - 1) / threads;
+    const size_t smem = (size_t)threads * h->N;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (h->N <= 32)
+        azb_cost_kernel<32><<<blocks, threads, smem, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope,
+                                                                  h->cost_l1, h->cost_mu, h->cost_c, h->cost_err);
+    else
+        azb_cost_kernel<64><<<blocks, threads, smem, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope,
+                                                                  h->cost_l1, h->cost_mu, h->cost_c, h->cost_err);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    uint32_t err = 0;
+    if (lambda1) CK(cudaMemcpyAsync(lambda1, h->cost_l1, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (mu) CK(cudaMemcpyAsync(mu, h->cost_mu, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (c) CK(cudaMemcpyAsync(c, h->cost_c, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&err, h->cost_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ms) CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    if (err) return fail(h, (int)err, "%s", azb_strerror((int)err));
+    return AZB_OK;
+}
+
+int azb_eval_costs(azb_handle *h, const uint8_t *parents, uint32_t m, double *lambda1, uint32_t *mu, float *c,
+                   float *ms) {
+    if (!h || !parents || m == 0) return AZB_ERR_INVALID;
+    for (uint32_t i = 0; i < m; ++i)
+        for (uint32_t v = 1; v < h->N; ++v)
+            if (parents[(size_t)i * h->N + v] >= v)
+                return fail(h, AZB_ERR_INVALID, "tree %u: parents[%u] is not < %u", i, v, v);
+    CK(cudaSetDevice(h->cfg.device));
+    return eval_costs_dev(h, parents, m, lambda1, mu, c, ms);
+}
+
+// ---- results ----
+int azb_get_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double *lambda1, uint32_t *mu, float *eval) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    AzbGlobals g;
+    CK(cudaMemcpyAsync(&g, h->L.g, sizeof(g), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    uint8_t par[AZB_MAX_VERTICES];
+    memcpy(par, g.argmin_state, h->N);
+    if (parents) memcpy(parents, par, h->N);
+    if (permitted) memcpy(permitted, g.argmin_state + 16, (size_t)h->W * 4);
+    // *cost = space.cost(state); *eval = space.evaluate(cost)  (optimizer/mod.rs:240-241)
+    double l1 = 0;
+    uint32_t m = 0;
+    float c = 0;
+    int rc = eval_costs_dev(h, par, 1, &l1, &m, &c, nullptr);
+    if (rc) return rc;
+    if (lambda1) *lambda1 = l1;
+    if (mu) *mu = m;
+    if (eval) *eval = c;
+    return AZB_OK;
+}
+
+int azb_get_walkers(azb_handle *h, uint8_t *parents, uint32_t *permitted, uint32_t *path, uint32_t *pos,
+                    uint32_t *path_len) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    const uint32_t N = h->N, W = h->W, PW = h->PW, WS = h->WS, B = h->L.B;
+    std::vector<uint32_t> blk((size_t)B * WS);
+    CK(cudaMemcpyAsync(blk.data(), h->L.walker, blk.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (uint32_t i = 0; i < B; ++i) {
+        const uint32_t *w = blk.data() + (size_t)i * WS;
+        if (parents) memcpy(parents + (size_t)i * N, w + WK_HDR, N);
+        if (permitted) memcpy(permitted + (size_t)i * W, w + WK_HDR + PW, (size_t)W * 4);
+        if (path) memcpy(path + (size_t)i * W, w + WK_HDR + PW + W, (size_t)W * 4);
+        if (pos) pos[i] = w[WK_POS];
+        if (path_len) path_len[i] = w[WK_DEPTH];
+    }
+    return check_device_error(h);
+}
+
+int azb_tree_sizes(azb_handle *h, uint32_t tree, uint32_t *n_nodes, uint32_t *n_arcs, uint32_t *n_preds) {
+    if (!h || tree >= h->L.B) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    uint32_t hdr[WK_HDR];
+    CK(cudaMemcpyAsync(hdr, h->L.walker + (size_t)tree * h->WS, sizeof(hdr), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_nodes) *n_nodes = hdr[WK_NNODES];
+    if (n_arcs) *n_arcs = hdr[WK_NARCS];
+    if (n_preds) *n_preds = hdr[WK_NPREDS];
+    return AZB_OK;
+}
+
+int azb_dump_tree(azb_handle *h, uint32_t tree, uint32_t *nodes, uint32_t *keys, uint32_t *preds, uint32_t *arcs) {
+    if (!h || tree >= h->L.B) return AZB_ERR_INVALID;
+    uint32_t nn = 0, na = 0, np = 0;
+    int rc = azb_tree_sizes(h, tree, &nn, &na, &np);
+    if (rc) return rc;
+    const AzbLayout &L = h->L;
+    std::vector<uint32_t> nd((size_t)nn * 8);
+    std::vector<uint2> pr(np), kd(np);
+    std::vector<uint32_t> as(np);
+    CK(cudaMemcpyAsync(nd.data(), (uint32_t *)L.node + (size_t)tree * L.cap_nodes * 8, nd.size() * 4,
+                       cudaMemcpyDeviceToHost, h->stream));
+    if (np) {
+        CK(cudaMemcpyAsync(pr.data(), L.pred + (size_t)tree * L.cap_preds, (size_t)np * 8, cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaMemcpyAsync(kd.data(), L.kid + (size_t)tree * L.cap_preds, (size_t)np * 8, cudaMemcpyDeviceToHost,
+                           h->stream));
+        CK(cudaMemcpyAsync(as.data(), L.arcseq + (size_t)tree * L.cap_preds, (size_t)np * 4, cudaMemcpyDeviceToHost,
+                           h->stream));
+    }
+    if (keys)
+        CK(cudaMemcpyAsync(keys, L.key + (size_t)tree * L.cap_nodes * L.W, (size_t)nn * L.W * 4, cudaMemcpyDeviceToHost,
+                           h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (preds)
+        for (uint32_t j = 0; j < np; ++j) {
+            preds[j * 3 + 0] = pr[j].y & 0xffffu;
+            preds[j * 3 + 1] = pr[j].x;
+            preds[j * 3 + 2] = AZB_NONE;
+        }
+    for (uint32_t i = 0; i < nn; ++i) {
+        const uint32_t *r = nd.data() + (size_t)i * 8;
+        const uint32_t ex = r[ND_EXCNT] & 0xffffu, cnt = r[ND_EXCNT] >> 16, lo = r[ND_LO], n_out = r[ND_OUTIN] & 0xffffu;
+        if (nodes) {
+            uint32_t *o = nodes + (size_t)i * 6;
+            o[0] = r[ND_C];
+            o[1] = r[ND_CSTAR];
+            o[2] = r[ND_NT];
+            o[3] = ex;
+            o[4] = cnt ? lo : 0u;  // StateWeight::new leaves actions = 0..0 (state_weight.rs:13-21)
+            o[5] = cnt ? lo + cnt : 0u;
+        }
+        for (uint32_t t = 0; t < n_out; ++t) {
+            if (lo + t >= np) return fail(h, AZB_ERR_CAPACITY, "corrupt arc slot in tree %u node %u", tree, i);
+            const uint32_t arc = as[lo + t], child = kd[lo + t].x, prel = kd[lo + t].y & 0xffffu;
+            if (arc >= na) return fail(h, AZB_ERR_CAPACITY, "corrupt arc index in tree %u node %u", tree, i);
+            if (arcs) {
+                arcs[(size_t)arc * 3 + 0] = i;
+                arcs[(size_t)arc * 3 + 1] = child;
+                arcs[(size_t)arc * 3 + 2] = lo + prel;
+            }
+            if (preds) preds[(size_t)(lo + prel) * 3 + 2] = arc;
+        }
+    }
+    return AZB_OK;
+}
+
+int azb_get_counters(azb_handle *h, azb_counters *out) {
+    if (!h || !out) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    static_assert(sizeof(azb_counters) == sizeof(AzbCounters), "counter layout");
+    CK(cudaMemcpyAsync(out, &h->L.g->counters, sizeof(AzbCounters), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+int azb_reset_counters(azb_handle *h) {
+    if (!h) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemsetAsync(&h->L.g->counters, 0, sizeof(AzbCounters), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+int azb_get_state_vecs(azb_handle *h, float *state_vecs) {
+    if (!h || !state_vecs) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, h->L.B,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+int azb_get_priors(azb_handle *h, float *priors) {
+    if (!h || !priors) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpy2DAsync(priors, (size_t)h->A * 4, h->L.h, (size_t)h->L.h_ld * 4, (size_t)h->A * 4, h->L.B,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+// ---- epoch boundary: observations (tree/mod.rs:242-264, optimizer/mod.rs:253-278) ----
+int azb_write_observations(azb_handle *h, uint32_t n_obs_tol, float *state_vecs, float *observations, float *weights) {
+    if (!h || !observations || !weights) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    const uint32_t B = h->L.B;
+    if (!h->obs) {
+        CK(dmalloc(h, &h->obs, (size_t)B * h->A));
+        CK(dmalloc(h, &h->obs_w, (size_t)B * h->A));
+    }
+    const uint32_t blocks = (B + 3) / 4;
+    azb_observe_kernel<<<blocks, 128, 0, h->stream>>>(h->L, n_obs_tol, h->obs, h->obs_w, state_vecs ? h->L.sv : nullptr);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(observations, h->obs, (size_t)B * h->A * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(weights, h->obs_w, (size_t)B * h->A * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (state_vecs)
+        CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, B,
+                             cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+// ---- measurement helpers ----
+int azb_kernel_launches(const azb_handle *h, uint64_t *n) {
+    if (!h || !n) return AZB_ERR_INVALID;
+    *n = h->launches;
+    return AZB_OK;
+}
+
+int azb_device_bytes(const azb_handle *h, uint64_t *bytes) {
+    if (!h || !bytes) return AZB_ERR_INVALID;
+    *bytes = h->dev_bytes;
+    return AZB_OK;
+}
+
+int azb_flush_l2(azb_handle *h) {
+    if (!h) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->flush_buf) {
+        h->flush_bytes = (size_t)256 << 20;  // > 126 MB of L2
+        CK(dmalloc(h, (uint8_t **)&h->flush_buf, h->flush_bytes));
+    }
+    CK(cudaMemsetAsync(h->flush_buf, 0x5a, h->flush_bytes, h->stream));
+    return AZB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// azb_common.cuh — device-side layout and helpers shared by every kernel.
+//
+// HBM layout (one slab per array, per tree contiguous):
+//   walker [B][WS]  u32   persistent walker + root state (optimizer/mod.rs:9-14)
+//   node   [B][cap_nodes] 32 B records  = StateWeight (tree/state_weight.rs:4-10) + list heads
+//   pred   [B][cap_preds] 8 B  {g, a_id|flags}          = ActionPrediction (tree/arc_weight.rs:11-16)
+//   kid    [B][cap_preds] 8 B  {child, prel|a_id<<16}   = out-arcs of a node in creation order, stored in the
+//                                                          node's own prediction range [lo, lo+n_out)
+//   arcseq [B][cap_preds] u32  petgraph EdgeIndex of kid[] entries (dumps only)
+//   inl    [B][cap_in]    u32  parents of a node, `depth` slots reserved at node creation
+//   key    [B][cap_nodes][W]   ActionSet bit mask of the node (path/set.rs:5-8)
+//   hash   [B][cap_hash]  u32  open-addressing transposition table: node index + 1
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AZB_WARPS_PER_BLOCK 4
+#define AZB_FRONTIER_CAP 256
+
+// walker block word offsets
+enum {
+    WK_POS = 0,
+    WK_DEPTH = 1,
+    WK_NNODES = 2,
+    WK_NPREDS = 3,
+    WK_NARCS = 4,
+    WK_INTOP = 5,
+    WK_FLAGS = 6,      // bit0: node `pos` awaits add_actions
+    WK_CAND_NODE = 7,  // first-minimum candidate node of the current step
+    WK_CAND_C = 8,     // its c (orderable bits)
+    WK_ERR = 9,
+    WK_HDR = 12
+};
+
+// node record words
+enum { ND_C = 0, ND_CSTAR = 1, ND_NT = 2, ND_EXCNT = 3, ND_LO = 4, ND_OUTIN = 5, ND_INOFF = 6, ND_DEPTH = 7 };
+
+struct AzbCounters {
+    unsigned long long v[16];
+};
+enum {
+    CT_SEL = 0, CT_DSEL, CT_CUR, CT_CAND, CT_PROBE, CT_INS, CT_TERM, CT_HIT, CT_ARC, CT_PRED, CT_CN, CT_DCN, CT_RESET,
+    CT_LIVE, CT_NOOP, CT_VISIT
+};
+
+struct AzbImprovementDev {
+    uint32_t step, tree, node;
+    float eval;
+};
+
+struct AzbGlobals {  // one per handle, in device memory
+    unsigned long long step_best;   // (orderable c bits << 32) | tree, atomicMin target of the current step
+    uint32_t best_c;                // orderable bits of ArgminData.eval
+    uint32_t blocks_done;           // last-block-done ticket
+    uint32_t step;                  // steps since init_trees
+    uint32_t n_improved;            // improvements logged since the last azb_step call began
+    uint32_t err;                   // first error code seen
+    uint32_t err_tree;
+    uint32_t improved_last;         // 1 if the last finalize improved
+    uint32_t pad;
+    uint32_t argmin_state[16 + 61]; // parents packed (16 words) + permitted (61 words)
+    AzbCounters counters;
+};
+
+struct AzbLayout {
+    uint32_t N, A, W, B, PW, WS;
+    uint32_t cap_nodes, cap_preds, cap_in, cap_hash;
+    uint32_t sv_ld, h_ld;
+    float c_lower, slope;
+    uint32_t tol[8];
+    uint32_t tol_len, tol_default;
+    uint32_t prior_mode, log_cap;
+    unsigned long long first_root, prior_seed;
+    uint32_t *walker;
+    uint4 *node;
+    uint2 *pred;
+    uint2 *kid;
+    uint32_t *arcseq;
+    uint32_t *inl;
+    uint32_t *key;
+    uint32_t *hash;
+    float *sv;
+    float *h;
+    AzbGlobals *g;
+    AzbImprovementDev *log;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long azb_mix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// counter-hash prior in [0,1): SURVEY.md §8d "injected priors from the same counter-based generator"
+__host__ __device__ __forceinline__ float azb_hash_prior(unsigned long long seed, unsigned long long root,
+                                                         unsigned long long step, uint32_t a) {
+    unsigned long long r = azb_mix64(azb_mix64(seed ^ 0xA0761D6478BD642Full) + root * 0x9E3779B97F4A7C15ull +
+                                     step * 0xE7037ED1A0B428DBull + (unsigned long long)a * 0x8EBC6AF09C88C6E3ull);
+    return (float)(r >> 40) * 5.9604644775390625e-08f;
+}
+
+// order-preserving map f32 -> u32 (all finite values)
+__host__ __device__ __forceinline__ uint32_t azb_f2ord(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float azb_ord2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+// A.1 indexing (simple_graph/edge.rs:48-65, rooted_tree/ordered_edge.rs:35-42): action a <-> edge at colex
+// position a+1; the actions of child v are the contiguous range [v(v-1)/2 - 1, v(v-1)/2 + v - 2].
+__host__ __device__ __forceinline__ uint32_t azb_child_first_action(uint32_t v) { return v * (v - 1) / 2 - 1; }
+__host__ __device__ __forceinline__ uint32_t azb_action_index(uint32_t parent, uint32_t child) {
+    return child * (child - 1) / 2 + parent - 1;
+}
+// closed form of the reference's linear search: largest v with v(v-1)/2 <= a+1
+__host__ __device__ __forceinline__ uint32_t azb_action_child(uint32_t a) {
+    uint32_t pos = a + 1;
+    uint32_t v = (uint32_t)((1.0f + sqrtf(8.0f * (float)pos + 1.0f)) * 0.5f);
+    while (v * (v - 1) / 2 > pos) --v;
+    while ((v + 1) * v / 2 <= pos) ++v;
+    return v;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(v, m);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        unsigned long long o = shfl_xor_u64(v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+#endif

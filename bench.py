@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — MCTS simulations/sec of the batched c21 search step (BASELINE.json's metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one NablaOptimizer::par_roll_out_episodes over the whole batch of roots
+(az-discrete-opt/src/nabla/optimizer/mod.rs:121-191): walks + pack + MLP forward + add_actions + argmin.
+One simulation = one root advanced by one step that ended on a newly expanded node; exhausted-root no-ops are
+counted separately and excluded.  Workload at N GPUs: `--roots` (4096, BASELINE configs[1]) roots PER GPU,
+N = 19, random-init MLP 304-512-1024-512-152, synthetic roots of the example's distribution (weak scaling; roots
+shard across ranks with no collective inside a step).
+
+torch is used here only for torch.distributed (barrier, max/sum over ranks) — the product is libazb.so.
+The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mcts_simulations_per_sec"
+UNIT = "simulations/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"  # /opt/skills/guides/B200_PROFILING.md
+
+
+def algorithmic_bytes(k: dict, n: int) -> float:
+    """compact record sizes x the workload counters of the launches."""
+    a = (n - 1) * (n - 2) // 2 - 1
+    w = (a + 31) // 32
+    NODE, EDGE, PRED = 32, 20, 12
+    KEY, ST, VEC, H = 4 * w + 4, 4 * ((n + 3) // 4) + 4 * w, 8 * a, 4 * a
+    tree = (k["n_sel"] * NODE + k["d_sel"] * (EDGE + NODE) + k["n_cand"] * PRED + k["n_probe"] * KEY
+            + k["n_ins"] * (NODE + KEY) + k["n_arc"] * (EDGE + 4) + k["n_pred"] * PRED + k["n_cn"] * 2 * NODE
+            + k["d_cn"] * EDGE)
+    state = k["n_reset"] * ST + k["n_live"] * (2 * ST + VEC + H)
+    return float(tree + state)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        if not rows:
+            return None
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({nm for r in rows for nm, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(rows)}
+
+
+def cpu_reference_run(n, roots, steps, warmup, seed, threads):
+    """The restated reference (oracle/azb_oracle.cpp: dense eigensolve, leaf-stripping matching, ordered maps) on
+    the host cores.  Tree + state + cost are timed; priors are the counter hash (the reference evaluates its MLP on
+    a GPU through dfdx — nabla/model/dfdx.rs:81-83 — so no CPU forward is part of its CPU path)."""
+    from oracle import oracle
+
+    oracle.build()
+    a = oracle.action_dim(n)
+    parents, masks = oracle.generate_roots(seed, 0, roots, n)
+    o = oracle.Optimizer(n, roots, lambda_method=oracle.LAMBDA_DENSE, n_threads=threads)
+    o.set_roots(parents, masks)
+    o.init_trees(oracle.hash_priors(seed, 0, roots, a, 0))
+    if warmup:
+        o.steps_hash(seed, 0, 1, warmup)
+    o.reset_counters()
+    t0 = time.perf_counter()
+    o.steps_hash(seed, 0, 1 + warmup, steps)
+    dt = time.perf_counter() - t0
+    k = o.counters()
+    return k["n_live"] / dt, dt, k
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--roots", type=int, default=4096, help="roots per GPU (BASELINE configs[1])")
+    ap.add_argument("--vertices", type=int, default=19)
+    ap.add_argument("--mlp", default=os.environ.get("AZB_MLP", "fp32"), choices=["fp32", "tc"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-baseline-roots", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n, b = args.vertices, args.roots
+    host_threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm: CPU path on the host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample_roots = min(b, 1024)
+        val, dt, k = cpu_reference_run(n, sample_roots, args.steps, args.warmup, args.seed, host_threads)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": f"c21 N={n}, {sample_roots}-root sample of the {b}-roots-per-GPU batch, "
+                                   f"n_as_tol=[200,50,50]->25, hash priors", "vertices": n, "roots": sample_roots},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads, "kind": "port",
+                             "sample": f"{sample_roots} roots x {args.steps} steps after {args.warmup} warm-up; the "
+                                       "reference is Rust and cannot be built here, so this is its C++ restatement "
+                                       "(oracle/), tree+state+cost on all host threads, MLP forward excluded"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from azdopt_b200 import capi
+
+    a = capi.action_dim(n)
+    total_steps = args.warmup + args.steps
+    prof_steps = min(args.steps, 100)
+    cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
+                              mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
+                              max_steps=total_steps + prof_steps + 8)
+    parents, masks = capi.generate_roots(args.seed, rank * b, b, n)
+    h = capi.Handle(cfg)
+    h.mlp_init(args.seed + 1)  # same seed on every rank: replicated weights
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # ---- device-resident timing: inputs in HBM, W warm-up steps, K timed steps
+    h.set_roots(parents, masks)
+    h.init_trees()
+    h.step(args.warmup)
+    h.reset_counters()
+    launches0 = h.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    t0 = time.time()
+    ms, _ = h.step_timed(args.steps)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    launches = h.kernel_launches() - launches0
+    k = h.counters()
+    ms_max = allreduce(ms, dist.ReduceOp.MAX if world > 1 else None)
+    sims = allreduce(float(k["n_live"]), dist.ReduceOp.SUM if world > 1 else None)
+    value = sims / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (the search kernel): per-launch events over a continuation of the run
+    h.reset_counters()
+    tree_ms, mlp_ms = h.step_profile(prof_steps)
+    kp = h.counters()
+    hbm_peak, peak_src = _peaks()
+    bytes_per_launch = algorithmic_bytes(kp, n) / prof_steps
+    tree_launch_s = tree_ms * 1e-3 / prof_steps
+    achieved = bytes_per_launch / tree_launch_s / 1e9
+    roofline = {"bound": "hbm", "kernel": "azb_tree_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "launch_us": tree_launch_s * 1e6,
+                "mlp_us_per_step": mlp_ms * 1e3 / prof_steps,
+                "tree_share_of_step": tree_ms / max(tree_ms + mlp_ms, 1e-9)}
+    dev_bytes = h.device_bytes()
+
+    # ---- e2e: a whole epoch through the C ABI with HOST buffers: roots H2D (set_roots), init, K per-step calls each
+    #      reading back the step's result (improvement record + status), final argmin D2H
+    h2 = h  # same handle: the reference's optimizer also re-seeds its trees in place (par_reset_trees)
+    barrier()
+    e0 = time.perf_counter()
+    h2.set_roots(parents, masks)
+    h2.init_trees()
+    n_live_before = h2.counters()["n_live"]
+    for _ in range(args.steps):
+        h2.step(1, cap=4)
+    am = h2.argmin()
+    torch.cuda.synchronize()
+    e1 = time.perf_counter()
+    e2e_sims = h2.counters()["n_live"] - n_live_before
+    e2e_s = allreduce(e1 - e0, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_sims = allreduce(float(e2e_sims), dist.ReduceOp.SUM if world > 1 else None)
+    roots_bytes = parents.nbytes + masks.nbytes
+    e2e = {"value": e2e_sims / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": roots_bytes / args.steps + 4,
+           "d2h_bytes_per_step": 40 + 16 + (n + 4 * capi.mask_words(n) + 16) / args.steps,
+           "what": "azb_set_roots(host) + azb_init_trees + K x azb_step(1 step, improvement log to host) + "
+                   "azb_get_argmin(host), wall clock, max over ranks"}
+    h.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = min(b, args.cpu_baseline_roots)
+        cs = min(args.steps, 200)
+        val, dt, _ = cpu_reference_run(n, cb, cs, 4, args.seed, host_threads)
+        cpu = {"value": val, "unit": UNIT, "cores": host_threads, "kind": "port",
+               "sample": f"{cb} roots x {cs} steps ({dt:.1f} s); restated reference (C++ oracle), tree+state+cost on "
+                         "all host threads, hash priors, MLP forward excluded"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 search + f64 lambda_1 + " + ("bf16 tensor-core MLP" if args.mlp == "tc" else "f32 MLP"),
+            "data": "synthetic",
+            "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
+                                   f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
+                       "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": args.mlp,
+                       "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
+                       "simulations_in_timed_region": sims, "noop_root_steps": k["n_noop"],
+                       "cost_evals_per_sec": allreduce(float(k["n_ins"]), dist.ReduceOp.SUM if world > 1 else None) / (ms_max * 1e-3)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "argmin_eval": float(am["eval"]),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,310 @@
+"""ctypes binding of the CPU oracle (oracle/libazb_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  Nothing under azdopt_b200/
+imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libazb_oracle.so")
+
+NONE = 0xFFFFFFFF
+LAMBDA_DENSE, LAMBDA_JACOBI, LAMBDA_MULTISECTION = 0, 1, 2
+
+COUNTER_FIELDS = [
+    "n_sel", "d_sel", "n_cur", "n_cand", "n_probe", "n_ins", "n_term", "n_hit", "n_arc", "n_pred",
+    "n_cn", "d_cn", "n_reset", "n_live", "n_noop", "n_visit",
+]
+
+
+class Counters(C.Structure):
+    _fields_ = [(f, C.c_uint64) for f in COUNTER_FIELDS]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f in COUNTER_FIELDS}
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (g++ only)."""
+    src = [os.path.join(_HERE, f) for f in ("azb_oracle.cpp", "azb_oracle.h", "Makefile")]
+    stale = not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libazb_oracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        build()
+    L = C.CDLL(_LIB_PATH)
+    u8p, u32p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    L.orc_colex_position.restype = C.c_uint32
+    L.orc_colex_position.argtypes = [C.c_uint32, C.c_uint32]
+    L.orc_from_colex_position.argtypes = [C.c_uint32, u32p, u32p]
+    L.orc_action_dim.restype = C.c_uint32
+    L.orc_action_dim.argtypes = [C.c_uint32]
+    L.orc_c_upper.restype = C.c_uint32
+    L.orc_c_upper.argtypes = [C.c_uint32]
+    L.orc_cost.restype = C.c_int
+    L.orc_cost.argtypes = [C.c_uint32, u8p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double), u32p, f32p]
+    L.orc_matching_greedy.restype = C.c_uint32
+    L.orc_matching_greedy.argtypes = [C.c_uint32, u8p]
+    L.orc_action_data.restype = C.c_uint32
+    L.orc_action_data.argtypes = [C.c_uint32, u8p, u32p, u32p]
+    L.orc_act.argtypes = [C.c_uint32, u8p, u32p, C.c_uint32]
+    L.orc_write_vec.argtypes = [C.c_uint32, u8p, u32p, f32p]
+    L.orc_generate_roots.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u8p, u32p]
+    L.orc_hash_priors.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, f32p]
+    L.orc_mlp_forward.argtypes = [f32p, u32p, C.c_uint32, f32p, f32p, C.c_int]
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float, u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_roots.argtypes = [C.c_void_p, u8p, u32p]
+    L.orc_init_trees.restype = C.c_int
+    L.orc_init_trees.argtypes = [C.c_void_p, f32p]
+    L.orc_root_vecs.argtypes = [C.c_void_p, f32p]
+    L.orc_rollout.restype = C.c_int
+    L.orc_rollout.argtypes = [C.c_void_p, f32p]
+    L.orc_add_actions.restype = C.c_int
+    L.orc_add_actions.argtypes = [C.c_void_p, f32p, C.POINTER(C.c_int)]
+    L.orc_steps_hash.restype = C.c_int
+    L.orc_steps_hash.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, u32p, C.c_uint32, u32p]
+    L.orc_get_counters.argtypes = [C.c_void_p, C.POINTER(Counters)]
+    L.orc_reset_counters.argtypes = [C.c_void_p]
+    L.orc_get_argmin.argtypes = [C.c_void_p, u8p, u32p, C.POINTER(C.c_double), u32p, f32p]
+    L.orc_get_walkers.argtypes = [C.c_void_p, u8p, u32p, u32p, u32p, u32p]
+    L.orc_tree_sizes.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p]
+    L.orc_dump_tree.argtypes = [C.c_void_p, C.c_uint32, u32p, u32p, u32p, u32p]
+    L.orc_write_observations.argtypes = [C.c_void_p, C.c_uint32, f32p, f32p, f32p]
+    _lib = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def action_dim(n: int) -> int:
+    return (n - 1) * (n - 2) // 2 - 1
+
+
+def mask_words(n: int) -> int:
+    return (action_dim(n) + 31) // 32
+
+
+def c_upper(n: int) -> int:
+    return int(lib().orc_c_upper(n))
+
+
+def colex_position(u, v):
+    return int(lib().orc_colex_position(u, v))
+
+
+def from_colex_position(pos):
+    mx, mn = C.c_uint32(), C.c_uint32()
+    lib().orc_from_colex_position(pos, C.byref(mx), C.byref(mn))
+    return mx.value, mn.value
+
+
+def cost(parents, method=LAMBDA_DENSE, c_lower=2.0, c_up=None):
+    """(lambda_1 f64, mu, c f32, rc) for one parent array."""
+    p = np.ascontiguousarray(parents, dtype=np.uint8)
+    n = p.shape[0]
+    if c_up is None:
+        c_up = c_upper(n)
+    lam, mu, c = C.c_double(), C.c_uint32(), C.c_float()
+    rc = lib().orc_cost(n, _p(p, C.c_uint8), method, c_lower, float(c_up), C.byref(lam), C.byref(mu), C.byref(c))
+    return lam.value, mu.value, np.float32(c.value), rc
+
+
+def matching_greedy(parents):
+    p = np.ascontiguousarray(parents, dtype=np.uint8)
+    return int(lib().orc_matching_greedy(p.shape[0], _p(p, C.c_uint8)))
+
+
+def mask_from_actions(n, actions):
+    m = np.zeros(mask_words(n), dtype=np.uint32)
+    for a in actions:
+        m[a >> 5] |= np.uint32(1 << (a & 31))
+    return m
+
+
+def actions_from_mask(mask):
+    out = []
+    for w, word in enumerate(np.asarray(mask, dtype=np.uint32)):
+        word = int(word)
+        while word:
+            b = (word & -word).bit_length() - 1
+            out.append(w * 32 + b)
+            word &= word - 1
+    return out
+
+
+def action_data(parents, mask):
+    p = np.ascontiguousarray(parents, dtype=np.uint8)
+    m = np.ascontiguousarray(mask, dtype=np.uint32)
+    out = np.zeros(action_dim(p.shape[0]), dtype=np.uint32)
+    k = lib().orc_action_data(p.shape[0], _p(p, C.c_uint8), _p(m, C.c_uint32), _p(out, C.c_uint32))
+    return out[:k].tolist()
+
+
+def act(parents, mask, action):
+    p = np.array(parents, dtype=np.uint8)
+    m = np.array(mask, dtype=np.uint32)
+    lib().orc_act(p.shape[0], _p(p, C.c_uint8), _p(m, C.c_uint32), action)
+    return p, m
+
+
+def write_vec(parents, mask):
+    p = np.ascontiguousarray(parents, dtype=np.uint8)
+    m = np.ascontiguousarray(mask, dtype=np.uint32)
+    v = np.zeros(2 * action_dim(p.shape[0]), dtype=np.float32)
+    lib().orc_write_vec(p.shape[0], _p(p, C.c_uint8), _p(m, C.c_uint32), _p(v, C.c_float))
+    return v
+
+
+def generate_roots(seed, first_root, count, n, k_min=5, k_max=None):
+    if k_max is None:
+        k_max = action_dim(n) // 2
+    parents = np.zeros((count, n), dtype=np.uint8)
+    masks = np.zeros((count, mask_words(n)), dtype=np.uint32)
+    lib().orc_generate_roots(seed, first_root, count, n, k_min, k_max, _p(parents, C.c_uint8), _p(masks, C.c_uint32))
+    return parents, masks
+
+
+def hash_priors(seed, first_root, count, a_dim, step):
+    out = np.zeros((count, a_dim), dtype=np.float32)
+    lib().orc_hash_priors(seed, first_root, count, a_dim, step, _p(out, C.c_float))
+    return out
+
+
+def mlp_forward(params, dims, x, n_threads=1):
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    d = np.asarray(dims, dtype=np.uint32)
+    y = np.zeros((x.shape[0], int(d[4])), dtype=np.float32)
+    lib().orc_mlp_forward(_p(params, C.c_float), _p(d, C.c_uint32), x.shape[0], _p(x, C.c_float), _p(y, C.c_float), n_threads)
+    return y
+
+
+class Optimizer:
+    """Mirror of NablaOptimizer (optimizer/mod.rs) over the oracle."""
+
+    def __init__(self, n, n_roots, n_as_tol=(200, 50, 50), n_as_tol_default=25, c_lower=2.0, c_up=None,
+                 lambda_method=LAMBDA_DENSE, n_threads=1):
+        self.n, self.b = n, n_roots
+        self.a = action_dim(n)
+        self.w = mask_words(n)
+        if c_up is None:
+            c_up = c_upper(n)
+        tol = np.asarray(n_as_tol, dtype=np.uint32)
+        self._h = lib().orc_create(n, n_roots, c_lower, float(c_up), _p(tol, C.c_uint32), len(tol), n_as_tol_default,
+                                   lambda_method, n_threads)
+        if not self._h:
+            raise ValueError("orc_create failed")
+
+    def close(self):
+        if self._h:
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_roots(self, parents, masks):
+        p = np.ascontiguousarray(parents, dtype=np.uint8)
+        m = np.ascontiguousarray(masks, dtype=np.uint32)
+        assert p.shape == (self.b, self.n) and m.shape == (self.b, self.w)
+        lib().orc_set_roots(self._h, _p(p, C.c_uint8), _p(m, C.c_uint32))
+
+    def init_trees(self, priors):
+        pr = np.ascontiguousarray(priors, dtype=np.float32)
+        assert pr.shape == (self.b, self.a)
+        rc = lib().orc_init_trees(self._h, _p(pr, C.c_float))
+        if rc:
+            raise RuntimeError(f"orc_init_trees rc={rc}")
+
+    def root_vecs(self):
+        v = np.zeros((self.b, 2 * self.a), dtype=np.float32)
+        lib().orc_root_vecs(self._h, _p(v, C.c_float))
+        return v
+
+    def rollout(self, state_vecs=None):
+        ptr = _p(state_vecs, C.c_float) if state_vecs is not None else None
+        rc = lib().orc_rollout(self._h, ptr)
+        if rc:
+            raise RuntimeError(f"orc_rollout rc={rc}")
+
+    def add_actions(self, priors):
+        pr = np.ascontiguousarray(priors, dtype=np.float32)
+        imp = C.c_int()
+        lib().orc_add_actions(self._h, _p(pr, C.c_float), C.byref(imp))
+        return bool(imp.value)
+
+    def steps_hash(self, seed, first_root, step0, n_steps):
+        imp = np.zeros(max(1, n_steps), dtype=np.uint32)
+        n_imp = C.c_uint32()
+        rc = lib().orc_steps_hash(self._h, seed, first_root, step0, n_steps, _p(imp, C.c_uint32), len(imp), C.byref(n_imp))
+        if rc:
+            raise RuntimeError(f"orc_steps_hash rc={rc}")
+        return imp[: n_imp.value].tolist()
+
+    def counters(self):
+        c = Counters()
+        lib().orc_get_counters(self._h, C.byref(c))
+        return c.as_dict()
+
+    def reset_counters(self):
+        lib().orc_reset_counters(self._h)
+
+    def argmin(self):
+        p = np.zeros(self.n, dtype=np.uint8)
+        m = np.zeros(self.w, dtype=np.uint32)
+        lam, mu, ev = C.c_double(), C.c_uint32(), C.c_float()
+        lib().orc_get_argmin(self._h, _p(p, C.c_uint8), _p(m, C.c_uint32), C.byref(lam), C.byref(mu), C.byref(ev))
+        return dict(parents=p, permitted=m, lambda1=lam.value, mu=mu.value, eval=np.float32(ev.value))
+
+    def walkers(self):
+        p = np.zeros((self.b, self.n), dtype=np.uint8)
+        m = np.zeros((self.b, self.w), dtype=np.uint32)
+        k = np.zeros((self.b, self.w), dtype=np.uint32)
+        pos = np.zeros(self.b, dtype=np.uint32)
+        ln = np.zeros(self.b, dtype=np.uint32)
+        lib().orc_get_walkers(self._h, _p(p, C.c_uint8), _p(m, C.c_uint32), _p(k, C.c_uint32), _p(pos, C.c_uint32),
+                              _p(ln, C.c_uint32))
+        return dict(parents=p, permitted=m, path=k, pos=pos, path_len=ln)
+
+    def tree_sizes(self, tree):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib().orc_tree_sizes(self._h, tree, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def dump_tree(self, tree):
+        nn, na, npred = self.tree_sizes(tree)
+        nodes = np.zeros((nn, 6), dtype=np.uint32)
+        keys = np.zeros((nn, self.w), dtype=np.uint32)
+        preds = np.zeros((npred, 3), dtype=np.uint32)
+        arcs = np.zeros((na, 3), dtype=np.uint32)
+        lib().orc_dump_tree(self._h, tree, _p(nodes, C.c_uint32), _p(keys, C.c_uint32), _p(preds, C.c_uint32),
+                            _p(arcs, C.c_uint32))
+        return dict(nodes=nodes, keys=keys, preds=preds, arcs=arcs)
+
+    def write_observations(self, n_obs_tol):
+        v = np.zeros((self.b, 2 * self.a), dtype=np.float32)
+        obs = np.zeros((self.b, self.a), dtype=np.float32)
+        w = np.zeros((self.b, self.a), dtype=np.float32)
+        lib().orc_write_observations(self._h, n_obs_tol, _p(v, C.c_float), _p(obs, C.c_float), _p(w, C.c_float))
+        return v, obs, w
