@@ -181,11 +181,11 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     if (cfg.max_steps == 0) cfg.max_steps = 800;
     for (int i = 0; i < 3; ++i)
         if (cfg.mlp_hidden[i] == 0) cfg.mlp_hidden[i] = i == 1 ? 1024 : 512;
-    if (cfg.cap_nodes == 0) cfg.cap_nodes = cfg.max_steps + cfg.max_steps / 2 + 64;
-    if (cfg.cap_preds == 0) {
-        uint32_t per = std::min<uint32_t>(std::max<uint32_t>(A / 12, 8), 256);
-        cfg.cap_preds = A + cfg.cap_nodes * per;
-    }
+    // arena growth measured with the oracle on the example's root distribution: at most ~1.9 nodes,
+    // ~A/7 predictions (A/4 in the first steps) and ~N in-arc slots per step per tree; sized with >= 1.5x head-room,
+    // overflow is reported as AZB_ERR_CAPACITY, never dropped
+    if (cfg.cap_nodes == 0) cfg.cap_nodes = 3 * cfg.max_steps + 64;
+    if (cfg.cap_preds == 0) cfg.cap_preds = 2 * A + cfg.max_steps * ((2 * A + 6) / 7);
     if (cfg.cap_parents == 0) cfg.cap_parents = cfg.cap_nodes * (N - 3);
     if (cfg.cap_nodes > 0x3fffffffu / 8) return fail(h, AZB_ERR_INVALID, "cap_nodes too large");
     h->cfg = cfg;
@@ -813,6 +813,10 @@ int azb_get_counters(azb_handle *h, azb_counters *out) {
     if (!h || !out) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     static_assert(sizeof(azb_counters) == sizeof(AzbCounters), "counter layout");
+    if (h->trees_init) {
+        int rc = flush_pending(h);  // the last step's add_actions belongs to the counters it reports
+        if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(out, &h->L.g->counters, sizeof(AzbCounters), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return AZB_OK;
@@ -821,6 +825,10 @@ int azb_get_counters(azb_handle *h, azb_counters *out) {
 int azb_reset_counters(azb_handle *h) {
     if (!h) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
+    if (h->trees_init) {
+        int rc = flush_pending(h);
+        if (rc) return rc;
+    }
     CK(cudaMemsetAsync(&h->L.g->counters, 0, sizeof(AzbCounters), h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return AZB_OK;
