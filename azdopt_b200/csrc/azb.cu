@@ -261,12 +261,13 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
 
     // shared memory per warp of the tree kernel: walker block + masks + children's c* + cascade frontiers
     h->lcap = (std::max<uint32_t>(A, 64) + 31) & ~31u;
-    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + h->lcap + 4 * AZB_FRONTIER_CAP;
+    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
     h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4;
-    if (N <= 32)
-        CK(cudaFuncSetAttribute(azb_tree_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    else
-        CK(cudaFuncSetAttribute(azb_tree_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    switch (azb_stack_depth(N)) {
+        case 3: CK(cudaFuncSetAttribute(azb_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
+        case 4: CK(cudaFuncSetAttribute(azb_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
+        default: CK(cudaFuncSetAttribute(azb_tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
+    }
     return AZB_OK;
 }
 
@@ -453,12 +454,12 @@ static int launch_tree(azb_handle *h, uint32_t flags, int prior_mode_override = 
     AzbLayout L = h->L;
     if (prior_mode_override >= 0) L.prior_mode = (uint32_t)prior_mode_override;
     const uint32_t blocks = (L.B + AZB_WARPS_PER_BLOCK - 1) / AZB_WARPS_PER_BLOCK;
-    if (h->N <= 32)
-        azb_tree_kernel<32><<<blocks, AZB_WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(L, flags,
-                                                                                           h->smem_words_per_warp, h->lcap);
-    else
-        azb_tree_kernel<64><<<blocks, AZB_WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(L, flags,
-                                                                                           h->smem_words_per_warp, h->lcap);
+    const dim3 block(AZB_WARPS_PER_BLOCK * 32);
+    switch (azb_stack_depth(h->N)) {
+        case 3: azb_tree_kernel<3><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap); break;
+        case 4: azb_tree_kernel<4><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap); break;
+        default: azb_tree_kernel<5><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap); break;
+    }
     h->launches += 1;
     CK(cudaGetLastError());
     return AZB_OK;
@@ -658,15 +659,13 @@ static int eval_costs_dev(azb_handle *h, const uint8_t *parents, uint32_t m, dou
     if (!h->cost_err) CK(dmalloc(h, &h->cost_err, 1));
     CK(cudaMemcpyAsync(h->cost_par, parents, (size_t)m * h->N, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(h->cost_err, 0, 4, h->stream));
-    const uint32_t threads = 128, blocks = (m + threads - 1) / threads;
-    const size_t smem = (size_t)threads * h->N;
+    const uint32_t threads = 256, blocks = (m + 7) / 8;
     CK(cudaEventRecord(h->ev0, h->stream));
-    if (h->N <= 32)
-        azb_cost_kernel<32><<<blocks, threads, smem, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope,
-                                                                  h->cost_l1, h->cost_mu, h->cost_c, h->cost_err);
-    else
-        azb_cost_kernel<64><<<blocks, threads, smem, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope,
-                                                                  h->cost_l1, h->cost_mu, h->cost_c, h->cost_err);
+    switch (azb_stack_depth(h->N)) {
+        case 3: azb_cost_kernel<3><<<blocks, threads, 0, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
+        case 4: azb_cost_kernel<4><<<blocks, threads, 0, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
+        default: azb_cost_kernel<5><<<blocks, threads, 0, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
+    }
     h->launches += 1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));

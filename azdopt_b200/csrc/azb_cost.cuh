@@ -5,138 +5,228 @@
 //
 // lambda_1 by sectioning.  For a tree, x > lambda_1(T) iff the characteristic polynomial
 // P_v(x) of every rooted subtree T_v is positive.  With Q_v = prod_{children c} P_c and
-// P_v = x Q_v - sum_c Q_c prod_{c' != c} P_c' the pair (P_v, Q_v) is carried leaves-first without a division;
-// parents[v] < v (rooted_tree/mod.rs:6) makes v = N-1..1 a leaves-first order.  The bracket
-// [sqrt(max degree), sqrt(max #2-walks)] is narrowed by 11 rounds of a 5-level binary search on a 32-point grid.
-// A warp evaluates the 31 interior grid points at once and then walks the binary search over the ballot; a single
-// thread evaluates the 5 points the search visits.  Both produce bit-identical f64 results, and so does the
-// oracle (oracle/azb_oracle.cpp lambda1_multisection), because every operation is a single IEEE f64 mul/add.
+// S_v = sum_c Q_c prod_{c' != c} P_c', P_v = x Q_v - S_v, and folding a child c into its parent's pair is
+//     S_v <- S_v P_c + Q_v Q_c ;  Q_v <- Q_v P_c            (no division; only signs are ever used).
+// One warp owns one tree; lane l evaluates grid point l+1 of a 32-interval grid over the current bracket, the
+// ballot of the 31 signs is walked as a 5-level binary search, and 11 rounds take the bracket
+// [sqrt(max degree), sqrt(max #2-walks)] down to f64 resolution.
+//
+// Register-resident evaluation.  The recursion is run as a stack program in Sethi–Ullman order: a vertex first
+// evaluates its "heaviest" internal child in place, then folds its leaves, then pushes one slot per remaining
+// internal child.  A subtree that needs k slots has at least m(k) = 2 m(k-1) + 1 vertices (m(1) = 2), so 3 slots
+// suffice for N <= 22, 4 for N <= 46 and 5 for N <= 94: the (Q, S) pairs of a whole evaluation live in 12-20
+// registers, the program (3 bits per op, the same for all lanes and all rounds) in shared memory.
+// The oracle (oracle/azb_oracle.cpp, lambda1_multisection) builds the same program and performs the same IEEE
+// operations in the same order, so lambda_1 is bit-identical on both sides.
 #pragma once
 #include "azb_common.cuh"
 
 #define AZB_SECTION_ROUNDS 11
 
-// P_v(x) > 0 for every v?  parents: N bytes (shared or local memory).
-template <int MAXV>
-__device__ __forceinline__ bool azb_section_positive(uint32_t n, const uint8_t *parents, double x) {
-    double Q[MAXV], S[MAXV];
-#pragma unroll
-    for (int v = 0; v < MAXV; ++v) {
-        Q[v] = 1.0;
-        S[v] = 0.0;
-    }
-    bool ok = true;
-    for (uint32_t v = n - 1; v >= 1; --v) {
-        double P = __dsub_rn(__dmul_rn(x, Q[v]), S[v]);
-        ok = ok && (P > 0.0);
-        uint32_t p = parents[v];
-        double t0 = __dmul_rn(S[p], P);
-        double t1 = __dmul_rn(Q[p], Q[v]);
-        S[p] = __dadd_rn(t0, t1);
-        Q[p] = __dmul_rn(Q[p], P);
-    }
-    double P0 = __dsub_rn(__dmul_rn(x, Q[0]), S[0]);
-    return ok && (P0 > 0.0);
-}
+enum { OP_END = 0, OP_L0 = 1, OP_L = 2, OP_T = 3, OP_PUSH = 4, OP_POPF = 5 };
 
-// bracket from vertex degrees; thread-serial (used by the thread-per-tree kernel)
-__device__ __forceinline__ void azb_bracket_serial(uint32_t n, const uint8_t *parents, double &lo, double &hi) {
-    uint32_t maxdeg = 0, maxw2 = 0;
-    for (uint32_t v = 0; v < n; ++v) {
-        uint32_t deg = v >= 1 ? 1u : 0u;
-        uint32_t w2 = 0;
-        for (uint32_t c = 1; c < n; ++c) deg += (parents[c] == v) ? 1u : 0u;
-        // neighbours' degrees
-        if (v >= 1) {
-            uint32_t p = parents[v];
-            uint32_t dp = p >= 1 ? 1u : 0u;
-            for (uint32_t c = 1; c < n; ++c) dp += (parents[c] == p) ? 1u : 0u;
-            w2 += dp;
+struct __align__(16) CostScratch {  // per-warp shared memory
+    uint32_t cnt[64];               // number of children
+    uint32_t w2[64];                // sum of the children's degrees
+    uint8_t su[64], s1[64], s2[64], heavy[64], len[64], start[64], cur[64];
+    uint8_t ops[112];
+    uint32_t prog[12];
+};
+#define AZB_COST_SCRATCH_WORDS ((uint32_t)(sizeof(CostScratch) / 4))
+
+__host__ __device__ __forceinline__ int azb_stack_depth(uint32_t n) { return n <= 22 ? 3 : (n <= 46 ? 4 : 5); }
+
+// Degrees, the bracket, and the stack program of the tree `par` (n bytes in shared memory).
+// Returns the number of ops; lo/hi receive the bracket.  Warp-collective.
+__device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *par, CostScratch *cs, int lane,
+                                                     double &lo, double &hi) {
+    const uint32_t FULL = 0xffffffffu;
+    cs->cnt[lane] = 0u;
+    cs->cnt[lane + 32] = 0u;
+    cs->w2[lane] = 0u;
+    cs->w2[lane + 32] = 0u;
+    cs->s1[lane] = 0;
+    cs->s1[lane + 32] = 0;
+    cs->s2[lane] = 0;
+    cs->s2[lane + 32] = 0;
+    cs->heavy[lane] = 0xff;
+    cs->heavy[lane + 32] = 0xff;
+    cs->len[lane] = 0;
+    cs->len[lane + 32] = 0;
+    __syncwarp();
+    const bool a0 = lane >= 1 && (uint32_t)lane < n, a1 = (uint32_t)lane + 32 < n;
+    const uint32_t p0 = a0 ? par[lane] : 0u, p1 = a1 ? par[lane + 32] : 0u;
+    {   // children counts: one shared-memory add per (parent, half)
+        uint32_t m = __match_any_sync(FULL, a0 ? p0 : (0x10000u | (uint32_t)lane));
+        if (a0 && (__ffs(m) - 1) == lane) atomicAdd(&cs->cnt[p0], (uint32_t)__popc(m));
+        if (n > 32) {
+            m = __match_any_sync(FULL, a1 ? p1 : (0x10000u | (uint32_t)lane));
+            if (a1 && (__ffs(m) - 1) == lane) atomicAdd(&cs->cnt[p1], (uint32_t)__popc(m));
         }
-        for (uint32_t c = 1; c < n; ++c) {
-            if (parents[c] == v) {
-                uint32_t dc = 1;
-                for (uint32_t c2 = 1; c2 < n; ++c2) dc += (parents[c2] == c) ? 1u : 0u;
-                w2 += dc;
-            }
-        }
-        maxdeg = max(maxdeg, deg);
-        maxw2 = max(maxw2, w2);
     }
+    __syncwarp();
+    // degree of v = children + (v has a parent); 2-walks from v = sum of the neighbours' degrees
+    if (a0) atomicAdd(&cs->w2[p0], cs->cnt[lane] + 1u);
+    if (a1) atomicAdd(&cs->w2[p1], cs->cnt[lane + 32] + 1u);
+    __syncwarp();
+    uint32_t maxdeg = 0, maxw2 = 0;
+    if ((uint32_t)lane < n) {
+        uint32_t d = cs->cnt[lane] + (lane >= 1 ? 1u : 0u);
+        uint32_t w = cs->w2[lane] + (lane >= 1 ? cs->cnt[p0] + (p0 >= 1 ? 1u : 0u) : 0u);
+        maxdeg = d;
+        maxw2 = w;
+    }
+    if (a1) {
+        uint32_t d = cs->cnt[lane + 32] + 1u;
+        uint32_t w = cs->w2[lane + 32] + cs->cnt[p1] + (p1 >= 1 ? 1u : 0u);
+        maxdeg = max(maxdeg, d);
+        maxw2 = max(maxw2, w);
+    }
+    maxdeg = __reduce_max_sync(FULL, maxdeg);
+    maxw2 = __reduce_max_sync(FULL, maxw2);
+    // sqrt(max degree) <= lambda_1 <= sqrt(max 2-walk count); widened by 2^-30 relative
     lo = __dmul_rn(__dsqrt_rn((double)maxdeg), 1.0 - 9.313225746154785e-10);
     hi = __dmul_rn(__dsqrt_rn((double)maxw2), 1.0 + 9.313225746154785e-10);
-}
 
-// one thread, lazily evaluated binary search on the 32-grid
-template <int MAXV>
-__device__ double azb_lambda1_thread(uint32_t n, const uint8_t *parents) {
-    double lo, hi;
-    azb_bracket_serial(n, parents, lo, hi);
-    for (int round = 0; round < AZB_SECTION_ROUNDS; ++round) {
-        double w = __dmul_rn(__dsub_rn(hi, lo), 0.03125);
-        int L = 0, H = 32;
-#pragma unroll 1
-        for (int lev = 0; lev < 5; ++lev) {
-            int mid = (L + H) >> 1;
-            double x = __dadd_rn(lo, __dmul_rn((double)mid, w));
-            if (azb_section_positive<MAXV>(n, parents, x))
-                H = mid;
-            else
-                L = mid;
+    if (lane == 0) {
+        // pass 1 (leaves first): slots needed by each internal vertex; heaviest internal child of each vertex
+        for (uint32_t v = n - 1; v >= 1; --v) {
+            if (cs->cnt[v] == 0u) continue;
+            const uint32_t suv = max((uint32_t)cs->s1[v], 1u + cs->s2[v]);
+            cs->su[v] = (uint8_t)suv;
+            const uint32_t p = par[v];
+            if (suv > cs->s1[p]) {
+                cs->s2[p] = cs->s1[p];
+                cs->s1[p] = (uint8_t)suv;
+                cs->heavy[p] = (uint8_t)v;
+            } else if (suv > cs->s2[p]) {
+                cs->s2[p] = (uint8_t)suv;
+            }
         }
-        double nlo = __dadd_rn(lo, __dmul_rn((double)L, w));
-        double nhi = H == 32 ? hi : __dadd_rn(lo, __dmul_rn((double)H, w));
-        lo = nlo;
-        hi = nhi;
+        // pass 2 (leaves first): program length of every subtree
+        for (uint32_t v = n - 1; v >= 1; --v) {
+            const uint32_t p = par[v];
+            const uint32_t sl = cs->cnt[v] == 0u ? 1u : cs->len[v] + (cs->heavy[p] == v ? 1u : 2u);
+            cs->len[p] = (uint8_t)(cs->len[p] + sl);
+        }
+        // pass 3 (root first): slot offsets; every vertex writes its own op(s)
+        cs->start[0] = 0;
+        cs->cur[0] = cs->heavy[0] != 0xff ? (uint8_t)(cs->len[cs->heavy[0]] + 1u) : 0;
+        for (uint32_t v = 1; v < n; ++v) {
+            const uint32_t p = par[v];
+            const bool internal = cs->cnt[v] != 0u, is_heavy = cs->heavy[p] == v;
+            const uint32_t lenv = cs->len[v];
+            uint32_t slot;
+            if (is_heavy) {
+                slot = cs->start[p];
+            } else {
+                slot = cs->cur[p];
+                cs->cur[p] = (uint8_t)(slot + (internal ? lenv + 2u : 1u));
+            }
+            if (!internal) {
+                cs->ops[slot] = (cs->heavy[p] == 0xff && slot == cs->start[p]) ? OP_L0 : OP_L;
+            } else {
+                uint32_t st = slot;
+                if (is_heavy) {
+                    cs->ops[slot + lenv] = OP_T;
+                } else {
+                    cs->ops[slot] = OP_PUSH;
+                    st = slot + 1u;
+                    cs->ops[st + lenv] = OP_POPF;
+                }
+                cs->start[v] = (uint8_t)st;
+                cs->cur[v] = (uint8_t)(st + (cs->heavy[v] != 0xff ? cs->len[cs->heavy[v]] + 1u : 0u));
+            }
+        }
+        cs->ops[cs->len[0]] = OP_END;
     }
-    return __dmul_rn(0.5, __dadd_rn(lo, hi));
+    __syncwarp();
+    const uint32_t nops = (uint32_t)cs->len[0] + 1u;
+    if (lane < 12) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const uint32_t i = lane * 10 + j;
+            if (i < nops) w |= (uint32_t)cs->ops[i] << (3 * j);
+        }
+        cs->prog[lane] = w;
+    }
+    __syncwarp();
+    return nops;
 }
 
-// a whole warp on one tree: lane l evaluates grid point l+1 (lane 31 idles), then everybody walks the search
-// over the ballot.  parents in shared memory; scratch: 2*n u32 of shared memory (degrees).
-template <int MAXV>
-__device__ double azb_lambda1_warp(uint32_t n, const uint8_t *parents, uint32_t *scratch, int lane) {
-    // degrees: lane v (and v+32) counts its children
-    uint32_t maxdeg = 0, maxw2 = 0;
-    for (uint32_t v = lane; v < n; v += 32) {
-        uint32_t deg = v >= 1 ? 1u : 0u;
-        for (uint32_t c = 1; c < n; ++c) deg += (parents[c] == v) ? 1u : 0u;
-        scratch[v] = deg;
-        maxdeg = max(maxdeg, deg);
+// run the stack program at x: true iff P_v(x) > 0 for every vertex v
+template <int DEPTH>
+__device__ __forceinline__ bool azb_section_positive(const uint32_t *prog, double x) {
+    double Q0 = 0., S0 = 0., Q1 = 0., S1 = 0., Q2 = 0., S2 = 0., Q3 = 0., S3 = 0., Q4 = 0., S4 = 0.;
+    bool ok = true;
+    uint32_t word = 0;
+#pragma unroll 1
+    for (uint32_t i = 0;; ++i) {
+        const uint32_t r = i % 10u;
+        if (r == 0u) word = prog[i / 10u];
+        const uint32_t op = word & 7u;
+        word >>= 3;
+        if (op == OP_L) {  // fold a leaf child (P = x, Q = 1)
+            S0 = __fma_rn(S0, x, Q0);
+            Q0 = __dmul_rn(Q0, x);
+        } else if (op == OP_L0) {  // first child is a leaf
+            Q0 = x;
+            S0 = 1.0;
+        } else if (op == OP_T) {  // the slot held the heaviest child; it becomes the parent's pair
+            const double P = __fma_rn(x, Q0, -S0);
+            ok = ok && (P > 0.0);
+            S0 = Q0;
+            Q0 = P;
+        } else if (op == OP_PUSH) {
+            if (DEPTH > 4) { Q4 = Q3; S4 = S3; }
+            if (DEPTH > 3) { Q3 = Q2; S3 = S2; }
+            Q2 = Q1; S2 = S1;
+            Q1 = Q0; S1 = S0;
+        } else if (op == OP_POPF) {  // finish the vertex on top, fold it into the pair below
+            const double P = __fma_rn(x, Q0, -S0);
+            ok = ok && (P > 0.0);
+            const double t = __dmul_rn(Q1, Q0);
+            S0 = __fma_rn(S1, P, t);
+            Q0 = __dmul_rn(Q1, P);
+            Q1 = Q2; S1 = S2;
+            if (DEPTH > 3) { Q2 = Q3; S2 = S3; }
+            if (DEPTH > 4) { Q3 = Q4; S3 = S4; }
+        } else {  // OP_END: the root
+            const double P = __fma_rn(x, Q0, -S0);
+            ok = ok && (P > 0.0);
+            break;
+        }
     }
-    __syncwarp();
-    for (uint32_t v = lane; v < n; v += 32) {
-        uint32_t w2 = v >= 1 ? scratch[parents[v]] : 0u;
-        for (uint32_t c = 1; c < n; ++c) w2 += (parents[c] == v) ? scratch[c] : 0u;
-        maxw2 = max(maxw2, w2);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, m));
-        maxw2 = max(maxw2, __shfl_xor_sync(0xffffffffu, maxw2, m));
-    }
-    __syncwarp();
-    double lo = __dmul_rn(__dsqrt_rn((double)maxdeg), 1.0 - 9.313225746154785e-10);
-    double hi = __dmul_rn(__dsqrt_rn((double)maxw2), 1.0 + 9.313225746154785e-10);
+    return ok;
+}
+
+// A whole warp on one tree.  par: n bytes of shared memory.  Warp-collective; every lane returns lambda_1.
+template <int DEPTH>
+__device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *par, CostScratch *cs, int lane) {
+    double lo, hi;
+    azb_cost_prepare(n, par, cs, lane, lo, hi);
+#pragma unroll 1
     for (int round = 0; round < AZB_SECTION_ROUNDS; ++round) {
-        double w = __dmul_rn(__dsub_rn(hi, lo), 0.03125);
-        double x = __dadd_rn(lo, __dmul_rn((double)(lane + 1), w));
-        bool pos = azb_section_positive<MAXV>(n, parents, x);
-        uint32_t bal = __ballot_sync(0xffffffffu, pos);  // bit l <-> grid point l+1
+        const double w = __dmul_rn(__dsub_rn(hi, lo), 0.03125);
+        const double x = __dadd_rn(lo, __dmul_rn((double)(lane + 1), w));
+        const bool pos = azb_section_positive<DEPTH>(cs->prog, x);
+        const uint32_t bal = __ballot_sync(0xffffffffu, pos);  // bit l <-> grid point l+1 (bit 31 is never used)
         int L = 0, H = 32;
 #pragma unroll
         for (int lev = 0; lev < 5; ++lev) {
-            int mid = (L + H) >> 1;
+            const int mid = (L + H) >> 1;
             if ((bal >> (mid - 1)) & 1u)
                 H = mid;
             else
                 L = mid;
         }
-        double nlo = __dadd_rn(lo, __dmul_rn((double)L, w));
-        double nhi = H == 32 ? hi : __dadd_rn(lo, __dmul_rn((double)H, w));
+        const double nlo = __dadd_rn(lo, __dmul_rn((double)L, w));
+        const double nhi = H == 32 ? hi : __dadd_rn(lo, __dmul_rn((double)H, w));
         lo = nlo;
         hi = nhi;
     }
+    __syncwarp();
     return __dmul_rn(0.5, __dadd_rn(lo, hi));
 }
 
@@ -164,24 +254,28 @@ __device__ __forceinline__ float azb_evaluate(uint32_t mu, double lambda1, float
     return __fmul_rn(slope, x);
 }
 
-// Stand-alone batched cost kernel: one thread per tree, parents staged through shared memory so that the
-// global read is coalesced; outputs are SoA.  (azb_eval_costs)
-template <int MAXV>
-__global__ void __launch_bounds__(128) azb_cost_kernel(const uint8_t *__restrict__ parents, uint32_t m, uint32_t n,
+// Stand-alone batched cost kernel (azb_eval_costs): one warp per tree, 8 trees per block; the parent arrays of a
+// block are one contiguous, coalesced read; outputs are SoA.
+template <int DEPTH>
+__global__ void __launch_bounds__(256) azb_cost_kernel(const uint8_t *__restrict__ parents, uint32_t m, uint32_t n,
                                                        float c_lower, float slope, double *__restrict__ lambda1,
                                                        uint32_t *__restrict__ mu, float *__restrict__ c,
                                                        uint32_t *__restrict__ err) {
-    extern __shared__ uint8_t sm_par[];  // [128][n]
-    const uint32_t first = blockIdx.x * blockDim.x;
-    const uint32_t count = min((uint32_t)blockDim.x, m - first);
-    for (uint32_t i = threadIdx.x; i < count * n; i += blockDim.x) sm_par[i] = parents[(size_t)first * n + i];
+    __shared__ CostScratch scratch[8];
+    __shared__ __align__(16) uint8_t sm_par[8 * 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t first = blockIdx.x * 8u;
+    const uint32_t count = min(8u, m - first);
+    for (uint32_t i = threadIdx.x; i < count * n; i += blockDim.x) sm_par[(i / n) * 64 + (i % n)] = parents[(size_t)first * n + i];
     __syncthreads();
-    if (threadIdx.x >= count) return;
-    const uint8_t *p = sm_par + threadIdx.x * n;
-    double l1 = azb_lambda1_thread<MAXV>(n, p);
-    uint32_t k = azb_matching(n, p);
-    lambda1[first + threadIdx.x] = l1;
-    mu[first + threadIdx.x] = k;
-    c[first + threadIdx.x] = azb_evaluate(k, l1, c_lower, slope);
-    if (!(l1 >= 1.4)) atomicMax(err, 5u);  // ordered_edge.rs:79
+    if ((uint32_t)warp >= count) return;
+    const uint8_t *p = sm_par + warp * 64;
+    const double l1 = azb_lambda1_warp<DEPTH>(n, p, &scratch[warp], lane);
+    const uint32_t k = azb_matching(n, p);
+    if (lane == 0) {
+        lambda1[first + warp] = l1;
+        mu[first + warp] = k;
+        c[first + warp] = azb_evaluate(k, l1, c_lower, slope);
+        if (!(l1 >= 1.4)) atomicMax(err, 5u);  // ordered_edge.rs:79
+    }
 }

@@ -31,6 +31,7 @@ struct WarpCtx {
     uint32_t *pfx;     // scratch [W+1]
     float *lbuf;       // children's c*, creation order [LCAP]
     uint32_t *fr;      // frontier buffers [4][FRONTIER_CAP]
+    CostScratch *cs;   // lambda_1 program scratch
     // per-tree slabs
     uint32_t *node;    // 8 words per node
     uint2 *pred;
@@ -300,7 +301,7 @@ __device__ __forceinline__ void tree_add_arc(WarpCtx &cx, uint32_t src, const No
     __syncwarp();
 }
 
-template <int MAXV>
+template <int DEPTH>
 __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint32_t best_c_start) {
     const int lane = cx.lane;
     uint32_t pos = cx.wk[WK_POS], depth = cx.wk[WK_DEPTH];
@@ -452,7 +453,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         // ---- new node (tree/mod.rs:181-216)
         walker_act(L, cx, a);
         const uint32_t ndepth = depth + 1;
-        double l1 = azb_lambda1_warp<MAXV>(L.N, cx.par, (uint32_t *)cx.lbuf, lane);
+        double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
         uint32_t mu = azb_matching(L.N, cx.par);
         if (!(l1 >= 1.4)) {  // ordered_edge.rs:79
             cx.err = 5;
@@ -560,7 +561,7 @@ __device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, uin
     for (uint32_t w = lane; w < 61; w += 32) L.g->argmin_state[16 + w] = w < L.W ? cx.perm[w] : 0u;
 }
 
-template <int MAXV>
+template <int DEPTH>
 __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
     azb_tree_kernel(const AzbLayout L, const uint32_t flags, const uint32_t smem_words_per_warp, const uint32_t lcap) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -590,6 +591,8 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
         cx.lbuf = (float *)p;
         p += lcap;
         cx.fr = p;
+        p += 4 * AZB_FRONTIER_CAP;
+        cx.cs = reinterpret_cast<CostScratch *>(p);
         cx.node = reinterpret_cast<uint32_t *>(L.node) + (size_t)tree * L.cap_nodes * 8;
         cx.pred = L.pred + (size_t)tree * L.cap_preds;
         cx.kid = L.kid + (size_t)tree * L.cap_preds;
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
         if (flags & AZB_F_INIT) {
             // tail of par_new / par_reset_trees (optimizer/mod.rs:62-101, 340-359): state <- root, root cost, root node
             walker_reset(L, cx);
-            double l1 = azb_lambda1_warp<MAXV>(L.N, cx.par, (uint32_t *)cx.lbuf, lane);
+            double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
             uint32_t mu = azb_matching(L.N, cx.par);
             if (!(l1 >= 1.4)) cx.err = 5;
             float c0 = azb_evaluate(mu, l1, L.c_lower, L.slope);
@@ -656,7 +659,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
                 }
                 __syncwarp();
             }
-            tree_rollout<MAXV>(L, cx, tree, best_c_start);
+            tree_rollout<DEPTH>(L, cx, tree, best_c_start);
             if (cx.err == 0) {
                 if (cx.wk[WK_DEPTH] != 0) {  // optimizer/mod.rs:171-173
                     cx.ct[CT_LIVE] += 1;

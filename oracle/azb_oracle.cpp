@@ -272,29 +272,109 @@ double lambda1_jacobi(uint32_t n, const uint8_t *parents) {
     return best;
 }
 
-// The tree-specific method the CUDA kernels use, restated serially with the
-// same IEEE operations in the same order (DESIGN.md "lambda_1 by 32-ary
-// section").  x > lambda_1(T) iff every subtree characteristic polynomial
-// P_v(x) is positive; P_v and Q_v = prod_children P_c are carried projectively
-// (no division), leaves first (parents[v] < v, rooted_tree/mod.rs:6).
-inline bool section_positive(uint32_t n, const uint8_t *parents, double x) {
-    double Q[MAXN], S[MAXN];
-    for (uint32_t v = 0; v < n; ++v) {
-        Q[v] = 1.0;
-        S[v] = 0.0;
+// The tree-specific method the CUDA kernels use, restated serially with the same IEEE operations in the same
+// order (DESIGN.md "lambda_1 by 32-ary section").  x > lambda_1(T) iff every subtree characteristic polynomial
+// P_v(x) is positive; P_v = x Q_v - S_v with Q_v = prod_children P_c, carried without division, leaves first
+// (parents[v] < v, rooted_tree/mod.rs:6).  The recursion is run as a stack program in Sethi-Ullman order (heaviest
+// internal child first and in place; one extra slot per further internal child), exactly the program
+// azdopt_b200/csrc/azb_cost.cuh builds: ops END, L0, L, T, PUSH, POPF.
+enum { OP_END = 0, OP_L0 = 1, OP_L = 2, OP_T = 3, OP_PUSH = 4, OP_POPF = 5 };
+
+inline uint32_t build_program(uint32_t n, const uint8_t *par, uint8_t *ops) {
+    uint32_t cnt[MAXN] = {0}, s1[MAXN] = {0}, s2[MAXN] = {0}, heavy[MAXN], len[MAXN] = {0}, start[MAXN] = {0}, cur[MAXN] = {0};
+    for (uint32_t v = 0; v < n; ++v) heavy[v] = 0xff;
+    for (uint32_t v = 1; v < n; ++v) cnt[par[v]]++;
+    for (uint32_t v = n - 1; v >= 1; --v) {  // slots needed; heaviest internal child (ties: the larger index)
+        if (cnt[v] == 0) continue;
+        uint32_t suv = std::max(s1[v], 1u + s2[v]);
+        uint32_t p = par[v];
+        if (suv > s1[p]) {
+            s2[p] = s1[p];
+            s1[p] = suv;
+            heavy[p] = v;
+        } else if (suv > s2[p]) {
+            s2[p] = suv;
+        }
     }
+    for (uint32_t v = n - 1; v >= 1; --v) {  // program length of every subtree
+        uint32_t p = par[v];
+        len[p] += cnt[v] == 0 ? 1u : len[v] + (heavy[p] == v ? 1u : 2u);
+    }
+    start[0] = 0;
+    cur[0] = heavy[0] != 0xff ? len[heavy[0]] + 1u : 0u;
+    for (uint32_t v = 1; v < n; ++v) {  // slot offsets, root first; children of a vertex in ascending order
+        uint32_t p = par[v];
+        bool internal = cnt[v] != 0, is_heavy = heavy[p] == v;
+        uint32_t slot;
+        if (is_heavy) {
+            slot = start[p];
+        } else {
+            slot = cur[p];
+            cur[p] = slot + (internal ? len[v] + 2u : 1u);
+        }
+        if (!internal) {
+            ops[slot] = (heavy[p] == 0xff && slot == start[p]) ? OP_L0 : OP_L;
+        } else {
+            uint32_t st = slot;
+            if (is_heavy) {
+                ops[slot + len[v]] = OP_T;
+            } else {
+                ops[slot] = OP_PUSH;
+                st = slot + 1;
+                ops[st + len[v]] = OP_POPF;
+            }
+            start[v] = st;
+            cur[v] = st + (heavy[v] != 0xff ? len[heavy[v]] + 1u : 0u);
+        }
+    }
+    ops[len[0]] = OP_END;
+    return len[0] + 1;
+}
+
+inline bool section_positive(const uint8_t *ops, double x) {
+    double Q[8] = {0}, S[8] = {0};  // Q[0], S[0] = top of the stack
     bool ok = true;
-    for (uint32_t v = n - 1; v >= 1; --v) {
-        double P = x * Q[v] - S[v];
-        ok = ok && (P > 0.0);
-        uint32_t p = parents[v];
-        double t0 = S[p] * P;
-        double t1 = Q[p] * Q[v];
-        S[p] = t0 + t1;
-        Q[p] = Q[p] * P;
+    for (uint32_t i = 0;; ++i) {
+        switch (ops[i]) {
+            case OP_L:
+                S[0] = std::fma(S[0], x, Q[0]);
+                Q[0] = Q[0] * x;
+                break;
+            case OP_L0:
+                Q[0] = x;
+                S[0] = 1.0;
+                break;
+            case OP_T: {
+                double P = std::fma(x, Q[0], -S[0]);
+                ok = ok && (P > 0.0);
+                S[0] = Q[0];
+                Q[0] = P;
+                break;
+            }
+            case OP_PUSH:
+                for (int k = 7; k >= 1; --k) {
+                    Q[k] = Q[k - 1];
+                    S[k] = S[k - 1];
+                }
+                break;
+            case OP_POPF: {
+                double P = std::fma(x, Q[0], -S[0]);
+                ok = ok && (P > 0.0);
+                double t = Q[1] * Q[0];
+                S[0] = std::fma(S[1], P, t);
+                Q[0] = Q[1] * P;
+                for (int k = 1; k < 7; ++k) {
+                    Q[k] = Q[k + 1];
+                    S[k] = S[k + 1];
+                }
+                break;
+            }
+            default: {
+                double P = std::fma(x, Q[0], -S[0]);
+                return ok && (P > 0.0);
+            }
+        }
     }
-    double P0 = x * Q[0] - S[0];
-    return ok && (P0 > 0.0);
 }
 
 double lambda1_multisection(uint32_t n, const uint8_t *parents) {
@@ -318,13 +398,15 @@ double lambda1_multisection(uint32_t n, const uint8_t *parents) {
     double hi = std::sqrt((double)maxw2) * (1.0 + 9.313225746154785e-10);
     // 11 rounds of a 5-level binary search on the 32-point grid lo + k*w (grid point 32 is `hi`, positive by
     // construction).  The CUDA warp evaluates all 31 interior points and walks the same search over its ballot.
+    uint8_t ops[2 * MAXN];
+    build_program(n, parents, ops);
     for (int round = 0; round < 11; ++round) {
         double w = (hi - lo) * 0.03125;
         int L = 0, H = 32;
         for (int lev = 0; lev < 5; ++lev) {
             int mid = (L + H) >> 1;
             double x = lo + (double)mid * w;
-            if (section_positive(n, parents, x))
+            if (section_positive(ops, x))
                 H = mid;
             else
                 L = mid;

@@ -297,3 +297,55 @@ def test_full_size_properties_4096_roots(capi, orc):
         # the global argmin is the minimum node cost over all trees (optimizer/mod.rs:208-221)
         best = min(h.dump_tree(i)["nodes"][:, 0].view(np.float32).min() for i in range(0, b, 97))
         assert h.argmin()["eval"] <= best
+
+
+def test_nabla_optimizer_mirror_host_model(capi, orc):
+    """azdopt_b200.nabla.NablaOptimizer with a host NablaModel (numpy) against the oracle driven the same way."""
+    from azdopt_b200 import nabla
+
+    n, b, steps = 19, 12, 30
+    a_dim = orc.action_dim(n)
+    parents, masks = orc.generate_roots(3, 0, b, n)
+
+    class HashModel:  # a deterministic stand-in for a host model: prediction depends on the state vector only
+        def write_predictions(self, states, predictions):
+            s = states.astype(np.float64)
+            idx = np.arange(states.shape[1], dtype=np.float64)
+            base = (s * (idx + 1.0)).sum(axis=1, keepdims=True)
+            predictions[:] = ((np.sin(base + np.arange(predictions.shape[1])) + 1.0) * 0.5).astype(np.float32)
+
+    model = HashModel()
+    opt = nabla.NablaOptimizer.par_new(nabla.ROTModifyParentsOnce(n), (parents, masks), model, b, max_steps=steps)
+    o = orc.Optimizer(n, b, lambda_method=orc.LAMBDA_MULTISECTION)
+    o.set_roots(parents, masks)
+    pri = np.zeros((b, a_dim), dtype=np.float32)
+    model.write_predictions(o.root_vecs(), pri)
+    o.init_trees(pri)
+    sv = o.root_vecs().copy()
+    for s in range(steps):
+        got = opt.par_roll_out_episodes(lambda d: [200, 50, 50][d] if d < 3 else 25)
+        o.rollout(sv)
+        model.write_predictions(sv, pri)
+        imp = o.add_actions(pri)
+        assert (got is not None) == imp
+        if imp:
+            assert got.eval == o.argmin()["eval"]
+    for i, d in enumerate(opt.get_trees()):
+        do = o.dump_tree(i)
+        for k in ("nodes", "keys", "preds", "arcs"):
+            assert np.array_equal(do[k], d[k]), (i, k)
+    with pytest.raises(ValueError):
+        opt.par_roll_out_episodes(lambda d: 7)
+    opt.close()
+
+
+def test_cpp_host_mirror_example_runs(capi):
+    import subprocess
+
+    import __graft_entry__ as g
+
+    g.build()
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "c21_epoch")
+    out = subprocess.run([exe, "64", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "observed root actions" in out.stdout
