@@ -51,6 +51,8 @@ struct azb_handle {
     uint64_t launches, dev_bytes;
     bool roots_set, trees_init, pending_add, first_init_done, params_set;
     int improved_last_rollout;
+    uint32_t steps_done;   // steps every tree has completed since init_trees
+    uint32_t argmin_from;  // first candidate slot the argmin pass has not consumed yet
     uint32_t lcap, smem_words_per_warp;
     size_t smem_bytes;
     bool graph_ok;
@@ -140,6 +142,7 @@ int azb_config_default(azb_config *cfg, uint32_t n_vertices, uint32_t n_roots) {
     cfg->prior_mode = AZB_PRIOR_MLP;
     cfg->prior_seed = 0;
     cfg->max_steps = 800;
+    cfg->max_episodes = 0;
     return AZB_OK;
 }
 
@@ -148,7 +151,7 @@ int azb_destroy(azb_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
-    void *ptrs[] = {h->L.walker, h->L.node, h->L.pred, h->L.kid, h->L.arcseq, h->L.inl, h->L.key, h->L.hash, h->L.sv,
+    void *ptrs[] = {h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, h->L.sv,
                     h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
                     h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf};
     for (void *p : ptrs)
@@ -186,8 +189,8 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     // overflow is reported as AZB_ERR_CAPACITY, never dropped
     if (cfg.cap_nodes == 0) cfg.cap_nodes = 3 * cfg.max_steps + 64;
     if (cfg.cap_preds == 0) cfg.cap_preds = 2 * A + cfg.max_steps * ((2 * A + 6) / 7);
-    if (cfg.cap_parents == 0) cfg.cap_parents = cfg.cap_nodes * (N - 3);
-    if (cfg.cap_nodes > 0x3fffffffu / 8) return fail(h, AZB_ERR_INVALID, "cap_nodes too large");
+    if (cfg.cap_parents == 0) cfg.cap_parents = cfg.cap_nodes * (N > 8 ? N - 7 : 1);  // in-arcs beyond the 4 inline ones
+    if (cfg.cap_nodes > (1u << 20) - 2) return fail(h, AZB_ERR_INVALID, "cap_nodes too large");
     h->cfg = cfg;
     h->N = N;
     h->A = A;
@@ -216,9 +219,11 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     L.PW = PW;
     L.WS = h->WS;
     L.cap_nodes = cfg.cap_nodes;
-    L.cap_preds = cfg.cap_preds;
+    L.cap_blk = AZB_BLK_PAD + 3 * cfg.cap_preds + 3 * cfg.cap_nodes;  // 8-byte units: preds + header + 2 per kid slot
+    L.cap_blk += L.cap_blk & 1u;
     L.cap_in = cfg.cap_parents;
     L.cap_hash = next_pow2(2 * cfg.cap_nodes);
+    L.cap_steps = cfg.max_steps + 8;
     L.sv_ld = h->S;
     L.h_ld = A;
     L.c_lower = cfg.c_lower;
@@ -231,13 +236,13 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     L.first_root = cfg.first_root;
     L.prior_seed = cfg.prior_seed;
     CK(dmalloc(h, &L.walker, (size_t)B * L.WS));
-    CK(dmalloc(h, &L.node, (size_t)B * L.cap_nodes * 2));
-    CK(dmalloc(h, &L.pred, (size_t)B * L.cap_preds));
-    CK(dmalloc(h, &L.kid, (size_t)B * L.cap_preds));
-    CK(dmalloc(h, &L.arcseq, (size_t)B * L.cap_preds));
+    CK(dmalloc(h, &L.node, (size_t)B * L.cap_nodes * 4));
+    CK(dmalloc(h, &L.blk, (size_t)B * L.cap_blk + 128));  // + slack for the speculative 32-entry reads
     CK(dmalloc(h, &L.inl, (size_t)B * L.cap_in));
     CK(dmalloc(h, &L.key, (size_t)B * L.cap_nodes * W));
     CK(dmalloc(h, &L.hash, (size_t)B * L.cap_hash));
+    CK(dmalloc(h, &L.cand, (size_t)(L.cap_steps + 1) * B));
+    CK(dmalloc(h, &L.stepmin, (size_t)L.cap_steps + 1));
     CK(dmalloc(h, &L.sv, (size_t)B * L.sv_ld));
     CK(dmalloc(h, &L.h, (size_t)B * L.h_ld));
     CK(dmalloc(h, &L.g, 1));
@@ -247,7 +252,6 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     CK(cudaMemsetAsync(L.h, 0, (size_t)B * L.h_ld * 4, h->stream));
     AzbGlobals g0;
     memset(&g0, 0, sizeof(g0));
-    g0.step_best = ~0ull;
     g0.best_c = 0xffffffffu;
     CK(cudaMemcpyAsync(L.g, &g0, sizeof(g0), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -261,8 +265,9 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
 
     // shared memory per warp of the tree kernel: walker block + masks + children's c* + cascade frontiers
     h->lcap = (std::max<uint32_t>(A, 64) + 31) & ~31u;
-    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
-    h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4;
+    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 16 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
+    h->smem_words_per_warp = (h->smem_words_per_warp + 3u) & ~3u;
+    h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4 + ((A + 15) & ~15u);  // + action->child LUT
     switch (azb_stack_depth(N)) {
         case 3: CK(cudaFuncSetAttribute(azb_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
         case 4: CK(cudaFuncSetAttribute(azb_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
@@ -450,27 +455,46 @@ int azb_model_write_predictions(azb_handle *h, const float *states, float *predi
 }
 
 // ---- tree kernel launches ----
-static int launch_tree(azb_handle *h, uint32_t flags, int prior_mode_override = -1) {
+static int launch_tree(azb_handle *h, uint32_t flags, uint32_t target_step, int prior_mode_override = -1) {
     AzbLayout L = h->L;
     if (prior_mode_override >= 0) L.prior_mode = (uint32_t)prior_mode_override;
     const uint32_t blocks = (L.B + AZB_WARPS_PER_BLOCK - 1) / AZB_WARPS_PER_BLOCK;
     const dim3 block(AZB_WARPS_PER_BLOCK * 32);
+    const uint32_t me = h->cfg.max_episodes;
     switch (azb_stack_depth(h->N)) {
-        case 3: azb_tree_kernel<3><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap); break;
-        case 4: azb_tree_kernel<4><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap); break;
-        default: azb_tree_kernel<5><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap); break;
+        case 3: azb_tree_kernel<3><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me); break;
+        case 4: azb_tree_kernel<4><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me); break;
+        default: azb_tree_kernel<5><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me); break;
     }
     h->launches += 1;
     CK(cudaGetLastError());
     return AZB_OK;
 }
 
+static int read_globals(azb_handle *h, AzbGlobals *g) {
+    CK(cudaMemcpyAsync(g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (g->err)
+        return fail(h, (int)g->err, "%s (tree %u, step %u)", azb_strerror((int)g->err), g->err_tree, g->err_step);
+    return AZB_OK;
+}
+
 // read the device error word; translate it
 static int check_device_error(azb_handle *h) {
     AzbGlobals g;
-    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    return read_globals(h, &g);
+}
+
+// par_update_argmmim_data (optimizer/mod.rs:194-246) over the candidate slots [argmin_from, slot_hi): per slot the
+// first minimum over trees, then the slots in step order against the running best
+static int run_argmin(azb_handle *h, uint32_t slot_hi) {
+    const uint32_t slot_lo = h->argmin_from;
+    if (slot_hi <= slot_lo) return AZB_OK;
+    azb_stepmin_kernel<<<slot_hi - slot_lo, 256, 0, h->stream>>>(h->L, slot_lo);
+    azb_argmin_kernel<<<1, 32, 0, h->stream>>>(h->L, slot_lo, slot_hi);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    h->argmin_from = slot_hi;
     return AZB_OK;
 }
 
@@ -478,7 +502,7 @@ static int check_device_error(azb_handle *h) {
 // runs it on its own
 static int flush_pending(azb_handle *h) {
     if (!h->pending_add) return AZB_OK;
-    int rc = launch_tree(h, AZB_F_ADD);
+    int rc = launch_tree(h, AZB_F_ADD, h->steps_done);
     if (rc) return rc;
     h->pending_add = false;
     return AZB_OK;
@@ -500,17 +524,23 @@ int azb_init_trees(azb_handle *h) {
     CK(cudaSetDevice(h->cfg.device));
     // SearchTree::clear (tree/mod.rs:45-49): only the transposition table needs wiping, the arenas are bump-allocated
     CK(cudaMemsetAsync(h->L.hash, 0, (size_t)h->L.B * h->L.cap_hash * 4, h->stream));
-    CK(cudaMemsetAsync(&h->L.g->step, 0, 4, h->stream));
-    CK(cudaMemsetAsync(&h->L.g->err, 0, 8, h->stream));
-    int rc = launch_tree(h, AZB_F_INIT | (h->first_init_done ? 0u : (uint32_t)AZB_F_FIRST));
+    CK(cudaMemsetAsync(&h->L.g->err, 0, 12, h->stream));
+    const bool first = !h->first_init_done;
+    int rc = launch_tree(h, AZB_F_INIT | (first ? (uint32_t)AZB_F_FIRST : 0u), 0);
     if (rc) return rc;
     if (h->cfg.prior_mode == AZB_PRIOR_MLP) {
         rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
         if (rc) return rc;
     }
-    rc = launch_tree(h, AZB_F_ADD);
+    rc = launch_tree(h, AZB_F_ADD, 0);
     if (rc) return rc;
     h->pending_add = false;
+    h->steps_done = 0;
+    h->argmin_from = first ? 0u : 1u;
+    if (first) {  // par_new's silent argmin over the roots (optimizer/mod.rs:95-101)
+        rc = run_argmin(h, 1);
+        if (rc) return rc;
+    }
     rc = check_device_error(h);
     if (rc) return rc;
     h->first_init_done = true;
@@ -518,16 +548,38 @@ int azb_init_trees(azb_handle *h) {
     return AZB_OK;
 }
 
-static int enqueue_steps(azb_handle *h, uint32_t n_steps) {
+// one launch = every tree below the target advances by at most one step; then the model forward over the batch
+static int enqueue_launch(azb_handle *h, uint32_t flags, uint32_t target) {
+    int rc = launch_tree(h, flags, target);
+    if (rc) return rc;
+    if ((flags & AZB_F_ADD) && h->cfg.prior_mode == AZB_PRIOR_MLP)
+        rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+    return rc;
+}
+
+static int enqueue_steps(azb_handle *h, uint32_t n_steps, uint32_t flags) {
+    if (h->steps_done + n_steps > h->L.cap_steps)
+        return fail(h, AZB_ERR_CAPACITY, "%u steps since azb_init_trees exceed max_steps", h->steps_done + n_steps);
+    const uint32_t target = h->steps_done + n_steps;
     for (uint32_t s = 0; s < n_steps; ++s) {
-        int rc = launch_tree(h, AZB_F_ADD | AZB_F_ROLLOUT);
+        int rc = enqueue_launch(h, flags, target);
         if (rc) return rc;
-        if (h->cfg.prior_mode == AZB_PRIOR_MLP) {
-            rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
-            if (rc) return rc;
-        }
-        h->pending_add = true;
     }
+    if (h->cfg.max_episodes) {
+        // bounded episodes per launch: some trees may still be finishing their step
+        for (;;) {
+            AzbGlobals g;
+            int rc = read_globals(h, &g);
+            if (rc) return rc;
+            if (g.n_behind == 0) break;
+            for (int k = 0; k < 2; ++k) {
+                rc = enqueue_launch(h, flags, target);
+                if (rc) return rc;
+            }
+        }
+    }
+    h->steps_done = target;
+    if (n_steps) h->pending_add = true;
     return AZB_OK;
 }
 
@@ -536,12 +588,13 @@ int azb_step(azb_handle *h, uint32_t n_steps, azb_improvement *improvements, uin
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemsetAsync(&h->L.g->n_improved, 0, 4, h->stream));
-    int rc = enqueue_steps(h, n_steps);
+    int rc = enqueue_steps(h, n_steps, AZB_F_ADD | AZB_F_ROLLOUT);
+    if (rc) return rc;
+    rc = run_argmin(h, h->steps_done + 1);
     if (rc) return rc;
     AzbGlobals g;
-    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    rc = read_globals(h, &g);
+    if (rc) return rc;
     if (n_improved) *n_improved = g.n_improved;
     const uint32_t take = std::min(std::min(g.n_improved, cap), h->L.log_cap);
     if (improvements && take) {
@@ -560,15 +613,16 @@ int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_impro
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemsetAsync(&h->L.g->n_improved, 0, 4, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    int rc = enqueue_steps(h, n_steps);
+    int rc = enqueue_steps(h, n_steps, AZB_F_ADD | AZB_F_ROLLOUT);
+    if (rc) return rc;
+    rc = run_argmin(h, h->steps_done + 1);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaEventSynchronize(h->ev1));
     if (ms) CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     AzbGlobals g;
-    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    rc = read_globals(h, &g);
+    if (rc) return rc;
     if (n_improved) *n_improved = g.n_improved;
     return AZB_OK;
 }
@@ -576,23 +630,38 @@ int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_impro
 int azb_step_profile(azb_handle *h, uint32_t n_steps, float *tree_ms, float *mlp_ms) {
     if (!h || n_steps == 0) return AZB_ERR_INVALID;
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    if (h->steps_done + n_steps > h->L.cap_steps) return fail(h, AZB_ERR_CAPACITY, "steps exceed max_steps");
     CK(cudaSetDevice(h->cfg.device));
-    std::vector<cudaEvent_t> ev((size_t)n_steps * 2 + 1);
-    for (auto &e : ev) CK(cudaEventCreate(&e));
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, h->stream);
+        ev.push_back(e);
+    };
     const bool mlp = h->cfg.prior_mode == AZB_PRIOR_MLP;
+    const uint32_t target = h->steps_done + n_steps;
     int rc = AZB_OK;
-    CK(cudaEventRecord(ev[0], h->stream));
-    for (uint32_t s = 0; s < n_steps && rc == AZB_OK; ++s) {
-        rc = launch_tree(h, AZB_F_ADD | AZB_F_ROLLOUT);
-        cudaEventRecord(ev[2 * s + 1], h->stream);
-        if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
-        cudaEventRecord(ev[2 * s + 2], h->stream);
-        h->pending_add = true;
+    mark();
+    uint32_t launched = 0;
+    for (;;) {
+        for (uint32_t s = 0; s < n_steps && rc == AZB_OK; ++s) {
+            rc = launch_tree(h, AZB_F_ADD | AZB_F_ROLLOUT, target);
+            mark();
+            if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+            mark();
+            ++launched;
+        }
+        if (rc || !h->cfg.max_episodes) break;
+        AzbGlobals g;
+        rc = read_globals(h, &g);
+        if (rc || g.n_behind == 0) break;
+        n_steps = 2;  // catch-up launches
     }
     cudaStreamSynchronize(h->stream);
     double t_tree = 0, t_mlp = 0;
     if (rc == AZB_OK)
-        for (uint32_t s = 0; s < n_steps; ++s) {
+        for (uint32_t s = 0; s < launched; ++s) {
             float a = 0, b = 0;
             cudaEventElapsedTime(&a, ev[2 * s], ev[2 * s + 1]);
             cudaEventElapsedTime(&b, ev[2 * s + 1], ev[2 * s + 2]);
@@ -601,8 +670,12 @@ int azb_step_profile(azb_handle *h, uint32_t n_steps, float *tree_ms, float *mlp
         }
     for (auto &e : ev) cudaEventDestroy(e);
     if (rc) return rc;
+    h->steps_done = target;
+    h->pending_add = true;
     if (tree_ms) *tree_ms = (float)t_tree;
     if (mlp_ms) *mlp_ms = (float)t_mlp;
+    rc = run_argmin(h, h->steps_done + 1);
+    if (rc) return rc;
     return check_device_error(h);
 }
 
@@ -611,15 +684,16 @@ int azb_rollout_host(azb_handle *h, float *state_vecs) {
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
     if (h->pending_add) return fail(h, AZB_ERR_STATE, "azb_add_actions_host must follow azb_rollout_host");
     CK(cudaSetDevice(h->cfg.device));
-    int rc = launch_tree(h, AZB_F_ROLLOUT);
+    CK(cudaMemsetAsync(&h->L.g->n_improved, 0, 4, h->stream));
+    int rc = enqueue_steps(h, 1, AZB_F_ROLLOUT);
     if (rc) return rc;
-    h->pending_add = true;
+    rc = run_argmin(h, h->steps_done + 1);
+    if (rc) return rc;
     CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, h->L.B,
                          cudaMemcpyDeviceToHost, h->stream));
     AzbGlobals g;
-    CK(cudaMemcpyAsync(&g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.step);
+    rc = read_globals(h, &g);
+    if (rc) return rc;
     h->improved_last_rollout = (int)g.improved_last;
     return AZB_OK;
 }
@@ -630,7 +704,7 @@ int azb_add_actions_host(azb_handle *h, const float *h_theta, int *improved) {
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpy2DAsync(h->L.h, (size_t)h->L.h_ld * 4, h_theta, (size_t)h->A * 4, (size_t)h->A * 4, h->L.B,
                          cudaMemcpyHostToDevice, h->stream));
-    int rc = launch_tree(h, AZB_F_ADD, AZB_PRIOR_INJECTED);
+    int rc = launch_tree(h, AZB_F_ADD, h->steps_done, AZB_PRIOR_INJECTED);
     if (rc) return rc;
     h->pending_add = false;
     rc = check_device_error(h);
@@ -758,51 +832,73 @@ int azb_dump_tree(azb_handle *h, uint32_t tree, uint32_t *nodes, uint32_t *keys,
     int rc = azb_tree_sizes(h, tree, &nn, &na, &np);
     if (rc) return rc;
     const AzbLayout &L = h->L;
-    std::vector<uint32_t> nd((size_t)nn * 8);
-    std::vector<uint2> pr(np), kd(np);
-    std::vector<uint32_t> as(np);
-    CK(cudaMemcpyAsync(nd.data(), (uint32_t *)L.node + (size_t)tree * L.cap_nodes * 8, nd.size() * 4,
+    uint32_t hdr[WK_HDR];
+    CK(cudaMemcpyAsync(hdr, L.walker + (size_t)tree * L.WS, sizeof(hdr), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint32_t nblk = hdr[WK_NBLK];
+    std::vector<uint32_t> nd((size_t)nn * 16);
+    std::vector<uint2> blk(nblk);
+    CK(cudaMemcpyAsync(nd.data(), (uint32_t *)L.node + (size_t)tree * L.cap_nodes * 16, nd.size() * 4,
                        cudaMemcpyDeviceToHost, h->stream));
-    if (np) {
-        CK(cudaMemcpyAsync(pr.data(), L.pred + (size_t)tree * L.cap_preds, (size_t)np * 8, cudaMemcpyDeviceToHost,
+    if (nblk)
+        CK(cudaMemcpyAsync(blk.data(), L.blk + (size_t)tree * L.cap_blk, (size_t)nblk * 8, cudaMemcpyDeviceToHost,
                            h->stream));
-        CK(cudaMemcpyAsync(kd.data(), L.kid + (size_t)tree * L.cap_preds, (size_t)np * 8, cudaMemcpyDeviceToHost,
-                           h->stream));
-        CK(cudaMemcpyAsync(as.data(), L.arcseq + (size_t)tree * L.cap_preds, (size_t)np * 4, cudaMemcpyDeviceToHost,
-                           h->stream));
-    }
     if (keys)
         CK(cudaMemcpyAsync(keys, L.key + (size_t)tree * L.cap_nodes * L.W, (size_t)nn * L.W * 4, cudaMemcpyDeviceToHost,
                            h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (preds)
-        for (uint32_t j = 0; j < np; ++j) {
-            preds[j * 3 + 0] = pr[j].y & 0xffffu;
-            preds[j * 3 + 1] = pr[j].x;
-            preds[j * 3 + 2] = AZB_NONE;
-        }
+    // the reference's `predictions` Vec grows by one add_actions call at a time (graph_operations.rs:43-54): blocks
+    // are bump-allocated in the same order, so ranking the blocks by address gives every node's prediction range
+    std::vector<std::pair<uint32_t, uint32_t>> order;  // (lo2, node)
     for (uint32_t i = 0; i < nn; ++i) {
-        const uint32_t *r = nd.data() + (size_t)i * 8;
-        const uint32_t ex = r[ND_EXCNT] & 0xffffu, cnt = r[ND_EXCNT] >> 16, lo = r[ND_LO], n_out = r[ND_OUTIN] & 0xffffu;
+        const uint32_t *r = nd.data() + (size_t)i * 16;
+        if ((r[3] >> 16) != 0u) order.emplace_back(r[4], i);
+    }
+    std::sort(order.begin(), order.end());
+    std::vector<uint32_t> start(nn, 0u);
+    uint32_t run = 0;
+    for (auto &pr : order) {
+        start[pr.second] = run;
+        run += nd[(size_t)pr.second * 16 + 3] >> 16;
+    }
+    if (run != np) return fail(h, AZB_ERR_CAPACITY, "corrupt prediction count in tree %u (%u vs %u)", tree, run, np);
+    for (uint32_t i = 0; i < nn; ++i) {
+        const uint32_t *r = nd.data() + (size_t)i * 16;
+        const uint32_t ex = r[3] & 0xffffu, cnt = r[3] >> 16, lo2 = r[4];
         if (nodes) {
             uint32_t *o = nodes + (size_t)i * 6;
-            o[0] = r[ND_C];
-            o[1] = r[ND_CSTAR];
-            o[2] = r[ND_NT];
+            o[0] = r[0];
+            o[1] = r[1];
+            o[2] = r[2];
             o[3] = ex;
-            o[4] = cnt ? lo : 0u;  // StateWeight::new leaves actions = 0..0 (state_weight.rs:13-21)
-            o[5] = cnt ? lo + cnt : 0u;
+            o[4] = cnt ? start[i] : 0u;  // StateWeight::new leaves actions = 0..0 (state_weight.rs:13-21)
+            o[5] = cnt ? start[i] + cnt : 0u;
+        }
+        if (!cnt) continue;
+        const uint32_t lo = 2 * lo2;
+        if (lo < cnt || lo + 2 + 2 * cnt > nblk) return fail(h, AZB_ERR_CAPACITY, "corrupt block in tree %u node %u", tree, i);
+        const uint32_t n_out = blk[lo].y & 0xffffu;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint2 p = blk[lo - 1 - j];
+            if (preds) {
+                preds[(size_t)(start[i] + j) * 3 + 0] = p.y & 0x7ffu;
+                preds[(size_t)(start[i] + j) * 3 + 1] = p.x;
+                preds[(size_t)(start[i] + j) * 3 + 2] = ((p.y >> 11) & 1u) ? (p.y >> 12) : AZB_NONE;
+            }
         }
         for (uint32_t t = 0; t < n_out; ++t) {
-            if (lo + t >= np) return fail(h, AZB_ERR_CAPACITY, "corrupt arc slot in tree %u node %u", tree, i);
-            const uint32_t arc = as[lo + t], child = kd[lo + t].x, prel = kd[lo + t].y & 0xffffu;
+            const uint32_t w0 = blk[lo + 2 + 2 * t].x;
+            const uint32_t child = w0 & 0xfffffu, a = w0 >> 20;
+            uint32_t j = 0;
+            while (j < cnt && (blk[lo - 1 - j].y & 0x7ffu) != a) ++j;
+            if (j == cnt) return fail(h, AZB_ERR_CAPACITY, "arc without prediction in tree %u node %u", tree, i);
+            const uint32_t arc = blk[lo - 1 - j].y >> 12;
             if (arc >= na) return fail(h, AZB_ERR_CAPACITY, "corrupt arc index in tree %u node %u", tree, i);
             if (arcs) {
                 arcs[(size_t)arc * 3 + 0] = i;
                 arcs[(size_t)arc * 3 + 1] = child;
-                arcs[(size_t)arc * 3 + 2] = lo + prel;
+                arcs[(size_t)arc * 3 + 2] = start[i] + j;
             }
-            if (preds) preds[(size_t)(lo + prel) * 3 + 2] = arc;
         }
     }
     return AZB_OK;

@@ -2,38 +2,48 @@
 //
 // HBM layout (one slab per array, per tree contiguous):
 //   walker [B][WS]  u32   persistent walker + root state (optimizer/mod.rs:9-14)
-//   node   [B][cap_nodes] 32 B records  = StateWeight (tree/state_weight.rs:4-10) + list heads
-//   pred   [B][cap_preds] 8 B  {g, a_id|flags}          = ActionPrediction (tree/arc_weight.rs:11-16)
-//   kid    [B][cap_preds] 8 B  {child, prel|a_id<<16}   = out-arcs of a node in creation order, stored in the
-//                                                          node's own prediction range [lo, lo+n_out)
-//   arcseq [B][cap_preds] u32  petgraph EdgeIndex of kid[] entries (dumps only)
-//   inl    [B][cap_in]    u32  parents of a node, `depth` slots reserved at node creation
+//   node   [B][cap_nodes] 64 B records = StateWeight (tree/state_weight.rs:4-10) + the first four in-arcs inline
+//   blk    [B][cap_blk]   8 B units: one BLOCK per expanded node, laid out around its header so that one
+//                         speculative, coalesced read fetches everything selection needs:
+//                             [pred cnt-1 .. pred 0][header 16 B][kid 0 .. kid cnt-1]
+//                         pred (8 B)  = ActionPrediction {g, a_id | has_arc | arc seq}   (tree/arc_weight.rs:11-16)
+//                         kid  (16 B) = one out-arc in creation order, carrying a COPY of what revisit_choice and
+//                                       the next descent step need from the child: {child | a_id, child block |
+//                                       active, n_t, c*}.  Cascades keep the copies coherent through the in-arc
+//                                       entries (parent, kid slot).
+//   inl    [B][cap_in]    8 B  in-arcs beyond the fourth of a node ((depth-4)+ slots reserved at creation)
 //   key    [B][cap_nodes][W]   ActionSet bit mask of the node (path/set.rs:5-8)
-//   hash   [B][cap_hash]  u32  open-addressing transposition table: node index + 1
+//   hash   [B][cap_hash]  u32  open-addressing transposition table: (node index + 1) | fingerprint << 21
+//   cand   [cap_steps+1][B] 8 B  per-step argmin candidate of every tree (slot 0 = the roots)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #define AZB_WARPS_PER_BLOCK 4
 #define AZB_FRONTIER_CAP 256
+#define AZB_BLK_PAD 64          // units kept free in front of a tree's block arena (speculative reads)
+#define AZB_LO_NONE 0x7fffffffu
 
 // walker block word offsets
 enum {
     WK_POS = 0,
     WK_DEPTH = 1,
     WK_NNODES = 2,
-    WK_NPREDS = 3,
+    WK_NBLK = 3,       // bump pointer of the block arena, in 8-byte units
     WK_NARCS = 4,
-    WK_INTOP = 5,
-    WK_FLAGS = 6,      // bit0: node `pos` awaits add_actions
-    WK_CAND_NODE = 7,  // first-minimum candidate node of the current step
-    WK_CAND_C = 8,     // its c (orderable bits)
-    WK_ERR = 9,
-    WK_HDR = 12
+    WK_INTOP = 5,      // bump pointer of the overflow in-arc arena
+    WK_FLAGS = 6,      // bit0: node `pos` awaits add_actions; bit1: root not yet seen by the argmin scan
+    WK_STEP = 7,       // completed steps since init_trees
+    WK_CAND_C = 8,     // first-minimum candidate of the running step: orderable c bits
+    WK_CAND_NODE = 9,
+    WK_PEND_C = 10,    // c of the node awaiting add_actions
+    WK_PKIDX = 11,     // 16-byte index of that node's kid entry in its creator's block (AZB_LO_NONE for a root)
+    WK_NPREDS = 12,    // predictions appended so far
+    WK_ROOTLO = 13,    // 16-byte index of the root's block header (AZB_LO_NONE while it has none)
+    WK_CURLO = 14,     // same for the walker's node
+    WK_ERR = 15,
+    WK_HDR = 16
 };
-
-// node record words
-enum { ND_C = 0, ND_CSTAR = 1, ND_NT = 2, ND_EXCNT = 3, ND_LO = 4, ND_OUTIN = 5, ND_INOFF = 6, ND_DEPTH = 7 };
 
 struct AzbCounters {
     unsigned long long v[16];
@@ -49,22 +59,23 @@ struct AzbImprovementDev {
 };
 
 struct AzbGlobals {  // one per handle, in device memory
-    unsigned long long step_best;   // (orderable c bits << 32) | tree, atomicMin target of the current step
     uint32_t best_c;                // orderable bits of ArgminData.eval
     uint32_t blocks_done;           // last-block-done ticket
-    uint32_t step;                  // steps since init_trees
     uint32_t n_improved;            // improvements logged since the last azb_step call began
     uint32_t err;                   // first error code seen
     uint32_t err_tree;
-    uint32_t improved_last;         // 1 if the last finalize improved
-    uint32_t pad;
+    uint32_t err_step;
+    uint32_t improved_last;         // 1 if the newest step of the last argmin pass improved
+    uint32_t behind_accum;          // trees below the step target, accumulated by the running launch
+    uint32_t n_behind;              // ... of the last finished launch
+    uint32_t argmin_tree, argmin_node, pad;
     uint32_t argmin_state[16 + 61]; // parents packed (16 words) + permitted (61 words)
     AzbCounters counters;
 };
 
 struct AzbLayout {
     uint32_t N, A, W, B, PW, WS;
-    uint32_t cap_nodes, cap_preds, cap_in, cap_hash;
+    uint32_t cap_nodes, cap_blk, cap_in, cap_hash, cap_steps;
     uint32_t sv_ld, h_ld;
     float c_lower, slope;
     uint32_t tol[8];
@@ -73,12 +84,12 @@ struct AzbLayout {
     unsigned long long first_root, prior_seed;
     uint32_t *walker;
     uint4 *node;
-    uint2 *pred;
-    uint2 *kid;
-    uint32_t *arcseq;
-    uint32_t *inl;
+    uint2 *blk;
+    uint2 *inl;
     uint32_t *key;
     uint32_t *hash;
+    uint2 *cand;
+    unsigned long long *stepmin;
     float *sv;
     float *h;
     AzbGlobals *g;

@@ -4,16 +4,23 @@
 // next_action / revisit_choice / max_curiosity (nabla/tree/next_action.rs:11-88), add_node / add_arc / add_actions
 // (nabla/tree/graph_operations.rs:8-56), cascade_new_terminal / cascade_old_node
 // (nabla/tree/empty_transitions.rs:50-127), the ROTModifyParentsOnce space (graph-state/src/rooted_tree/space.rs:
-// 37-125), write_vec (space.rs:91-101) and the argmin scan (nabla/optimizer/mod.rs:194-246).
+// 37-125), write_vec (space.rs:91-101) and the per-tree half of the argmin scan (nabla/optimizer/mod.rs:194-221).
 //
-// Design notes:
-//  * out-arcs of a node live in the node's own prediction range, in creation order: kid[lo + t] is the t-th arc.
-//    petgraph iterates newest-first, so "first minimum" == highest t among equal keys and the curiosity sum runs
-//    t = n_out-1 .. 0.  One coalesced read replaces a linked-list walk.
-//  * in-arcs (parents) of a node live in `depth` reserved slots (a node of depth d has at most d parents, because
-//    keys are action sets and every parent key is the child key minus one action).
-//  * the transposition map BTreeMap<ActionSet, NodeIndex> is an open-addressing table keyed by the W-word mask.
+// Design notes.  The walk is a chain of dependent memory round trips, so the layout is built to
+// need ONE round trip per level:
+//  * an expanded node owns a block [preds | header | kids]; a kid entry carries a copy of the child's n_t, c*,
+//    activity and block address, so revisit_choice never touches the children's records and the next level's
+//    block can be requested as soon as the child is chosen; header, first 32 kids and first 32 predictions are
+//    requested together without knowing their counts;
+//  * out-arcs are stored in creation order: petgraph iterates newest-first, so "first minimum" == highest slot
+//    among equal keys and the curiosity sum runs from the last slot down;
+//  * a node record holds its first four in-arcs (parent, kid slot) inline, so a cascade level is one 64-byte read
+//    per frontier node; the in-arc's kid slot is where the cascade refreshes the parent's copy;
+//  * the transposition map BTreeMap<ActionSet, NodeIndex> is an open-addressing table keyed by the W-word mask;
 //  * walker state (parents, permitted mask, path mask) sits in shared memory while the warp runs.
+// A launch advances every tree that is below `target_step` by at most one step; with max_episodes != 0 a tree
+// that keeps hitting terminal nodes / transpositions yields after that many episodes and finishes its step in a
+// later launch (trees are independent, so results do not depend on the interleaving).
 #pragma once
 #include "azb_common.cuh"
 #include "azb_cost.cuh"
@@ -31,26 +38,28 @@ struct WarpCtx {
     uint32_t *pfx;     // scratch [W+1]
     float *lbuf;       // children's c*, creation order [LCAP]
     uint32_t *fr;      // frontier buffers [4][FRONTIER_CAP]
+    uint32_t *ct;      // workload counters [16]
     CostScratch *cs;   // lambda_1 program scratch
+    const uint8_t *lut;  // child vertex of every action (block-shared)
     // per-tree slabs
-    uint32_t *node;    // 8 words per node
-    uint2 *pred;
-    uint2 *kid;
-    uint32_t *arcseq;
-    uint32_t *inl;
+    uint4 *node;       // 4 x uint4 per node
+    uint2 *blk;        // 8-byte units
+    uint4 *blk4;       // the same arena in 16-byte units
+    uint2 *inl;
     uint32_t *key;
     uint32_t *hash;
     int lane;
     uint32_t err;
-    uint32_t ct[16];
 };
+
+__device__ __forceinline__ void count(WarpCtx &cx, int which, uint32_t n) {
+    if (cx.lane == 0) cx.ct[which] += n;
+}
 
 __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t r) {
     for (uint32_t i = 0; i < r; ++i) mask &= mask - 1;
     return __ffs(mask) - 1;
 }
-
-__device__ __forceinline__ uint32_t lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
 // hash of a W-word action-set mask held as (k0 = word lane, k1 = word lane+32) across the warp
 __device__ __forceinline__ uint32_t key_hash(uint32_t k0, uint32_t k1, int lane, uint32_t W) {
@@ -58,8 +67,7 @@ __device__ __forceinline__ uint32_t key_hash(uint32_t k0, uint32_t k1, int lane,
     hv ^= hv >> 15;
     hv *= 0x2C1B3C6Du;
     hv = (uint32_t)lane < W ? hv : 0u;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) hv ^= __shfl_xor_sync(0xffffffffu, hv, m);
+    hv = __reduce_xor_sync(0xffffffffu, hv);
     hv ^= hv >> 13;
     hv *= 0x297A2D39u;
     hv ^= hv >> 16;
@@ -79,16 +87,16 @@ __device__ __forceinline__ void build_cur_mask(const AzbLayout &L, WarpCtx &cx) 
 
 // act (rooted_tree/space.rs:56-73): set the parent, drop every action of that child, extend the path set
 __device__ __forceinline__ void walker_act(const AzbLayout &L, WarpCtx &cx, uint32_t a) {
-    uint32_t child = azb_action_child(a);
-    uint32_t first = azb_child_first_action(child);
-    uint32_t last = first + child;  // exclusive
+    const uint32_t child = cx.lut[a];
+    const uint32_t first = azb_child_first_action(child);
+    const uint32_t last = first + child;  // exclusive
     if (cx.lane == 0) cx.par[child] = (uint8_t)(a - first);
     for (uint32_t w = cx.lane; w < L.W; w += 32) {
-        uint32_t b0 = w * 32, b1 = b0 + 32;
-        uint32_t s = max(first, b0), e = min(last, b1);
+        const uint32_t b0 = w * 32, b1 = b0 + 32;
+        const uint32_t s = max(first, b0), e = min(last, b1);
         if (s < e) {
-            uint32_t len = e - s;
-            uint32_t m = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << (s - b0);
+            const uint32_t len = e - s;
+            const uint32_t m = (len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << (s - b0);
             cx.perm[w] &= ~m;
         }
         if (w == (a >> 5)) cx.keym[w] |= 1u << (a & 31);
@@ -105,39 +113,19 @@ __device__ __forceinline__ void walker_reset(const AzbLayout &L, WarpCtx &cx) { 
     __syncwarp();
 }
 
-// the 8 words of node `id`, broadcast to every lane
-struct NodeRec {
-    float c, cstar;
-    uint32_t nt, ex, cnt, lo, n_out, n_in, in_off, depth;
-};
-__device__ __forceinline__ NodeRec load_node(const WarpCtx &cx, uint32_t id) {
-    uint32_t w = cx.lane < 8 ? cx.node[(size_t)id * 8 + cx.lane] : 0u;
-    NodeRec r;
-    r.c = __uint_as_float(__shfl_sync(0xffffffffu, w, ND_C));
-    r.cstar = __uint_as_float(__shfl_sync(0xffffffffu, w, ND_CSTAR));
-    r.nt = __shfl_sync(0xffffffffu, w, ND_NT);
-    uint32_t excnt = __shfl_sync(0xffffffffu, w, ND_EXCNT);
-    r.ex = excnt & 0xffffu;
-    r.cnt = excnt >> 16;
-    r.lo = __shfl_sync(0xffffffffu, w, ND_LO);
-    uint32_t outin = __shfl_sync(0xffffffffu, w, ND_OUTIN);
-    r.n_out = outin & 0xffffu;
-    r.n_in = outin >> 16;
-    r.in_off = __shfl_sync(0xffffffffu, w, ND_INOFF);
-    r.depth = __shfl_sync(0xffffffffu, w, ND_DEPTH);
-    return r;
-}
-
 __device__ __forceinline__ float prior_of(const AzbLayout &L, uint32_t tree, uint32_t a, uint32_t prior_step) {
     if (L.prior_mode == 1) return azb_hash_prior(L.prior_seed, L.first_root + tree, prior_step, a);
     return L.h[(size_t)tree * L.h_ld + a];
 }
 
-// add_actions (graph_operations.rs:32-56): one prediction per legal action, ascending; g = c_s - h (04-c21-tree.rs:103)
-__device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint32_t prior_step) {
+// add_actions (graph_operations.rs:32-56): one prediction per legal action, ascending; g = c_s - h (04-c21-tree.rs:103).
+// Allocates the node's block [preds | header | kids] and publishes its address to the node record and to the copy in
+// the creator's kid entry.
+__device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
     const int lane = cx.lane;
-    uint32_t pos = cx.wk[WK_POS];
-    float c_s = __uint_as_float(cx.wk[10]);
+    const uint32_t pos = cx.wk[WK_POS];
+    const float c_s = __uint_as_float(cx.wk[WK_PEND_C]);
+    const uint32_t prior_step = cx.wk[WK_STEP];
     build_cur_mask(L, cx);
     // legal = permitted minus current edges (space.rs:75-89); counts per word -> exclusive prefix
     uint32_t l0 = (uint32_t)lane < L.W ? (cx.perm[lane] & ~cx.cur[lane]) : 0u;
@@ -151,8 +139,8 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree,
             s1 += t1;
         }
     }
-    uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
-    uint32_t cnt = tot0 + __shfl_sync(0xffffffffu, s1, 31);
+    const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
+    const uint32_t cnt = tot0 + __shfl_sync(0xffffffffu, s1, 31);
     __syncwarp();
     if ((uint32_t)lane < L.W) {
         cx.cur[lane] = l0;
@@ -164,11 +152,19 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree,
     }
     if (lane == 0) cx.pfx[0] = 0u;
     __syncwarp();
-    uint32_t lo = cx.wk[WK_NPREDS];
-    if (lo + cnt > L.cap_preds || cnt > 0xffffu) {
+    if (cnt == 0u) {  // only a root can be terminal here: it stays without a block and inactive
+        if (lane == 0) cx.wk[WK_FLAGS] &= ~1u;
+        __syncwarp();
+        return;
+    }
+    uint32_t lo = cx.wk[WK_NBLK] + cnt;  // header position in units; predictions sit right below it
+    lo += lo & 1u;
+    const uint32_t top = lo + 2u + 2u * cnt;
+    if (top > L.cap_blk || cnt > 0xffffu) {
         cx.err = 3;
         return;
     }
+    const uint32_t lo2 = lo >> 1;
     for (uint32_t j = lane; j < cnt; j += 32) {
         // word holding the j-th legal action: largest w with pfx[w] <= j
         uint32_t a0 = 0, a1 = L.W;  // invariant pfx[a0] <= j < pfx[a1]
@@ -179,28 +175,37 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree,
             else
                 a1 = mid;
         }
-        uint32_t a = a0 * 32 + nth_set_bit(cx.cur[a0], j - cx.pfx[a0]);
-        float h = prior_of(L, tree, a, prior_step);
+        const uint32_t a = a0 * 32 + nth_set_bit(cx.cur[a0], j - cx.pfx[a0]);
+        const float h = prior_of(L, tree, a, prior_step);
         if (h != h) cx.err = 4;
-        float g = __fsub_rn(c_s, h);
-        cx.pred[lo + j] = make_uint2(__float_as_uint(g), a);
+        const float g = __fsub_rn(c_s, h);
+        cx.blk[lo - 1u - j] = make_uint2(__float_as_uint(g), a);
     }
     cx.err = __reduce_or_sync(0xffffffffu, cx.err);
     if (lane == 0) {
-        cx.node[(size_t)pos * 8 + ND_EXCNT] = cnt << 16;  // exhausted_children = 0
-        cx.node[(size_t)pos * 8 + ND_LO] = lo;
-        cx.wk[WK_NPREDS] = lo + cnt;
+        cx.blk4[lo2] = make_uint4(__float_as_uint(c_s), cnt << 16, pos, 0u);
+        uint32_t *rec = reinterpret_cast<uint32_t *>(cx.node + (size_t)pos * 4);
+        rec[3] = cnt << 16;  // exhausted_children = 0
+        rec[4] = lo2;
+        const uint32_t pk = cx.wk[WK_PKIDX];
+        if (pk != AZB_LO_NONE) reinterpret_cast<uint32_t *>(cx.blk4 + pk)[1] = lo2 | 0x80000000u;  // now active
+        if (pos == 0u) cx.wk[WK_ROOTLO] = lo2;
+        cx.wk[WK_CURLO] = lo2;
+        cx.wk[WK_NBLK] = top;
+        cx.wk[WK_NPREDS] += cnt;
         cx.wk[WK_FLAGS] &= ~1u;
+        cx.ct[CT_PRED] += cnt;
     }
-    cx.ct[CT_PRED] += cnt;
     __syncwarp();
 }
 
 // cascade_new_terminal / cascade_old_node (empty_transitions.rs:50-127).  The value carried upward is the start
 // node's c* unchanged (:71-74,111-114), so a level's merge only has to sum the newly-exhausted counts per parent.
+// Every touched node also refreshes the copies of (activity, n_t, c*) held by its parents' kid entries.
 __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, float cstar, uint32_t ntt, uint32_t e0,
                              bool old) {
     const int lane = cx.lane;
+    const uint32_t FULL = 0xffffffffu;
     uint32_t *curN = cx.fr, *curE = cx.fr + AZB_FRONTIER_CAP;
     uint32_t *nxtN = cx.fr + 2 * AZB_FRONTIER_CAP, *nxtE = cx.fr + 3 * AZB_FRONTIER_CAP;
     if (lane == 0) {
@@ -209,64 +214,93 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, floa
     }
     uint32_t ncur = 1;
     __syncwarp();
-    uint4 *node4 = reinterpret_cast<uint4 *>(cx.node);
     while (ncur > 0 && cx.err == 0) {
         uint32_t nnxt = 0;
-        cx.ct[CT_CN] += ncur;
+        count(cx, CT_CN, ncur);
         for (uint32_t base = 0; base < ncur; base += 32) {
-            uint32_t i = base + lane;
-            bool valid = i < ncur;
-            uint32_t nin = 0, off = 0, up = 0;
+            const uint32_t i = base + lane;
+            const bool valid = i < ncur;
+            uint32_t nin = 0, in_off = 0, up = 0, w1 = 0, w2 = 0, w3 = 0;
+            uint4 q2 = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
             if (valid) {
-                uint32_t p = curN[i], e = curE[i];
-                uint4 r0 = node4[(size_t)p * 2], r1 = node4[(size_t)p * 2 + 1];
-                uint32_t ex = (r0.w & 0xffffu) + e, cnt = r0.w >> 16;
-                float cs = __uint_as_float(r0.y);
-                uint32_t nt = r0.z;
+                const uint32_t p = curN[i], e = curE[i];
+                uint4 *rec = cx.node + (size_t)p * 4;
+                uint4 q0 = rec[0];
+                const uint4 q1 = rec[1];
+                q2 = rec[2];
+                q3 = rec[3];
+                const uint32_t ex = (q0.w & 0xffffu) + e, cnt = q0.w >> 16;
+                float cs = __uint_as_float(q0.y);
+                uint32_t nt = q0.z;
                 if (cs > cstar)
                     cs = cstar;
                 else
                     nt += 1;
                 if (old) nt = max(nt, ntt);
-                r0.y = __float_as_uint(cs);
-                r0.z = nt;
-                r0.w = ex | (cnt << 16);
-                node4[(size_t)p * 2] = r0;
+                q0.y = __float_as_uint(cs);
+                q0.z = nt;
+                q0.w = ex | (cnt << 16);
+                rec[0] = q0;
                 up = (ex < cnt) ? 0u : 1u;
-                nin = r1.y >> 16;
-                off = r1.z;
-            }
-            uint32_t nvalid = min(32u, ncur - base);
-            for (uint32_t l = 0; l < nvalid; ++l) {
-                uint32_t nin_l = __shfl_sync(0xffffffffu, nin, l);
-                uint32_t off_l = __shfl_sync(0xffffffffu, off, l);
-                uint32_t up_l = __shfl_sync(0xffffffffu, up, l);
-                cx.ct[CT_DCN] += nin_l;
-                for (uint32_t q0 = 0; q0 < nin_l; q0 += 32) {
-                    bool has = q0 + lane < nin_l;
-                    uint32_t q = has ? cx.inl[off_l + q0 + lane] : 0u;
-                    int idx = -1;
-                    if (has)
-                        for (uint32_t k = 0; k < nnxt; ++k)
-                            if (nxtN[k] == q) {
-                                idx = (int)k;
-                                break;
-                            }
-                    bool fresh = has && idx < 0;
-                    uint32_t bal = __ballot_sync(0xffffffffu, fresh);
-                    if (fresh) {
-                        uint32_t at = nnxt + __popc(bal & lanemask_lt(lane));
-                        if (at < AZB_FRONTIER_CAP) {
-                            nxtN[at] = q;
-                            nxtE[at] = up_l;
-                        }
-                    } else if (has) {
-                        nxtE[idx] += up_l;
+                nin = q1.y;
+                in_off = q1.z;
+                w1 = q1.x | (up ? 0u : 0x80000000u);
+                w2 = nt;
+                w3 = q0.y;
+                // refresh the copies in the parents' kid entries (first four in-arcs are inline)
+                const uint32_t k4 = min(nin, 4u);
+                const uint32_t kx[4] = {q2.y, q2.w, q3.y, q3.w};
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (k < k4) {
+                        uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + kx[k]);
+                        kp[1] = w1;
+                        *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(w2, w3);
                     }
-                    nnxt += __popc(bal);
-                    if (nnxt > AZB_FRONTIER_CAP) {
-                        cx.err = 3;
-                        nnxt = AZB_FRONTIER_CAP;
+            }
+            const uint32_t nvalid = min(32u, ncur - base);
+            for (uint32_t l = 0; l < nvalid; ++l) {
+                const uint32_t nin_l = __shfl_sync(FULL, nin, l);
+                const uint32_t up_l = __shfl_sync(FULL, up, l);
+                count(cx, CT_DCN, nin_l);
+                for (uint32_t k = 0; k < nin_l; ++k) {
+                    uint32_t q;
+                    if (k < 4u) {
+                        const uint32_t sel = k == 0 ? q2.x : (k == 1 ? q2.z : (k == 2 ? q3.x : q3.z));
+                        q = __shfl_sync(FULL, sel, l);
+                    } else {  // overflow in-arcs: refresh the copy here as well
+                        const uint2 ent = cx.inl[__shfl_sync(FULL, in_off, l) + k - 4u];
+                        q = ent.x;
+                        const uint32_t a1 = __shfl_sync(FULL, w1, l), a2 = __shfl_sync(FULL, w2, l),
+                                       a3 = __shfl_sync(FULL, w3, l);
+                        if (lane == 0) {
+                            uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + ent.y);
+                            kp[1] = a1;
+                            *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(a2, a3);
+                        }
+                    }
+                    // merge into the next level (empty_transitions.rs:28-40): one entry per parent
+                    int found = -1;
+                    for (uint32_t s = 0; s < nnxt; s += 32) {
+                        const bool hit = s + lane < nnxt && nxtN[s + lane] == q;
+                        const uint32_t bal = __ballot_sync(FULL, hit);
+                        if (bal) {
+                            found = (int)(s + __ffs(bal) - 1);
+                            break;
+                        }
+                    }
+                    if (found >= 0) {
+                        if (lane == 0) nxtE[found] += up_l;
+                    } else {
+                        if (nnxt >= AZB_FRONTIER_CAP) {
+                            cx.err = 3;
+                        } else {
+                            if (lane == 0) {
+                                nxtN[nnxt] = q;
+                                nxtE[nnxt] = up_l;
+                            }
+                            nnxt += 1;
+                        }
                     }
                     __syncwarp();
                 }
@@ -283,117 +317,121 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, floa
     }
 }
 
-// add_arc (graph_operations.rs:18-30): the new arc becomes kid[lo + n_out] of `src`, and `src` joins dst's parents
-__device__ __forceinline__ void tree_add_arc(WarpCtx &cx, uint32_t src, const NodeRec &s, uint32_t j, uint32_t a,
-                                             float g_bits_as_float, uint32_t dst, uint32_t dst_in_off,
-                                             uint32_t dst_n_in, uint32_t dst_outin_word) {
+// the step of `tree` is complete: publish its argmin candidate (optimizer/mod.rs:203-219) and advance its clock
+__device__ __forceinline__ void step_done(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
     if (cx.lane == 0) {
-        uint32_t slot = s.lo + s.n_out;
-        cx.kid[slot] = make_uint2(dst, j | (a << 16));
-        cx.arcseq[slot] = cx.wk[WK_NARCS];
-        cx.wk[WK_NARCS] += 1;
-        cx.pred[s.lo + j] = make_uint2(__float_as_uint(g_bits_as_float), a | (1u << 16));
-        cx.node[(size_t)src * 8 + ND_OUTIN] = (s.n_out + 1) | (s.n_in << 16);
-        cx.inl[dst_in_off + dst_n_in] = src;
-        cx.node[(size_t)dst * 8 + ND_OUTIN] = (dst_outin_word & 0xffffu) | ((dst_n_in + 1) << 16);
+        const uint32_t step = cx.wk[WK_STEP];
+        if (step < L.cap_steps)
+            L.cand[(size_t)(step + 1u) * L.B + tree] = make_uint2(cx.wk[WK_CAND_C], cx.wk[WK_CAND_NODE]);
+        else
+            cx.err = 3;
+        cx.wk[WK_STEP] = step + 1u;
+        cx.wk[WK_CAND_C] = 0xffffffffu;
+        cx.wk[WK_CAND_NODE] = 0u;
     }
-    cx.ct[CT_ARC] += 1;
-    __syncwarp();
+    cx.err = __reduce_or_sync(0xffffffffu, cx.err);
 }
 
 template <int DEPTH>
-__device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint32_t best_c_start) {
+__device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint32_t max_episodes) {
     const int lane = cx.lane;
-    uint32_t pos = cx.wk[WK_POS], depth = cx.wk[WK_DEPTH];
-    uint4 *node4 = reinterpret_cast<uint4 *>(cx.node);
-    uint32_t guard = 0;
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t pos = cx.wk[WK_POS], depth = cx.wk[WK_DEPTH], lo2 = cx.wk[WK_CURLO];
+    uint32_t guard = 0, episodes = 0;
     for (;;) {
         if (cx.err) break;
-        if (++guard > 4u * L.cap_preds + 64u) {
+        if (++guard > 4u * L.cap_nodes + 64u) {
             cx.err = 6;
             break;
         }
-        NodeRec s = load_node(cx, pos);
-        if (!(s.ex < s.cnt)) {  // next_action.rs:12-14
-            if (depth != 0) cx.err = 6;  // tree/mod.rs:227 unreachable!()
+        // ---- next_action (next_action.rs:11-26) at `pos`
+        bool active = lo2 != AZB_LO_NONE;
+        uint4 hd = make_uint4(0, 0, 0, 0), kd = make_uint4(0, 0, 0, 0);
+        uint2 pr = make_uint2(0, 0);
+        if (active) {  // one round trip: header, first 32 kids, first 32 predictions (+ the root's own record)
+            hd = cx.blk4[lo2];
+            kd = cx.blk4[lo2 + 1u + lane];
+            pr = cx.blk[2u * lo2 - 1u - lane];
+            if (pos == 0u) {
+                const uint4 r0 = cx.node[0];
+                active = (r0.w & 0xffffu) < (r0.w >> 16);
+            }
+        }
+        if (!active) {  // next_action.rs:12-14; only an exhausted root can be here (tree/mod.rs:220-229)
+            if (depth != 0u)
+                cx.err = 6;
+            else {
+                count(cx, CT_NOOP, 1);
+                step_done(L, cx, tree);
+            }
             break;
         }
-        cx.ct[CT_SEL] += 1;
-        cx.ct[CT_DSEL] += s.n_out;
+        const float c_s = __uint_as_float(hd.x);
+        const uint32_t n_out = hd.y & 0xffffu, cnt = hd.y >> 16;
+        count(cx, CT_SEL, 1);
+        count(cx, CT_DSEL, n_out);
         // ---- revisit_choice (next_action.rs:28-53): first minimum of (n_t, c*) over active children, newest first
         unsigned long long best_key = ~0ull;
         int best_t = -1;
-        uint32_t best_child = 0, best_aid = 0;
-        for (uint32_t base = 0; base < s.n_out; base += 32) {
-            uint32_t t = base + lane;
-            bool valid = t < s.n_out;
+        uint32_t best_w0 = 0, best_w1 = 0;
+        for (uint32_t base = 0; base < n_out; base += 32) {
+            if (base) kd = cx.blk4[lo2 + 1u + base + lane];
+            const uint32_t t = base + lane;
             unsigned long long k = ~0ull;
-            uint32_t child = 0, kd_y = 0;
-            if (valid) {
-                uint2 kd = cx.kid[s.lo + t];
-                child = kd.x;
-                kd_y = kd.y;
-                uint4 r0 = node4[(size_t)child * 2];
-                cx.lbuf[t] = __uint_as_float(r0.y);
-                bool act = (r0.w & 0xffffu) < (r0.w >> 16);
-                if (act) k = ((unsigned long long)r0.z << 32) | azb_f2ord(__uint_as_float(r0.y));
+            if (t < n_out) {
+                cx.lbuf[t] = __uint_as_float(kd.w);
+                if (kd.y >> 31) k = ((unsigned long long)kd.z << 32) | azb_f2ord(__uint_as_float(kd.w));
             }
-            unsigned long long mk = warp_min_u64(k);
+            const unsigned long long mk = warp_min_u64(k);
             if (mk != ~0ull && mk <= best_key) {  // a later chunk holds newer arcs: it wins ties
-                uint32_t bal = __ballot_sync(0xffffffffu, k == mk);
-                int wl = 31 - __clz(bal);  // newest arc among equals
+                const uint32_t bal = __ballot_sync(FULL, k == mk);
+                const int wl = 31 - __clz(bal);  // newest arc among equals
                 best_key = mk;
                 best_t = (int)base + wl;
-                best_child = __shfl_sync(0xffffffffu, child, wl);
-                best_aid = __shfl_sync(0xffffffffu, kd_y, wl) >> 16;
+                best_w0 = __shfl_sync(FULL, kd.x, wl);
+                best_w1 = __shfl_sync(FULL, kd.y, wl);
             }
         }
         __syncwarp();
-        bool have_r = best_t >= 0;
-        uint32_t tol = depth < L.tol_len ? L.tol[depth] : L.tol_default;  // 04-c21-tree.rs:136-138
-        bool visit = have_r && (uint32_t)(best_key >> 32) < tol;          // next_action.rs:16-20
+        const bool have_r = best_t >= 0;
+        const uint32_t tol = depth < L.tol_len ? L.tol[depth] : L.tol_default;  // 04-c21-tree.rs:136-138
+        bool visit = have_r && (uint32_t)(best_key >> 32) < tol;               // next_action.rs:16-20
         int chosen_j = -1;
-        uint32_t chosen_a = 0;
-        float chosen_g = 0.f;
+        uint32_t chosen_y = 0;
         if (!visit) {
             // ---- max_curiosity (next_action.rs:55-88)
-            cx.ct[CT_CUR] += 1;
-            cx.ct[CT_CAND] += s.cnt;
-            const bool no_kids = s.n_out == 0;
+            count(cx, CT_CUR, 1);
+            count(cx, CT_CAND, cnt);
+            const bool no_kids = n_out == 0;
             unsigned long long bk = no_kids ? ~0ull : 0ull;
-            for (uint32_t base = 0; base < s.cnt; base += 32) {
-                uint32_t j = base + lane;
-                bool valid = j < s.cnt;
+            for (uint32_t base = 0; base < cnt; base += 32) {
+                if (base) pr = cx.blk[2u * lo2 - 1u - base - lane];
+                const uint32_t j = base + lane;
                 unsigned long long kk = no_kids ? ~0ull : 0ull;
-                uint2 pr = make_uint2(0u, 0u);
-                if (valid) {
-                    pr = cx.pred[s.lo + j];
-                    if (((pr.y >> 16) & 1u) == 0u) {  // no arc yet (:68-71)
-                        float v = __fsub_rn(s.c, __uint_as_float(pr.x));
-                        if (no_kids) {
-                            if (v != v) cx.err = 4;
-                            kk = ((unsigned long long)azb_f2ord(v) << 32) | j;  // first minimum (:73-75)
-                        } else {
-                            float cur = 0.f;
-                            for (int t = (int)s.n_out - 1; t >= 0; --t)  // newest first, left fold (:79-82)
-                                cur = __fadd_rn(cur, __fsqrt_rn(fabsf(__fsub_rn(cx.lbuf[t], v))));
-                            if (cur != cur) cx.err = 4;
-                            kk = ((unsigned long long)azb_f2ord(cur) << 32) | j;  // last maximum (:85)
-                        }
+                if (j < cnt && ((pr.y >> 11) & 1u) == 0u) {  // no arc yet (:68-71)
+                    const float v = __fsub_rn(c_s, __uint_as_float(pr.x));
+                    if (no_kids) {
+                        if (v != v) cx.err = 4;
+                        kk = ((unsigned long long)azb_f2ord(v) << 32) | j;  // first minimum (:73-75)
+                    } else {
+                        float cur = 0.f;
+                        for (int t = (int)n_out - 1; t >= 0; --t)  // newest first, left fold (:79-82)
+                            cur = __fadd_rn(cur, __fsqrt_rn(fabsf(__fsub_rn(cx.lbuf[t], v))));
+                        if (cur != cur) cx.err = 4;
+                        kk = ((unsigned long long)azb_f2ord(cur) << 32) | j;  // last maximum (:85)
                     }
                 }
-                unsigned long long red = no_kids ? warp_min_u64(kk) : warp_max_u64(kk);
-                bool better = no_kids ? (red < bk) : (red > bk);
+                const unsigned long long red = no_kids ? warp_min_u64(kk) : warp_max_u64(kk);
+                const bool better = no_kids ? (red < bk) : (red > bk);
                 if (better) {
                     bk = red;
-                    uint32_t bal = __ballot_sync(0xffffffffu, kk == red);
-                    int wl = __ffs(bal) - 1;
+                    const uint32_t bal = __ballot_sync(FULL, kk == red);
+                    const int wl = __ffs(bal) - 1;
                     chosen_j = (int)(red & 0xffffffffu);
-                    chosen_a = __shfl_sync(0xffffffffu, pr.y, wl) & 0xffffu;
-                    chosen_g = __uint_as_float(__shfl_sync(0xffffffffu, pr.x, wl));
+                    chosen_y = __shfl_sync(FULL, pr.y, wl);
                 }
             }
-            cx.err = __reduce_or_sync(0xffffffffu, cx.err);
+            cx.err = __reduce_or_sync(FULL, cx.err);
             if (cx.err) break;
             if (chosen_j < 0) {
                 if (have_r)
@@ -405,138 +443,334 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
         }
         if (visit) {  // tree/mod.rs:139-159
-            cx.ct[CT_VISIT] += 1;
-            walker_act(L, cx, best_aid);
-            pos = best_child;
+            count(cx, CT_VISIT, 1);
+            walker_act(L, cx, best_w0 >> 20);
+            pos = best_w0 & 0xfffffu;
+            lo2 = best_w1 & 0x7fffffffu;
             depth += 1;
             continue;
         }
         // ---- Unvisited(j) (tree/mod.rs:160-218)
-        const uint32_t a = chosen_a, j = (uint32_t)chosen_j;
-        cx.ct[CT_PROBE] += 1;
-        // key of the successor = path + a; hash it
-        uint32_t k0 = (uint32_t)lane < L.W ? (cx.keym[lane] | (((a >> 5) == (uint32_t)lane) ? 1u << (a & 31) : 0u)) : 0u;
-        uint32_t k1 = (uint32_t)lane + 32 < L.W
-                          ? (cx.keym[lane + 32] | (((a >> 5) == (uint32_t)lane + 32) ? 1u << (a & 31) : 0u))
-                          : 0u;
-        uint32_t hv = key_hash(k0, k1, lane, L.W);
+        const uint32_t a = chosen_y & 0x7ffu, j = (uint32_t)chosen_j;
+        count(cx, CT_PROBE, 1);
+        // key of the successor = path + a; look it up
+        const uint32_t k0 = (uint32_t)lane < L.W ? (cx.keym[lane] | (((a >> 5) == (uint32_t)lane) ? 1u << (a & 31) : 0u)) : 0u;
+        const uint32_t k1 = (uint32_t)lane + 32 < L.W
+                                ? (cx.keym[lane + 32] | (((a >> 5) == (uint32_t)lane + 32) ? 1u << (a & 31) : 0u))
+                                : 0u;
+        const uint32_t hv = key_hash(k0, k1, lane, L.W);
+        const uint32_t fp = hv >> 21;
         uint32_t slot = hv & (L.cap_hash - 1);
         int hit = -1;
         for (uint32_t probes = 0; probes < L.cap_hash; ++probes) {
-            uint32_t e = cx.hash[slot];
+            const uint32_t e = cx.hash[slot];
             if (e == 0u) break;
-            uint32_t idx = e - 1;
-            bool eq = true;
-            if ((uint32_t)lane < L.W) eq = cx.key[(size_t)idx * L.W + lane] == k0;
-            if ((uint32_t)lane + 32 < L.W) eq = eq && (cx.key[(size_t)idx * L.W + lane + 32] == k1);
-            if (__all_sync(0xffffffffu, eq)) {
-                hit = (int)idx;
-                break;
+            if ((e >> 21) == fp) {
+                const uint32_t idx = (e & 0x1fffffu) - 1u;
+                bool eq = true;
+                if ((uint32_t)lane < L.W) eq = cx.key[(size_t)idx * L.W + lane] == k0;
+                if ((uint32_t)lane + 32 < L.W) eq = eq && (cx.key[(size_t)idx * L.W + lane + 32] == k1);
+                if (__all_sync(FULL, eq)) {
+                    hit = (int)idx;
+                    break;
+                }
             }
             slot = (slot + 1) & (L.cap_hash - 1);
         }
-        if (hit >= 0) {  // transposition (tree/mod.rs:172-179)
-            cx.ct[CT_HIT] += 1;
-            NodeRec o = load_node(cx, (uint32_t)hit);
-            if (o.n_in >= o.depth) {
-                cx.err = 3;
-                break;
-            }
-            tree_add_arc(cx, pos, s, j, a, chosen_g, (uint32_t)hit, o.in_off, o.n_in, o.n_out);
-            tree_cascade(L, cx, pos, o.cstar, o.nt, (o.ex < o.cnt) ? 0u : 1u, true);
-            walker_reset(L, cx);
-            pos = 0;
-            depth = 0;
-            cx.ct[CT_RESET] += 1;
-            continue;
-        }
-        // ---- new node (tree/mod.rs:181-216)
-        walker_act(L, cx, a);
-        const uint32_t ndepth = depth + 1;
-        double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
-        uint32_t mu = azb_matching(L.N, cx.par);
-        if (!(l1 >= 1.4)) {  // ordered_edge.rs:79
-            cx.err = 5;
-            break;
-        }
-        float c_new = azb_evaluate(mu, l1, L.c_lower, L.slope);
-        cx.ct[CT_INS] += 1;
-        const uint32_t nn = cx.wk[WK_NNODES], in_off = cx.wk[WK_INTOP];
-        if (nn >= L.cap_nodes || in_off + ndepth > L.cap_in) {
+        const uint32_t kidx = lo2 + 1u + n_out;  // this arc's kid entry (16-byte index)
+        const uint32_t narcs = cx.wk[WK_NARCS];
+        if (narcs >= (1u << 20)) {
             cx.err = 3;
             break;
         }
-        __syncwarp();
-        if (lane < 8) {
-            uint32_t w = 0u;
-            if (lane == ND_C || lane == ND_CSTAR) w = __float_as_uint(c_new);  // StateWeight::new (state_weight.rs:13-21)
-            if (lane == ND_OUTIN) w = 0u;  // n_out = 0, n_in = 0 (add_arc below makes it 1)
-            if (lane == ND_INOFF) w = in_off;
-            if (lane == ND_DEPTH) w = ndepth;
-            cx.node[(size_t)nn * 8 + lane] = w;
-        }
-        if ((uint32_t)lane < L.W) cx.key[(size_t)nn * L.W + lane] = k0;
-        if ((uint32_t)lane + 32 < L.W) cx.key[(size_t)nn * L.W + lane + 32] = k1;
-        if (lane == 0) {
-            cx.hash[slot] = nn + 1;
-            cx.wk[WK_NNODES] = nn + 1;
-            cx.wk[WK_INTOP] = in_off + ndepth;
-        }
-        __syncwarp();
-        tree_add_arc(cx, pos, s, j, a, chosen_g, nn, in_off, 0u, 0u);
-        // argmin candidate: first minimum of c over this step's new nodes that beats the best (optimizer/mod.rs:208-213)
-        uint32_t oc = azb_f2ord(c_new);
-        if (oc < best_c_start && oc < cx.wk[WK_CAND_C]) {
-            if (lane == 0) {
-                cx.wk[WK_CAND_C] = oc;
-                cx.wk[WK_CAND_NODE] = nn;
+        bool reset = false;
+        if (hit >= 0) {  // transposition (tree/mod.rs:172-179)
+            count(cx, CT_HIT, 1);
+            uint4 *rec = cx.node + (size_t)hit * 4;
+            const uint4 q0 = rec[0], q1 = rec[1];
+            const bool act_o = (q0.w & 0xffffu) < (q0.w >> 16);
+            const uint32_t nin = q1.y;
+            if (nin >= q1.w) {  // a node of depth d has at most d parents
+                cx.err = 3;
+                break;
+            }
+            if (lane == 0) {  // add_arc (graph_operations.rs:18-30)
+                cx.blk4[kidx] = make_uint4((uint32_t)hit | (a << 20), q1.x | (act_o ? 0x80000000u : 0u), q0.z, q0.y);
+                reinterpret_cast<uint32_t *>(cx.blk4 + lo2)[1] = (n_out + 1u) | (cnt << 16);
+                cx.blk[2u * lo2 - 1u - j].y = a | (1u << 11) | (narcs << 12);
+                if (nin < 4u)
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<uint32_t *>(rec) + 8 + 2 * nin) = make_uint2(pos, kidx);
+                else
+                    cx.inl[q1.z + nin - 4u] = make_uint2(pos, kidx);
+                reinterpret_cast<uint32_t *>(rec)[5] = nin + 1u;
+                cx.wk[WK_NARCS] = narcs + 1u;
+                cx.ct[CT_ARC] += 1;
             }
             __syncwarp();
+            tree_cascade(L, cx, pos, __uint_as_float(q0.y), q0.z, act_o ? 0u : 1u, true);
+            reset = true;
+        } else {
+            // ---- new node (tree/mod.rs:181-216)
+            walker_act(L, cx, a);
+            const uint32_t ndepth = depth + 1;
+            const double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
+            const uint32_t mu = azb_matching(L.N, cx.par);
+            if (!(l1 >= 1.4)) {  // ordered_edge.rs:79
+                cx.err = 5;
+                break;
+            }
+            const float c_new = azb_evaluate(mu, l1, L.c_lower, L.slope);
+            count(cx, CT_INS, 1);
+            const uint32_t nn = cx.wk[WK_NNODES], in_off = cx.wk[WK_INTOP];
+            const uint32_t in_need = ndepth > 4u ? ndepth - 4u : 0u;
+            if (nn >= L.cap_nodes || in_off + in_need > L.cap_in) {
+                cx.err = 3;
+                break;
+            }
+            // is_terminal (nabla/space/mod.rs:27-29)
+            build_cur_mask(L, cx);
+            bool any = false;
+            for (uint32_t w = lane; w < L.W; w += 32) any = any || ((cx.perm[w] & ~cx.cur[w]) != 0u);
+            any = __any_sync(FULL, any);
+            if (lane < 4) {  // StateWeight::new (state_weight.rs:13-21) + the creating arc as in-arc 0
+                uint4 q;
+                if (lane == 0)
+                    q = make_uint4(__float_as_uint(c_new), __float_as_uint(c_new), 0u, 0u);
+                else if (lane == 1)
+                    q = make_uint4(AZB_LO_NONE, 1u, in_off, ndepth);
+                else if (lane == 2)
+                    q = make_uint4(pos, kidx, 0u, 0u);
+                else
+                    q = make_uint4(0u, 0u, 0u, 0u);
+                cx.node[(size_t)nn * 4 + lane] = q;
+            }
+            if ((uint32_t)lane < L.W) cx.key[(size_t)nn * L.W + lane] = k0;
+            if ((uint32_t)lane + 32 < L.W) cx.key[(size_t)nn * L.W + lane + 32] = k1;
+            if (lane == 0) {
+                cx.hash[slot] = (nn + 1u) | (fp << 21);
+                cx.wk[WK_NNODES] = nn + 1;
+                cx.wk[WK_INTOP] = in_off + in_need;
+                // add_arc: the child is inactive until its own add_actions (actions = 0..0)
+                cx.blk4[kidx] = make_uint4(nn | (a << 20), AZB_LO_NONE, 0u, __float_as_uint(c_new));
+                reinterpret_cast<uint32_t *>(cx.blk4 + lo2)[1] = (n_out + 1u) | (cnt << 16);
+                cx.blk[2u * lo2 - 1u - j].y = a | (1u << 11) | (narcs << 12);
+                cx.wk[WK_NARCS] = narcs + 1u;
+                cx.ct[CT_ARC] += 1;
+                // argmin candidate: first minimum of c over this step's new nodes (optimizer/mod.rs:208-213)
+                const uint32_t oc = azb_f2ord(c_new);
+                if (oc < cx.wk[WK_CAND_C]) {
+                    cx.wk[WK_CAND_C] = oc;
+                    cx.wk[WK_CAND_NODE] = nn;
+                }
+            }
+            __syncwarp();
+            if (!any) {
+                count(cx, CT_TERM, 1);
+                tree_cascade(L, cx, pos, c_new, 0u, 1u, false);
+                reset = true;
+            } else {
+                pos = nn;
+                depth = ndepth;
+                lo2 = AZB_LO_NONE;
+                if (lane == 0) {
+                    cx.wk[WK_FLAGS] |= 1u;
+                    cx.wk[WK_PEND_C] = __float_as_uint(c_new);
+                    cx.wk[WK_PKIDX] = kidx;
+                    cx.ct[CT_LIVE] += 1;
+                }
+                __syncwarp();
+                step_done(L, cx, tree);
+                break;  // tree/mod.rs:212-215
+            }
         }
-        // is_terminal (nabla/space/mod.rs:27-29)
-        build_cur_mask(L, cx);
-        bool any = false;
-        for (uint32_t w = lane; w < L.W; w += 32) any = any || ((cx.perm[w] & ~cx.cur[w]) != 0u);
-        any = __any_sync(0xffffffffu, any);
-        if (!any) {
-            cx.ct[CT_TERM] += 1;
-            tree_cascade(L, cx, pos, c_new, 0u, 1u, false);
+        if (reset) {
             walker_reset(L, cx);
             pos = 0;
             depth = 0;
-            cx.ct[CT_RESET] += 1;
-            continue;
+            lo2 = cx.wk[WK_ROOTLO];
+            count(cx, CT_RESET, 1);
+            if (max_episodes && ++episodes >= max_episodes) break;  // yield: the step continues in the next launch
         }
-        pos = nn;
-        depth = ndepth;
-        if (lane == 0) {
-            cx.wk[WK_FLAGS] |= 1u;
-            cx.wk[10] = __float_as_uint(c_new);
-        }
-        __syncwarp();
-        break;  // tree/mod.rs:212-215
     }
     if (lane == 0) {
         cx.wk[WK_POS] = pos;
         cx.wk[WK_DEPTH] = depth;
+        cx.wk[WK_CURLO] = lo2;
     }
     __syncwarp();
 }
 
 // write_vec (rooted_tree/space.rs:91-101): [A one-hot of current edges | A permitted mask] as f32
 __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
-    build_cur_mask(L, cx);
     float *row = L.sv + (size_t)tree * L.sv_ld;
     for (uint32_t i = cx.lane; i < 2 * L.A; i += 32) {
-        uint32_t b = i < L.A ? (cx.cur[i >> 5] >> (i & 31)) : (cx.perm[(i - L.A) >> 5] >> ((i - L.A) & 31));
-        row[i] = (b & 1u) ? 1.0f : 0.0f;
+        bool one;
+        if (i < L.A) {
+            const uint32_t child = cx.lut[i];
+            one = (uint32_t)cx.par[child] == i - azb_child_first_action(child);
+        } else {
+            one = (cx.perm[(i - L.A) >> 5] >> ((i - L.A) & 31)) & 1u;
+        }
+        row[i] = one ? 1.0f : 0.0f;
+    }
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
+    azb_tree_kernel(const AzbLayout L, const uint32_t flags, const uint32_t smem_words_per_warp, const uint32_t lcap,
+                    const uint32_t target_step, const uint32_t max_episodes) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t s_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tree = blockIdx.x * AZB_WARPS_PER_BLOCK + warp;
+    uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)AZB_WARPS_PER_BLOCK * smem_words_per_warp);
+    for (uint32_t a = threadIdx.x; a < L.A; a += blockDim.x) lut[a] = (uint8_t)azb_action_child(a);
+    __syncthreads();
+    uint32_t *base = smem + (size_t)warp * smem_words_per_warp;
+    if (tree < L.B) {
+        WarpCtx cx;
+        cx.lane = lane;
+        cx.err = 0;
+        cx.lut = lut;
+        cx.wk = base;
+        cx.par = (uint8_t *)(base + WK_HDR);
+        cx.perm = base + WK_HDR + L.PW;
+        cx.keym = cx.perm + L.W;
+        cx.rpar = (uint8_t *)(cx.keym + L.W);
+        cx.rperm = cx.keym + L.W + L.PW;
+        uint32_t *p = base + ((L.WS + 3u) & ~3u);
+        cx.cur = p;
+        p += 64;
+        cx.pfx = p;
+        p += 64;
+        cx.ct = p;
+        p += 16;
+        cx.lbuf = (float *)p;
+        p += lcap;
+        cx.fr = p;
+        p += 4 * AZB_FRONTIER_CAP;
+        cx.cs = reinterpret_cast<CostScratch *>(p);
+        cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
+        cx.blk = L.blk + (size_t)tree * L.cap_blk;
+        cx.blk4 = reinterpret_cast<uint4 *>(cx.blk);
+        cx.inl = L.inl + (size_t)tree * L.cap_in;
+        cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
+        cx.hash = L.hash + (size_t)tree * L.cap_hash;
+        uint32_t *gw = L.walker + (size_t)tree * L.WS;
+        for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gw[i];
+        if (lane < 16) cx.ct[lane] = 0u;
+        __syncwarp();
+
+        if (flags & AZB_F_INIT) {
+            // tail of par_new / par_reset_trees (optimizer/mod.rs:62-101, 340-359): state <- root, root cost, root node
+            walker_reset(L, cx);
+            const double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
+            const uint32_t mu = azb_matching(L.N, cx.par);
+            if (!(l1 >= 1.4)) cx.err = 5;
+            const float c0 = azb_evaluate(mu, l1, L.c_lower, L.slope);
+            if (lane < 4) {
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (lane == 0) q = make_uint4(__float_as_uint(c0), __float_as_uint(c0), 0u, 0u);
+                if (lane == 1) q = make_uint4(AZB_LO_NONE, 0u, 0u, 0u);
+                cx.node[lane] = q;
+            }
+            if ((uint32_t)lane < L.W) cx.key[lane] = 0u;
+            if ((uint32_t)lane + 32 < L.W) cx.key[lane + 32] = 0u;
+            const uint32_t hv = key_hash(0u, 0u, lane, L.W);  // the empty path hashes like every other key
+            if (lane == 0) {
+                cx.hash[hv & (L.cap_hash - 1)] = 1u | ((hv >> 21) << 21);
+                cx.wk[WK_POS] = 0;
+                cx.wk[WK_DEPTH] = 0;
+                cx.wk[WK_NNODES] = 1;
+                cx.wk[WK_NBLK] = AZB_BLK_PAD;
+                cx.wk[WK_NARCS] = 0;
+                cx.wk[WK_INTOP] = 0;
+                cx.wk[WK_STEP] = 0;
+                cx.wk[WK_PEND_C] = __float_as_uint(c0);
+                cx.wk[WK_PKIDX] = AZB_LO_NONE;
+                cx.wk[WK_NPREDS] = 0;
+                cx.wk[WK_ROOTLO] = AZB_LO_NONE;
+                cx.wk[WK_CURLO] = AZB_LO_NONE;
+                cx.wk[WK_ERR] = 0;
+                cx.wk[WK_FLAGS] = 1u;
+                if (flags & AZB_F_FIRST) {
+                    // par_new: silent argmin over the roots (optimizer/mod.rs:95-101) = candidate slot 0
+                    L.cand[tree] = make_uint2(azb_f2ord(c0), 0u);
+                    cx.wk[WK_CAND_C] = 0xffffffffu;
+                    cx.wk[WK_CAND_NODE] = 0u;
+                } else {
+                    // par_reset_trees zeroes num_inspected_nodes (optimizer/mod.rs:359): the new root is looked at by
+                    // the first step's argmin scan; node 0 wins ties against later nodes
+                    cx.wk[WK_CAND_C] = azb_f2ord(c0);
+                    cx.wk[WK_CAND_NODE] = 0u;
+                }
+            }
+            __syncwarp();
+            tree_pack(L, cx, tree);
+        }
+        if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions(L, cx, tree);
+        if ((flags & AZB_F_ROLLOUT) && cx.err == 0 && cx.wk[WK_STEP] < target_step && !(cx.wk[WK_FLAGS] & 1u)) {
+            tree_rollout<DEPTH>(L, cx, tree, max_episodes);
+            if (cx.err == 0 && (cx.wk[WK_FLAGS] & 1u)) tree_pack(L, cx, tree);  // optimizer/mod.rs:171-173
+        }
+        __syncwarp();
+        // publish: walker block (without the root part), counters, errors, distance to the target
+        const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
+        for (uint32_t i = lane; i < live_words; i += 32) gw[i] = cx.wk[i];
+        if (lane < 16) {
+            const uint32_t v = cx.ct[lane];
+            if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
+        }
+        if (lane == 0 && (flags & AZB_F_ROLLOUT) && cx.wk[WK_STEP] < target_step) atomicAdd(&L.g->behind_accum, 1u);
+        const uint32_t e = __reduce_or_sync(0xffffffffu, cx.err);
+        if (e && lane == 0) {
+            if (atomicCAS(&L.g->err, 0u, e) == 0u) {
+                L.g->err_tree = tree;
+                L.g->err_step = cx.wk[WK_STEP];
+            }
+        }
+    }
+    // ---- last block done: publish how many trees still have to reach the target
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&L.g->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        AzbGlobals *g = L.g;
+        g->n_behind = *((volatile uint32_t *)&g->behind_accum);
+        g->behind_accum = 0u;
+        g->blocks_done = 0u;
+        __threadfence();
+    }
+}
+
+// ---- par_update_argmmim_data across trees and steps (optimizer/mod.rs:194-246) -----------------------------------
+// pass 1: per candidate slot, the first minimum over trees (lowest tree index wins ties)
+__global__ void __launch_bounds__(256) azb_stepmin_kernel(const AzbLayout L, const uint32_t slot_lo) {
+    __shared__ unsigned long long red[8];
+    const uint32_t slot = slot_lo + blockIdx.x;
+    const uint2 *row = L.cand + (size_t)slot * L.B;
+    unsigned long long m = ~0ull;
+    for (uint32_t t = threadIdx.x; t < L.B; t += blockDim.x) {
+        const unsigned long long k = ((unsigned long long)row[t].x << 32) | t;
+        m = k < m ? k : m;
+    }
+    m = warp_min_u64(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = red[i] < m ? red[i] : m;
+        L.stepmin[slot] = m;
     }
 }
 
 // replay a node's action set on its tree's root (optimizer/mod.rs:224-239) into g->argmin_state; one warp
-__device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, uint32_t tree, uint32_t node, int lane) {
+__device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, const uint8_t *lut, uint32_t tree,
+                                      uint32_t node, int lane) {
     WarpCtx cx;
     cx.lane = lane;
+    cx.lut = lut;
     cx.wk = scratch;
     cx.par = (uint8_t *)(scratch + WK_HDR);
     cx.perm = scratch + WK_HDR + L.PW;
@@ -561,176 +795,53 @@ __device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, uin
     for (uint32_t w = lane; w < 61; w += 32) L.g->argmin_state[16 + w] = w < L.W ? cx.perm[w] : 0u;
 }
 
-template <int DEPTH>
-__global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
-    azb_tree_kernel(const AzbLayout L, const uint32_t flags, const uint32_t smem_words_per_warp, const uint32_t lcap) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ uint32_t s_last;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tree = blockIdx.x * AZB_WARPS_PER_BLOCK + warp;
-    uint32_t *base = smem + (size_t)warp * smem_words_per_warp;
-    const uint32_t best_c_start = L.g->best_c;
-    const uint32_t prior_step = (flags & AZB_F_INIT) ? 0u : L.g->step;  // priors of step t feed the add_actions after rollout t-1
-    if (tree < L.B) {
-        WarpCtx cx;
-        cx.lane = lane;
-        cx.err = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cx.ct[i] = 0;
-        cx.wk = base;
-        cx.par = (uint8_t *)(base + WK_HDR);
-        cx.perm = base + WK_HDR + L.PW;
-        cx.keym = cx.perm + L.W;
-        cx.rpar = (uint8_t *)(cx.keym + L.W);
-        cx.rperm = cx.keym + L.W + L.PW;
-        uint32_t *p = base + L.WS;
-        cx.cur = p;
-        p += 64;
-        cx.pfx = p;
-        p += 64;
-        cx.lbuf = (float *)p;
-        p += lcap;
-        cx.fr = p;
-        p += 4 * AZB_FRONTIER_CAP;
-        cx.cs = reinterpret_cast<CostScratch *>(p);
-        cx.node = reinterpret_cast<uint32_t *>(L.node) + (size_t)tree * L.cap_nodes * 8;
-        cx.pred = L.pred + (size_t)tree * L.cap_preds;
-        cx.kid = L.kid + (size_t)tree * L.cap_preds;
-        cx.arcseq = L.arcseq + (size_t)tree * L.cap_preds;
-        cx.inl = L.inl + (size_t)tree * L.cap_in;
-        cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
-        cx.hash = L.hash + (size_t)tree * L.cap_hash;
-        uint32_t *gw = L.walker + (size_t)tree * L.WS;
-        for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gw[i];
-        __syncwarp();
-        if (lane == 0) cx.wk[WK_CAND_C] = 0xffffffffu;
-        __syncwarp();
-
-        if (flags & AZB_F_INIT) {
-            // tail of par_new / par_reset_trees (optimizer/mod.rs:62-101, 340-359): state <- root, root cost, root node
-            walker_reset(L, cx);
-            double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
-            uint32_t mu = azb_matching(L.N, cx.par);
-            if (!(l1 >= 1.4)) cx.err = 5;
-            float c0 = azb_evaluate(mu, l1, L.c_lower, L.slope);
-            if (lane < 8) {
-                uint32_t w = 0u;
-                if (lane == ND_C || lane == ND_CSTAR) w = __float_as_uint(c0);
-                cx.node[lane] = w;
-            }
-            if ((uint32_t)lane < L.W) cx.key[lane] = 0u;
-            if ((uint32_t)lane + 32 < L.W) cx.key[lane + 32] = 0u;
-            // empty path hashes like every other key
-            uint32_t hv = key_hash(0u, 0u, lane, L.W);
-            if (lane == 0) {
-                cx.hash[hv & (L.cap_hash - 1)] = 1u;
-                cx.wk[WK_POS] = 0;
-                cx.wk[WK_DEPTH] = 0;
-                cx.wk[WK_NNODES] = 1;
-                cx.wk[WK_NPREDS] = 0;
-                cx.wk[WK_NARCS] = 0;
-                cx.wk[WK_INTOP] = 0;
-                cx.wk[10] = __float_as_uint(c0);
-                if (flags & AZB_F_FIRST) {
-                    // par_new: silent argmin over the roots (optimizer/mod.rs:95-101)
-                    cx.wk[WK_FLAGS] = 1u;
-                    cx.wk[WK_CAND_C] = azb_f2ord(c0);
-                    cx.wk[WK_CAND_NODE] = 0;
-                } else {
-                    // par_reset_trees zeroes num_inspected_nodes (optimizer/mod.rs:359): the new root is looked at by
-                    // the first step's argmin scan
-                    cx.wk[WK_FLAGS] = 3u;
+// pass 2: walk the slots in step order with the running best; log the improving steps; rebuild the argmin state.
+// slot 0 holds the roots of par_new and is silent.
+__global__ void __launch_bounds__(32) azb_argmin_kernel(const AzbLayout L, const uint32_t slot_lo, const uint32_t slot_hi) {
+    __shared__ uint32_t scratch[WK_HDR + 16 + 2 * 61 + 8];
+    __shared__ uint8_t lut[2048];
+    const int lane = threadIdx.x;
+    for (uint32_t a = lane; a < L.A; a += 32) lut[a] = (uint8_t)azb_action_child(a);
+    __syncwarp();
+    AzbGlobals *g = L.g;
+    uint32_t best = g->best_c, n_imp = g->n_improved, last = 0, have = 0, tree = 0, node = 0;
+    for (uint32_t s = slot_lo; s < slot_hi; ++s) {
+        const unsigned long long m = L.stepmin[s];
+        const uint32_t oc = (uint32_t)(m >> 32);
+        last = 0;
+        if (oc < best) {
+            best = oc;
+            tree = (uint32_t)m;
+            node = L.cand[(size_t)s * L.B + tree].y;
+            have = 1;
+            if (s != 0u) {
+                last = 1;
+                if (lane == 0 && n_imp < L.log_cap) {
+                    L.log[n_imp].step = s - 1u;
+                    L.log[n_imp].tree = tree;
+                    L.log[n_imp].node = node;
+                    L.log[n_imp].eval = azb_ord2f(oc);
                 }
+                n_imp += 1;
             }
-            __syncwarp();
-            tree_pack(L, cx, tree);
-        }
-        if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions(L, cx, tree, prior_step);
-        if (flags & AZB_F_ROLLOUT) {
-            if (cx.wk[WK_FLAGS] & 2u) {  // root not yet inspected by par_update_argmmim_data (optimizer/mod.rs:203-219)
-                uint32_t oc = azb_f2ord(__uint_as_float(cx.node[ND_C]));
-                __syncwarp();
-                if (lane == 0) {
-                    cx.wk[WK_FLAGS] &= ~2u;
-                    if (oc < best_c_start) {
-                        cx.wk[WK_CAND_C] = oc;
-                        cx.wk[WK_CAND_NODE] = 0;
-                    }
-                }
-                __syncwarp();
-            }
-            tree_rollout<DEPTH>(L, cx, tree, best_c_start);
-            if (cx.err == 0) {
-                if (cx.wk[WK_DEPTH] != 0) {  // optimizer/mod.rs:171-173
-                    cx.ct[CT_LIVE] += 1;
-                    tree_pack(L, cx, tree);
-                } else {
-                    cx.ct[CT_NOOP] += 1;
-                }
-            }
-        }
-        __syncwarp();
-        // publish: walker block (without the root part), the step's argmin candidate, counters, errors
-        const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
-        for (uint32_t i = lane; i < live_words; i += 32) gw[i] = cx.wk[i];
-        if (lane == 0 && cx.wk[WK_CAND_C] != 0xffffffffu)
-            atomicMin(&L.g->step_best, ((unsigned long long)cx.wk[WK_CAND_C] << 32) | tree);
-        if (lane < 16) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (lane == i) v = cx.ct[i];
-            if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
-        }
-        uint32_t e = __reduce_or_sync(0xffffffffu, cx.err);
-        if (e && lane == 0) {
-            if (atomicCAS(&L.g->err, 0u, e) == 0u) L.g->err_tree = tree;
         }
     }
-    // ---- last block done: par_update_argmmim_data's cross-tree minimum (optimizer/mod.rs:221-245)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&L.g->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (s_last && warp == 0) {
-        __threadfence();
-        AzbGlobals *g = L.g;
-        unsigned long long sb = *((volatile unsigned long long *)&g->step_best);
-        uint32_t improved = 0;
-        if (sb != ~0ull) {
-            uint32_t oc = (uint32_t)(sb >> 32), t = (uint32_t)sb;
-            if (oc < g->best_c) {
-                uint32_t node = *((volatile uint32_t *)&L.walker[(size_t)t * L.WS + WK_CAND_NODE]);
-                improved = (flags & AZB_F_INIT) ? 0u : 1u;
-                if (lane == 0) {
-                    g->best_c = oc;
-                    if (improved) {
-                        uint32_t n = g->n_improved;
-                        if (n < L.log_cap) {
-                            L.log[n].step = g->step;
-                            L.log[n].tree = t;
-                            L.log[n].node = node;
-                            L.log[n].eval = azb_ord2f(oc);
-                        }
-                        g->n_improved = n + 1;
-                    }
-                }
-                finalize_argmin_state(L, base, t, node, lane);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            g->step_best = ~0ull;
-            g->improved_last = improved;
-            if (flags & AZB_F_ROLLOUT) g->step += 1;
-            g->blocks_done = 0u;
-            __threadfence();
+    if (have) finalize_argmin_state(L, scratch, lut, tree, node, lane);
+    __syncwarp();
+    if (lane == 0) {
+        g->best_c = best;
+        g->n_improved = n_imp;
+        g->improved_last = last;
+        if (have) {
+            g->argmin_tree = tree;
+            g->argmin_node = node;
         }
     }
 }
 
 // write_observations (tree/mod.rs:242-264) for every tree, plus the root vectors par_update_model packs first
-// (optimizer/mod.rs:253-259).  One warp per tree; h_sa = c*_as (04-c21-tree.rs:104).
+// (optimizer/mod.rs:253-259).  One warp per tree; h_sa = c*_as (04-c21-tree.rs:104).  The root's kid entries carry
+// everything needed.
 __global__ void __launch_bounds__(128) azb_observe_kernel(const AzbLayout L, const uint32_t n_obs_tol,
                                                           float *__restrict__ obs, float *__restrict__ wts,
                                                           float *__restrict__ root_vecs) {
@@ -743,23 +854,21 @@ __global__ void __launch_bounds__(128) azb_observe_kernel(const AzbLayout L, con
         w[a] = 0.f;
     }
     __syncwarp();
-    const uint4 *node4 = L.node + (size_t)tree * L.cap_nodes * 2;
-    const uint2 *kid = L.kid + (size_t)tree * L.cap_preds;
-    const uint4 r0 = node4[0], r1 = node4[1];
-    const uint32_t lo = r1.x, n_out = r1.y & 0xffffu;
-    for (uint32_t t = lane; t < n_out; t += 32) {
-        const uint2 kd = kid[lo + t];
-        const uint4 c0 = node4[(size_t)kd.x * 2];
-        const bool active = (c0.w & 0xffffu) < (c0.w >> 16);
-        if (!active || c0.z >= n_obs_tol) {
-            const uint32_t a = kd.y >> 16;
-            o[a] = __uint_as_float(c0.y);
-            w[a] = 1.0f;
+    const uint32_t *wk = L.walker + (size_t)tree * L.WS;
+    const uint32_t lo2 = wk[WK_ROOTLO];
+    if (lo2 != AZB_LO_NONE) {
+        const uint4 *blk4 = reinterpret_cast<const uint4 *>(L.blk + (size_t)tree * L.cap_blk);
+        const uint32_t n_out = blk4[lo2].y & 0xffffu;
+        for (uint32_t t = lane; t < n_out; t += 32) {
+            const uint4 kd = blk4[lo2 + 1u + t];
+            if (!(kd.y >> 31) || kd.z >= n_obs_tol) {
+                const uint32_t a = kd.x >> 20;
+                o[a] = __uint_as_float(kd.w);
+                w[a] = 1.0f;
+            }
         }
     }
-    (void)r0;
     if (root_vecs) {
-        const uint32_t *wk = L.walker + (size_t)tree * L.WS;
         const uint8_t *rpar = (const uint8_t *)(wk + WK_HDR + L.PW + 2 * L.W);
         const uint32_t *rperm = wk + WK_HDR + 2 * L.PW + 2 * L.W;
         float *row = root_vecs + (size_t)tree * L.sv_ld;

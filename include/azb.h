@@ -78,7 +78,10 @@ typedef struct azb_config {
     uint32_t cap_nodes;         /* per-tree capacities; 0 = derive from max_steps */
     uint32_t cap_preds;
     uint32_t cap_parents;
-    uint32_t reserved[8];
+    uint32_t max_episodes;      /* 0: every launch runs each tree to the end of its step (the reference's lock step).
+                                   k > 0: a tree that keeps hitting terminal nodes / transpositions yields after k
+                                   episodes and finishes the step in a later launch; same results, shorter launches */
+    uint32_t reserved[7];
 } azb_config;
 
 typedef struct azb_counters {   /* workload counters; definitions in oracle/azb_oracle.h and DESIGN.md */

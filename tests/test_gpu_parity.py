@@ -349,3 +349,42 @@ def test_cpp_host_mirror_example_runs(capi):
     out = subprocess.run([exe, "64", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "observed root actions" in out.stdout
+
+
+@pytest.mark.parametrize("max_episodes", [1, 2, 5])
+def test_bounded_episode_launches_give_identical_trees(capi, orc, max_episodes):
+    """max_episodes != 0: trees yield after k episodes and finish their step in later launches.  Trees are
+    independent, so every tree, the counters and the improvement log must equal the lock-step oracle run."""
+    n, b, steps, seed = 19, 96, 150, 11
+    a_dim = orc.action_dim(n)
+    parents, masks = orc.generate_roots(seed, 0, b, n)
+    o = orc.Optimizer(n, b, lambda_method=orc.LAMBDA_MULTISECTION, n_threads=4)
+    o.set_roots(parents, masks)
+    o.init_trees(orc.hash_priors(seed, 0, b, a_dim, 0))
+    imp_o = o.steps_hash(seed, 0, 1, steps)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_HASH, prior_seed=seed, max_steps=steps, max_episodes=max_episodes) as h:
+        h.set_roots(parents, masks)
+        h.init_trees()
+        imp_g = []
+        for k in (1, 7, steps - 8):
+            imp_g += [s for (s, _, _, _) in h.step(k, cap=1024)[1]]
+        _cmp_trees(o, h, b)
+        _cmp_walkers(o, h)
+        assert [s - 1 for s in imp_o] == imp_g
+        assert h.counters() == o.counters()
+        assert h.argmin()["eval"] == o.argmin()["eval"]
+
+
+def test_bounded_episodes_with_mlp_priors(capi, orc):
+    """Same property with the device MLP as the prior source: lock step vs bounded episodes, tree by tree."""
+    n, b, steps = 19, 64, 60
+    parents, masks = capi.generate_roots(5, 0, b, n)
+    dumps = []
+    for me in (0, 2):
+        with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_FP32, max_steps=steps, max_episodes=me) as h:
+            h.mlp_init(3)
+            h.set_roots(parents, masks)
+            h.init_trees()
+            n_imp, imps = h.step(steps, cap=1024)
+            dumps.append(([digest(h.dump_tree(i)) for i in range(b)], imps, h.counters()))
+    assert dumps[0] == dumps[1]
