@@ -17,7 +17,7 @@ NVCC_FLAGS = [
 
 
 def lib_path() -> str:
-    return _LIB
+    return os.environ.get("AZB_LIB", _LIB)
 
 
 def _nvcc() -> str:
@@ -34,6 +34,14 @@ def _stale() -> bool:
     srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)]
     srcs.append(os.path.join(_HERE, "..", "include", "azb.h"))
     return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build_profile_flavour() -> str:
+    """lib/libazb_prof.so: the same library with -DAZB_PROFILE (per-phase clock64 accumulators; tools/phase_probe.py)."""
+    out = os.path.join(_HERE, "lib", "libazb_prof.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call([_nvcc(), *NVCC_FLAGS, "-DAZB_PROFILE", "-o", out, os.path.join(_CSRC, "azb.cu")])
+    return out
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -265,7 +265,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
 
     // shared memory per warp of the tree kernel: walker block + masks + children's c* + cascade frontiers
     h->lcap = (std::max<uint32_t>(A, 64) + 31) & ~31u;
-    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 16 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
+    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 32 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
     h->smem_words_per_warp = (h->smem_words_per_warp + 3u) & ~3u;
     h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4 + ((A + 15) & ~15u);  // + action->child LUT
     switch (azb_stack_depth(N)) {
@@ -914,6 +914,16 @@ int azb_get_counters(azb_handle *h, azb_counters *out) {
     }
     CK(cudaMemcpyAsync(out, &h->L.g->counters, sizeof(AzbCounters), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+// -DAZB_PROFILE builds only: cycles of lane 0 per phase (tools/phase_probe.py)
+int azb_debug_phase_cycles(azb_handle *h, unsigned long long *out16) {
+    if (!h || !out16) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaMemcpyAsync(out16, h->L.g->prof, sizeof(h->L.g->prof), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemsetAsync(h->L.g->prof, 0, sizeof(h->L.g->prof), h->stream));
     return AZB_OK;
 }
 

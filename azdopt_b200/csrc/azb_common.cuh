@@ -71,6 +71,7 @@ struct AzbGlobals {  // one per handle, in device memory
     uint32_t argmin_tree, argmin_node, pad;
     uint32_t argmin_state[16 + 61]; // parents packed (16 words) + permitted (61 words)
     AzbCounters counters;
+    unsigned long long prof[16];    // -DAZB_PROFILE: lane-0 cycles per phase
 };
 
 struct AzbLayout {

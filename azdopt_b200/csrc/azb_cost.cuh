@@ -32,7 +32,7 @@ struct __align__(16) CostScratch {  // per-warp shared memory
     uint8_t ops[112];
     uint32_t prog[12];
 };
-#define AZB_COST_SCRATCH_WORDS ((uint32_t)(sizeof(CostScratch) / 4))
+
 
 __host__ __device__ __forceinline__ int azb_stack_depth(uint32_t n) { return n <= 22 ? 3 : (n <= 46 ? 4 : 5); }
 
@@ -230,6 +230,155 @@ __device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *pa
     return __dmul_rn(0.5, __dadd_rn(lo, hi));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// N <= 22: lambda_1 AND mu from the matching polynomial.
+// The characteristic polynomial of a forest is its matching polynomial: phi(x) = sum_k (-1)^k m_k x^(N-2k), with
+// m_k the number of k-matchings; so lambda_1^2 is the largest root of p(y) = sum_k (-1)^k m_k y^(K-k) and K, the
+// largest k with m_k > 0, IS the matching number.  m_k <= C(22-k, k) <= 6435, exact in u32.
+//   1. m_k by a leaves-first DP over the tree, lane = k:  a_v = matchings of T_v, b_v = matchings of T_v - v;
+//      folding child c into v:  b' = b * a_c,  a' = a * a_c + shift(b * b_c)   (polynomial products in k);
+//   2. Newton from y0 = max #2-walks >= lambda_1^2: for a real-rooted polynomial Newton from the right of the largest
+//      root decreases monotonically onto it (plain Horner, p and p' together);
+//   3. three Newton steps with a compensated Horner evaluation of p (error-free TwoProd/TwoSum), which removes the
+//      cancellation error of the alternating sum: worst relative error 1.3e-16 over random trees, paths, stars and
+//      brooms (tests/test_oracle_golden.py), i.e. the f32 cost equals the dense eigensolver's.
+// Every lane runs steps 2-3 redundantly (uniform); all operations are single IEEE f64 ops, mirrored by the oracle.
+#define AZB_POLY_KMAX 11
+#define AZB_POLY_NV 22
+
+struct __align__(16) PolyScratch {  // per-warp shared memory, lives in the same bytes as CostScratch
+    uint32_t A[AZB_POLY_NV][AZB_POLY_KMAX + 1];
+    uint32_t B[AZB_POLY_NV][AZB_POLY_KMAX + 1];
+    uint32_t cnt[32];
+    uint32_t w2[32];
+    uint8_t dA[32], dB[32];
+};
+
+__device__ __forceinline__ void azb_two_sum(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+}
+
+// n <= 22.  par: n bytes of shared memory.  Warp-collective; every lane returns lambda_1 and *mu_out.
+__device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *par, PolyScratch *ps, int lane,
+                                                   uint32_t *mu_out) {
+    const uint32_t FULL = 0xffffffffu;
+    constexpr int KM = AZB_POLY_KMAX;
+    // ---- max #2-walks (the Newton start) ----
+    ps->cnt[lane] = 0u;
+    ps->w2[lane] = 0u;
+    if (lane < AZB_POLY_NV) {
+        ps->dA[lane] = 0;
+        ps->dB[lane] = 0;
+    }
+    for (uint32_t i = lane; i < n * (KM + 1); i += 32) {
+        const uint32_t one = (i % (KM + 1)) == 0u ? 1u : 0u;
+        (&ps->A[0][0])[i] = one;
+        (&ps->B[0][0])[i] = one;
+    }
+    __syncwarp();
+    const bool act = lane >= 1 && (uint32_t)lane < n;
+    const uint32_t p0 = act ? par[lane] : 0u;
+    {
+        const uint32_t m = __match_any_sync(FULL, act ? p0 : (0x10000u | (uint32_t)lane));
+        if (act && (__ffs(m) - 1) == lane) ps->cnt[p0] = (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    if (act) atomicAdd(&ps->w2[p0], ps->cnt[lane] + 1u);
+    __syncwarp();
+    uint32_t maxw2 = 0;
+    if ((uint32_t)lane < n) maxw2 = ps->w2[lane] + (lane >= 1 ? ps->cnt[p0] + (p0 >= 1 ? 1u : 0u) : 0u);
+    maxw2 = __reduce_max_sync(FULL, maxw2);
+    // ---- 1. matching counts, leaves first (parents[v] < v) ----
+    const int k = lane;
+    for (uint32_t v = n - 1; v >= 1; --v) {
+        const uint32_t p = par[v];
+        const uint32_t dav = ps->dA[v], dbv = ps->dB[v], dap = ps->dA[p], dbp = ps->dB[p];
+        uint32_t na = 0, nb = 0;
+        if (k <= KM) {
+            if (dav == 0u) {  // leaf child: a_c = b_c = 1
+                na = ps->A[p][k] + (k >= 1 ? ps->B[p][k - 1] : 0u);
+                nb = ps->B[p][k];
+            } else {
+                for (uint32_t i = 0; i <= dav; ++i) {
+                    if ((int)i > k) break;
+                    const uint32_t ac = ps->A[v][i], bc = ps->B[v][i];
+                    const uint32_t bpk = ps->B[p][k - i];
+                    nb += ac * bpk;
+                    na += ac * ps->A[p][k - i];
+                    if ((int)i < k) na += bc * ps->B[p][k - 1 - i];
+                }
+            }
+        }
+        __syncwarp();
+        if (k <= KM) {
+            ps->A[p][k] = na;
+            ps->B[p][k] = nb;
+        }
+        if (lane == 0) {
+            const uint32_t ndb = dbp + dav;
+            const uint32_t nda = max(dap + dav, dbp + dbv + 1u);
+            ps->dA[p] = (uint8_t)min(nda, (uint32_t)KM);
+            ps->dB[p] = (uint8_t)min(ndb, (uint32_t)KM);
+        }
+        __syncwarp();
+    }
+    // degree bookkeeping above is an upper bound; the matching number is the largest k with m_k > 0
+    const uint32_t mk = k <= KM ? ps->A[0][k] : 0u;
+    const uint32_t nz = __ballot_sync(FULL, mk != 0u);
+    const uint32_t K = 31u - __clz(nz);
+    *mu_out = K;
+    // ---- coefficients, leading zeros in front so that a fixed-length Horner is the K-term Horner ----
+    double c[KM + 1];
+#pragma unroll
+    for (int j = 0; j <= KM; ++j) {
+        const int kk = j - (KM - (int)K);  // coefficient index of position j
+        const uint32_t m = __shfl_sync(FULL, mk, kk < 0 ? 0 : kk);
+        const double v = (double)m;
+        c[j] = kk < 0 ? 0.0 : ((kk & 1) ? -v : v);
+    }
+    // ---- 2. Newton from the right (plain Horner) ----
+    double y = (double)maxw2;
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+        double s = c[0], d = 0.0;
+#pragma unroll
+        for (int j = 1; j <= KM; ++j) {
+            d = __fma_rn(d, y, s);
+            s = __fma_rn(s, y, c[j]);
+        }
+        if (!(d > 0.0)) break;
+        const double yn = __dsub_rn(y, __ddiv_rn(s, d));
+        if (!(yn < y)) break;
+        y = yn;
+    }
+    // ---- 3. polish: compensated Horner for p ----
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        double s = c[0], e = 0.0, t = c[0], d = 0.0;
+#pragma unroll
+        for (int j = 1; j <= KM; ++j) {
+            d = __fma_rn(d, y, t);
+            t = __fma_rn(t, y, c[j]);
+            const double pr = __dmul_rn(s, y);
+            const double pi = __fma_rn(s, y, -pr);
+            double sg;
+            azb_two_sum(pr, c[j], s, sg);
+            e = __dadd_rn(__dmul_rn(e, y), __dadd_rn(pi, sg));
+        }
+        const double pv = __dadd_rn(s, e);
+        if (!(d > 0.0)) break;
+        y = __dsub_rn(y, __ddiv_rn(pv, d));
+    }
+    __syncwarp();
+    return __dsqrt_rn(y);
+}
+
+// cost of the tree in `par`: picks the method by size; every lane gets (lambda_1, mu)
+template <int DEPTH>
+__device__ __forceinline__ double azb_cost_warp(uint32_t n, const uint8_t *par, CostScratch *cs, int lane, uint32_t *mu);
+
 // Maximum matching of a tree: leaves-first greedy over v = N-1..1 (a leaves-first order because parents[v] < v).
 // The reference strips leaves round by round (ordered_edge.rs:94-124); both are maximum matchings, so the sizes
 // agree and only the size enters the cost (04-c21-tree.rs:100).
@@ -247,12 +396,23 @@ __device__ __forceinline__ uint32_t azb_matching(uint32_t n, const uint8_t *pare
     return m;
 }
 
+template <int DEPTH>
+__device__ __forceinline__ double azb_cost_warp(uint32_t n, const uint8_t *par, CostScratch *cs, int lane, uint32_t *mu) {
+    if (n <= AZB_POLY_NV) return azb_lambda1_poly(n, par, reinterpret_cast<PolyScratch *>(cs), lane, mu);
+    const double l1 = azb_lambda1_warp<DEPTH>(n, par, cs, lane);
+    *mu = azb_matching(n, par);
+    return l1;
+}
+
 // evaluate + squish: 04-c21-tree.rs:70-74,98-102
 __device__ __forceinline__ float azb_evaluate(uint32_t mu, double lambda1, float c_lower, float slope) {
     float x = __fadd_rn((float)mu, (float)lambda1);
     x = __fsub_rn(x, c_lower);
     return __fmul_rn(slope, x);
 }
+
+#define AZB_COST_SCRATCH_BYTES (sizeof(CostScratch) > sizeof(PolyScratch) ? sizeof(CostScratch) : sizeof(PolyScratch))
+#define AZB_COST_SCRATCH_WORDS ((uint32_t)(AZB_COST_SCRATCH_BYTES / 4))
 
 // Stand-alone batched cost kernel (azb_eval_costs): one warp per tree, 8 trees per block; the parent arrays of a
 // block are one contiguous, coalesced read; outputs are SoA.
@@ -261,7 +421,7 @@ __global__ void __launch_bounds__(256) azb_cost_kernel(const uint8_t *__restrict
                                                        float c_lower, float slope, double *__restrict__ lambda1,
                                                        uint32_t *__restrict__ mu, float *__restrict__ c,
                                                        uint32_t *__restrict__ err) {
-    __shared__ CostScratch scratch[8];
+    __shared__ __align__(16) uint8_t scratch_bytes[8][AZB_COST_SCRATCH_BYTES];
     __shared__ __align__(16) uint8_t sm_par[8 * 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t first = blockIdx.x * 8u;
@@ -270,8 +430,8 @@ __global__ void __launch_bounds__(256) azb_cost_kernel(const uint8_t *__restrict
     __syncthreads();
     if ((uint32_t)warp >= count) return;
     const uint8_t *p = sm_par + warp * 64;
-    const double l1 = azb_lambda1_warp<DEPTH>(n, p, &scratch[warp], lane);
-    const uint32_t k = azb_matching(n, p);
+    uint32_t k = 0;
+    const double l1 = azb_cost_warp<DEPTH>(n, p, reinterpret_cast<CostScratch *>(scratch_bytes[warp]), lane, &k);
     if (lane == 0) {
         lambda1[first + warp] = l1;
         mu[first + warp] = k;

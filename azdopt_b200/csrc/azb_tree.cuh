@@ -27,6 +27,21 @@
 
 enum { AZB_F_ADD = 1, AZB_F_ROLLOUT = 2, AZB_F_INIT = 4, AZB_F_FIRST = 8 };
 
+// optional phase timing (-DAZB_PROFILE): cycles of lane 0 per phase, summed into AzbGlobals::prof
+#ifdef AZB_PROFILE
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(cx, ph)                                       \
+    do {                                                       \
+        long long prof_t1 = clock64();                         \
+        if ((cx).lane == 0) (cx).ct[16 + (ph)] += (uint32_t)(prof_t1 - prof_t0); \
+        prof_t0 = prof_t1;                                     \
+    } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(cx, ph) do {} while (0)
+#endif
+enum { PH_SEL = 0, PH_CUR, PH_PROBE, PH_ARC, PH_CASCADE, PH_COST, PH_INSERT, PH_RESET, PH_ADD, PH_PACK, PH_LOAD, PH_STORE };
+
 struct WarpCtx {
     uint32_t *wk;      // walker block copy [WS]
     uint8_t *par;      // parents (bytes) inside wk
@@ -345,6 +360,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             break;
         }
         // ---- next_action (next_action.rs:11-26) at `pos`
+        PROF_T0();
         bool active = lo2 != AZB_LO_NONE;
         uint4 hd = make_uint4(0, 0, 0, 0), kd = make_uint4(0, 0, 0, 0);
         uint2 pr = make_uint2(0, 0);
@@ -393,6 +409,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
         }
         __syncwarp();
+        PROF_ADD(cx, PH_SEL);
         const bool have_r = best_t >= 0;
         const uint32_t tol = depth < L.tol_len ? L.tol[depth] : L.tol_default;  // 04-c21-tree.rs:136-138
         bool visit = have_r && (uint32_t)(best_key >> 32) < tol;               // next_action.rs:16-20
@@ -432,6 +449,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 }
             }
             cx.err = __reduce_or_sync(FULL, cx.err);
+            PROF_ADD(cx, PH_CUR);
             if (cx.err) break;
             if (chosen_j < 0) {
                 if (have_r)
@@ -448,6 +466,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             pos = best_w0 & 0xfffffu;
             lo2 = best_w1 & 0x7fffffffu;
             depth += 1;
+            PROF_ADD(cx, PH_SEL);
             continue;
         }
         // ---- Unvisited(j) (tree/mod.rs:160-218)
@@ -477,6 +496,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
             slot = (slot + 1) & (L.cap_hash - 1);
         }
+        PROF_ADD(cx, PH_PROBE);
         const uint32_t kidx = lo2 + 1u + n_out;  // this arc's kid entry (16-byte index)
         const uint32_t narcs = cx.wk[WK_NARCS];
         if (narcs >= (1u << 20)) {
@@ -507,19 +527,22 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 cx.ct[CT_ARC] += 1;
             }
             __syncwarp();
+            PROF_ADD(cx, PH_ARC);
             tree_cascade(L, cx, pos, __uint_as_float(q0.y), q0.z, act_o ? 0u : 1u, true);
+            PROF_ADD(cx, PH_CASCADE);
             reset = true;
         } else {
             // ---- new node (tree/mod.rs:181-216)
             walker_act(L, cx, a);
             const uint32_t ndepth = depth + 1;
-            const double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
-            const uint32_t mu = azb_matching(L.N, cx.par);
+            uint32_t mu = 0;
+            const double l1 = azb_cost_warp<DEPTH>(L.N, cx.par, cx.cs, lane, &mu);
             if (!(l1 >= 1.4)) {  // ordered_edge.rs:79
                 cx.err = 5;
                 break;
             }
             const float c_new = azb_evaluate(mu, l1, L.c_lower, L.slope);
+            PROF_ADD(cx, PH_COST);
             count(cx, CT_INS, 1);
             const uint32_t nn = cx.wk[WK_NNODES], in_off = cx.wk[WK_INTOP];
             const uint32_t in_need = ndepth > 4u ? ndepth - 4u : 0u;
@@ -564,9 +587,11 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 }
             }
             __syncwarp();
+            PROF_ADD(cx, PH_INSERT);
             if (!any) {
                 count(cx, CT_TERM, 1);
                 tree_cascade(L, cx, pos, c_new, 0u, 1u, false);
+                PROF_ADD(cx, PH_CASCADE);
                 reset = true;
             } else {
                 pos = nn;
@@ -589,6 +614,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             depth = 0;
             lo2 = cx.wk[WK_ROOTLO];
             count(cx, CT_RESET, 1);
+            PROF_ADD(cx, PH_RESET);
             if (max_episodes && ++episodes >= max_episodes) break;  // yield: the step continues in the next launch
         }
     }
@@ -644,7 +670,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
         cx.pfx = p;
         p += 64;
         cx.ct = p;
-        p += 16;
+        p += 32;
         cx.lbuf = (float *)p;
         p += lcap;
         cx.fr = p;
@@ -657,15 +683,17 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
         cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
         cx.hash = L.hash + (size_t)tree * L.cap_hash;
         uint32_t *gw = L.walker + (size_t)tree * L.WS;
+        PROF_T0();
+        cx.ct[lane] = 0u;
         for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gw[i];
-        if (lane < 16) cx.ct[lane] = 0u;
         __syncwarp();
+        PROF_ADD(cx, PH_LOAD);
 
         if (flags & AZB_F_INIT) {
             // tail of par_new / par_reset_trees (optimizer/mod.rs:62-101, 340-359): state <- root, root cost, root node
             walker_reset(L, cx);
-            const double l1 = azb_lambda1_warp<DEPTH>(L.N, cx.par, cx.cs, lane);
-            const uint32_t mu = azb_matching(L.N, cx.par);
+            uint32_t mu = 0;
+            const double l1 = azb_cost_warp<DEPTH>(L.N, cx.par, cx.cs, lane, &mu);
             if (!(l1 >= 1.4)) cx.err = 5;
             const float c0 = azb_evaluate(mu, l1, L.c_lower, L.slope);
             if (lane < 4) {
@@ -709,10 +737,18 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
             tree_pack(L, cx, tree);
         }
         if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions(L, cx, tree);
+        PROF_ADD(cx, PH_ADD);
         if ((flags & AZB_F_ROLLOUT) && cx.err == 0 && cx.wk[WK_STEP] < target_step && !(cx.wk[WK_FLAGS] & 1u)) {
             tree_rollout<DEPTH>(L, cx, tree, max_episodes);
+#ifdef AZB_PROFILE
+            prof_t0 = clock64();
+#endif
             if (cx.err == 0 && (cx.wk[WK_FLAGS] & 1u)) tree_pack(L, cx, tree);  // optimizer/mod.rs:171-173
+            PROF_ADD(cx, PH_PACK);
         }
+#ifdef AZB_PROFILE
+        prof_t0 = clock64();
+#endif
         __syncwarp();
         // publish: walker block (without the root part), counters, errors, distance to the target
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
@@ -721,6 +757,14 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
             const uint32_t v = cx.ct[lane];
             if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
         }
+        PROF_ADD(cx, PH_STORE);
+#ifdef AZB_PROFILE
+        __syncwarp();
+        if (lane >= 16) {
+            const uint32_t v = cx.ct[lane];
+            if (v) atomicAdd(&L.g->prof[lane - 16], (unsigned long long)v);
+        }
+#endif
         if (lane == 0 && (flags & AZB_F_ROLLOUT) && cx.wk[WK_STEP] < target_step) atomicAdd(&L.g->behind_accum, 1u);
         const uint32_t e = __reduce_or_sync(0xffffffffu, cx.err);
         if (e && lane == 0) {

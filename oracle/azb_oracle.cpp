@@ -419,6 +419,99 @@ double lambda1_multisection(uint32_t n, const uint8_t *parents) {
     return 0.5 * (lo + hi);
 }
 
+// N <= 22, the method azdopt_b200/csrc/azb_cost.cuh uses there: lambda_1^2 is the largest root of the matching
+// polynomial p(y) = sum_k (-1)^k m_k y^(K-k) (a forest's characteristic polynomial is its matching polynomial).
+// m_k by a leaves-first DP, Newton from y0 = max #2-walks (plain Horner), three Newton steps with a compensated
+// Horner.  Same IEEE operations in the same order as the kernel => bit-identical lambda_1.
+inline void two_sum(double a, double b, double &s, double &e) {
+    s = a + b;
+    double bb = s - a;
+    e = (a - (s - bb)) + (b - bb);
+}
+
+double lambda1_poly(uint32_t n, const uint8_t *par, uint32_t *mu_out) {
+    constexpr int KM = 11;
+    uint32_t A[22][KM + 1], B[22][KM + 1];
+    uint32_t dA[22] = {0}, dB[22] = {0};
+    for (uint32_t v = 0; v < n; ++v)
+        for (int k = 0; k <= KM; ++k) A[v][k] = B[v][k] = k == 0 ? 1u : 0u;
+    for (uint32_t v = n - 1; v >= 1; --v) {
+        uint32_t p = par[v];
+        uint32_t na[KM + 1], nb[KM + 1];
+        for (int k = 0; k <= KM; ++k) {
+            uint32_t a = 0, b = 0;
+            if (dA[v] == 0) {
+                a = A[p][k] + (k >= 1 ? B[p][k - 1] : 0u);
+                b = B[p][k];
+            } else {
+                for (uint32_t i = 0; i <= dA[v] && (int)i <= k; ++i) {
+                    b += A[v][i] * B[p][k - i];
+                    a += A[v][i] * A[p][k - i];
+                    if ((int)i < k) a += B[v][i] * B[p][k - 1 - i];
+                }
+            }
+            na[k] = a;
+            nb[k] = b;
+        }
+        uint32_t nda = std::max(dA[p] + dA[v], dB[p] + dB[v] + 1u), ndb = dB[p] + dA[v];
+        for (int k = 0; k <= KM; ++k) {
+            A[p][k] = na[k];
+            B[p][k] = nb[k];
+        }
+        dA[p] = std::min<uint32_t>(nda, KM);
+        dB[p] = std::min<uint32_t>(ndb, KM);
+    }
+    uint32_t K = 0;
+    for (int k = 0; k <= KM; ++k)
+        if (A[0][k] != 0) K = (uint32_t)k;
+    if (mu_out) *mu_out = K;
+    double c[KM + 1];
+    for (int j = 0; j <= KM; ++j) {
+        int kk = j - (KM - (int)K);
+        double v = kk < 0 ? 0.0 : (double)A[0][kk];
+        c[j] = kk < 0 ? 0.0 : ((kk & 1) ? -v : v);
+    }
+    uint32_t deg[22] = {0}, w2[22] = {0};
+    for (uint32_t v = 1; v < n; ++v) {
+        deg[v]++;
+        deg[par[v]]++;
+    }
+    for (uint32_t v = 1; v < n; ++v) {
+        w2[v] += deg[par[v]];
+        w2[par[v]] += deg[v];
+    }
+    uint32_t maxw2 = 0;
+    for (uint32_t v = 0; v < n; ++v) maxw2 = std::max(maxw2, w2[v]);
+    double y = (double)maxw2;
+    for (int it = 0; it < 64; ++it) {
+        double s = c[0], d = 0.0;
+        for (int j = 1; j <= KM; ++j) {
+            d = std::fma(d, y, s);
+            s = std::fma(s, y, c[j]);
+        }
+        if (!(d > 0.0)) break;
+        double yn = y - s / d;
+        if (!(yn < y)) break;
+        y = yn;
+    }
+    for (int it = 0; it < 3; ++it) {
+        double s = c[0], e = 0.0, t = c[0], d = 0.0;
+        for (int j = 1; j <= KM; ++j) {
+            d = std::fma(d, y, t);
+            t = std::fma(t, y, c[j]);
+            double pr = s * y;
+            double pi = std::fma(s, y, -pr);
+            double sg;
+            two_sum(pr, c[j], s, sg);
+            e = e * y + (pi + sg);
+        }
+        double pv = s + e;
+        if (!(d > 0.0)) break;
+        y = y - pv / d;
+    }
+    return std::sqrt(y);
+}
+
 // ordered_edge.rs:94-124 — repeated leaf stripping; only the size is used by the cost
 uint32_t maximum_matching(uint32_t n, const uint8_t *parents) {
     bool available[MAXN];
@@ -476,7 +569,11 @@ struct Space {  // rooted_tree/space.rs:13-19 with the example's closures (04-c2
         Cost c;
         switch (lambda_method) {
             case ORC_LAMBDA_JACOBI: c.lambda_1 = lambda1_jacobi(n, s.parents.data()); break;
-            case ORC_LAMBDA_MULTISECTION: c.lambda_1 = lambda1_multisection(n, s.parents.data()); break;
+            case ORC_LAMBDA_MULTISECTION:  // "what the CUDA kernels do": matching polynomial up to 22 vertices
+                c.lambda_1 = n <= 22 ? lambda1_poly(n, s.parents.data(), nullptr) : lambda1_multisection(n, s.parents.data());
+                break;
+            case ORC_LAMBDA_SECTION_ONLY: c.lambda_1 = lambda1_multisection(n, s.parents.data()); break;
+            case ORC_LAMBDA_POLY: c.lambda_1 = lambda1_poly(n, s.parents.data(), nullptr); break;
             default: c.lambda_1 = lambda1_dense(n, s.parents.data()); break;
         }
         if (bad && !(c.lambda_1 >= 1.4)) *bad = true;  // ordered_edge.rs:79 assert
@@ -904,6 +1001,11 @@ int orc_cost(uint32_t n, const uint8_t *parents, int method, float c_lower, floa
 }
 
 uint32_t orc_matching_greedy(uint32_t n, const uint8_t *parents) { return matching_greedy(n, parents); }
+uint32_t orc_matching_poly(uint32_t n, const uint8_t *parents) {
+    uint32_t mu = 0;
+    if (n <= 22) lambda1_poly(n, parents, &mu);
+    return mu;
+}
 
 static State make_state(uint32_t n, const uint8_t *parents, const uint32_t *mask) {
     State s;

@@ -30,7 +30,9 @@ extern "C" {
 /* lambda_1 methods */
 #define ORC_LAMBDA_DENSE 0        /* Householder tridiagonalisation + implicit QL: what the reference's faer call does (ordered_edge.rs:72-78) */
 #define ORC_LAMBDA_JACOBI 1       /* cyclic Jacobi, independent cross-check */
-#define ORC_LAMBDA_MULTISECTION 2 /* the tree-specific 32-ary section the CUDA kernels use (bit-identical arithmetic) */
+#define ORC_LAMBDA_MULTISECTION 2 /* what the CUDA kernels do, bit-identical: matching-polynomial Newton for N <= 22, 32-ary section of the subtree recursion above */
+#define ORC_LAMBDA_SECTION_ONLY 3 /* the 32-ary section at every N */
+#define ORC_LAMBDA_POLY 4         /* the matching-polynomial method (N <= 22 only) */
 
 typedef struct orc_counters {
     uint64_t n_sel;    /* next_action calls on an active node            (next_action.rs:11) */
@@ -60,6 +62,7 @@ uint32_t orc_c_upper(uint32_t n);                                       /* 04-c2
 int orc_cost(uint32_t n, const uint8_t *parents, int method, float c_lower, float c_upper,
              double *lambda1, uint32_t *mu, float *c);
 uint32_t orc_matching_greedy(uint32_t n, const uint8_t *parents);       /* independent O(N) matching for cross-checks */
+uint32_t orc_matching_poly(uint32_t n, const uint8_t *parents);         /* degree of the matching polynomial (N <= 22) */
 /* legal actions of (parents, permitted mask) ascending; returns count (space.rs:75-89) */
 uint32_t orc_action_data(uint32_t n, const uint8_t *parents, const uint32_t *permitted_mask, uint32_t *out);
 void orc_act(uint32_t n, uint8_t *parents, uint32_t *permitted_mask, uint32_t action); /* space.rs:56-73 */

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libazb_oracle.so")
 
 NONE = 0xFFFFFFFF
-LAMBDA_DENSE, LAMBDA_JACOBI, LAMBDA_MULTISECTION = 0, 1, 2
+LAMBDA_DENSE, LAMBDA_JACOBI, LAMBDA_MULTISECTION, LAMBDA_SECTION_ONLY, LAMBDA_POLY = 0, 1, 2, 3, 4
 
 COUNTER_FIELDS = [
     "n_sel", "d_sel", "n_cur", "n_cand", "n_probe", "n_ins", "n_term", "n_hit", "n_arc", "n_pred",
@@ -62,6 +62,8 @@ def lib():
     L.orc_cost.argtypes = [C.c_uint32, u8p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double), u32p, f32p]
     L.orc_matching_greedy.restype = C.c_uint32
     L.orc_matching_greedy.argtypes = [C.c_uint32, u8p]
+    L.orc_matching_poly.restype = C.c_uint32
+    L.orc_matching_poly.argtypes = [C.c_uint32, u8p]
     L.orc_action_data.restype = C.c_uint32
     L.orc_action_data.argtypes = [C.c_uint32, u8p, u32p, u32p]
     L.orc_act.argtypes = [C.c_uint32, u8p, u32p, C.c_uint32]
@@ -133,6 +135,11 @@ def cost(parents, method=LAMBDA_DENSE, c_lower=2.0, c_up=None):
 def matching_greedy(parents):
     p = np.ascontiguousarray(parents, dtype=np.uint8)
     return int(lib().orc_matching_greedy(p.shape[0], _p(p, C.c_uint8)))
+
+
+def matching_poly(parents):
+    p = np.ascontiguousarray(parents, dtype=np.uint8)
+    return int(lib().orc_matching_poly(p.shape[0], _p(p, C.c_uint8)))
 
 
 def mask_from_actions(n, actions):

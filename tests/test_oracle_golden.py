@@ -109,21 +109,32 @@ def _random_parents(rng, n):
     return p
 
 
-@pytest.mark.parametrize("n", [5, 8, 19, 33, 64])
+@pytest.mark.parametrize("n", [5, 8, 19, 22, 33, 64])
 def test_lambda1_methods_agree_with_lapack(orc, n):
     rng = np.random.default_rng(n)
     flips = 0
-    for _ in range(150):
-        p = _random_parents(rng, n)
+    methods = [orc.LAMBDA_DENSE, orc.LAMBDA_JACOBI, orc.LAMBDA_MULTISECTION, orc.LAMBDA_SECTION_ONLY]
+    if n <= 22:
+        methods.append(orc.LAMBDA_POLY)
+    trees = [_random_parents(rng, n) for _ in range(150)]
+    trees.append(np.maximum(np.arange(n) - 1, 0).astype(np.uint8))  # path: clustered eigenvalues, worst conditioning
+    trees.append(np.zeros(n, dtype=np.uint8))  # star
+    broom = np.zeros(n, dtype=np.uint8)
+    broom[3::2] = 1
+    trees.append(broom)  # two hubs: lambda_1 and lambda_2 close
+    for p in trees:
         ref = pyref.lambda1(n, p)
-        vals = [orc.cost(p, method=m) for m in (0, 1, 2)]
+        vals = [orc.cost(p, method=m) for m in methods]
         for lam, mu, c, rc in vals:
             assert rc == 0
             assert abs(lam - ref) <= 1e-12 * ref
         assert vals[0][1] == vals[2][1] == pyref.maximum_matching(n, list(p)) == orc.matching_greedy(p)
-        flips += int(vals[0][2].view(np.uint32) != vals[2][2].view(np.uint32))
+        if n <= 22:
+            assert orc.matching_poly(p) == vals[0][1]  # degree of the matching polynomial = matching number
+            assert abs(vals[4][0] - ref) <= 4e-15 * ref
+        flips += sum(int(vals[0][2].view(np.uint32) != v[2].view(np.uint32)) for v in vals[2:])
         assert vals[0][2] == pyref.evaluate(n, vals[0][1], vals[0][0])
-    assert flips == 0  # the f32 cost of the sectioning method equals the dense one's
+    assert flips == 0  # the f32 cost of the kernels' methods equals the dense one's
 
 
 def test_matching_against_networkx(orc):
