@@ -85,6 +85,7 @@ SIGNATURES = {
     "azb_dump_tree": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u32p, u32p, u32p]),
     "azb_get_counters": (C.c_int, [C.c_void_p, C.POINTER(Counters)]),
     "azb_reset_counters": (C.c_int, [C.c_void_p]),
+    "azb_set_counter_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "azb_get_state_vecs": (C.c_int, [C.c_void_p, f32p]),
     "azb_get_priors": (C.c_int, [C.c_void_p, f32p]),
     "azb_eval_costs": (C.c_int, [C.c_void_p, u8p, C.c_uint32, f64p, u32p, f32p, f32p]),
@@ -319,6 +320,9 @@ class Handle:
         c = Counters()
         self._ck(self._L.azb_get_counters(self._h, C.byref(c)))
         return c.as_dict()
+
+    def set_counter_mode(self, full: bool):
+        self._ck(self._L.azb_set_counter_mode(self._h, 1 if full else 0))
 
     def reset_counters(self):
         self._ck(self._L.azb_reset_counters(self._h))

@@ -49,7 +49,7 @@ struct azb_handle {
     void *flush_buf;
     size_t flush_bytes;
     uint64_t launches, dev_bytes;
-    bool roots_set, trees_init, pending_add, first_init_done, params_set;
+    bool roots_set, trees_init, pending_add, first_init_done, params_set, count_full;
     int improved_last_rollout;
     uint32_t steps_done;   // steps every tree has completed since init_trees
     uint32_t argmin_from;  // first candidate slot the argmin pass has not consumed yet
@@ -151,7 +151,7 @@ int azb_destroy(azb_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
-    void *ptrs[] = {h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, h->L.sv,
+    void *ptrs[] = {h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
                     h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
                     h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf};
     for (void *p : ptrs)
@@ -243,6 +243,16 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     CK(dmalloc(h, &L.hash, (size_t)B * L.cap_hash));
     CK(dmalloc(h, &L.cand, (size_t)(L.cap_steps + 1) * B));
     CK(dmalloc(h, &L.stepmin, (size_t)L.cap_steps + 1));
+    {
+        std::vector<uint8_t> lut((A + 3) & ~3u, 0);
+        for (uint32_t a = 0; a < A; ++a) lut[a] = (uint8_t)azb_action_child(a);
+        uint8_t *dl = nullptr;
+        CK(dmalloc(h, &dl, lut.size()));
+        CK(cudaMemcpyAsync(dl, lut.data(), lut.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        L.lut = dl;
+    }
+    h->count_full = true;
     CK(dmalloc(h, &L.sv, (size_t)B * L.sv_ld));
     CK(dmalloc(h, &L.h, (size_t)B * L.h_ld));
     CK(dmalloc(h, &L.g, 1));
@@ -268,10 +278,23 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 32 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
     h->smem_words_per_warp = (h->smem_words_per_warp + 3u) & ~3u;
     h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4 + ((A + 15) & ~15u);  // + action->child LUT
-    switch (azb_stack_depth(N)) {
-        case 3: CK(cudaFuncSetAttribute(azb_tree_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
-        case 4: CK(cudaFuncSetAttribute(azb_tree_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
-        default: CK(cudaFuncSetAttribute(azb_tree_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); break;
+    {
+        const int sb = (int)h->smem_bytes;
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        switch (azb_stack_depth(N)) {
+            case 3:
+                CK(cudaFuncSetAttribute(azb_tree_kernel<3, true>, attr, sb));
+                CK(cudaFuncSetAttribute(azb_tree_kernel<3, false>, attr, sb));
+                break;
+            case 4:
+                CK(cudaFuncSetAttribute(azb_tree_kernel<4, true>, attr, sb));
+                CK(cudaFuncSetAttribute(azb_tree_kernel<4, false>, attr, sb));
+                break;
+            default:
+                CK(cudaFuncSetAttribute(azb_tree_kernel<5, true>, attr, sb));
+                CK(cudaFuncSetAttribute(azb_tree_kernel<5, false>, attr, sb));
+                break;
+        }
     }
     return AZB_OK;
 }
@@ -461,11 +484,17 @@ static int launch_tree(azb_handle *h, uint32_t flags, uint32_t target_step, int 
     const uint32_t blocks = (L.B + AZB_WARPS_PER_BLOCK - 1) / AZB_WARPS_PER_BLOCK;
     const dim3 block(AZB_WARPS_PER_BLOCK * 32);
     const uint32_t me = h->cfg.max_episodes;
-    switch (azb_stack_depth(h->N)) {
-        case 3: azb_tree_kernel<3><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me); break;
-        case 4: azb_tree_kernel<4><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me); break;
-        default: azb_tree_kernel<5><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me); break;
+#define AZB_LAUNCH_TREE(D, C) \
+    azb_tree_kernel<D, C><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me)
+    switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
+        case 6: AZB_LAUNCH_TREE(3, false); break;
+        case 7: AZB_LAUNCH_TREE(3, true); break;
+        case 8: AZB_LAUNCH_TREE(4, false); break;
+        case 9: AZB_LAUNCH_TREE(4, true); break;
+        case 10: AZB_LAUNCH_TREE(5, false); break;
+        default: AZB_LAUNCH_TREE(5, true); break;
     }
+#undef AZB_LAUNCH_TREE
     h->launches += 1;
     CK(cudaGetLastError());
     return AZB_OK;
@@ -924,6 +953,12 @@ int azb_debug_phase_cycles(azb_handle *h, unsigned long long *out16) {
     CK(cudaMemcpyAsync(out16, h->L.g->prof, sizeof(h->L.g->prof), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemsetAsync(h->L.g->prof, 0, sizeof(h->L.g->prof), h->stream));
+    return AZB_OK;
+}
+
+int azb_set_counter_mode(azb_handle *h, int full) {
+    if (!h) return AZB_ERR_INVALID;
+    h->count_full = full != 0;
     return AZB_OK;
 }
 

@@ -83,6 +83,7 @@ struct AzbLayout {
     uint32_t tol_len, tol_default;
     uint32_t prior_mode, log_cap;
     unsigned long long first_root, prior_seed;
+    const uint8_t *lut;   // child vertex of every action (A bytes, padded to a multiple of 4)
     uint32_t *walker;
     uint4 *node;
     uint2 *blk;

@@ -237,8 +237,8 @@ __device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *pa
 // largest k with m_k > 0, IS the matching number.  m_k <= C(22-k, k) <= 6435, exact in u32.
 //   1. m_k by a leaves-first DP over the tree, lane = k:  a_v = matchings of T_v, b_v = matchings of T_v - v;
 //      folding child c into v:  b' = b * a_c,  a' = a * a_c + shift(b * b_c)   (polynomial products in k);
-//   2. Newton from y0 = max #2-walks >= lambda_1^2: for a real-rooted polynomial Newton from the right of the largest
-//      root decreases monotonically onto it (plain Horner, p and p' together);
+//   2. Laguerre's iteration from y0 = max #2-walks >= lambda_1^2: for a real-rooted polynomial the iterates from the
+//      right of the largest root decrease monotonically onto it, cubically (plain Horner for p, p', p'');
 //   3. three Newton steps with a compensated Horner evaluation of p (error-free TwoProd/TwoSum), which removes the
 //      cancellation error of the alternating sum: worst relative error 1.3e-16 over random trees, paths, stars and
 //      brooms (tests/test_oracle_golden.py), i.e. the f32 cost equals the dense eigensolver's.
@@ -338,18 +338,25 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         const double v = (double)m;
         c[j] = kk < 0 ? 0.0 : ((kk & 1) ? -v : v);
     }
-    // ---- 2. Newton from the right (plain Horner) ----
+    // ---- 2. Laguerre from the right (plain Horner for p, p', p''/2): for a real-rooted polynomial the iterates
+    //         decrease monotonically onto the largest root, cubically
     double y = (double)maxw2;
+    const double nn = (double)K, nm1 = (double)(K - 1u);
 #pragma unroll 1
-    for (int it = 0; it < 64; ++it) {
-        double s = c[0], d = 0.0;
+    for (int it = 0; it < 40; ++it) {
+        double s = c[0], d = 0.0, h = 0.0;
 #pragma unroll
         for (int j = 1; j <= KM; ++j) {
+            h = __fma_rn(h, y, d);
             d = __fma_rn(d, y, s);
             s = __fma_rn(s, y, c[j]);
         }
-        if (!(d > 0.0)) break;
-        const double yn = __dsub_rn(y, __ddiv_rn(s, d));
+        const double dd = __dmul_rn(2.0, h);
+        double disc = __dmul_rn(nm1, __dsub_rn(__dmul_rn(nm1, __dmul_rn(d, d)), __dmul_rn(nn, __dmul_rn(s, dd))));
+        if (!(disc >= 0.0)) disc = 0.0;
+        const double den = __dadd_rn(d, __dsqrt_rn(disc));
+        if (!(den > 0.0)) break;
+        const double yn = __dsub_rn(y, __ddiv_rn(__dmul_rn(nn, s), den));
         if (!(yn < y)) break;
         y = yn;
     }

@@ -65,10 +65,12 @@ struct WarpCtx {
     uint32_t *hash;
     int lane;
     uint32_t err;
+    bool full_count;   // all 16 workload counters (tests, roofline pass) or only LIVE / NOOP / INS
+    uint32_t n_ins, n_live, n_noop;
 };
 
 __device__ __forceinline__ void count(WarpCtx &cx, int which, uint32_t n) {
-    if (cx.lane == 0) cx.ct[which] += n;
+    if (cx.full_count && cx.lane == 0) cx.ct[which] += n;
 }
 
 __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t r) {
@@ -209,7 +211,7 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
         cx.wk[WK_NBLK] = top;
         cx.wk[WK_NPREDS] += cnt;
         cx.wk[WK_FLAGS] &= ~1u;
-        cx.ct[CT_PRED] += cnt;
+        if (cx.full_count) cx.ct[CT_PRED] += cnt;
     }
     __syncwarp();
 }
@@ -232,6 +234,53 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, floa
     while (ncur > 0 && cx.err == 0) {
         uint32_t nnxt = 0;
         count(cx, CT_CN, ncur);
+        if (ncur == 1u) {
+            // the common case: one node on the level.  Every lane reads the same record (one broadcast request), its
+            // parents are distinct, so the next level needs no merge.
+            const uint32_t p = curN[0], e = curE[0];
+            uint4 *rec = cx.node + (size_t)p * 4;
+            uint4 q0 = rec[0];
+            const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
+            const uint32_t ex = (q0.w & 0xffffu) + e, cnt = q0.w >> 16, nin = q1.y;
+            float cs = __uint_as_float(q0.y);
+            uint32_t nt = q0.z;
+            if (cs > cstar)
+                cs = cstar;
+            else
+                nt += 1;
+            if (old) nt = max(nt, ntt);
+            q0.y = __float_as_uint(cs);
+            q0.z = nt;
+            q0.w = ex | (cnt << 16);
+            const uint32_t up = (ex < cnt) ? 0u : 1u;
+            const uint32_t w1 = q1.x | (up ? 0u : 0x80000000u);
+            count(cx, CT_DCN, nin);
+            if (nin <= 4u) {
+                __syncwarp();
+                if (lane == 0) rec[0] = q0;
+                if ((uint32_t)lane < nin) {
+                    const uint32_t qq = lane == 0 ? q2.x : (lane == 1 ? q2.z : (lane == 2 ? q3.x : q3.z));
+                    const uint32_t kx = lane == 0 ? q2.y : (lane == 1 ? q2.w : (lane == 2 ? q3.y : q3.w));
+                    uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + kx);
+                    kp[1] = w1;
+                    *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(nt, q0.y);
+                    nxtN[lane] = qq;
+                    nxtE[lane] = up;
+                }
+                nnxt = nin;
+                uint32_t *t = curN;
+                curN = nxtN;
+                nxtN = t;
+                t = curE;
+                curE = nxtE;
+                nxtE = t;
+                ncur = nnxt;
+                __syncwarp();
+                continue;
+            }
+            // more than four in-arcs: fall through to the general path (which re-reads the record)
+            if (cx.full_count && lane == 0) cx.ct[CT_DCN] -= nin;
+        }
         for (uint32_t base = 0; base < ncur; base += 32) {
             const uint32_t i = base + lane;
             const bool valid = i < ncur;
@@ -377,7 +426,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             if (depth != 0u)
                 cx.err = 6;
             else {
-                count(cx, CT_NOOP, 1);
+                cx.n_noop += 1;
                 step_done(L, cx, tree);
             }
             break;
@@ -393,19 +442,26 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         for (uint32_t base = 0; base < n_out; base += 32) {
             if (base) kd = cx.blk4[lo2 + 1u + base + lane];
             const uint32_t t = base + lane;
-            unsigned long long k = ~0ull;
+            bool act_t = false;
+            uint32_t oc = 0xffffffffu;
             if (t < n_out) {
                 cx.lbuf[t] = __uint_as_float(kd.w);
-                if (kd.y >> 31) k = ((unsigned long long)kd.z << 32) | azb_f2ord(__uint_as_float(kd.w));
+                act_t = (kd.y >> 31) != 0u;
+                oc = azb_f2ord(__uint_as_float(kd.w));
             }
-            const unsigned long long mk = warp_min_u64(k);
-            if (mk != ~0ull && mk <= best_key) {  // a later chunk holds newer arcs: it wins ties
-                const uint32_t bal = __ballot_sync(FULL, k == mk);
-                const int wl = 31 - __clz(bal);  // newest arc among equals
-                best_key = mk;
-                best_t = (int)base + wl;
-                best_w0 = __shfl_sync(FULL, kd.x, wl);
-                best_w1 = __shfl_sync(FULL, kd.y, wl);
+            const uint32_t ntmin = __reduce_min_sync(FULL, act_t ? kd.z : 0xffffffffu);
+            if (__any_sync(FULL, act_t)) {
+                const bool cand_t = act_t && kd.z == ntmin;
+                const uint32_t cmin = __reduce_min_sync(FULL, cand_t ? oc : 0xffffffffu);
+                const unsigned long long mk = ((unsigned long long)ntmin << 32) | cmin;
+                if (mk <= best_key) {  // a later chunk holds newer arcs: it wins ties
+                    const uint32_t bal = __ballot_sync(FULL, cand_t && oc == cmin);
+                    const int wl = 31 - __clz(bal);  // newest arc among equals
+                    best_key = mk;
+                    best_t = (int)base + wl;
+                    best_w0 = __shfl_sync(FULL, kd.x, wl);
+                    best_w1 = __shfl_sync(FULL, kd.y, wl);
+                }
             }
         }
         __syncwarp();
@@ -420,32 +476,43 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             count(cx, CT_CUR, 1);
             count(cx, CT_CAND, cnt);
             const bool no_kids = n_out == 0;
-            unsigned long long bk = no_kids ? ~0ull : 0ull;
+            uint32_t bk32 = 0u;
             for (uint32_t base = 0; base < cnt; base += 32) {
                 if (base) pr = cx.blk[2u * lo2 - 1u - base - lane];
                 const uint32_t j = base + lane;
-                unsigned long long kk = no_kids ? ~0ull : 0ull;
+                bool cand_j = false;
+                uint32_t ov = 0u;
                 if (j < cnt && ((pr.y >> 11) & 1u) == 0u) {  // no arc yet (:68-71)
+                    cand_j = true;
                     const float v = __fsub_rn(c_s, __uint_as_float(pr.x));
                     if (no_kids) {
                         if (v != v) cx.err = 4;
-                        kk = ((unsigned long long)azb_f2ord(v) << 32) | j;  // first minimum (:73-75)
+                        ov = azb_f2ord(v);
                     } else {
                         float cur = 0.f;
                         for (int t = (int)n_out - 1; t >= 0; --t)  // newest first, left fold (:79-82)
                             cur = __fadd_rn(cur, __fsqrt_rn(fabsf(__fsub_rn(cx.lbuf[t], v))));
                         if (cur != cur) cx.err = 4;
-                        kk = ((unsigned long long)azb_f2ord(cur) << 32) | j;  // last maximum (:85)
+                        ov = azb_f2ord(cur);
                     }
                 }
-                const unsigned long long red = no_kids ? warp_min_u64(kk) : warp_max_u64(kk);
-                const bool better = no_kids ? (red < bk) : (red > bk);
-                if (better) {
-                    bk = red;
-                    const uint32_t bal = __ballot_sync(FULL, kk == red);
-                    const int wl = __ffs(bal) - 1;
-                    chosen_j = (int)(red & 0xffffffffu);
-                    chosen_y = __shfl_sync(FULL, pr.y, wl);
+                if (!__any_sync(FULL, cand_j)) continue;
+                if (no_kids) {  // first minimum (:73-75): earlier chunks win ties
+                    const uint32_t red = __reduce_min_sync(FULL, cand_j ? ov : 0xffffffffu);
+                    if (chosen_j < 0 || red < bk32) {
+                        bk32 = red;
+                        const int wl = __ffs(__ballot_sync(FULL, cand_j && ov == red)) - 1;
+                        chosen_j = (int)base + wl;
+                        chosen_y = __shfl_sync(FULL, pr.y, wl);
+                    }
+                } else {  // last maximum (:85): later chunks win ties
+                    const uint32_t red = __reduce_max_sync(FULL, cand_j ? ov : 0u);
+                    if (chosen_j < 0 || red >= bk32) {
+                        bk32 = red;
+                        const int wl = 31 - __clz(__ballot_sync(FULL, cand_j && ov == red));
+                        chosen_j = (int)base + wl;
+                        chosen_y = __shfl_sync(FULL, pr.y, wl);
+                    }
                 }
             }
             cx.err = __reduce_or_sync(FULL, cx.err);
@@ -524,7 +591,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                     cx.inl[q1.z + nin - 4u] = make_uint2(pos, kidx);
                 reinterpret_cast<uint32_t *>(rec)[5] = nin + 1u;
                 cx.wk[WK_NARCS] = narcs + 1u;
-                cx.ct[CT_ARC] += 1;
+                if (cx.full_count) cx.ct[CT_ARC] += 1;
             }
             __syncwarp();
             PROF_ADD(cx, PH_ARC);
@@ -543,7 +610,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
             const float c_new = azb_evaluate(mu, l1, L.c_lower, L.slope);
             PROF_ADD(cx, PH_COST);
-            count(cx, CT_INS, 1);
+            cx.n_ins += 1;
             const uint32_t nn = cx.wk[WK_NNODES], in_off = cx.wk[WK_INTOP];
             const uint32_t in_need = ndepth > 4u ? ndepth - 4u : 0u;
             if (nn >= L.cap_nodes || in_off + in_need > L.cap_in) {
@@ -578,7 +645,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 reinterpret_cast<uint32_t *>(cx.blk4 + lo2)[1] = (n_out + 1u) | (cnt << 16);
                 cx.blk[2u * lo2 - 1u - j].y = a | (1u << 11) | (narcs << 12);
                 cx.wk[WK_NARCS] = narcs + 1u;
-                cx.ct[CT_ARC] += 1;
+                if (cx.full_count) cx.ct[CT_ARC] += 1;
                 // argmin candidate: first minimum of c over this step's new nodes (optimizer/mod.rs:208-213)
                 const uint32_t oc = azb_f2ord(c_new);
                 if (oc < cx.wk[WK_CAND_C]) {
@@ -601,8 +668,8 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                     cx.wk[WK_FLAGS] |= 1u;
                     cx.wk[WK_PEND_C] = __float_as_uint(c_new);
                     cx.wk[WK_PKIDX] = kidx;
-                    cx.ct[CT_LIVE] += 1;
                 }
+                cx.n_live += 1;
                 __syncwarp();
                 step_done(L, cx, tree);
                 break;  // tree/mod.rs:212-215
@@ -627,22 +694,29 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
 }
 
 // write_vec (rooted_tree/space.rs:91-101): [A one-hot of current edges | A permitted mask] as f32
+__device__ __forceinline__ float pack_bit(const AzbLayout &L, const WarpCtx &cx, uint32_t i) {
+    bool one;
+    if (i < L.A) {
+        const uint32_t child = cx.lut[i];
+        one = (uint32_t)cx.par[child] == i - azb_child_first_action(child);
+    } else {
+        one = (cx.perm[(i - L.A) >> 5] >> ((i - L.A) & 31)) & 1u;
+    }
+    return one ? 1.0f : 0.0f;
+}
 __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
     float *row = L.sv + (size_t)tree * L.sv_ld;
-    for (uint32_t i = cx.lane; i < 2 * L.A; i += 32) {
-        bool one;
-        if (i < L.A) {
-            const uint32_t child = cx.lut[i];
-            one = (uint32_t)cx.par[child] == i - azb_child_first_action(child);
-        } else {
-            one = (cx.perm[(i - L.A) >> 5] >> ((i - L.A) & 31)) & 1u;
-        }
-        row[i] = one ? 1.0f : 0.0f;
+    if ((L.A & 1u) == 0u && (L.sv_ld & 3u) == 0u) {  // rows are 16-byte aligned: one 128-bit store per four entries
+        for (uint32_t i = 4u * cx.lane; i < 2 * L.A; i += 128)
+            *reinterpret_cast<float4 *>(row + i) =
+                make_float4(pack_bit(L, cx, i), pack_bit(L, cx, i + 1), pack_bit(L, cx, i + 2), pack_bit(L, cx, i + 3));
+    } else {
+        for (uint32_t i = cx.lane; i < 2 * L.A; i += 32) row[i] = pack_bit(L, cx, i);
     }
 }
 
-template <int DEPTH>
-__global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
+template <int DEPTH, bool COUNT>
+__global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
     azb_tree_kernel(const AzbLayout L, const uint32_t flags, const uint32_t smem_words_per_warp, const uint32_t lcap,
                     const uint32_t target_step, const uint32_t max_episodes) {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -650,13 +724,16 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tree = blockIdx.x * AZB_WARPS_PER_BLOCK + warp;
     uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)AZB_WARPS_PER_BLOCK * smem_words_per_warp);
-    for (uint32_t a = threadIdx.x; a < L.A; a += blockDim.x) lut[a] = (uint8_t)azb_action_child(a);
+    for (uint32_t a = threadIdx.x; 4u * a < L.A; a += blockDim.x)
+        reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
     __syncthreads();
     uint32_t *base = smem + (size_t)warp * smem_words_per_warp;
     if (tree < L.B) {
         WarpCtx cx;
         cx.lane = lane;
         cx.err = 0;
+        cx.full_count = COUNT;
+        cx.n_ins = cx.n_live = cx.n_noop = 0u;
         cx.lut = lut;
         cx.wk = base;
         cx.par = (uint8_t *)(base + WK_HDR);
@@ -754,7 +831,10 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32)
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
         for (uint32_t i = lane; i < live_words; i += 32) gw[i] = cx.wk[i];
         if (lane < 16) {
-            const uint32_t v = cx.ct[lane];
+            uint32_t v = COUNT ? cx.ct[lane] : 0u;
+            if (lane == CT_INS) v = cx.n_ins;
+            if (lane == CT_LIVE) v = cx.n_live;
+            if (lane == CT_NOOP) v = cx.n_noop;
             if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
         }
         PROF_ADD(cx, PH_STORE);
@@ -814,6 +894,7 @@ __device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, con
                                       uint32_t node, int lane) {
     WarpCtx cx;
     cx.lane = lane;
+    cx.full_count = false;
     cx.lut = lut;
     cx.wk = scratch;
     cx.par = (uint8_t *)(scratch + WK_HDR);

@@ -165,6 +165,8 @@ int azb_tree_sizes(azb_handle *h, uint32_t tree, uint32_t *n_nodes, uint32_t *n_
 int azb_dump_tree(azb_handle *h, uint32_t tree, uint32_t *nodes, uint32_t *keys, uint32_t *preds, uint32_t *arcs);
 int azb_get_counters(azb_handle *h, azb_counters *out);
 int azb_reset_counters(azb_handle *h);
+/* full != 0 (default): all 16 workload counters; 0: only n_live, n_noop, n_ins (the timed bench pass) */
+int azb_set_counter_mode(azb_handle *h, int full);
 /* current state vectors / priors held on the device (state_vecs, h_theta_host: optimizer/mod.rs:15-16) */
 int azb_get_state_vecs(azb_handle *h, float *state_vecs /*[B*S]*/);
 int azb_get_priors(azb_handle *h, float *priors /*[B*A]*/);

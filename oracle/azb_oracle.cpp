@@ -483,14 +483,20 @@ double lambda1_poly(uint32_t n, const uint8_t *par, uint32_t *mu_out) {
     uint32_t maxw2 = 0;
     for (uint32_t v = 0; v < n; ++v) maxw2 = std::max(maxw2, w2[v]);
     double y = (double)maxw2;
-    for (int it = 0; it < 64; ++it) {
-        double s = c[0], d = 0.0;
+    const double nn = (double)K, nm1 = (double)(K - 1u);
+    for (int it = 0; it < 40; ++it) {  // Laguerre from the right of the largest root
+        double s = c[0], d = 0.0, h = 0.0;
         for (int j = 1; j <= KM; ++j) {
+            h = std::fma(h, y, d);
             d = std::fma(d, y, s);
             s = std::fma(s, y, c[j]);
         }
-        if (!(d > 0.0)) break;
-        double yn = y - s / d;
+        double dd = 2.0 * h;
+        double disc = nm1 * ((nm1 * (d * d)) - (nn * (s * dd)));
+        if (!(disc >= 0.0)) disc = 0.0;
+        double den = d + std::sqrt(disc);
+        if (!(den > 0.0)) break;
+        double yn = y - (nn * s) / den;
         if (!(yn < y)) break;
         y = yn;
     }

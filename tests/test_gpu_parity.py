@@ -388,3 +388,52 @@ def test_bounded_episodes_with_mlp_priors(capi, orc):
             n_imp, imps = h.step(steps, cap=1024)
             dumps.append(([digest(h.dump_tree(i)) for i in range(b)], imps, h.counters()))
     assert dumps[0] == dumps[1]
+
+
+def test_mlp_tensor_core_matches_f32_reference(capi, orc):
+    """AZB_MLP_TC (tcgen05, bf16 operands, fp32 accumulate in TMEM) against the f32 CPU forward.  Tolerance: 2e-2
+    absolute on the sigmoid outputs (bf16 weights/activations; inputs are exactly 0/1)."""
+    n, b = 19, 300  # 300 rows: a full 128-row tile, a second one, and a ragged third
+    a_dim = orc.action_dim(n)
+    rng = np.random.default_rng(2)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC) as h:
+        h.mlp_init(42)
+        params = h.mlp_get_params()
+        x = (rng.random((b, 2 * a_dim)) < 0.2).astype(np.float32)
+        y = h.model_write_predictions(x)
+        want = orc.mlp_forward(params, [2 * a_dim, 512, 1024, 512, a_dim], x, n_threads=4)
+        err = np.abs(y - want).max()
+        assert err < 2e-2, err
+        assert np.abs(y - want).mean() < 3e-3
+        # a sharper check of the GEMM plumbing: emulate the kernel's rounding (bf16 weights and hidden activations)
+        import torch
+
+        dims = [2 * a_dim, 512, 1024, 512, a_dim]
+        cur = torch.from_numpy(x)
+        off = 0
+        for l in range(4):
+            w = torch.from_numpy(params[off:off + dims[l] * dims[l + 1]].reshape(dims[l + 1], dims[l]).copy())
+            bias = torch.from_numpy(params[off + dims[l] * dims[l + 1]:off + dims[l] * dims[l + 1] + dims[l + 1]].copy())
+            off += dims[l] * dims[l + 1] + dims[l + 1]
+            z = cur.to(torch.bfloat16).to(torch.float32) @ w.to(torch.bfloat16).to(torch.float32).T + bias
+            cur = torch.relu(z) if l < 3 else torch.sigmoid(z)
+        assert np.abs(y - cur.numpy()).max() < 2e-3
+        assert np.array_equal(h.model_write_predictions(x[:5]), y[:5])
+
+
+def test_tensor_core_mlp_in_the_fused_loop(capi, orc):
+    """The fused loop with the tcgen05 MLP: trees must match the oracle when it is fed the device's priors."""
+    n, b, steps = 19, 40, 20
+    parents, masks = orc.generate_roots(8, 0, b, n)
+    o = orc.Optimizer(n, b, lambda_method=orc.LAMBDA_MULTISECTION)
+    o.set_roots(parents, masks)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=steps) as h:
+        h.mlp_init(9)
+        h.set_roots(parents, masks)
+        h.init_trees()
+        o.init_trees(h.priors())
+        for s in range(steps):
+            h.step(1)
+            o.rollout()
+            o.add_actions(h.priors())
+        _cmp_trees(o, h, b)
