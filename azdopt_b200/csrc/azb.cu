@@ -953,6 +953,15 @@ int azb_debug_phase_cycles(azb_handle *h, unsigned long long *out16) {
     CK(cudaMemcpyAsync(out16, h->L.g->prof, sizeof(h->L.g->prof), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemsetAsync(h->L.g->prof, 0, sizeof(h->L.g->prof), h->stream));
+#ifdef AZB_PROFILE
+    {
+        unsigned long long cp[8];
+        CK(cudaMemcpyFromSymbol(cp, g_cost_prof, sizeof(cp)));
+        for (int i = 0; i < 4; ++i) out16[12 + i] = cp[i] + (i == 3 ? cp[4] : 0ull);
+        memset(cp, 0, sizeof(cp));
+        CK(cudaMemcpyToSymbol(g_cost_prof, cp, sizeof(cp)));
+    }
+#endif
     return AZB_OK;
 }
 

@@ -90,6 +90,7 @@ __device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *
 
     if (lane == 0) {
         // pass 1 (leaves first): slots needed by each internal vertex; heaviest internal child of each vertex
+#pragma unroll 1
         for (uint32_t v = n - 1; v >= 1; --v) {
             if (cs->cnt[v] == 0u) continue;
             const uint32_t suv = max((uint32_t)cs->s1[v], 1u + cs->s2[v]);
@@ -104,6 +105,7 @@ __device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *
             }
         }
         // pass 2 (leaves first): program length of every subtree
+#pragma unroll 1
         for (uint32_t v = n - 1; v >= 1; --v) {
             const uint32_t p = par[v];
             const uint32_t sl = cs->cnt[v] == 0u ? 1u : cs->len[v] + (cs->heavy[p] == v ? 1u : 2u);
@@ -112,6 +114,7 @@ __device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *
         // pass 3 (root first): slot offsets; every vertex writes its own op(s)
         cs->start[0] = 0;
         cs->cur[0] = cs->heavy[0] != 0xff ? (uint8_t)(cs->len[cs->heavy[0]] + 1u) : 0;
+#pragma unroll 1
         for (uint32_t v = 1; v < n; ++v) {
             const uint32_t p = par[v];
             const bool internal = cs->cnt[v] != 0u, is_heavy = cs->heavy[p] == v;
@@ -239,19 +242,32 @@ __device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *pa
 //      folding child c into v:  b' = b * a_c,  a' = a * a_c + shift(b * b_c)   (polynomial products in k);
 //   2. Laguerre's iteration from y0 = max #2-walks >= lambda_1^2: for a real-rooted polynomial the iterates from the
 //      right of the largest root decrease monotonically onto it, cubically (plain Horner for p, p', p'');
-//   3. three Newton steps with a compensated Horner evaluation of p (error-free TwoProd/TwoSum), which removes the
+//   3. two Newton steps with a compensated Horner evaluation of p (error-free TwoProd/TwoSum), which removes the
 //      cancellation error of the alternating sum: worst relative error 1.3e-16 over random trees, paths, stars and
 //      brooms (tests/test_oracle_golden.py), i.e. the f32 cost equals the dense eigensolver's.
 // Every lane runs steps 2-3 redundantly (uniform); all operations are single IEEE f64 ops, mirrored by the oracle.
 #define AZB_POLY_KMAX 11
 #define AZB_POLY_NV 22
 
+#ifdef AZB_PROFILE
+__device__ unsigned long long g_cost_prof[8];
+#define CPROF_T0() long long cprof_t = clock64()
+#define CPROF(i)                                                            \
+    do {                                                                    \
+        long long t1_ = clock64();                                          \
+        if (lane == 0) atomicAdd(&g_cost_prof[i], (unsigned long long)(t1_ - cprof_t)); \
+        cprof_t = t1_;                                                      \
+    } while (0)
+#else
+#define CPROF_T0() do {} while (0)
+#define CPROF(i) do {} while (0)
+#endif
+
 struct __align__(16) PolyScratch {  // per-warp shared memory, lives in the same bytes as CostScratch
     uint32_t A[AZB_POLY_NV][AZB_POLY_KMAX + 1];
     uint32_t B[AZB_POLY_NV][AZB_POLY_KMAX + 1];
     uint32_t cnt[32];
     uint32_t w2[32];
-    uint8_t dA[32], dB[32];
 };
 
 __device__ __forceinline__ void azb_two_sum(double a, double b, double &s, double &e) {
@@ -262,21 +278,13 @@ __device__ __forceinline__ void azb_two_sum(double a, double b, double &s, doubl
 
 // n <= 22.  par: n bytes of shared memory.  Warp-collective; every lane returns lambda_1 and *mu_out.
 __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *par, PolyScratch *ps, int lane,
-                                                   uint32_t *mu_out) {
+                                                uint32_t *mu_out) {
     const uint32_t FULL = 0xffffffffu;
     constexpr int KM = AZB_POLY_KMAX;
-    // ---- max #2-walks (the Newton start) ----
+    CPROF_T0();
+    // ---- children counts, max #2-walks (the start of the root iteration) ----
     ps->cnt[lane] = 0u;
     ps->w2[lane] = 0u;
-    if (lane < AZB_POLY_NV) {
-        ps->dA[lane] = 0;
-        ps->dB[lane] = 0;
-    }
-    for (uint32_t i = lane; i < n * (KM + 1); i += 32) {
-        const uint32_t one = (i % (KM + 1)) == 0u ? 1u : 0u;
-        (&ps->A[0][0])[i] = one;
-        (&ps->B[0][0])[i] = one;
-    }
     __syncwarp();
     const bool act = lane >= 1 && (uint32_t)lane < n;
     const uint32_t p0 = act ? par[lane] : 0u;
@@ -285,30 +293,49 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         if (act && (__ffs(m) - 1) == lane) ps->cnt[p0] = (uint32_t)__popc(m);
     }
     __syncwarp();
-    if (act) atomicAdd(&ps->w2[p0], ps->cnt[lane] + 1u);
+    const uint32_t mycnt = ps->cnt[lane];
+    if (act) atomicAdd(&ps->w2[p0], mycnt + 1u);
+    const uint32_t leaf_mask = __ballot_sync(FULL, mycnt == 0u);  // bit v: vertex v has no children
+    // leaf children fold as (a, b) -> (a + x b, b); the folds commute (polynomial products), so all L leaf
+    // children of a vertex are folded at once by starting it at a = 1 + L x, b = 1
+    uint32_t nleaf = 0;
+    {
+        const bool lf = act && mycnt == 0u;
+        const uint32_t m = __match_any_sync(FULL, lf ? p0 : (0x10000u | (uint32_t)lane));
+        // every leaf child of p0 sees the same group; the parent's lane needs the count: publish through cnt's
+        // sibling array w2 is taken, so reuse A[p][1] directly below
+        if (lf && (__ffs(m) - 1) == lane) nleaf = (uint32_t)__popc(m);
+    }
+    for (uint32_t i = lane; i < n * (KM + 1); i += 32) {
+        const uint32_t one = (i % (KM + 1)) == 0u ? 1u : 0u;
+        (&ps->A[0][0])[i] = one;
+        (&ps->B[0][0])[i] = one;
+    }
     __syncwarp();
+    if (nleaf) ps->A[p0][1] = nleaf;
     uint32_t maxw2 = 0;
     if ((uint32_t)lane < n) maxw2 = ps->w2[lane] + (lane >= 1 ? ps->cnt[p0] + (p0 >= 1 ? 1u : 0u) : 0u);
     maxw2 = __reduce_max_sync(FULL, maxw2);
-    // ---- 1. matching counts, leaves first (parents[v] < v) ----
+    __syncwarp();
+    CPROF(0);
+    // ---- 1. matching counts: fold the internal children, leaves first (parents[v] < v); lane = k ----
     const int k = lane;
-    for (uint32_t v = n - 1; v >= 1; --v) {
+    uint32_t todo = ~leaf_mask & ((n >= 32 ? 0u : (1u << n)) - 1u) & ~1u;  // internal vertices except the root
+    while (todo) {
+        const uint32_t v = 31u - __clz(todo);
+        todo &= ~(1u << v);
         const uint32_t p = par[v];
-        const uint32_t dav = ps->dA[v], dbv = ps->dB[v], dap = ps->dA[p], dbp = ps->dB[p];
         uint32_t na = 0, nb = 0;
-        if (k <= KM) {
-            if (dav == 0u) {  // leaf child: a_c = b_c = 1
-                na = ps->A[p][k] + (k >= 1 ? ps->B[p][k - 1] : 0u);
-                nb = ps->B[p][k];
-            } else {
-                for (uint32_t i = 0; i <= dav; ++i) {
-                    if ((int)i > k) break;
-                    const uint32_t ac = ps->A[v][i], bc = ps->B[v][i];
-                    const uint32_t bpk = ps->B[p][k - i];
-                    nb += ac * bpk;
-                    na += ac * ps->A[p][k - i];
-                    if ((int)i < k) na += bc * ps->B[p][k - 1 - i];
-                }
+        // the child's polynomials sit one coefficient per lane; their degree bounds the product loop
+        const uint32_t av = k <= KM ? ps->A[v][k] : 0u, bv = k <= KM ? ps->B[v][k] : 0u;
+        const int dav = 31 - __clz(__ballot_sync(FULL, av != 0u));
+        for (int i = 0; i <= dav; ++i) {
+            const uint32_t ac = __shfl_sync(FULL, av, i), bc = __shfl_sync(FULL, bv, i);
+            if (k <= KM && i <= k) {
+                const uint32_t bpk = ps->B[p][k - i];
+                nb += ac * bpk;
+                na += ac * ps->A[p][k - i];
+                if (i < k) na += bc * ps->B[p][k - 1 - i];
             }
         }
         __syncwarp();
@@ -316,40 +343,44 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
             ps->A[p][k] = na;
             ps->B[p][k] = nb;
         }
-        if (lane == 0) {
-            const uint32_t ndb = dbp + dav;
-            const uint32_t nda = max(dap + dav, dbp + dbv + 1u);
-            ps->dA[p] = (uint8_t)min(nda, (uint32_t)KM);
-            ps->dB[p] = (uint8_t)min(ndb, (uint32_t)KM);
-        }
         __syncwarp();
     }
-    // degree bookkeeping above is an upper bound; the matching number is the largest k with m_k > 0
+    CPROF(1);
+    // the matching number is the largest k with m_k > 0
     const uint32_t mk = k <= KM ? ps->A[0][k] : 0u;
     const uint32_t nz = __ballot_sync(FULL, mk != 0u);
     const uint32_t K = 31u - __clz(nz);
     *mu_out = K;
-    // ---- coefficients, leading zeros in front so that a fixed-length Horner is the K-term Horner ----
-    double c[KM + 1];
+    // ---- coefficients: position j of a fixed 12-term Horner holds m_(j - sh), sh = KM - K leading zeros, so the
+    //      fixed-length Horner IS the K-term Horner; m_k <= 6435, two per register; sign (-1)^(j - sh)
+    const int sh = KM - (int)K;
+    uint32_t pk[(KM + 1) / 2];
 #pragma unroll
-    for (int j = 0; j <= KM; ++j) {
-        const int kk = j - (KM - (int)K);  // coefficient index of position j
-        const uint32_t m = __shfl_sync(FULL, mk, kk < 0 ? 0 : kk);
-        const double v = (double)m;
-        c[j] = kk < 0 ? 0.0 : ((kk & 1) ? -v : v);
+    for (int j = 0; j <= KM; j += 2) {
+        const uint32_t lo16 = j >= sh ? ps->A[0][j - sh] : 0u;
+        const uint32_t hi16 = j + 1 >= sh ? ps->A[0][j + 1 - sh] : 0u;
+        pk[j / 2] = lo16 | (hi16 << 16);
     }
+    const bool shodd = (sh & 1) != 0;
+#define AZB_COEF(j) ((((j) & 1) != 0) != shodd ? -(double)((pk[(j) / 2] >> (((j) & 1) * 16)) & 0xffffu) \
+                                                : (double)((pk[(j) / 2] >> (((j) & 1) * 16)) & 0xffffu))
+    CPROF(2);
     // ---- 2. Laguerre from the right (plain Horner for p, p', p''/2): for a real-rooted polynomial the iterates
     //         decrease monotonically onto the largest root, cubically
     double y = (double)maxw2;
     const double nn = (double)K, nm1 = (double)(K - 1u);
 #pragma unroll 1
     for (int it = 0; it < 40; ++it) {
-        double s = c[0], d = 0.0, h = 0.0;
+        // keep the coefficients packed across iterations: without this the int->f64 conversions are hoisted out of
+        // the loop and cost 24 registers for the whole kernel
+#pragma unroll
+        for (int q = 0; q < (KM + 1) / 2; ++q) asm volatile("" : "+r"(pk[q]));
+        double s = AZB_COEF(0), d = 0.0, h = 0.0;
 #pragma unroll
         for (int j = 1; j <= KM; ++j) {
             h = __fma_rn(h, y, d);
             d = __fma_rn(d, y, s);
-            s = __fma_rn(s, y, c[j]);
+            s = __fma_rn(s, y, AZB_COEF(j));
         }
         const double dd = __dmul_rn(2.0, h);
         double disc = __dmul_rn(nm1, __dsub_rn(__dmul_rn(nm1, __dmul_rn(d, d)), __dmul_rn(nn, __dmul_rn(s, dd))));
@@ -358,26 +389,34 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         if (!(den > 0.0)) break;
         const double yn = __dsub_rn(y, __ddiv_rn(__dmul_rn(nn, s), den));
         if (!(yn < y)) break;
+        const bool close = __dsub_rn(y, yn) < __dmul_rn(1e-5, yn);  // the two polishing steps finish from here
         y = yn;
+        if (close) break;
     }
+    CPROF(3);
     // ---- 3. polish: compensated Horner for p ----
 #pragma unroll 1
-    for (int it = 0; it < 3; ++it) {
-        double s = c[0], e = 0.0, t = c[0], d = 0.0;
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int q = 0; q < (KM + 1) / 2; ++q) asm volatile("" : "+r"(pk[q]));
+        double s = AZB_COEF(0), e = 0.0, t = s, d = 0.0;
 #pragma unroll
         for (int j = 1; j <= KM; ++j) {
+            const double cj = AZB_COEF(j);
             d = __fma_rn(d, y, t);
-            t = __fma_rn(t, y, c[j]);
+            t = __fma_rn(t, y, cj);
             const double pr = __dmul_rn(s, y);
             const double pi = __fma_rn(s, y, -pr);
             double sg;
-            azb_two_sum(pr, c[j], s, sg);
+            azb_two_sum(pr, cj, s, sg);
             e = __dadd_rn(__dmul_rn(e, y), __dadd_rn(pi, sg));
         }
         const double pv = __dadd_rn(s, e);
         if (!(d > 0.0)) break;
         y = __dsub_rn(y, __ddiv_rn(pv, d));
     }
+#undef AZB_COEF
+    CPROF(4);
     __syncwarp();
     return __dsqrt_rn(y);
 }
@@ -392,6 +431,7 @@ __device__ __forceinline__ double azb_cost_warp(uint32_t n, const uint8_t *par, 
 __device__ __forceinline__ uint32_t azb_matching(uint32_t n, const uint8_t *parents) {
     unsigned long long used = 0ull;
     uint32_t m = 0;
+#pragma unroll 1
     for (uint32_t v = n - 1; v >= 1; --v) {
         uint32_t p = parents[v];
         unsigned long long pair = (1ull << v) | (1ull << p);
@@ -405,10 +445,14 @@ __device__ __forceinline__ uint32_t azb_matching(uint32_t n, const uint8_t *pare
 
 template <int DEPTH>
 __device__ __forceinline__ double azb_cost_warp(uint32_t n, const uint8_t *par, CostScratch *cs, int lane, uint32_t *mu) {
-    if (n <= AZB_POLY_NV) return azb_lambda1_poly(n, par, reinterpret_cast<PolyScratch *>(cs), lane, mu);
-    const double l1 = azb_lambda1_warp<DEPTH>(n, par, cs, lane);
-    *mu = azb_matching(n, par);
-    return l1;
+    // DEPTH == 3 <=> N <= 22 (azb_stack_depth): each instantiation carries only the method it uses
+    if constexpr (DEPTH == 3) {
+        return azb_lambda1_poly(n, par, reinterpret_cast<PolyScratch *>(cs), lane, mu);
+    } else {
+        const double l1 = azb_lambda1_warp<DEPTH>(n, par, cs, lane);
+        *mu = azb_matching(n, par);
+        return l1;
+    }
 }
 
 // evaluate + squish: 04-c21-tree.rs:70-74,98-102

@@ -498,9 +498,11 @@ double lambda1_poly(uint32_t n, const uint8_t *par, uint32_t *mu_out) {
         if (!(den > 0.0)) break;
         double yn = y - (nn * s) / den;
         if (!(yn < y)) break;
+        bool close = (y - yn) < 1e-5 * yn;  // the two polishing steps finish from here
         y = yn;
+        if (close) break;
     }
-    for (int it = 0; it < 3; ++it) {
+    for (int it = 0; it < 2; ++it) {
         double s = c[0], e = 0.0, t = c[0], d = 0.0;
         for (int j = 1; j <= KM; ++j) {
             d = std::fma(d, y, t);

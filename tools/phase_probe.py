@@ -12,7 +12,7 @@ PH = ["sel", "cur", "probe", "arc", "cascade", "cost", "insert", "reset", "add",
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 L = capi.lib()
 L.azb_debug_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-for b in (1, 4096):
+for b in (1,):
     cfg = capi.default_config(n, b, prior_mode=capi.PRIOR_HASH, max_steps=400)
     p, m = capi.generate_roots(0, 0, b, n)
     with capi.Handle(cfg) as h:
@@ -32,5 +32,6 @@ for b in (1, 4096):
         ev = {"sel": k["n_sel"], "cur": k["n_cur"], "probe": k["n_probe"], "arc": k["n_hit"], "cascade": k["n_hit"] + k["n_term"],
               "cost": k["n_ins"], "insert": k["n_ins"], "reset": k["n_reset"], "add": k["n_live"], "pack": k["n_live"],
               "load": per, "store": per}
+        print(f"   cost split: init {buf[12] / max(k['n_ins'],1):.0f}  dp {buf[13] / max(k['n_ins'],1):.0f}  coef {buf[14] / max(k['n_ins'],1):.0f}  laguerre+polish {buf[15] / max(k['n_ins'],1):.0f} cyc/eval")
         for i, name in enumerate(PH):
             print(f"   {name:8s} {buf[i] / per:9.0f} cyc/tree-step  {buf[i] / max(ev[name], 1):9.0f} cyc/event  ({ev[name] / per:.2f} events/tree-step)")
