@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("n_as_tol", C.c_uint32 * MAX_TOL), ("n_as_tol_len", C.c_uint32), ("n_as_tol_default", C.c_uint32),
         ("mlp_hidden", C.c_uint32 * 3), ("mlp_mode", C.c_uint32), ("prior_mode", C.c_uint32),
         ("prior_seed", C.c_uint64), ("max_steps", C.c_uint32), ("cap_nodes", C.c_uint32), ("cap_preds", C.c_uint32),
-        ("cap_parents", C.c_uint32), ("max_episodes", C.c_uint32), ("reserved", C.c_uint32 * 7),
+        ("cap_parents", C.c_uint32), ("max_episodes", C.c_uint32), ("n_groups", C.c_uint32), ("reserved", C.c_uint32 * 6),
     ]
 
 
@@ -75,6 +75,7 @@ SIGNATURES = {
     "azb_set_priors": (C.c_int, [C.c_void_p, f32p]),
     "azb_init_trees": (C.c_int, [C.c_void_p]),
     "azb_step": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Improvement), C.c_uint32, u32p]),
+    "azb_step_enqueue": (C.c_int, [C.c_void_p, C.c_uint32]),
     "azb_step_timed": (C.c_int, [C.c_void_p, C.c_uint32, f32p, u32p]),
     "azb_step_profile": (C.c_int, [C.c_void_p, C.c_uint32, f32p, f32p]),
     "azb_rollout_host": (C.c_int, [C.c_void_p, f32p]),
@@ -258,6 +259,9 @@ class Handle:
         self._ck(self._L.azb_step(self._h, n_steps, imp, cap, C.byref(n)))
         k = min(int(n.value), cap)
         return int(n.value), [(imp[i].step, imp[i].tree, imp[i].node, np.float32(imp[i].eval)) for i in range(k)]
+
+    def step_enqueue(self, n_steps):
+        self._ck(self._L.azb_step_enqueue(self._h, n_steps))
 
     def step_timed(self, n_steps):
         ms = C.c_float()

@@ -55,6 +55,9 @@ struct azb_handle {
     uint32_t argmin_from;  // first candidate slot the argmin pass has not consumed yet
     uint32_t lcap, smem_words_per_warp;
     size_t smem_bytes;
+    uint32_t n_groups, group_trees;
+    cudaStream_t gstream[64];
+    cudaEvent_t gevent[64], fork_event;
     bool graph_ok;
     cudaGraphExec_t step_graph;
     char err[512];
@@ -143,6 +146,7 @@ int azb_config_default(azb_config *cfg, uint32_t n_vertices, uint32_t n_roots) {
     cfg->prior_seed = 0;
     cfg->max_steps = 800;
     cfg->max_episodes = 0;
+    cfg->n_groups = 1;
     return AZB_OK;
 }
 
@@ -157,6 +161,11 @@ int azb_destroy(azb_handle *h) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     azb_mlp_tc_destroy(h->tc);
+    for (uint32_t g = 0; g < 64; ++g) {
+        if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+        if (h->gevent[g]) cudaEventDestroy(h->gevent[g]);
+    }
+    if (h->fork_event) cudaEventDestroy(h->fork_event);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -182,6 +191,9 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     if (cfg.c_upper == 0.0f) cfg.c_upper = (float)(isqrt_ceil(N - 1) + (N + 1) / 2);  // 04-c21-tree.rs:59-68
     if (!(cfg.c_upper > cfg.c_lower)) return fail(h, AZB_ERR_INVALID, "c_upper must exceed c_lower");
     if (cfg.max_steps == 0) cfg.max_steps = 800;
+    if (cfg.n_groups == 0) cfg.n_groups = 1;
+    if (cfg.n_groups > 64) return fail(h, AZB_ERR_INVALID, "n_groups > 64");
+    if (cfg.n_groups > 1 && cfg.max_episodes) return fail(h, AZB_ERR_INVALID, "n_groups > 1 needs max_episodes = 0");
     for (int i = 0; i < 3; ++i)
         if (cfg.mlp_hidden[i] == 0) cfg.mlp_hidden[i] = i == 1 ? 1024 : 512;
     // arena growth measured with the oracle on the example's root distribution: at most ~1.9 nodes,
@@ -210,6 +222,18 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+    {
+        // concurrent groups of trees: contiguous ranges, a multiple of 128 trees each (MLP row tiles)
+        uint32_t per = (cfg.n_roots + cfg.n_groups - 1) / cfg.n_groups;
+        per = (per + 127u) & ~127u;
+        h->group_trees = per;
+        h->n_groups = (cfg.n_roots + per - 1) / per;
+        for (uint32_t g = 0; g < h->n_groups && h->n_groups > 1; ++g) {
+            CK(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->gevent[g], cudaEventDisableTiming));
+        }
+    }
 
     AzbLayout &L = h->L;
     L.N = N;
@@ -271,6 +295,10 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     if (cfg.mlp_mode == AZB_MLP_TC) {
         const char *why = azb_mlp_tc_create(h->tc, B, h->dims, &h->dev_bytes);
         if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
+        if (cfg.prior_mode == AZB_PRIOR_MLP) {  // write_vec feeds the first GEMM directly
+            L.sv16 = reinterpret_cast<uint16_t *>(h->tc.act[0]);
+            L.sv16_ld = h->tc.kpad[0];
+        }
     }
 
     // shared memory per warp of the tree kernel: walker block + masks + children's c* + cascade frontiers
@@ -431,27 +459,29 @@ int azb_mlp_get_params(azb_handle *h, float *params) {
     return AZB_OK;
 }
 
-// ActionModel::forward (nabla/model/dfdx.rs:81-83) on device rows
-static int mlp_forward(azb_handle *h, const float *x, uint32_t ldx, float *y, uint32_t ldy, uint32_t rows) {
+// ActionModel::forward (nabla/model/dfdx.rs:81-83) on device rows [row0, row0 + rows)
+static int mlp_forward(azb_handle *h, const float *x, uint32_t ldx, float *y, uint32_t ldy, uint32_t row0, uint32_t rows,
+                       cudaStream_t stream) {
     if (h->cfg.mlp_mode == AZB_MLP_TC) {
-        const char *why = azb_mlp_tc_forward(h->tc, x, ldx, y, ldy, rows, h->stream, &h->launches);
+        const bool packed = h->L.sv16 != nullptr && x == h->L.sv;  // tree_pack already wrote the bf16 rows
+        const char *why = azb_mlp_tc_forward(h->tc, packed ? nullptr : x, ldx, y, ldy, row0, rows, stream, &h->launches);
         if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
         return AZB_OK;
     }
-    const float *in = x;
+    const float *in = x + (size_t)row0 * ldx;
     uint32_t ld_in = ldx;
     const float *p = h->params;
     for (int l = 0; l < 4; ++l) {
         const uint32_t K = h->dims[l], Nout = h->dims[l + 1];
-        float *outp = l < 3 ? h->act[l] : y;
+        float *outp = l < 3 ? h->act[l] + (size_t)row0 * Nout : y + (size_t)row0 * ldy;
         const uint32_t ld_out = l < 3 ? Nout : ldy;
         dim3 grid((Nout + 63) / 64, (rows + 63) / 64);
         if (l < 3)
-            azb_linear_fp32_kernel<AZB_ACT_RELU><<<grid, 256, 0, h->stream>>>(in, ld_in, p, p + (size_t)K * Nout, outp,
-                                                                              ld_out, rows, K, Nout);
+            azb_linear_fp32_kernel<AZB_ACT_RELU><<<grid, 256, 0, stream>>>(in, ld_in, p, p + (size_t)K * Nout, outp, ld_out,
+                                                                         rows, K, Nout);
         else
-            azb_linear_fp32_kernel<AZB_ACT_SIGMOID><<<grid, 256, 0, h->stream>>>(in, ld_in, p, p + (size_t)K * Nout,
-                                                                                 outp, ld_out, rows, K, Nout);
+            azb_linear_fp32_kernel<AZB_ACT_SIGMOID><<<grid, 256, 0, stream>>>(in, ld_in, p, p + (size_t)K * Nout, outp,
+                                                                            ld_out, rows, K, Nout);
         h->launches += 1;
         in = outp;
         ld_in = ld_out;
@@ -470,22 +500,42 @@ int azb_model_write_predictions(azb_handle *h, const float *states, float *predi
         CK(dmalloc(h, &h->mlp_y, (size_t)h->L.B * h->A));
     }
     CK(cudaMemcpyAsync(h->mlp_x, states, (size_t)rows * h->S * 4, cudaMemcpyHostToDevice, h->stream));
-    int rc = mlp_forward(h, h->mlp_x, h->S, h->mlp_y, h->A, rows);
+    int rc = mlp_forward(h, h->mlp_x, h->S, h->mlp_y, h->A, 0, rows, h->stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(predictions, h->mlp_y, (size_t)rows * h->A * 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return AZB_OK;
 }
 
+// state_vecs (optimizer/mod.rs:15) to a host buffer; the tensor-core configuration keeps them as bf16 {0, 1} rows
+static int copy_state_vecs(azb_handle *h, float *dst) {
+    if (!h->L.sv16) {
+        CK(cudaMemcpy2DAsync(dst, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, h->L.B,
+                             cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return AZB_OK;
+    }
+    std::vector<uint16_t> tmp((size_t)h->L.B * h->S);
+    CK(cudaMemcpy2DAsync(tmp.data(), (size_t)h->S * 2, h->L.sv16, (size_t)h->L.sv16_ld * 2, (size_t)h->S * 2, h->L.B,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < tmp.size(); ++i) dst[i] = tmp[i] ? 1.0f : 0.0f;
+    return AZB_OK;
+}
+
 // ---- tree kernel launches ----
-static int launch_tree(azb_handle *h, uint32_t flags, uint32_t target_step, int prior_mode_override = -1) {
+static int launch_tree(azb_handle *h, uint32_t flags, uint32_t target_step, int prior_mode_override = -1,
+                       uint32_t tree0 = 0, uint32_t ntrees = 0xffffffffu, cudaStream_t stream = nullptr) {
     AzbLayout L = h->L;
     if (prior_mode_override >= 0) L.prior_mode = (uint32_t)prior_mode_override;
-    const uint32_t blocks = (L.B + AZB_WARPS_PER_BLOCK - 1) / AZB_WARPS_PER_BLOCK;
+    if (!stream) stream = h->stream;
+    const uint32_t tree_end = ntrees == 0xffffffffu ? L.B : std::min(L.B, tree0 + ntrees);
+    const uint32_t blocks = (tree_end - tree0 + AZB_WARPS_PER_BLOCK - 1) / AZB_WARPS_PER_BLOCK;
     const dim3 block(AZB_WARPS_PER_BLOCK * 32);
     const uint32_t me = h->cfg.max_episodes;
-#define AZB_LAUNCH_TREE(D, C) \
-    azb_tree_kernel<D, C><<<blocks, block, h->smem_bytes, h->stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, me)
+#define AZB_LAUNCH_TREE(D, C)                                                                                       \
+    azb_tree_kernel<D, C><<<blocks, block, h->smem_bytes, stream>>>(L, flags, h->smem_words_per_warp, h->lcap, target_step, \
+                                                                    me, tree0, tree_end)
     switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
         case 6: AZB_LAUNCH_TREE(3, false); break;
         case 7: AZB_LAUNCH_TREE(3, true); break;
@@ -558,7 +608,7 @@ int azb_init_trees(azb_handle *h) {
     int rc = launch_tree(h, AZB_F_INIT | (first ? (uint32_t)AZB_F_FIRST : 0u), 0);
     if (rc) return rc;
     if (h->cfg.prior_mode == AZB_PRIOR_MLP) {
-        rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+        rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
         if (rc) return rc;
     }
     rc = launch_tree(h, AZB_F_ADD, 0);
@@ -582,7 +632,7 @@ static int enqueue_launch(azb_handle *h, uint32_t flags, uint32_t target) {
     int rc = launch_tree(h, flags, target);
     if (rc) return rc;
     if ((flags & AZB_F_ADD) && h->cfg.prior_mode == AZB_PRIOR_MLP)
-        rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+        rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
     return rc;
 }
 
@@ -590,6 +640,30 @@ static int enqueue_steps(azb_handle *h, uint32_t n_steps, uint32_t flags) {
     if (h->steps_done + n_steps > h->L.cap_steps)
         return fail(h, AZB_ERR_CAPACITY, "%u steps since azb_init_trees exceed max_steps", h->steps_done + n_steps);
     const uint32_t target = h->steps_done + n_steps;
+    if (h->n_groups > 1 && n_steps) {
+        // groups of trees advance on their own streams: a group's launch only waits for its own slowest tree, and
+        // its model forward overlaps the other groups' walks.  Trees are independent, so results are unchanged.
+        const bool mlp = (flags & AZB_F_ADD) && h->cfg.prior_mode == AZB_PRIOR_MLP;
+        CK(cudaEventRecord(h->fork_event, h->stream));
+        for (uint32_t g = 0; g < h->n_groups; ++g) CK(cudaStreamWaitEvent(h->gstream[g], h->fork_event, 0));
+        for (uint32_t s = 0; s < n_steps; ++s)
+            for (uint32_t g = 0; g < h->n_groups; ++g) {
+                const uint32_t t0 = g * h->group_trees, nt = std::min(h->group_trees, h->L.B - t0);
+                int rc = launch_tree(h, flags, target, -1, t0, nt, h->gstream[g]);
+                if (rc) return rc;
+                if (mlp) {
+                    rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, t0, nt, h->gstream[g]);
+                    if (rc) return rc;
+                }
+            }
+        for (uint32_t g = 0; g < h->n_groups; ++g) {
+            CK(cudaEventRecord(h->gevent[g], h->gstream[g]));
+            CK(cudaStreamWaitEvent(h->stream, h->gevent[g], 0));
+        }
+        h->steps_done = target;
+        h->pending_add = true;
+        return AZB_OK;
+    }
     for (uint32_t s = 0; s < n_steps; ++s) {
         int rc = enqueue_launch(h, flags, target);
         if (rc) return rc;
@@ -636,6 +710,16 @@ int azb_step(azb_handle *h, uint32_t n_steps, azb_improvement *improvements, uin
     return AZB_OK;
 }
 
+// enqueue n_steps without waiting (several handles on one GPU can then run concurrently); azb_step(h, 0, ...) or any
+// reading call completes them
+int azb_step_enqueue(azb_handle *h, uint32_t n_steps) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    if (h->cfg.max_episodes) return fail(h, AZB_ERR_INVALID, "azb_step_enqueue needs max_episodes = 0");
+    CK(cudaSetDevice(h->cfg.device));
+    return enqueue_steps(h, n_steps, AZB_F_ADD | AZB_F_ROLLOUT);
+}
+
 int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_improved) {
     if (!h) return AZB_ERR_INVALID;
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
@@ -677,7 +761,7 @@ int azb_step_profile(azb_handle *h, uint32_t n_steps, float *tree_ms, float *mlp
         for (uint32_t s = 0; s < n_steps && rc == AZB_OK; ++s) {
             rc = launch_tree(h, AZB_F_ADD | AZB_F_ROLLOUT, target);
             mark();
-            if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, h->L.B);
+            if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
             mark();
             ++launched;
         }
@@ -718,8 +802,8 @@ int azb_rollout_host(azb_handle *h, float *state_vecs) {
     if (rc) return rc;
     rc = run_argmin(h, h->steps_done + 1);
     if (rc) return rc;
-    CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, h->L.B,
-                         cudaMemcpyDeviceToHost, h->stream));
+    rc = copy_state_vecs(h, state_vecs);
+    if (rc) return rc;
     AzbGlobals g;
     rc = read_globals(h, &g);
     if (rc) return rc;
@@ -986,10 +1070,7 @@ int azb_reset_counters(azb_handle *h) {
 int azb_get_state_vecs(azb_handle *h, float *state_vecs) {
     if (!h || !state_vecs) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
-    CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, h->L.B,
-                         cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return AZB_OK;
+    return copy_state_vecs(h, state_vecs);
 }
 
 int azb_get_priors(azb_handle *h, float *priors) {

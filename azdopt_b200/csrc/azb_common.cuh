@@ -93,6 +93,8 @@ struct AzbLayout {
     uint2 *cand;
     unsigned long long *stepmin;
     float *sv;
+    uint16_t *sv16;       // bf16 rows for the tensor-core MLP (null otherwise): write_vec goes there instead of sv
+    uint32_t sv16_ld;
     float *h;
     AzbGlobals *g;
     AzbImprovementDev *log;

@@ -97,13 +97,13 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
     azb_linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                          const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out_bf16,
-                         float *__restrict__ out_f32, uint32_t ld_out, uint32_t rows, uint32_t n_valid, uint32_t k_blocks,
-                         uint32_t bn) {
+                         float *__restrict__ out_f32, uint32_t ld_out, uint32_t row0, uint32_t rows_end, uint32_t n_valid,
+                         uint32_t k_blocks, uint32_t bn) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_slot;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * bn;
+    const uint32_t m0 = row0 + blockIdx.y * TC_BM, n0 = blockIdx.x * bn;
     const uint32_t a_bytes = TC_BM * TC_BK * 2, b_bytes = bn * TC_BK * 2, stage_bytes = a_bytes + b_bytes;
     uint8_t *smem = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
     // TMEM columns: power of two >= BN
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (uint32_t c0 = 0; c0 < bn; c0 += 32) {
             uint32_t r[32];
             tc_tmem_ld32(tmem_d + ((q * 32u) << 16) + c0, r);
-            if (row < rows) {
+            if (row < rows_end) {
                 if (out_bf16) {
                     __nv_bfloat16 *dst = out_bf16 + (size_t)row * ld_out + n0 + c0;
 #pragma unroll
@@ -320,18 +320,22 @@ static inline const char *azb_mlp_tc_load(AzbMlpTc &t, const float *params, cuda
     return cudaGetLastError() == cudaSuccess ? nullptr : "weight conversion launch failed";
 }
 
-// x: f32 rows [rows x ldx] (the write_vec vectors); y: f32 [rows x ldy]
+// rows [row0, row0 + rows) of the batch; row0 is a multiple of 128.  x: f32 rows [.. x ldx] to convert first, or null
+// when the bf16 input rows are already in place (tree_pack wrote them); y: f32 [.. x ldy]
 static inline const char *azb_mlp_tc_forward(AzbMlpTc &t, const float *x, uint32_t ldx, float *y, uint32_t ldy,
-                                             uint32_t rows, cudaStream_t stream, uint64_t *launches) {
+                                             uint32_t row0, uint32_t rows, cudaStream_t stream, uint64_t *launches) {
     if (!t.ready) return "not created";
-    azb_rows_to_bf16_kernel<<<rows, 128, 0, stream>>>(x, ldx, t.dims[0], t.act[0], t.kpad[0], rows);
-    if (launches) *launches += 1;
+    if (x) {
+        azb_rows_to_bf16_kernel<<<rows, 128, 0, stream>>>(x + (size_t)row0 * ldx, ldx, t.dims[0],
+                                                          t.act[0] + (size_t)row0 * t.kpad[0], t.kpad[0], rows);
+        if (launches) *launches += 1;
+    }
     for (int l = 0; l < 4; ++l) {
         dim3 grid(t.npad[l] / t.bn[l], (rows + TC_BM - 1) / TC_BM);
         const bool head = l == 3;
         azb_linear_tc_kernel<<<grid, TC_THREADS, t.smem_bytes[l], stream>>>(
             t.map_x[l], t.map_w[l], t.bias[l], head ? nullptr : t.act[l + 1], head ? y : nullptr,
-            head ? ldy : t.kpad[l + 1], rows, t.dims[l + 1], t.kpad[l] / TC_BK, t.bn[l]);
+            head ? ldy : t.kpad[l + 1], row0, row0 + rows, t.dims[l + 1], t.kpad[l] / TC_BK, t.bn[l]);
         if (launches) *launches += 1;
     }
     return cudaGetLastError() == cudaSuccess ? nullptr : "tensor-core forward launch failed";

@@ -705,6 +705,22 @@ __device__ __forceinline__ float pack_bit(const AzbLayout &L, const WarpCtx &cx,
     return one ? 1.0f : 0.0f;
 }
 __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
+    if (L.sv16) {
+        // tensor-core MLP: the row goes out as bf16 (1.0 = 0x3F80), eight entries per 128-bit store; the row pitch is
+        // a multiple of 64 entries and the tail beyond 2A stays zero
+        uint16_t *row = L.sv16 + (size_t)tree * L.sv16_ld;
+        for (uint32_t i = 8u * cx.lane; i < 2 * L.A; i += 256) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t lo = (i + 2 * q < 2 * L.A && pack_bit(L, cx, i + 2 * q) != 0.f) ? 0x3F80u : 0u;
+                const uint32_t hi = (i + 2 * q + 1 < 2 * L.A && pack_bit(L, cx, i + 2 * q + 1) != 0.f) ? 0x3F80u : 0u;
+                w[q] = lo | (hi << 16);
+            }
+            *reinterpret_cast<uint4 *>(row + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return;
+    }
     float *row = L.sv + (size_t)tree * L.sv_ld;
     if ((L.A & 1u) == 0u && (L.sv_ld & 3u) == 0u) {  // rows are 16-byte aligned: one 128-bit store per four entries
         for (uint32_t i = 4u * cx.lane; i < 2 * L.A; i += 128)
@@ -718,17 +734,18 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
 template <int DEPTH, bool COUNT>
 __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
     azb_tree_kernel(const AzbLayout L, const uint32_t flags, const uint32_t smem_words_per_warp, const uint32_t lcap,
-                    const uint32_t target_step, const uint32_t max_episodes) {
+                    const uint32_t target_step, const uint32_t max_episodes, const uint32_t tree0,
+                    const uint32_t tree_end) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tree = blockIdx.x * AZB_WARPS_PER_BLOCK + warp;
+    const uint32_t tree = tree0 + blockIdx.x * AZB_WARPS_PER_BLOCK + warp;
     uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)AZB_WARPS_PER_BLOCK * smem_words_per_warp);
     for (uint32_t a = threadIdx.x; 4u * a < L.A; a += blockDim.x)
         reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
     __syncthreads();
     uint32_t *base = smem + (size_t)warp * smem_words_per_warp;
-    if (tree < L.B) {
+    if (tree < tree_end) {
         WarpCtx cx;
         cx.lane = lane;
         cx.err = 0;
@@ -845,7 +862,8 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
             if (v) atomicAdd(&L.g->prof[lane - 16], (unsigned long long)v);
         }
 #endif
-        if (lane == 0 && (flags & AZB_F_ROLLOUT) && cx.wk[WK_STEP] < target_step) atomicAdd(&L.g->behind_accum, 1u);
+        if (max_episodes != 0u && lane == 0 && (flags & AZB_F_ROLLOUT) && cx.wk[WK_STEP] < target_step)
+            atomicAdd(&L.g->behind_accum, 1u);
         const uint32_t e = __reduce_or_sync(0xffffffffu, cx.err);
         if (e && lane == 0) {
             if (atomicCAS(&L.g->err, 0u, e) == 0u) {
@@ -854,7 +872,8 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
             }
         }
     }
-    // ---- last block done: publish how many trees still have to reach the target
+    // ---- last block done: publish how many trees still have to reach the target (bounded-episode launches only)
+    if (max_episodes == 0u) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&L.g->blocks_done, 1u) == gridDim.x - 1) ? 1u : 0u;

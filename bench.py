@@ -132,7 +132,9 @@ def main():
     ap.add_argument("--roots", type=int, default=4096, help="roots per GPU (BASELINE configs[1])")
     ap.add_argument("--vertices", type=int, default=19)
     ap.add_argument("--mlp", default=os.environ.get("AZB_MLP", "tc"), choices=["fp32", "tc"])
-    ap.add_argument("--max-episodes", type=int, default=int(os.environ.get("AZB_MAX_EPISODES", "2")))
+    ap.add_argument("--max-episodes", type=int, default=int(os.environ.get("AZB_MAX_EPISODES", "0")))
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("AZB_GROUPS", "8")),
+                    help="concurrent tree groups per GPU (own CUDA stream each); needs --max-episodes 0")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-baseline-roots", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -182,7 +184,8 @@ def main():
     prof_steps = min(args.steps, 100)
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
                               mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
-                              max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes)
+                              max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
+                              n_groups=1 if args.max_episodes else args.groups)
     parents, masks = capi.generate_roots(args.seed, rank * b, b, n)
     h = capi.Handle(cfg)
     h.mlp_init(args.seed + 1)  # same seed on every rank: replicated weights
@@ -280,7 +283,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
-                       "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": args.mlp, "max_episodes_per_launch": args.max_episodes,
+                       "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": args.mlp, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
                        "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
                        "simulations_in_timed_region": sims, "noop_root_steps": k["n_noop"],
                        "cost_evals_per_sec": allreduce(float(k["n_ins"]), dist.ReduceOp.SUM if world > 1 else None) / (ms_max * 1e-3)},

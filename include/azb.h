@@ -81,7 +81,9 @@ typedef struct azb_config {
     uint32_t max_episodes;      /* 0: every launch runs each tree to the end of its step (the reference's lock step).
                                    k > 0: a tree that keeps hitting terminal nodes / transpositions yields after k
                                    episodes and finishes the step in a later launch; same results, shorter launches */
-    uint32_t reserved[7];
+    uint32_t n_groups;          /* >1: the trees of this handle advance as that many independent groups on their own
+                                   CUDA streams (needs max_episodes = 0); results are identical, launches overlap */
+    uint32_t reserved[6];
 } azb_config;
 
 typedef struct azb_counters {   /* workload counters; definitions in oracle/azb_oracle.h and DESIGN.md */
@@ -137,7 +139,10 @@ int azb_init_trees(azb_handle *h);
  *      the device (no host round trip per step).  The reference reports an improvement per step
  *      (04-c21-tree.rs:143-148); `improvements` receives up to `cap` of them, `*n_improved` the total. ---- */
 int azb_step(azb_handle *h, uint32_t n_steps, azb_improvement *improvements, uint32_t cap, uint32_t *n_improved);
-/* same, timed with CUDA events on the library's stream; *ms = device time of the n_steps */
+/* enqueue only (no wait, no read-back; needs max_episodes = 0): lets several handles share one GPU concurrently.
+ * azb_step(h, 0, ...) or any reading call completes the work and reports errors. */
+int azb_step_enqueue(azb_handle *h, uint32_t n_steps);
+/* same as azb_step, timed with CUDA events on the library's stream; *ms = device time of the n_steps */
 int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_improved);
 
 /* same again, with an event between the kernels of every step: *tree_ms = summed device time of the search kernel

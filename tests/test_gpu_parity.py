@@ -437,3 +437,33 @@ def test_tensor_core_mlp_in_the_fused_loop(capi, orc):
             o.rollout()
             o.add_actions(h.priors())
         _cmp_trees(o, h, b)
+
+
+@pytest.mark.parametrize("n_groups,mlp", [(4, "hash"), (3, "fp32"), (2, "tc")])
+def test_concurrent_tree_groups_give_identical_results(capi, orc, n_groups, mlp):
+    """n_groups > 1: groups of trees advance on their own CUDA streams.  Trees are independent, so trees, counters,
+    improvement log and argmin must equal the single-stream run."""
+    n, b, steps = 19, 300, 40
+    parents, masks = capi.generate_roots(6, 0, b, n)
+    outs = []
+    for g in (1, n_groups):
+        kw = dict(max_steps=steps, n_groups=g)
+        if mlp == "hash":
+            kw.update(prior_mode=capi.PRIOR_HASH, prior_seed=6)
+        else:
+            kw.update(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC if mlp == "tc" else capi.MLP_FP32)
+        with _mk(capi, n, b, **kw) as h:
+            if mlp != "hash":
+                h.mlp_init(4)
+            h.set_roots(parents, masks)
+            h.init_trees()
+            imps = h.step(1, cap=256)[1] + h.step(steps - 1, cap=256)[1]
+            outs.append(([digest(h.dump_tree(i)) for i in range(b)], imps, h.counters(), h.argmin()["eval"],
+                         h.state_vecs().tobytes()))
+    assert outs[0] == outs[1]
+    if mlp == "hash":
+        o = orc.Optimizer(n, b, lambda_method=orc.LAMBDA_MULTISECTION, n_threads=4)
+        o.set_roots(parents, masks)
+        o.init_trees(orc.hash_priors(6, 0, b, orc.action_dim(n), 0))
+        o.steps_hash(6, 0, 1, steps)
+        assert [digest(o.dump_tree(i)) for i in range(b)] == outs[1][0]
