@@ -303,7 +303,10 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
 
     // shared memory per warp of the tree kernel: walker block + masks + children's c* + cascade frontiers
     h->lcap = (std::max<uint32_t>(A, 64) + 31) & ~31u;
-    h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 32 + h->lcap + 4 * AZB_FRONTIER_CAP + AZB_COST_SCRATCH_WORDS;
+    {
+        const uint32_t shared_region = std::max(std::max(h->lcap, 4u * AZB_FRONTIER_CAP), AZB_COST_SCRATCH_WORDS);
+        h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 32 + shared_region;
+    }
     h->smem_words_per_warp = (h->smem_words_per_warp + 3u) & ~3u;
     h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4 + ((A + 15) & ~15u);  // + action->child LUT
     {

@@ -20,7 +20,7 @@
 #include <stdint.h>
 
 #define AZB_WARPS_PER_BLOCK 4
-#define AZB_FRONTIER_CAP 256
+#define AZB_FRONTIER_CAP 128
 #define AZB_BLK_PAD 64          // units kept free in front of a tree's block arena (speculative reads)
 #define AZB_LO_NONE 0x7fffffffu
 

@@ -765,11 +765,11 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
         p += 64;
         cx.ct = p;
         p += 32;
+        // children's c* (selection), cascade frontiers and the cost scratch are never live together: one region
         cx.lbuf = (float *)p;
-        p += lcap;
         cx.fr = p;
-        p += 4 * AZB_FRONTIER_CAP;
         cx.cs = reinterpret_cast<CostScratch *>(p);
+        (void)lcap;
         cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
         cx.blk = L.blk + (size_t)tree * L.cap_blk;
         cx.blk4 = reinterpret_cast<uint4 *>(cx.blk);
