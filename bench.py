@@ -10,7 +10,8 @@ counted separately and excluded.  Workload at N GPUs: `--roots` (4096, BASELINE 
 N = 19, random-init MLP 304-512-1024-512-152, synthetic roots of the example's distribution (weak scaling; roots
 shard across ranks with no collective inside a step).
 
-torch is used here only for torch.distributed (barrier, max/sum over ranks) — the product is libazb.so.
+torch is used here only for torch.distributed (barrier, max/sum over ranks; gloo on host scalars) and
+torch.cuda.synchronize — the product is libazb.so.
 The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference.
 """
 from __future__ import annotations
@@ -175,8 +176,13 @@ def main():
     import torch.distributed as dist
 
     if world > 1:
+        # roots shard across ranks with no collective inside a step; the only cross-rank traffic of this benchmark
+        # is the barrier and two scalar reductions, which go over gloo on host tensors (NCCL is reserved for the
+        # epoch-boundary collectives: azdopt_b200/shard.py)
+        import datetime
+
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=180))
     from azdopt_b200 import capi
 
     a = capi.action_dim(n)
@@ -199,7 +205,7 @@ def main():
     def allreduce(x, op):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=op)
         return float(t.item())
 
@@ -224,6 +230,8 @@ def main():
     h.set_counter_mode(True)
     ms_max = allreduce(ms, dist.ReduceOp.MAX if world > 1 else None)
     sims = allreduce(float(k["n_live"]), dist.ReduceOp.SUM if world > 1 else None)
+    evals = allreduce(float(k["n_ins"]), dist.ReduceOp.SUM if world > 1 else None)
+    noops = allreduce(float(k["n_noop"]), dist.ReduceOp.SUM if world > 1 else None)
     value = sims / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (the search kernel): per-launch events over a continuation of the run
@@ -285,8 +293,8 @@ def main():
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
                        "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": args.mlp, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
                        "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
-                       "simulations_in_timed_region": sims, "noop_root_steps": k["n_noop"],
-                       "cost_evals_per_sec": allreduce(float(k["n_ins"]), dist.ReduceOp.SUM if world > 1 else None) / (ms_max * 1e-3)},
+                       "simulations_in_timed_region": sims, "noop_root_steps": noops,
+                       "cost_evals_per_sec": evals / (ms_max * 1e-3)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "argmin_eval": float(am["eval"]),
         }
