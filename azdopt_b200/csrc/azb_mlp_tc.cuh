@@ -191,17 +191,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         }
                         *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
-                } else {
-                    float *dst = out_f32 + (size_t)row * ld_out;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const uint32_t n = n0 + c0 + j;
-                        if (n < n_valid) {
-                            const float v = __uint_as_float(r[j]) + bias[n];
-                            dst[n] = 1.0f / (1.0f + expf(-v));
-                        }
-                    }
                 }
+            }
+            if (!out_bf16) {
+                // Sigmoid head, f32 rows: transpose the warp's 32x32 chunk through shared memory (the operand ring is
+                // idle once the accumulator is complete) so that every store instruction writes one contiguous row piece
+                float *tile = reinterpret_cast<float *>(smem) + q * (32 * 33);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t n = n0 + c0 + j;
+                    const float v = __uint_as_float(r[j]) + bias[n];
+                    tile[lane * 33 + j] = __fdividef(1.0f, 1.0f + __expf(-v));
+                }
+                __syncwarp();
+                const uint32_t n = n0 + c0 + lane;
+                for (uint32_t rr = 0; rr < 32; ++rr) {
+                    const uint32_t orow = m0 + q * 32u + rr;
+                    if (orow < rows_end && n < n_valid) out_f32[(size_t)orow * ld_out + n] = tile[rr * 33 + lane];
+                }
+                __syncwarp();
             }
         }
     }
