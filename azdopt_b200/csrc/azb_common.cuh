@@ -42,7 +42,8 @@ enum {
     WK_ROOTLO = 13,    // 16-byte index of the root's block header (AZB_LO_NONE while it has none)
     WK_CURLO = 14,     // same for the walker's node
     WK_ERR = 15,
-    WK_HDR = 16
+    WK_PATH = 16,      // node ids of the walker's path, root first: path[d] = node at depth d (64 words)
+    WK_HDR = 80        // the state part (parents, masks, root) starts here
 };
 
 struct AzbCounters {

@@ -216,84 +216,49 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
     __syncwarp();
 }
 
-// cascade_new_terminal / cascade_old_node (empty_transitions.rs:50-127).  The value carried upward is the start
-// node's c* unchanged (:71-74,111-114), so a level's merge only has to sum the newly-exhausted counts per parent.
-// Every touched node also refreshes the copies of (activity, n_t, c*) held by its parents' kid entries.
-__device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, float cstar, uint32_t ntt, uint32_t e0,
-                             bool old) {
+// cascade_new_terminal / cascade_old_node (empty_transitions.rs:50-127).
+// The reference walks the ancestors of the arc's source level by level; every ancestor is updated exactly once with
+// the same (c*, n_t of the target), and only the exhausted-children counts flow between levels.  That allows a
+// two-phase form that needs far fewer dependent round trips:
+//   A. value pass over ALL ancestors: the walker's own path (known, WK_PATH) is the first work list and is processed
+//      in one go; in-arcs that lead off the path (transposition arcs) seed further work lists; a bitmap keeps every
+//      node to one visit.  Each node gets "c* <- min / else n_t += 1 (old: n_t = max(n_t, n_t of target))" and
+//      refreshes the copies held by its parents' kid entries.
+//   B. exhaustion pass: exhausted_children += 1 at the source if the arc's target is inactive; a node whose count
+//      thereby reaches its prediction count became inactive and hands +1 to each of its parents (rare, serial).
+// Before a cascade every ancestor of the (active) source is active, so "inactive after the update" in the reference
+// (:65-70) is exactly "became inactive in this cascade".
+__device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint32_t depth, float cstar, uint32_t ntt,
+                             uint32_t e0, bool old) {
     const int lane = cx.lane;
-    const uint32_t FULL = 0xffffffffu;
-    uint32_t *curN = cx.fr, *curE = cx.fr + AZB_FRONTIER_CAP;
-    uint32_t *nxtN = cx.fr + 2 * AZB_FRONTIER_CAP, *nxtE = cx.fr + 3 * AZB_FRONTIER_CAP;
-    if (lane == 0) {
-        curN[0] = src;
-        curE[0] = e0;
-    }
-    uint32_t ncur = 1;
+    const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    uint32_t *wa = cx.fr, *wb = cx.fr + AZB_FRONTIER_CAP, *qb = cx.fr + 2 * AZB_FRONTIER_CAP;
+    uint32_t *vis = cx.fr + 3 * AZB_FRONTIER_CAP;
+    const uint32_t nwords = (L.cap_nodes + 31u) >> 5;
+    for (uint32_t w = lane; w < nwords; w += 32) vis[w] = 0u;
     __syncwarp();
+    uint32_t ncur = depth + 1u;
+    for (uint32_t i = lane; i < ncur; i += 32) {
+        const uint32_t p = cx.wk[WK_PATH + i];
+        wa[i] = p;
+        atomicOr(&vis[p >> 5], 1u << (p & 31));
+    }
+    __syncwarp();
+    // ---- A. value pass
     while (ncur > 0 && cx.err == 0) {
-        uint32_t nnxt = 0;
+        uint32_t nnext = 0, links = 0;
         count(cx, CT_CN, ncur);
-        if (ncur == 1u) {
-            // the common case: one node on the level.  Every lane reads the same record (one broadcast request), its
-            // parents are distinct, so the next level needs no merge.
-            const uint32_t p = curN[0], e = curE[0];
-            uint4 *rec = cx.node + (size_t)p * 4;
-            uint4 q0 = rec[0];
-            const uint4 q1 = rec[1], q2 = rec[2], q3 = rec[3];
-            const uint32_t ex = (q0.w & 0xffffu) + e, cnt = q0.w >> 16, nin = q1.y;
-            float cs = __uint_as_float(q0.y);
-            uint32_t nt = q0.z;
-            if (cs > cstar)
-                cs = cstar;
-            else
-                nt += 1;
-            if (old) nt = max(nt, ntt);
-            q0.y = __float_as_uint(cs);
-            q0.z = nt;
-            q0.w = ex | (cnt << 16);
-            const uint32_t up = (ex < cnt) ? 0u : 1u;
-            const uint32_t w1 = q1.x | (up ? 0u : 0x80000000u);
-            count(cx, CT_DCN, nin);
-            if (nin <= 4u) {
-                __syncwarp();
-                if (lane == 0) rec[0] = q0;
-                if ((uint32_t)lane < nin) {
-                    const uint32_t qq = lane == 0 ? q2.x : (lane == 1 ? q2.z : (lane == 2 ? q3.x : q3.z));
-                    const uint32_t kx = lane == 0 ? q2.y : (lane == 1 ? q2.w : (lane == 2 ? q3.y : q3.w));
-                    uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + kx);
-                    kp[1] = w1;
-                    *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(nt, q0.y);
-                    nxtN[lane] = qq;
-                    nxtE[lane] = up;
-                }
-                nnxt = nin;
-                uint32_t *t = curN;
-                curN = nxtN;
-                nxtN = t;
-                t = curE;
-                curE = nxtE;
-                nxtE = t;
-                ncur = nnxt;
-                __syncwarp();
-                continue;
-            }
-            // more than four in-arcs: fall through to the general path (which re-reads the record)
-            if (cx.full_count && lane == 0) cx.ct[CT_DCN] -= nin;
-        }
         for (uint32_t base = 0; base < ncur; base += 32) {
             const uint32_t i = base + lane;
             const bool valid = i < ncur;
-            uint32_t nin = 0, in_off = 0, up = 0, w1 = 0, w2 = 0, w3 = 0;
+            uint32_t nin = 0, in_off = 0, w1 = 0, w2 = 0, w3 = 0;
             uint4 q2 = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
             if (valid) {
-                const uint32_t p = curN[i], e = curE[i];
-                uint4 *rec = cx.node + (size_t)p * 4;
+                uint4 *rec = cx.node + (size_t)wa[i] * 4;
                 uint4 q0 = rec[0];
                 const uint4 q1 = rec[1];
                 q2 = rec[2];
                 q3 = rec[3];
-                const uint32_t ex = (q0.w & 0xffffu) + e, cnt = q0.w >> 16;
                 float cs = __uint_as_float(q0.y);
                 uint32_t nt = q0.z;
                 if (cs > cstar)
@@ -303,80 +268,88 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, floa
                 if (old) nt = max(nt, ntt);
                 q0.y = __float_as_uint(cs);
                 q0.z = nt;
-                q0.w = ex | (cnt << 16);
-                rec[0] = q0;
-                up = (ex < cnt) ? 0u : 1u;
+                rec[0] = q0;  // exhausted_children is untouched here (phase B)
                 nin = q1.y;
                 in_off = q1.z;
-                w1 = q1.x | (up ? 0u : 0x80000000u);
+                w1 = q1.x | (((q0.w & 0xffffu) < (q0.w >> 16)) ? 0x80000000u : 0u);
                 w2 = nt;
                 w3 = q0.y;
-                // refresh the copies in the parents' kid entries (first four in-arcs are inline)
-                const uint32_t k4 = min(nin, 4u);
-                const uint32_t kx[4] = {q2.y, q2.w, q3.y, q3.w};
-#pragma unroll
-                for (uint32_t k = 0; k < 4; ++k)
-                    if (k < k4) {
-                        uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + kx[k]);
-                        kp[1] = w1;
-                        *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(w2, w3);
-                    }
+                links += nin;
             }
-            const uint32_t nvalid = min(32u, ncur - base);
-            for (uint32_t l = 0; l < nvalid; ++l) {
-                const uint32_t nin_l = __shfl_sync(FULL, nin, l);
-                const uint32_t up_l = __shfl_sync(FULL, up, l);
-                count(cx, CT_DCN, nin_l);
-                for (uint32_t k = 0; k < nin_l; ++k) {
-                    uint32_t q;
+            // parents: refresh the copy in their kid entry, enlist the ones not seen yet
+            const uint32_t maxin = __reduce_max_sync(FULL, nin);
+            for (uint32_t k = 0; k < maxin; ++k) {
+                const bool has = valid && k < nin;
+                uint32_t q = 0, kx = 0;
+                if (has) {
                     if (k < 4u) {
-                        const uint32_t sel = k == 0 ? q2.x : (k == 1 ? q2.z : (k == 2 ? q3.x : q3.z));
-                        q = __shfl_sync(FULL, sel, l);
-                    } else {  // overflow in-arcs: refresh the copy here as well
-                        const uint2 ent = cx.inl[__shfl_sync(FULL, in_off, l) + k - 4u];
-                        q = ent.x;
-                        const uint32_t a1 = __shfl_sync(FULL, w1, l), a2 = __shfl_sync(FULL, w2, l),
-                                       a3 = __shfl_sync(FULL, w3, l);
-                        if (lane == 0) {
-                            uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + ent.y);
-                            kp[1] = a1;
-                            *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(a2, a3);
-                        }
-                    }
-                    // merge into the next level (empty_transitions.rs:28-40): one entry per parent
-                    int found = -1;
-                    for (uint32_t s = 0; s < nnxt; s += 32) {
-                        const bool hit = s + lane < nnxt && nxtN[s + lane] == q;
-                        const uint32_t bal = __ballot_sync(FULL, hit);
-                        if (bal) {
-                            found = (int)(s + __ffs(bal) - 1);
-                            break;
-                        }
-                    }
-                    if (found >= 0) {
-                        if (lane == 0) nxtE[found] += up_l;
+                        q = k == 0 ? q2.x : (k == 1 ? q2.z : (k == 2 ? q3.x : q3.z));
+                        kx = k == 0 ? q2.y : (k == 1 ? q2.w : (k == 2 ? q3.y : q3.w));
                     } else {
-                        if (nnxt >= AZB_FRONTIER_CAP) {
-                            cx.err = 3;
-                        } else {
-                            if (lane == 0) {
-                                nxtN[nnxt] = q;
-                                nxtE[nnxt] = up_l;
-                            }
-                            nnxt += 1;
-                        }
+                        const uint2 ent = cx.inl[in_off + k - 4u];
+                        q = ent.x;
+                        kx = ent.y;
                     }
-                    __syncwarp();
+                    uint32_t *kp = reinterpret_cast<uint32_t *>(cx.blk4 + kx);
+                    kp[1] = w1;
+                    *reinterpret_cast<uint2 *>(kp + 2) = make_uint2(w2, w3);
                 }
+                bool fresh = false;
+                if (has) {
+                    const uint32_t bit = 1u << (q & 31);
+                    fresh = (atomicOr(&vis[q >> 5], bit) & bit) == 0u;
+                }
+                const uint32_t bal = __ballot_sync(FULL, fresh);
+                if (fresh) {
+                    const uint32_t at = nnext + __popc(bal & lt);
+                    if (at < AZB_FRONTIER_CAP) wb[at] = q;
+                }
+                nnext += __popc(bal);
             }
         }
-        uint32_t *t = curN;
-        curN = nxtN;
-        nxtN = t;
-        t = curE;
-        curE = nxtE;
-        nxtE = t;
-        ncur = nnxt;
+        if (cx.full_count) {
+            links = __reduce_add_sync(FULL, links);
+            count(cx, CT_DCN, links);
+        }
+        if (nnext > AZB_FRONTIER_CAP) {
+            cx.err = 3;
+            break;
+        }
+        uint32_t *t = wa;
+        wa = wb;
+        wb = t;
+        ncur = nnext;
+        __syncwarp();
+    }
+    // ---- B. exhaustion pass
+    if (e0 == 0u || cx.err) return;
+    if (lane == 0) qb[0] = src;
+    uint32_t nq = 1, head = 0;
+    __syncwarp();
+    while (head < nq) {
+        const uint32_t p = qb[head];
+        ++head;
+        uint4 *rec = cx.node + (size_t)p * 4;
+        const uint4 q0 = rec[0], q1 = rec[1];
+        const uint32_t ex = (q0.w & 0xffffu) + 1u, cnt = q0.w >> 16, nin = q1.y;
+        __syncwarp();
+        if (lane == 0) reinterpret_cast<uint32_t *>(rec)[3] = ex | (cnt << 16);
+        if (ex >= cnt && ex - 1u < cnt) {  // p just became inactive: tell its parents
+            if (nq + nin > AZB_FRONTIER_CAP) {
+                cx.err = 3;
+                break;
+            }
+            for (uint32_t k = lane; k < nin; k += 32) {
+                uint2 ent;
+                if (k < 4u)
+                    ent = reinterpret_cast<const uint2 *>(rec + 2)[k];
+                else
+                    ent = cx.inl[q1.z + k - 4u];
+                reinterpret_cast<uint32_t *>(cx.blk4 + ent.y)[1] = q1.x;  // the copy loses its active bit
+                qb[nq + k] = ent.x;
+            }
+            nq += nin;
+        }
         __syncwarp();
     }
 }
@@ -533,6 +506,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             pos = best_w0 & 0xfffffu;
             lo2 = best_w1 & 0x7fffffffu;
             depth += 1;
+            if (lane == 0) cx.wk[WK_PATH + depth] = pos;
             PROF_ADD(cx, PH_SEL);
             continue;
         }
@@ -595,7 +569,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
             __syncwarp();
             PROF_ADD(cx, PH_ARC);
-            tree_cascade(L, cx, pos, __uint_as_float(q0.y), q0.z, act_o ? 0u : 1u, true);
+            tree_cascade(L, cx, pos, depth, __uint_as_float(q0.y), q0.z, act_o ? 0u : 1u, true);
             PROF_ADD(cx, PH_CASCADE);
             reset = true;
         } else {
@@ -657,7 +631,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             PROF_ADD(cx, PH_INSERT);
             if (!any) {
                 count(cx, CT_TERM, 1);
-                tree_cascade(L, cx, pos, c_new, 0u, 1u, false);
+                tree_cascade(L, cx, pos, depth, c_new, 0u, 1u, false);
                 PROF_ADD(cx, PH_CASCADE);
                 reset = true;
             } else {
@@ -665,6 +639,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 depth = ndepth;
                 lo2 = AZB_LO_NONE;
                 if (lane == 0) {
+                    cx.wk[WK_PATH + ndepth] = nn;
                     cx.wk[WK_FLAGS] |= 1u;
                     cx.wk[WK_PEND_C] = __float_as_uint(c_new);
                     cx.wk[WK_PKIDX] = kidx;
@@ -814,6 +789,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
                 cx.wk[WK_ROOTLO] = AZB_LO_NONE;
                 cx.wk[WK_CURLO] = AZB_LO_NONE;
                 cx.wk[WK_ERR] = 0;
+                cx.wk[WK_PATH] = 0;
                 cx.wk[WK_FLAGS] = 1u;
                 if (flags & AZB_F_FIRST) {
                     // par_new: silent argmin over the roots (optimizer/mod.rs:95-101) = candidate slot 0
