@@ -329,14 +329,16 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         // the child's polynomials sit one coefficient per lane; their degree bounds the product loop
         const uint32_t av = k <= KM ? ps->A[v][k] : 0u, bv = k <= KM ? ps->B[v][k] : 0u;
         const int dav = 31 - __clz(__ballot_sync(FULL, av != 0u));
+        // branch-free product loop: lanes beyond the useful range read clamped slots and multiply by zero (lanes above
+        // KM read a few words past their row, still inside the scratch, and are never stored)
+        const uint32_t *Ap = ps->A[p], *Bp = ps->B[p];
         for (int i = 0; i <= dav; ++i) {
             const uint32_t ac = __shfl_sync(FULL, av, i), bc = __shfl_sync(FULL, bv, i);
-            if (k <= KM && i <= k) {
-                const uint32_t bpk = ps->B[p][k - i];
-                nb += ac * bpk;
-                na += ac * ps->A[p][k - i];
-                if (i < k) na += bc * ps->B[p][k - 1 - i];
-            }
+            const int j = k - i;
+            const uint32_t acm = j >= 0 ? ac : 0u, bcm = j >= 1 ? bc : 0u;
+            const int j0 = j >= 0 ? j : 0, j1 = j >= 1 ? j - 1 : 0;
+            nb += acm * Bp[j0];
+            na += acm * Ap[j0] + bcm * Bp[j1];
         }
         __syncwarp();
         if (k <= KM) {

@@ -143,6 +143,12 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
     const uint32_t pos = cx.wk[WK_POS];
     const float c_s = __uint_as_float(cx.wk[WK_PEND_C]);
     const uint32_t prior_step = cx.wk[WK_STEP];
+    // the prior row streams into shared memory (coalesced) while the legal-action mask is built
+    const bool hashed = L.prior_mode == 1;
+    if (!hashed) {
+        const float *hrow = L.h + (size_t)tree * L.h_ld;
+        for (uint32_t a = lane; a < L.A; a += 32) cx.lbuf[a] = hrow[a];
+    }
     build_cur_mask(L, cx);
     // legal = permitted minus current edges (space.rs:75-89); counts per word -> exclusive prefix
     uint32_t l0 = (uint32_t)lane < L.W ? (cx.perm[lane] & ~cx.cur[lane]) : 0u;
@@ -193,7 +199,7 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
                 a1 = mid;
         }
         const uint32_t a = a0 * 32 + nth_set_bit(cx.cur[a0], j - cx.pfx[a0]);
-        const float h = prior_of(L, tree, a, prior_step);
+        const float h = hashed ? azb_hash_prior(L.prior_seed, L.first_root + tree, prior_step, a) : cx.lbuf[a];
         if (h != h) cx.err = 4;
         const float g = __fsub_rn(c_s, h);
         cx.blk[lo - 1u - j] = make_uint2(__float_as_uint(g), a);
@@ -418,7 +424,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             bool act_t = false;
             uint32_t oc = 0xffffffffu;
             if (t < n_out) {
-                cx.lbuf[t] = __uint_as_float(kd.w);
+                if (n_out > 32u) cx.lbuf[t] = __uint_as_float(kd.w);  // single-chunk nodes store only if curiosity runs
                 act_t = (kd.y >> 31) != 0u;
                 oc = azb_f2ord(__uint_as_float(kd.w));
             }
@@ -446,6 +452,10 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         uint32_t chosen_y = 0;
         if (!visit) {
             // ---- max_curiosity (next_action.rs:55-88)
+            if (n_out <= 32u) {
+                if ((uint32_t)lane < n_out) cx.lbuf[lane] = __uint_as_float(kd.w);
+                __syncwarp();
+            }
             count(cx, CT_CUR, 1);
             count(cx, CT_CAND, cnt);
             const bool no_kids = n_out == 0;
@@ -668,16 +678,12 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
     __syncwarp();
 }
 
-// write_vec (rooted_tree/space.rs:91-101): [A one-hot of current edges | A permitted mask] as f32
-__device__ __forceinline__ float pack_bit(const AzbLayout &L, const WarpCtx &cx, uint32_t i) {
-    bool one;
-    if (i < L.A) {
-        const uint32_t child = cx.lut[i];
-        one = (uint32_t)cx.par[child] == i - azb_child_first_action(child);
-    } else {
-        one = (cx.perm[(i - L.A) >> 5] >> ((i - L.A) & 31)) & 1u;
-    }
-    return one ? 1.0f : 0.0f;
+// write_vec (rooted_tree/space.rs:91-101): [A one-hot of current edges | A permitted mask].  Both halves are bit
+// masks in shared memory (cx.cur must hold the current-edge mask of the walker state: build_cur_mask).
+__device__ __forceinline__ uint32_t pack_bit(const AzbLayout &L, const WarpCtx &cx, uint32_t i) {
+    const uint32_t j = i < L.A ? i : i - L.A;
+    const uint32_t word = i < L.A ? cx.cur[j >> 5] : cx.perm[j >> 5];
+    return (word >> (j & 31)) & 1u;
 }
 __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
     if (L.sv16) {
@@ -688,8 +694,8 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
             uint32_t w[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t lo = (i + 2 * q < 2 * L.A && pack_bit(L, cx, i + 2 * q) != 0.f) ? 0x3F80u : 0u;
-                const uint32_t hi = (i + 2 * q + 1 < 2 * L.A && pack_bit(L, cx, i + 2 * q + 1) != 0.f) ? 0x3F80u : 0u;
+                const uint32_t lo = (i + 2 * q < 2 * L.A && pack_bit(L, cx, i + 2 * q)) ? 0x3F80u : 0u;
+                const uint32_t hi = (i + 2 * q + 1 < 2 * L.A && pack_bit(L, cx, i + 2 * q + 1)) ? 0x3F80u : 0u;
                 w[q] = lo | (hi << 16);
             }
             *reinterpret_cast<uint4 *>(row + i) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -700,9 +706,10 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
     if ((L.A & 1u) == 0u && (L.sv_ld & 3u) == 0u) {  // rows are 16-byte aligned: one 128-bit store per four entries
         for (uint32_t i = 4u * cx.lane; i < 2 * L.A; i += 128)
             *reinterpret_cast<float4 *>(row + i) =
-                make_float4(pack_bit(L, cx, i), pack_bit(L, cx, i + 1), pack_bit(L, cx, i + 2), pack_bit(L, cx, i + 3));
+                make_float4(pack_bit(L, cx, i) ? 1.f : 0.f, pack_bit(L, cx, i + 1) ? 1.f : 0.f,
+                            pack_bit(L, cx, i + 2) ? 1.f : 0.f, pack_bit(L, cx, i + 3) ? 1.f : 0.f);
     } else {
-        for (uint32_t i = cx.lane; i < 2 * L.A; i += 32) row[i] = pack_bit(L, cx, i);
+        for (uint32_t i = cx.lane; i < 2 * L.A; i += 32) row[i] = pack_bit(L, cx, i) ? 1.f : 0.f;
     }
 }
 
@@ -804,6 +811,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
                 }
             }
             __syncwarp();
+            build_cur_mask(L, cx);
             tree_pack(L, cx, tree);
         }
         if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions(L, cx, tree);
