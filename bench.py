@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--vertices", type=int, default=19)
     ap.add_argument("--mlp", default=os.environ.get("AZB_MLP", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--max-episodes", type=int, default=int(os.environ.get("AZB_MAX_EPISODES", "0")))
-    ap.add_argument("--groups", type=int, default=int(os.environ.get("AZB_GROUPS", "8")),
+    ap.add_argument("--groups", type=int, default=int(os.environ.get("AZB_GROUPS", "1")),
                     help="concurrent tree groups per GPU (own CUDA stream each); needs --max-episodes 0")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-baseline-roots", type=int, default=512)
