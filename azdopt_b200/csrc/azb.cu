@@ -1103,6 +1103,15 @@ int azb_set_counter_mode(azb_handle *h, int full) {
     return AZB_OK;
 }
 
+#ifdef AZB_PROFILE
+extern "C" int azb_debug_tree_prof(azb_handle *h, uint32_t *out4, uint32_t ntrees) {
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyFromSymbol(out4, g_tree_prof, (size_t)ntrees * 16));
+    return AZB_OK;
+}
+#endif
+
 int azb_reset_counters(azb_handle *h) {
     if (!h) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));

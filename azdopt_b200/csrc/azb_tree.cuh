@@ -40,6 +40,9 @@ enum { AZB_F_ADD = 1, AZB_F_ROLLOUT = 2, AZB_F_INIT = 4, AZB_F_FIRST = 8 };
 #define PROF_T0() do {} while (0)
 #define PROF_ADD(cx, ph) do {} while (0)
 #endif
+#ifdef AZB_PROFILE
+__device__ uint4 g_tree_prof[65536];  // per tree, last launch: cycles, episodes(resets)+1, cost evals, sqrt terms
+#endif
 enum { PH_SEL = 0, PH_CUR, PH_PROBE, PH_ARC, PH_CASCADE, PH_COST, PH_INSERT, PH_RESET, PH_ADD, PH_PACK, PH_LOAD, PH_STORE };
 
 struct WarpCtx {
@@ -458,6 +461,9 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
             count(cx, CT_CUR, 1);
             count(cx, CT_CAND, cnt);
+#ifdef AZB_PROFILE
+            if (lane == 0) cx.ct[30] += cnt * n_out;
+#endif
             const bool no_kids = n_out == 0;
             uint32_t bk32 = 0u;
             for (uint32_t base = 0; base < cnt; base += 32) {
@@ -841,6 +847,11 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
         PROF_ADD(cx, PH_STORE);
 #ifdef AZB_PROFILE
         __syncwarp();
+        if (lane == 0 && tree < 65536u) {
+            uint32_t tot = 0;
+            for (int q = 16; q < 28; ++q) tot += cx.ct[q];
+            g_tree_prof[tree] = make_uint4(tot, cx.ct[CT_RESET] + 1u, cx.n_ins, cx.ct[30]);
+        }
         if (lane >= 16) {
             const uint32_t v = cx.ct[lane];
             if (v) atomicAdd(&L.g->prof[lane - 16], (unsigned long long)v);

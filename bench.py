@@ -193,7 +193,16 @@ def main():
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
                               n_groups=1 if args.max_episodes else args.groups)
     parents, masks = capi.generate_roots(args.seed, rank * b, b, n)
-    h = capi.Handle(cfg)
+    mlp_note = args.mlp
+    try:
+        h = capi.Handle(cfg)
+    except capi.AzbError as e:  # e.g. no tensor-map driver entry point: still a CUDA path, and the line says so
+        if args.mlp != "tc":
+            raise
+        cfg.mlp_mode = capi.MLP_FP32
+        h = capi.Handle(cfg)
+        mlp_note = f"fp32 (tensor-core path unavailable: {e})"
+        args.mlp = "fp32"
     h.mlp_init(args.seed + 1)  # same seed on every rank: replicated weights
 
     def barrier():
@@ -242,8 +251,16 @@ def main():
     bytes_per_launch = algorithmic_bytes(kp, n) / prof_steps
     tree_launch_s = tree_ms * 1e-3 / prof_steps
     achieved = bytes_per_launch / tree_launch_s / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full, profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("roots") == b and tr.get("vertices") == n:
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "azb_tree_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_us": tree_launch_s * 1e6,
                 "mlp_us_per_step": mlp_ms * 1e3 / prof_steps,
                 "tree_share_of_step": tree_ms / max(tree_ms + mlp_ms, 1e-9)}
@@ -291,7 +308,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
-                       "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": args.mlp, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
+                       "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": mlp_note, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
                        "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
                        "simulations_in_timed_region": sims, "noop_root_steps": noops,
                        "cost_evals_per_sec": evals / (ms_max * 1e-3)},
