@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -127,7 +127,7 @@ def cpu_reference_run(n, roots, steps, warmup, seed, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=800, help="timed steps (800 = one epoch of the example)")
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--roots", type=int, default=4096, help="roots per GPU (BASELINE configs[1])")
