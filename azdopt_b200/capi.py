@@ -91,6 +91,14 @@ SIGNATURES = {
     "azb_get_priors": (C.c_int, [C.c_void_p, f32p]),
     "azb_eval_costs": (C.c_int, [C.c_void_p, u8p, C.c_uint32, f64p, u32p, f32p, f32p]),
     "azb_write_observations": (C.c_int, [C.c_void_p, C.c_uint32, f32p, f32p, f32p]),
+    "azb_adam_config": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "azb_model_update": (C.c_int, [C.c_void_p, f32p, f32p, f32p, C.c_uint32, f32p]),
+    "azb_model_gradients": (C.c_int, [C.c_void_p, f32p, f32p, f32p, C.c_uint32, f32p, f32p]),
+    "azb_update_model": (C.c_int, [C.c_void_p, C.c_uint32, f32p]),
+    "azb_comm_unique_id": (C.c_int, [u8p]),
+    "azb_comm_init": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int]),
+    "azb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "azb_comm_argmin": (C.c_int, [C.c_void_p, u8p, u32p, f64p, u32p, f32p, C.POINTER(C.c_int)]),
     "azb_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "azb_device_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "azb_flush_l2": (C.c_int, [C.c_void_p]),
@@ -148,6 +156,14 @@ def default_config(n_vertices: int, n_roots: int, **kw) -> Config:
                 raise TypeError(f"unknown config field {k}")
             setattr(cfg, k, v)
     return cfg
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    rc = lib().azb_comm_unique_id(buf)
+    if rc:
+        raise AzbError(rc, "azb_comm_unique_id (is libnccl.so.2 loadable?)")
+    return bytes(buf)
 
 
 def generate_roots(seed, first_root, count, n, k_min=5, k_max=0):
@@ -358,6 +374,49 @@ class Handle:
         w = np.zeros((self.b, self.a), dtype=np.float32)
         self._ck(self._L.azb_write_observations(self._h, n_obs_tol, _p(v, C.c_float), _p(obs, C.c_float), _p(w, C.c_float)))
         return v, obs, w
+
+    # ---- epoch boundary: training step and communicator ----
+    def adam_config(self, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, l2=1e-6):
+        self._ck(self._L.azb_adam_config(self._h, lr, beta1, beta2, eps, l2))
+
+    def _train_args(self, states, observations, weights):
+        x = np.ascontiguousarray(states, dtype=np.float32).reshape(-1, self.s)
+        o = np.ascontiguousarray(observations, dtype=np.float32).reshape(-1, self.a)
+        w = np.ascontiguousarray(weights, dtype=np.float32).reshape(-1, self.a)
+        assert x.shape[0] == o.shape[0] == w.shape[0]
+        return x, o, w
+
+    def model_update(self, states, observations, weights) -> float:
+        x, o, w = self._train_args(states, observations, weights)
+        loss = C.c_float()
+        self._ck(self._L.azb_model_update(self._h, _p(x, C.c_float), _p(o, C.c_float), _p(w, C.c_float), x.shape[0],
+                                          C.byref(loss)))
+        return float(loss.value)
+
+    def model_gradients(self, states, observations, weights):
+        x, o, w = self._train_args(states, observations, weights)
+        loss = C.c_float()
+        g = np.zeros(self.mlp_num_params(), dtype=np.float32)
+        self._ck(self._L.azb_model_gradients(self._h, _p(x, C.c_float), _p(o, C.c_float), _p(w, C.c_float), x.shape[0],
+                                             C.byref(loss), _p(g, C.c_float)))
+        return float(loss.value), g
+
+    def update_model(self, n_obs_tol: int) -> float:
+        loss = C.c_float()
+        self._ck(self._L.azb_update_model(self._h, n_obs_tol, C.byref(loss)))
+        return float(loss.value)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._L.azb_comm_init(self._h, buf, rank, world))
+
+    def comm_argmin(self):
+        p = np.zeros(self.n, dtype=np.uint8)
+        m = np.zeros(self.w, dtype=np.uint32)
+        lam, mu, ev, owner = C.c_double(), C.c_uint32(), C.c_float(), C.c_int()
+        self._ck(self._L.azb_comm_argmin(self._h, _p(p, C.c_uint8), _p(m, C.c_uint32), C.byref(lam), C.byref(mu),
+                                         C.byref(ev), C.byref(owner)))
+        return p, m, float(lam.value), int(mu.value), float(ev.value), int(owner.value)
 
     def kernel_launches(self) -> int:
         n = C.c_uint64()

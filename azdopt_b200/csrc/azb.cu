@@ -21,6 +21,9 @@
 #include "azb_mlp.cuh"
 #include "azb_mlp_tc.cuh"
 #include "azb_tree.cuh"
+#include "azb_train.cuh"
+
+#include <dlfcn.h>
 
 // ---------------------------------------------------------------------------------------------------------------
 struct azb_handle {
@@ -46,6 +49,15 @@ struct azb_handle {
     uint32_t cost_cap;
     // observations scratch
     float *obs, *obs_w;
+    // training step (azb_train.cuh): gradient (parameter order), Adam moments, predictions, two dZ buffers, scalars
+    float *grad, *adam_m, *adam_v, *tr_p, *tr_dz[2], *tr_x;
+    double *tr_scal, *tr_part;   // [0] weight sum, [1] loss; per-block partials
+    uint32_t adam_t;
+    AzbAdam adam;
+    // epoch-boundary collectives (NCCL, loaded on demand)
+    void *nccl_lib, *nccl_comm;
+    int comm_rank, comm_world;
+    uint32_t *comm_buf;
     void *flush_buf;
     size_t flush_bytes;
     uint64_t launches, dev_bytes;
@@ -60,11 +72,15 @@ struct azb_handle {
     cudaEvent_t gevent[64], fork_event;
     cudaGraphExec_t ggraph[64];   // per group: AZB_GRAPH_STEPS steps of (search kernel + model forward)
     uint32_t ggraph_key[64];      // flags | counter mode the cached graph was captured with
-    cudaGraphExec_t step_graph;
+    cudaGraphExec_t step_graph;   // one step incl. the argmin pass and the read-back of the globals (azb_step(h, 1, ...))
+    uint32_t step_graph_key;
+    AzbGlobals *pin_g;            // pinned host copy of the globals' head, written by the step graph
+    azb_improvement *pin_log;
     char err[512];
 };
 
 static const char *k_empty = "";
+extern "C" { static void azb_comm_destroy_impl(azb_handle *h); }
 
 static int fail(azb_handle *h, int code, const char *fmt, ...) {
     if (h) {
@@ -158,7 +174,9 @@ int azb_destroy(azb_handle *h) {
     if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
     for (uint32_t g = 0; g < 64; ++g)
         if (h->ggraph[g]) cudaGraphExecDestroy(h->ggraph[g]);
-    void *ptrs[] = {h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
+    if (h->nccl_comm) azb_comm_destroy_impl(h);
+    void *ptrs[] = {h->grad, h->adam_m, h->adam_v, h->tr_p, h->tr_dz[0], h->tr_dz[1], h->tr_x, h->tr_scal, h->tr_part, h->comm_buf,
+                    h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
                     h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
                     h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf};
     for (void *p : ptrs)
@@ -169,6 +187,8 @@ int azb_destroy(azb_handle *h) {
         if (h->gevent[g]) cudaEventDestroy(h->gevent[g]);
     }
     if (h->fork_event) cudaEventDestroy(h->fork_event);
+    if (h->pin_g) cudaFreeHost(h->pin_g);
+    if (h->pin_log) cudaFreeHost(h->pin_log);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -226,6 +246,8 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreateWithFlags(&h->fork_event, cudaEventDisableTiming));
+    CK(cudaMallocHost((void **)&h->pin_g, sizeof(AzbGlobals)));
+    CK(cudaMallocHost((void **)&h->pin_log, sizeof(azb_improvement)));
     {
         // concurrent groups of trees: contiguous ranges, a multiple of 128 trees each (MLP row tiles)
         uint32_t per = (cfg.n_roots + cfg.n_groups - 1) / cfg.n_groups;
@@ -280,6 +302,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
         L.lut = dl;
     }
     h->count_full = true;
+    h->adam = AzbAdam{1e-4f, 0.9f, 0.999f, 1e-8f, 1e-6f, 1.f, 1.f};  // 04-c21-tree.rs:87-92
     CK(dmalloc(h, &L.sv, (size_t)B * L.sv_ld));
     CK(dmalloc(h, &L.h, (size_t)B * L.h_ld));
     CK(dmalloc(h, &L.g, 1));
@@ -629,6 +652,9 @@ int azb_init_trees(azb_handle *h) {
     if (first) {  // par_new's silent argmin over the roots (optimizer/mod.rs:95-101)
         rc = run_argmin(h, 1);
         if (rc) return rc;
+    } else {
+        static const uint32_t one = 1u;
+        CK(cudaMemcpyAsync(&h->L.g->next_slot, &one, 4, cudaMemcpyHostToDevice, h->stream));
     }
     rc = check_device_error(h);
     if (rc) return rc;
@@ -734,10 +760,57 @@ static int enqueue_steps(azb_handle *h, uint32_t n_steps, uint32_t flags) {
     return AZB_OK;
 }
 
+// azb_step(h, 1, ...) in lock-step mode: the whole step — search kernel, model forward, argmin pass, read-back of the
+// globals and of the (at most one) improvement record into pinned host memory — is ONE CUDA graph launch, so the
+// per-step call of the reference's API (optimizer/mod.rs:121) costs one launch and one synchronisation.
+static int step_once_graph(azb_handle *h, azb_improvement *improvements, uint32_t cap, uint32_t *n_improved) {
+    const uint32_t flags = AZB_F_ADD | AZB_F_ROLLOUT;
+    const bool mlp = h->cfg.prior_mode == AZB_PRIOR_MLP;
+    const uint32_t key = 0x2000u | (h->count_full ? 0x100u : 0u);
+    if (!h->step_graph || h->step_graph_key != key) {
+        if (h->step_graph) {
+            cudaGraphExecDestroy(h->step_graph);
+            h->step_graph = nullptr;
+        }
+        const uint64_t launches_before = h->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = launch_tree(h, flags, 0xffffffffu);
+        if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
+        if (rc == AZB_OK) {
+            azb_argmin1_kernel<<<1, 256, 0, h->stream>>>(h->L);
+            cudaMemcpyAsync(h->pin_g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream);
+            cudaMemcpyAsync(h->pin_log, h->L.log, sizeof(azb_improvement), cudaMemcpyDeviceToHost, h->stream);
+        }
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        h->launches = launches_before;
+        if (rc) return rc;
+        if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "stream capture: %s", cudaGetErrorString(ce));
+        CK(cudaGraphInstantiate(&h->step_graph, graph, 0));
+        cudaGraphDestroy(graph);
+        h->step_graph_key = key;
+    }
+    CK(cudaGraphLaunch(h->step_graph, h->stream));
+    h->launches += 2 + (mlp ? 4 : 0);
+    h->steps_done += 1;
+    h->argmin_from = h->steps_done + 1;
+    h->pending_add = true;
+    CK(cudaStreamSynchronize(h->stream));
+    const AzbGlobals &g = *h->pin_g;
+    if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.err_step);
+    if (n_improved) *n_improved = g.n_improved;
+    if (improvements && cap && g.n_improved) improvements[0] = *h->pin_log;
+    h->improved_last_rollout = (int)g.improved_last;
+    return AZB_OK;
+}
+
 int azb_step(azb_handle *h, uint32_t n_steps, azb_improvement *improvements, uint32_t cap, uint32_t *n_improved) {
     if (!h) return AZB_ERR_INVALID;
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
     CK(cudaSetDevice(h->cfg.device));
+    if (n_steps == 1 && h->cfg.max_episodes == 0 && h->n_groups == 1 && h->argmin_from == h->steps_done + 1 &&
+        h->steps_done + 1 <= h->L.cap_steps)
+        return step_once_graph(h, improvements, cap, n_improved);
     CK(cudaMemsetAsync(&h->L.g->n_improved, 0, 4, h->stream));
     int rc = enqueue_steps(h, n_steps, AZB_F_ADD | AZB_F_ROLLOUT);
     if (rc) return rc;
@@ -1161,6 +1234,303 @@ int azb_write_observations(azb_handle *h, uint32_t n_obs_tol, float *state_vecs,
         CK(cudaMemcpy2DAsync(state_vecs, (size_t)h->S * 4, h->L.sv, (size_t)h->L.sv_ld * 4, (size_t)h->S * 4, B,
                              cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return AZB_OK;
+}
+
+
+// ---- epoch boundary: the training step (nabla/model/dfdx.rs:86-131; optimizer/mod.rs:249-281) -------------------
+// NCCL is loaded on demand (dlopen) so that the library has no hard dependency on it; only the epoch boundary
+// communicates: all-reduce of the weight sum, the gradient and the loss, all-gather of the argmins.
+typedef struct { char internal[128]; } azb_nccl_uid;
+typedef int (*nccl_get_uid_fn)(azb_nccl_uid *);
+typedef int (*nccl_init_rank_fn)(void **, int, azb_nccl_uid, int);
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*nccl_allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_destroy_fn)(void *);
+typedef const char *(*nccl_errstr_fn)(int);
+enum { AZB_NCCL_UINT32 = 3, AZB_NCCL_FLOAT32 = 7, AZB_NCCL_FLOAT64 = 8, AZB_NCCL_SUM = 0 };  // nccl.h: ncclDataType_t / ncclRedOp_t
+
+static void *nccl_open(void) {
+    static void *lib = nullptr;
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return lib;
+}
+
+static void azb_comm_destroy_impl(azb_handle *h) {
+    if (h->nccl_comm && h->nccl_lib) {
+        auto destroy = (nccl_destroy_fn)dlsym(h->nccl_lib, "ncclCommDestroy");
+        if (destroy) destroy(h->nccl_comm);
+    }
+    h->nccl_comm = nullptr;
+}
+
+#define NCCLCK(call)                                                                                   \
+    do {                                                                                               \
+        int r_ = (call);                                                                               \
+        if (r_ != 0) {                                                                                 \
+            auto es_ = (nccl_errstr_fn)dlsym(h->nccl_lib, "ncclGetErrorString");                       \
+            return fail(h, AZB_ERR_CUDA, "%s: NCCL error %d (%s)", #call, r_, es_ ? es_(r_) : "?");  \
+        }                                                                                              \
+    } while (0)
+
+static int comm_allreduce(azb_handle *h, void *buf, size_t count, int dtype) {
+    if (!h->nccl_comm || h->comm_world <= 1) return AZB_OK;
+    auto ar = (nccl_allreduce_fn)dlsym(h->nccl_lib, "ncclAllReduce");
+    if (!ar) return fail(h, AZB_ERR_CUDA, "ncclAllReduce not found");
+    NCCLCK(ar(buf, buf, count, dtype, AZB_NCCL_SUM, h->nccl_comm, h->stream));
+    return AZB_OK;
+}
+
+static int train_alloc(azb_handle *h) {
+    if (h->grad) return AZB_OK;
+    const size_t B = h->L.B;
+    uint32_t widest = h->A;
+    for (int l = 1; l < 4; ++l) widest = std::max(widest, h->dims[l]);
+    CK(dmalloc(h, &h->grad, h->n_params));
+    CK(dmalloc(h, &h->adam_m, h->n_params));
+    CK(dmalloc(h, &h->adam_v, h->n_params));
+    CK(dmalloc(h, &h->tr_p, B * h->A));
+    CK(dmalloc(h, &h->tr_dz[0], B * widest));
+    CK(dmalloc(h, &h->tr_dz[1], B * widest));
+    CK(dmalloc(h, &h->tr_scal, 4));
+    CK(dmalloc(h, &h->tr_part, 1024));
+    CK(cudaMemsetAsync(h->grad, 0, h->n_params * 4, h->stream));
+    CK(cudaMemsetAsync(h->adam_m, 0, h->n_params * 4, h->stream));
+    CK(cudaMemsetAsync(h->adam_v, 0, h->n_params * 4, h->stream));
+    if (!h->obs) {
+        CK(dmalloc(h, &h->obs, B * h->A));
+        CK(dmalloc(h, &h->obs_w, B * h->A));
+    }
+    return AZB_OK;
+}
+
+// forward (f32, activations kept) + loss + backward into h->grad for device rows x[rows][ldx], o, w [rows][A];
+// with a communicator the weight sum, the gradient and the loss are global sums.  Leaves the loss in tr_scal[1].
+static int train_backward(azb_handle *h, const float *x, uint32_t ldx, const float *o, const float *w, uint32_t rows) {
+    if (!h->params_set) return fail(h, AZB_ERR_STATE, "model parameters not set");
+    int rc = train_alloc(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    const size_t n_out = (size_t)rows * h->A;
+    const uint32_t nblk = (uint32_t)std::min<size_t>(1024, (n_out + 255) / 256);
+    // weight_sum = action_weights.iter().sum() (dfdx.rs:105)
+    azb_sum_partial_kernel<<<nblk, 256, 0, st>>>(w, n_out, h->tr_part);
+    azb_sum_final_kernel<<<1, 256, 0, st>>>(h->tr_part, nblk, h->tr_scal);
+    h->launches += 2;
+    rc = comm_allreduce(h, h->tr_scal, 1, AZB_NCCL_FLOAT64);
+    if (rc) return rc;
+    // forward, f32 (dfdx.rs:115-116)
+    {
+        const float *in = x;
+        uint32_t ld_in = ldx;
+        const float *p = h->params;
+        for (int l = 0; l < 4; ++l) {
+            const uint32_t K = h->dims[l], Nout = h->dims[l + 1];
+            float *outp = l < 3 ? h->act[l] : h->tr_p;
+            dim3 grid((Nout + 63) / 64, (rows + 63) / 64);
+            if (l < 3)
+                azb_linear_fp32_kernel<AZB_ACT_RELU><<<grid, 256, 0, st>>>(in, ld_in, p, p + (size_t)K * Nout, outp, Nout, rows, K, Nout);
+            else
+                azb_linear_fp32_kernel<AZB_ACT_SIGMOID><<<grid, 256, 0, st>>>(in, ld_in, p, p + (size_t)K * Nout, outp, Nout, rows, K, Nout);
+            h->launches += 1;
+            in = outp;
+            ld_in = Nout;
+            p += (size_t)K * Nout + Nout;
+        }
+    }
+    // loss and d loss / d z4 (dfdx.rs:118-126)
+    azb_loss_grad_kernel<<<nblk, 256, 0, st>>>(h->tr_p, o, w, n_out, h->tr_scal, h->tr_dz[0], h->tr_part);
+    azb_sum_final_kernel<<<1, 256, 0, st>>>(h->tr_part, nblk, h->tr_scal + 1);
+    h->launches += 2;
+    // backward, last layer first
+    size_t off[5];
+    off[0] = 0;
+    for (int l = 0; l < 4; ++l) off[l + 1] = off[l] + (size_t)h->dims[l] * h->dims[l + 1] + h->dims[l + 1];
+    int cur = 0;
+    for (int l = 3; l >= 0; --l) {
+        const uint32_t K = h->dims[l], Nout = h->dims[l + 1];
+        const float *dz = h->tr_dz[cur];
+        const float *xin = l == 0 ? x : h->act[l - 1];
+        const uint32_t ld_in = l == 0 ? ldx : K;
+        {   // dW[out][in] = dZ^T X
+            dim3 grid((K + 63) / 64, (Nout + 63) / 64);
+            azb_gemm_fp32_kernel<false, true, false><<<grid, 256, 0, st>>>(dz, Nout, xin, ld_in, h->grad + off[l], K, Nout, K, rows, nullptr, 0);
+        }
+        azb_colsum_kernel<<<(Nout + 31) / 32, 256, 0, st>>>(dz, Nout, rows, Nout, h->grad + off[l] + (size_t)K * Nout);
+        h->launches += 2;
+        if (l > 0) {  // dX = (dZ W) * relu'(input)
+            dim3 grid((K + 63) / 64, (rows + 63) / 64);
+            azb_gemm_fp32_kernel<true, true, true><<<grid, 256, 0, st>>>(dz, Nout, h->params + off[l], K, h->tr_dz[cur ^ 1], K, rows, K, Nout, h->act[l - 1], K);
+            h->launches += 1;
+            cur ^= 1;
+        }
+    }
+    CK(cudaGetLastError());
+    rc = comm_allreduce(h, h->grad, h->n_params, AZB_NCCL_FLOAT32);
+    if (rc) return rc;
+    return comm_allreduce(h, h->tr_scal + 1, 1, AZB_NCCL_FLOAT64);
+}
+
+static int train_adam(azb_handle *h) {
+    h->adam_t += 1;
+    AzbAdam cfg = h->adam;
+    cfg.bc1 = 1.0f / (1.0f - powf(cfg.beta1, (float)h->adam_t));
+    cfg.bc2 = 1.0f / (1.0f - powf(cfg.beta2, (float)h->adam_t));
+    const uint32_t nblk = (uint32_t)std::min<size_t>(148 * 8, (h->n_params + 255) / 256);
+    azb_adam_kernel<<<nblk, 256, 0, h->stream>>>(h->params, h->grad, h->adam_m, h->adam_v, h->n_params, cfg);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (h->cfg.mlp_mode == AZB_MLP_TC) {
+        const char *why = azb_mlp_tc_load(h->tc, h->params, h->stream, &h->launches);
+        if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
+    }
+    return AZB_OK;
+}
+
+static int train_read_loss(azb_handle *h, float *loss) {
+    double l = 0;
+    CK(cudaMemcpyAsync(&l, h->tr_scal + 1, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (loss) *loss = (float)l;
+    return AZB_OK;
+}
+
+int azb_adam_config(azb_handle *h, float lr, float beta1, float beta2, float eps, float l2) {
+    if (!h || !(lr >= 0.f) || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f)) return AZB_ERR_INVALID;
+    h->adam = AzbAdam{lr, beta1, beta2, eps, l2, 1.f, 1.f};
+    return AZB_OK;
+}
+
+static int train_stage_host(azb_handle *h, const float *states, const float *observations, const float *weights,
+                            uint32_t rows) {
+    int rc = train_alloc(h);
+    if (rc) return rc;
+    if (!h->tr_x) CK(dmalloc(h, &h->tr_x, (size_t)h->L.B * h->S));
+    CK(cudaMemcpyAsync(h->tr_x, states, (size_t)rows * h->S * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->obs, observations, (size_t)rows * h->A * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->obs_w, weights, (size_t)rows * h->A * 4, cudaMemcpyHostToDevice, h->stream));
+    return AZB_OK;
+}
+
+int azb_model_gradients(azb_handle *h, const float *states, const float *observations, const float *action_weights,
+                        uint32_t rows, float *loss, float *grads) {
+    if (!h || !states || !observations || !action_weights || rows == 0 || rows > h->L.B) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = train_stage_host(h, states, observations, action_weights, rows);
+    if (rc) return rc;
+    rc = train_backward(h, h->tr_x, h->S, h->obs, h->obs_w, rows);
+    if (rc) return rc;
+    if (grads) CK(cudaMemcpyAsync(grads, h->grad, h->n_params * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemsetAsync(h->grad, 0, h->n_params * 4, h->stream));
+    return train_read_loss(h, loss);
+}
+
+int azb_model_update(azb_handle *h, const float *states, const float *observations, const float *action_weights,
+                     uint32_t rows, float *loss) {
+    if (!h || !states || !observations || !action_weights || rows == 0 || rows > h->L.B) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = train_stage_host(h, states, observations, action_weights, rows);
+    if (rc) return rc;
+    rc = train_backward(h, h->tr_x, h->S, h->obs, h->obs_w, rows);
+    if (rc) return rc;
+    rc = train_adam(h);
+    if (rc) return rc;
+    return train_read_loss(h, loss);
+}
+
+int azb_update_model(azb_handle *h, uint32_t n_obs_tol, float *loss) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    rc = train_alloc(h);
+    if (rc) return rc;
+    // write_vec of the roots + write_observations of every tree (optimizer/mod.rs:253-278), all on the device
+    azb_observe_kernel<<<(h->L.B + 3) / 4, 128, 0, h->stream>>>(h->L, n_obs_tol, h->obs, h->obs_w, h->L.sv);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    rc = train_backward(h, h->L.sv, h->L.sv_ld, h->obs, h->obs_w, h->L.B);
+    if (rc) return rc;
+    rc = train_adam(h);
+    if (rc) return rc;
+    rc = train_read_loss(h, loss);
+    if (rc) return rc;
+    return check_device_error(h);
+}
+
+// ---- epoch-boundary communicator ----
+int azb_comm_unique_id(uint8_t *id128) {
+    if (!id128) return AZB_ERR_INVALID;
+    void *lib = nccl_open();
+    if (!lib) return AZB_ERR_CUDA;
+    auto get = (nccl_get_uid_fn)dlsym(lib, "ncclGetUniqueId");
+    azb_nccl_uid id;
+    if (!get || get(&id) != 0) return AZB_ERR_CUDA;
+    memcpy(id128, &id, 128);
+    return AZB_OK;
+}
+
+int azb_comm_init(azb_handle *h, const uint8_t *id128, int rank, int world) {
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (h->nccl_comm) azb_comm_destroy_impl(h);
+    h->nccl_lib = nccl_open();
+    if (!h->nccl_lib) return fail(h, AZB_ERR_CUDA, "libnccl.so.2 not found: %s", dlerror());
+    auto init = (nccl_init_rank_fn)dlsym(h->nccl_lib, "ncclCommInitRank");
+    if (!init) return fail(h, AZB_ERR_CUDA, "ncclCommInitRank not found");
+    azb_nccl_uid id;
+    memcpy(&id, id128, 128);
+    NCCLCK(init(&h->nccl_comm, world, id, rank));
+    h->comm_rank = rank;
+    h->comm_world = world;
+    if (!h->comm_buf) CK(dmalloc(h, &h->comm_buf, (size_t)80 * (world + 1)));
+    return AZB_OK;
+}
+
+// global argmin over all ranks' roots (optimizer/mod.rs:221 over the sharded batch): all-gather of
+// {orderable eval, state}; the lowest rank wins ties (ranks own ascending blocks of roots = the first minimum)
+int azb_comm_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double *lambda1, uint32_t *mu, float *eval,
+                    int *owner_rank) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    if (!h->nccl_comm) return fail(h, AZB_ERR_STATE, "azb_comm_init has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    const int world = h->comm_world;
+    // record = best_c (1 word) + pad (2) + argmin_state (77 words) = 80 words, contiguous in AzbGlobals
+    uint32_t *mine = h->comm_buf + (size_t)80 * world;
+    CK(cudaMemcpyAsync(mine, &h->L.g->best_c, 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(mine + 3, h->L.g->argmin_state, 77 * 4, cudaMemcpyDeviceToDevice, h->stream));
+    auto ag = (nccl_allgather_fn)dlsym(h->nccl_lib, "ncclAllGather");
+    if (!ag) return fail(h, AZB_ERR_CUDA, "ncclAllGather not found");
+    NCCLCK(ag(mine, h->comm_buf, 80, AZB_NCCL_UINT32, h->nccl_comm, h->stream));
+    std::vector<uint32_t> all((size_t)80 * world);
+    CK(cudaMemcpyAsync(all.data(), h->comm_buf, all.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+        if (all[(size_t)80 * r] < all[(size_t)80 * best]) best = r;
+    const uint32_t *rec = all.data() + (size_t)80 * best;
+    uint8_t par[AZB_MAX_VERTICES];
+    memcpy(par, rec + 3, h->N);
+    if (parents) memcpy(parents, par, h->N);
+    if (permitted) memcpy(permitted, rec + 3 + 16, (size_t)h->W * 4);
+    double l1 = 0;
+    uint32_t m = 0;
+    float c = 0;
+    int rc = eval_costs_dev(h, par, 1, &l1, &m, &c, nullptr);
+    if (rc) return rc;
+    if (lambda1) *lambda1 = l1;
+    if (mu) *mu = m;
+    if (eval) *eval = c;
+    if (owner_rank) *owner_rank = best;
+    return AZB_OK;
+}
+
+int azb_comm_destroy(azb_handle *h) {
+    if (!h) return AZB_ERR_INVALID;
+    azb_comm_destroy_impl(h);
     return AZB_OK;
 }
 

@@ -69,7 +69,8 @@ struct AzbGlobals {  // one per handle, in device memory
     uint32_t improved_last;         // 1 if the newest step of the last argmin pass improved
     uint32_t behind_accum;          // trees below the step target, accumulated by the running launch
     uint32_t n_behind;              // ... of the last finished launch
-    uint32_t argmin_tree, argmin_node, pad;
+    uint32_t argmin_tree, argmin_node;
+    uint32_t next_slot;             // first candidate slot the argmin pass has not consumed (device copy; single-step graph)
     uint32_t argmin_state[16 + 61]; // parents packed (16 words) + permitted (61 words)
     AzbCounters counters;
     unsigned long long prof[16];    // -DAZB_PROFILE: lane-0 cycles per phase

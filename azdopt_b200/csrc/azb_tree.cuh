@@ -971,10 +971,65 @@ __global__ void __launch_bounds__(32) azb_argmin_kernel(const AzbLayout L, const
         g->best_c = best;
         g->n_improved = n_imp;
         g->improved_last = last;
+        g->next_slot = slot_hi;
         if (have) {
             g->argmin_tree = tree;
             g->argmin_node = node;
         }
+    }
+}
+
+// both passes for ONE slot, the slot index read from device memory: the argmin step of the single-step CUDA graph
+// (azb_step(h, 1, ...)), whose kernel arguments must not change from replay to replay.  Resets n_improved first
+// (the log of an azb_step call starts empty).
+__global__ void __launch_bounds__(256) azb_argmin1_kernel(const AzbLayout L) {
+    __shared__ unsigned long long red[8];
+    __shared__ uint32_t scratch[WK_HDR + 16 + 2 * 61 + 8];
+    __shared__ uint8_t lut[2048];
+    AzbGlobals *g = L.g;
+    const uint32_t slot = g->next_slot;
+    const uint2 *row = L.cand + (size_t)slot * L.B;
+    unsigned long long m = ~0ull;
+    for (uint32_t t = threadIdx.x; t < L.B; t += blockDim.x) {
+        const unsigned long long k = ((unsigned long long)row[t].x << 32) | t;
+        m = k < m ? k : m;
+    }
+    m = warp_min_u64(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    for (uint32_t a = threadIdx.x; a < L.A; a += blockDim.x) lut[a] = (uint8_t)azb_action_child(a);
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    for (int i = 1; i < 8; ++i) m = red[i] < m ? red[i] : m;
+    const uint32_t oc = (uint32_t)(m >> 32), tree = (uint32_t)m;
+    uint32_t n_imp = 0, last = 0;
+    const bool better = oc < g->best_c;
+    uint32_t node = 0;
+    if (better) {
+        node = L.cand[(size_t)slot * L.B + tree].y;
+        if (slot != 0u) {
+            last = 1;
+            if (lane == 0) {
+                L.log[0].step = slot - 1u;
+                L.log[0].tree = tree;
+                L.log[0].node = node;
+                L.log[0].eval = azb_ord2f(oc);
+            }
+            n_imp = 1;
+        }
+        finalize_argmin_state(L, scratch, lut, tree, node, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        L.stepmin[slot] = m;
+        if (better) {
+            g->best_c = oc;
+            g->argmin_tree = tree;
+            g->argmin_node = node;
+        }
+        g->n_improved = n_imp;
+        g->improved_last = last;
+        g->next_slot = slot + 1u;
     }
 }
 

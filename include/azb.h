@@ -186,6 +186,32 @@ int azb_eval_costs(azb_handle *h, const uint8_t *parents /*[M*N]*/, uint32_t m, 
 int azb_write_observations(azb_handle *h, uint32_t n_obs_tol, float *state_vecs, float *observations,
                            float *weights);
 
+/* ---- epoch boundary: the training step.  NablaModel::update_model (nabla/model/mod.rs:7; ActionModel:
+ *      nabla/model/dfdx.rs:86-131): w_n = w / sum(w); loss = sum (forward(states) - observations)^2 * w_n; backward;
+ *      Adam (04-c21-tree.rs:87-92: lr 1e-4, betas .9/.999, eps 1e-8, WeightDecay::L2(1e-6)); gradients zeroed.
+ *      f32 throughout, like the reference.  Returns the loss (dfdx.rs:125,130). ---- */
+int azb_adam_config(azb_handle *h, float lr, float beta1, float beta2, float eps, float l2);  /* AdamConfig */
+/* update_model with host buffers [rows*S], [rows*A], [rows*A]; rows <= B */
+int azb_model_update(azb_handle *h, const float *states, const float *observations, const float *action_weights,
+                     uint32_t rows, float *loss);
+/* test hook: loss and d loss / d params (parameter order) of the same objective, no Adam step */
+int azb_model_gradients(azb_handle *h, const float *states, const float *observations, const float *action_weights,
+                        uint32_t rows, float *loss, float *grads);
+/* NablaOptimizer::par_update_model (optimizer/mod.rs:249-281): root vectors + observations + update_model, all on
+ * the device.  With a communicator attached (below) the weight sum, the gradient and the loss are all-reduced, so
+ * every rank applies the same global-batch Adam step. */
+int azb_update_model(azb_handle *h, uint32_t n_obs_tol, float *loss);
+
+/* ---- epoch-boundary communicator (NCCL, loaded on demand; no collective ever runs inside azb_step).  Rank 0 makes
+ *      an id, the host program hands it to every rank (any out-of-band channel), each rank attaches its handle. ---- */
+int azb_comm_unique_id(uint8_t *id128 /*[128]*/);
+int azb_comm_init(azb_handle *h, const uint8_t *id128, int rank, int world);
+int azb_comm_destroy(azb_handle *h);
+/* argmin over ALL ranks' roots (the sharded form of optimizer/mod.rs:221 + argmin_data): same outputs as
+ * azb_get_argmin plus the owning rank; the lowest rank wins ties */
+int azb_comm_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double *lambda1, uint32_t *mu, float *eval,
+                    int *owner_rank);
+
 /* ---- measurement helpers ---- */
 int azb_kernel_launches(const azb_handle *h, uint64_t *n);   /* kernels launched by this handle so far */
 int azb_device_bytes(const azb_handle *h, uint64_t *bytes);  /* HBM held by this handle */

@@ -315,3 +315,72 @@ class Optimizer:
         w = np.zeros((self.b, self.a), dtype=np.float32)
         lib().orc_write_observations(self._h, n_obs_tol, _p(v, C.c_float), _p(obs, C.c_float), _p(w, C.c_float))
         return v, obs, w
+
+
+# ---- epoch boundary: the training step (numpy restatement; TEST INFRASTRUCTURE like the rest of this file) -------
+class AdamState:
+    """dfdx 0.13 Adam (tensor_ops/adam; optim/adam): moments per parameter and the step counter t."""
+
+    def __init__(self, n_params, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, l2=1e-6):  # 04-c21-tree.rs:87-92
+        self.m = np.zeros(n_params, dtype=np.float32)
+        self.v = np.zeros(n_params, dtype=np.float32)
+        self.t = 0
+        self.lr, self.beta1, self.beta2, self.eps, self.l2 = (np.float32(x) for x in (lr, beta1, beta2, eps, l2))
+
+
+def _split_params(params, dims):
+    out, off = [], 0
+    for l in range(4):
+        din, dout = int(dims[l]), int(dims[l + 1])
+        w = params[off:off + din * dout].reshape(dout, din)  # weight[out][in] (dfdx Linear)
+        b = params[off + din * dout:off + din * dout + dout]
+        out.append((w, b, off))
+        off += din * dout + dout
+    return out
+
+
+def model_gradients(params, dims, states, observations, weights):
+    """loss and d loss / d params of ActionModel::update_model's objective (nabla/model/dfdx.rs:104-126), f32:
+    w_n = w / sum(w); loss = sum (forward(states) - observations)^2 * w_n."""
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    x = np.ascontiguousarray(states, dtype=np.float32)
+    o = np.ascontiguousarray(observations, dtype=np.float32)
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    layers = _split_params(params, dims)
+    acts = [x]
+    for l, (wt, b, _) in enumerate(layers):
+        z = acts[-1] @ wt.T + b
+        acts.append(np.maximum(z, np.float32(0)) if l < 3 else (np.float32(1) / (np.float32(1) + np.exp(-z))).astype(np.float32))
+    wsum = np.float32(w.sum(dtype=np.float64))  # dfdx.rs:105 (exact for 0/1 weights below 2^24)
+    wn = (w / wsum).astype(np.float32)
+    p = acts[-1]
+    d = p - o
+    loss = np.float32((d * d * wn).sum(dtype=np.float64))
+    dz = (np.float32(2) * d * wn * (p * (np.float32(1) - p))).astype(np.float32)
+    grads = np.zeros_like(params)
+    for l in range(3, -1, -1):
+        wt, b, off = layers[l]
+        din, dout = wt.shape[1], wt.shape[0]
+        grads[off:off + din * dout] = (dz.T @ acts[l]).reshape(-1)
+        grads[off + din * dout:off + din * dout + dout] = dz.sum(axis=0, dtype=np.float32)
+        if l > 0:
+            dz = ((dz @ wt) * (acts[l] > 0)).astype(np.float32)
+    return loss, grads
+
+
+def adam_step(params, grads, st: AdamState):
+    """One dfdx Adam update with WeightDecay::L2 (g += l2 p before the moments)."""
+    one = np.float32(1)
+    st.t += 1
+    g = (grads + st.l2 * params).astype(np.float32)
+    st.m = (st.m * st.beta1 + g * (one - st.beta1)).astype(np.float32)
+    st.v = (st.v * st.beta2 + g * g * (one - st.beta2)).astype(np.float32)
+    mh = st.m * np.float32(1.0 / (1.0 - float(st.beta1) ** st.t))
+    vh = st.v * np.float32(1.0 / (1.0 - float(st.beta2) ** st.t))
+    return (params - st.lr * mh / (np.sqrt(vh) + st.eps)).astype(np.float32)
+
+
+def update_model(params, dims, states, observations, weights, st: AdamState):
+    """NablaModel::update_model (nabla/model/dfdx.rs:86-131): returns (loss, new params)."""
+    loss, grads = model_gradients(params, dims, states, observations, weights)
+    return loss, adam_step(np.ascontiguousarray(params, dtype=np.float32), grads, st)

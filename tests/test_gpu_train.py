@@ -1,0 +1,98 @@
+"""GPU parity of the epoch-boundary training step (azb_model_gradients / azb_model_update / azb_update_model)
+against the numpy oracle (oracle.model_gradients / adam_step, pinned to torch autograd + torch Adam in
+tests/test_oracle_train.py).  Floating point: tolerance 1e-5 relative (north_star), written at each assert."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(capi, n, b, **kw):
+    return capi.Handle(capi.default_config(n, b, **kw))
+
+
+def _dims(a):
+    return [2 * a, 512, 1024, 512, a]
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
+
+
+@pytest.mark.parametrize("n,rows", [(19, 96), (8, 33)])
+def test_gradients_match_oracle(capi, orc, n, rows):
+    a = orc.action_dim(n)
+    rng = np.random.default_rng(n)
+    x = (rng.random((rows, 2 * a)) < 0.3).astype(np.float32)
+    o = rng.random((rows, a)).astype(np.float32)
+    w = (rng.random((rows, a)) < 0.2).astype(np.float32)
+    with _mk(capi, n, rows, prior_mode=capi.PRIOR_HASH) as h:
+        h.mlp_init(3)
+        params = h.mlp_get_params()
+        loss, g = h.model_gradients(x, o, w)
+        want_loss, want_g = orc.model_gradients(params, _dims(a), x, o, w)
+        assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)      # 1e-5 relative
+        assert _rel(g, want_g) <= 1e-5                             # 1e-5 relative, norm-wise
+        assert np.allclose(g, want_g, rtol=1e-3, atol=1e-6 * np.abs(want_g).max())
+        # the hook leaves the model untouched and the gradient buffer zeroed: same answer twice
+        loss2, g2 = h.model_gradients(x, o, w)
+        assert loss2 == loss and np.array_equal(g, g2)
+        assert np.array_equal(h.mlp_get_params(), params)
+
+
+def test_model_update_matches_oracle_adam(capi, orc):
+    n, rows = 19, 64
+    a = orc.action_dim(n)
+    rng = np.random.default_rng(5)
+    with _mk(capi, n, rows, prior_mode=capi.PRIOR_HASH) as h:
+        h.mlp_init(11)
+        cur = h.mlp_get_params()
+        st = orc.AdamState(cur.size)
+        for it in range(4):
+            x = (rng.random((rows, 2 * a)) < 0.3).astype(np.float32)
+            o = rng.random((rows, a)).astype(np.float32)
+            w = (rng.random((rows, a)) < 0.2).astype(np.float32)
+            loss = h.model_update(x, o, w)
+            want_loss, cur = orc.update_model(cur, _dims(a), x, o, w, st)
+            assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)
+            got = h.mlp_get_params()
+            # one Adam step moves a parameter by at most ~lr = 1e-4; agree to 1% of that and 1e-5 relative overall
+            assert np.abs(got - cur).max() <= 1e-6
+            assert _rel(got, cur) <= 1e-5
+        assert np.abs(cur - h.mlp_get_params()).max() <= 1e-6
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc"])
+def test_update_model_on_device_trees(capi, orc, mode):
+    """par_update_model (optimizer/mod.rs:249-281) fused on the device == write_observations + the oracle's update."""
+    n, b, steps, tol = 19, 48, 60, 3
+    a = orc.action_dim(n)
+    parents, masks = orc.generate_roots(6, 0, b, n)
+    kw = dict(prior_mode=capi.PRIOR_HASH, prior_seed=9, max_steps=steps)
+    if mode == "tc":
+        kw["mlp_mode"] = capi.MLP_TC
+    with _mk(capi, n, b, **kw) as h:
+        h.mlp_init(2)
+        h.set_roots(parents, masks)
+        h.init_trees()
+        h.step(steps)
+        sv, obs, w = h.write_observations(tol)
+        assert w.sum() > 0
+        params = h.mlp_get_params()
+        st = orc.AdamState(params.size)
+        want_loss, want = orc.update_model(params, _dims(a), sv, obs, w, st)
+        loss = h.update_model(tol)
+        assert abs(loss - want_loss) <= 1e-5 * abs(want_loss)
+        got = h.mlp_get_params()
+        assert np.abs(got - want).max() <= 1e-6 and _rel(got, want) <= 1e-5
+        assert np.abs(got - params).max() > 5e-5  # it did train
+        # the rollout model sees the new parameters (the tensor-core copy is reloaded)
+        x = (np.random.default_rng(0).random((b, 2 * a)) < 0.2).astype(np.float32)
+        y = h.model_write_predictions(x)
+        ref = orc.mlp_forward(got, _dims(a), x, n_threads=4)
+        assert np.abs(y - ref).max() < (2e-2 if mode == "tc" else 1e-5)
+        # a second epoch boundary keeps the Adam state (t = 2)
+        want_loss2, want2 = orc.update_model(want, _dims(a), sv, obs, w, st)
+        loss2 = h.update_model(tol)
+        assert abs(loss2 - want_loss2) <= 2e-5 * abs(want_loss2)
+        assert np.abs(h.mlp_get_params() - want2).max() <= 2e-6

@@ -12,7 +12,7 @@ PH = ["sel", "cur", "probe", "arc", "cascade", "cost", "insert", "reset", "add",
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 L = capi.lib()
 L.azb_debug_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-for b in (1,):
+for b in (1, 4096):
     cfg = capi.default_config(n, b, prior_mode=capi.PRIOR_HASH, max_steps=400)
     p, m = capi.generate_roots(0, 0, b, n)
     with capi.Handle(cfg) as h:
