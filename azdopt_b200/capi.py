@@ -95,6 +95,7 @@ SIGNATURES = {
     "azb_model_update": (C.c_int, [C.c_void_p, f32p, f32p, f32p, C.c_uint32, f32p]),
     "azb_model_gradients": (C.c_int, [C.c_void_p, f32p, f32p, f32p, C.c_uint32, f32p, f32p]),
     "azb_update_model": (C.c_int, [C.c_void_p, C.c_uint32, f32p]),
+    "azb_reset_trees": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]),
     "azb_comm_unique_id": (C.c_int, [u8p]),
     "azb_comm_init": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int]),
     "azb_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -405,6 +406,9 @@ class Handle:
         loss = C.c_float()
         self._ck(self._L.azb_update_model(self._h, n_obs_tol, C.byref(loss)))
         return float(loss.value)
+
+    def reset_trees(self, seed: int, k_min: int = 0, k_max: int = 0):
+        self._ck(self._L.azb_reset_trees(self._h, seed, k_min, k_max))
 
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

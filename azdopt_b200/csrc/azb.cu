@@ -53,6 +53,7 @@ struct azb_handle {
     float *grad, *adam_m, *adam_v, *tr_p, *tr_dz[2], *tr_x;
     double *tr_scal, *tr_part;   // [0] weight sum, [1] loss; per-block partials
     uint32_t adam_t;
+    uint64_t epoch;              // azb_reset_trees calls so far (keys the root re-selection draws)
     AzbAdam adam;
     // epoch-boundary collectives (NCCL, loaded on demand)
     void *nccl_lib, *nccl_comm;
@@ -1458,6 +1459,26 @@ int azb_update_model(azb_handle *h, uint32_t n_obs_tol, float *loss) {
     rc = train_read_loss(h, loss);
     if (rc) return rc;
     return check_device_error(h);
+}
+
+// NablaOptimizer::par_reset_trees (optimizer/mod.rs:284-360) with the example's modify_root policy
+// (04-c21-tree.rs:172-206) on the device, then the tail shared with par_new (azb_init_trees)
+int azb_reset_trees(azb_handle *h, uint64_t seed, uint32_t k_min, uint32_t k_max) {
+    if (!h) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    if (k_max == 0) k_max = h->A / 2;  // num_permitted_actions_range = 5..=(ACTION / 2) (04-c21-tree.rs:85)
+    if (k_min == 0) k_min = 5;
+    if (k_min > k_max || k_max > h->A || h->A > 2048) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = flush_pending(h);
+    if (rc) return rc;
+    azb_modify_roots_kernel<<<(h->L.B + 3) / 4, 128, 0, h->stream>>>(h->L, seed, h->epoch, k_min, k_max);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->epoch += 1;
+    rc = check_device_error(h);
+    if (rc) return rc;
+    return azb_init_trees(h);
 }
 
 // ---- epoch-boundary communicator ----

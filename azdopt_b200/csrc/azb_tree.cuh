@@ -1078,3 +1078,133 @@ __global__ void __launch_bounds__(128) azb_observe_kernel(const AzbLayout L, con
         }
     }
 }
+
+// ---- par_reset_trees' modify_root (optimizer/mod.rs:284-339) with the example's policy (04-c21-tree.rs:172-206) ----
+// One warp per tree, once per epoch.  n[0] is the root (the empty ActionSet is the smallest BTreeMap key):
+//   c_root == c*_root (nothing better was found below this root):
+//       |permitted| == k_max : a fresh random state (ROTWithActionPermissions::generate, k ~ U{k_min..k_max})
+//       otherwise            : move to a uniformly chosen node with c == c_root, k ~ U{|permitted|..k_max}
+//   else                     : move to a uniformly chosen node with c <= (c_root + 3 c*_root) / 4, k ~ U{k_min..k_max}
+//   and in both "move" cases re-draw the permitted set (randomize_permitted_actions, modify_parent_once.rs:27-37).
+// The reference draws from an unseeded thread_rng, so only the distribution is defined; here the draws come from a
+// counter generator keyed by (seed, epoch, GLOBAL root index) — the same stream the oracle uses — and candidates
+// are enumerated in node-index order (any fixed order gives the same uniform choice).
+__device__ __forceinline__ uint32_t azb_bounded(unsigned long long r, uint32_t n) {
+    return (uint32_t)(((r >> 32) * (unsigned long long)n) >> 32);
+}
+
+__global__ void __launch_bounds__(128) azb_modify_roots_kernel(const AzbLayout L, const unsigned long long seed,
+                                                               const unsigned long long epoch, const uint32_t k_min,
+                                                               const uint32_t k_max) {
+    __shared__ uint16_t s_perm[4][2048];
+    __shared__ uint32_t s_mask[4][64];
+    __shared__ uint8_t s_par[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tree = blockIdx.x * 4 + warp;
+    if (tree >= L.B) return;
+    const uint32_t FULL = 0xffffffffu;
+    uint32_t *wk = L.walker + (size_t)tree * L.WS;
+    uint32_t *g_rpar = wk + WK_HDR + L.PW + 2 * L.W, *g_rperm = g_rpar + L.PW;
+    uint16_t *perm = s_perm[warp];
+    uint32_t *mask = s_mask[warp];
+    uint8_t *par = s_par[warp];
+    for (uint32_t i = lane; i < L.PW; i += 32) reinterpret_cast<uint32_t *>(par)[i] = g_rpar[i];
+    uint32_t kcur = 0;
+    for (uint32_t w = lane; w < L.W; w += 32) kcur += __popc(g_rperm[w]);
+    kcur = warp_sum_u32(kcur);
+    __syncwarp();
+    const uint4 *node = L.node + (size_t)tree * L.cap_nodes * 4;
+    const uint32_t nn = wk[WK_NNODES];
+    const uint4 r0 = node[0];
+    const float c_root = __uint_as_float(r0.x), c_star = __uint_as_float(r0.y);
+    unsigned long long s = azb_mix64(seed ^ azb_mix64(L.first_root + tree + 0x5851F42D4C957F2Dull) ^
+                                     azb_mix64(epoch * 0xA24BAED4963EE407ull + 0x9FB21C651E98DF25ull));
+    unsigned long long ctr = 0;
+    auto next = [&]() { return azb_mix64(s + (ctr++) * 0xD1342543DE82EF95ull); };  // every lane keeps the same stream
+    const bool stuck = c_root == c_star;
+    uint32_t num = 0;
+    uint32_t err = 0;
+    if (stuck && kcur == k_max) {
+        num = k_min + azb_bounded(next(), k_max - k_min + 1);
+        if (lane == 0) {  // RootedOrderedTree::generate (rooted_tree/mod.rs:14-20)
+            for (uint32_t i = 0; i < L.N; ++i) par[i] = 0;
+        }
+        __syncwarp();
+        for (uint32_t i = 2; i + 1 < L.N; ++i) {
+            const uint32_t p = azb_bounded(next(), i);
+            if (lane == 0) par[i] = (uint8_t)p;
+        }
+    } else {
+        if (stuck && (kcur < k_min || kcur > k_max)) err = 6;  // the reference's unreachable!() (04-c21-tree.rs:179)
+        const float thr = __fdiv_rn(__fadd_rn(c_root, __fmul_rn(3.0f, c_star)), 4.0f);
+        // candidates in node order: count, draw, locate
+        uint32_t count = 0;
+        for (uint32_t base = 0; base < nn; base += 32) {
+            const uint32_t i = base + lane;
+            bool cand = false;
+            if (i < nn) {
+                const float c = __uint_as_float(node[(size_t)i * 4].x);
+                cand = stuck ? (c == c_root) : (c <= thr);
+            }
+            count += __popc(__ballot_sync(FULL, cand));
+        }
+        uint32_t chosen = 0;
+        if (count == 0) {
+            err = 6;  // n.choose(..).unwrap() on an empty list panics in the reference
+        } else {
+            const uint32_t r = azb_bounded(next(), count);
+            uint32_t seen = 0;
+            for (uint32_t base = 0; base < nn; base += 32) {
+                const uint32_t i = base + lane;
+                bool cand = false;
+                if (i < nn) {
+                    const float c = __uint_as_float(node[(size_t)i * 4].x);
+                    cand = stuck ? (c == c_root) : (c <= thr);
+                }
+                const uint32_t bal = __ballot_sync(FULL, cand);
+                const uint32_t here = __popc(bal);
+                if (r < seen + here) {
+                    chosen = base + nth_set_bit(bal, r - seen);
+                    break;
+                }
+                seen += here;
+            }
+            // p.actions_taken().for_each(|a| space.act(state, a)): only the parents survive the re-draw below
+            const uint32_t *key = L.key + ((size_t)tree * L.cap_nodes + chosen) * L.W;
+            for (uint32_t w = lane; w < L.W; w += 32) {
+                uint32_t word = key[w];
+                while (word) {
+                    const uint32_t a = w * 32 + (__ffs(word) - 1);
+                    word &= word - 1;
+                    const uint32_t child = azb_action_child(a);
+                    par[child] = (uint8_t)(a - azb_child_first_action(child));  // distinct children: no race
+                }
+            }
+        }
+        num = stuck ? kcur + azb_bounded(next(), k_max - kcur + 1) : k_min + azb_bounded(next(), k_max - k_min + 1);
+    }
+    __syncwarp();
+    // choose_multiple(rng, num) over 0..A as a partial Fisher-Yates (the host generator's algorithm)
+    for (uint32_t i = lane; i < L.A; i += 32) perm[i] = (uint16_t)i;
+    for (uint32_t w = lane; w < 64; w += 32) mask[w] = 0u;
+    __syncwarp();
+    if (err == 0) {
+        for (uint32_t t = 0; t < num; ++t) {
+            const uint32_t j = t + azb_bounded(next(), L.A - t);
+            if (lane == 0) {
+                const uint16_t pt = perm[t], pj = perm[j];
+                perm[t] = pj;
+                perm[j] = pt;
+                mask[pj >> 5] |= 1u << (pj & 31);
+            }
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < L.PW; i += 32) g_rpar[i] = reinterpret_cast<uint32_t *>(par)[i];
+        for (uint32_t w = lane; w < L.W; w += 32) g_rperm[w] = mask[w];
+    } else if (lane == 0) {
+        if (atomicCAS(&L.g->err, 0u, err) == 0u) {
+            L.g->err_tree = tree;
+            L.g->err_step = wk[WK_STEP];
+        }
+    }
+}

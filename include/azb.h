@@ -202,6 +202,15 @@ int azb_model_gradients(azb_handle *h, const float *states, const float *observa
  * every rank applies the same global-batch Adam step. */
 int azb_update_model(azb_handle *h, uint32_t n_obs_tol, float *loss);
 
+/* NablaOptimizer::par_reset_trees (optimizer/mod.rs:284-360) with the example's modify_root policy
+ * (04-c21-tree.rs:172-206) evaluated on the device, followed by the tail shared with par_new (= azb_init_trees):
+ * a root that found nothing better moves to an equal-cost node and widens its permitted set (or is regenerated
+ * once that set is at k_max); otherwise it moves to a uniformly chosen node with c <= (c + 3 c*) / 4 and re-draws
+ * the permitted set.  The reference draws from an unseeded thread_rng; here every draw is a counter hash of
+ * (seed, number of resets so far, GLOBAL root index), so a sharded run re-selects exactly like an unsharded one.
+ * k_min / k_max = num_permitted_actions_range (0, 0 = the example's 5 ..= ACTION_DIM / 2). */
+int azb_reset_trees(azb_handle *h, uint64_t seed, uint32_t k_min, uint32_t k_max);
+
 /* ---- epoch-boundary communicator (NCCL, loaded on demand; no collective ever runs inside azb_step).  Rank 0 makes
  *      an id, the host program hands it to every rank (any out-of-band channel), each rank attaches its handle. ---- */
 int azb_comm_unique_id(uint8_t *id128 /*[128]*/);

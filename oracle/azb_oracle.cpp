@@ -1112,7 +1112,11 @@ void orc_set_roots(orc_optimizer *o, const uint8_t *parents, const uint32_t *mas
 }
 
 // optimizer/mod.rs:62-101 (and the tail of par_reset_trees :340-359)
-int orc_init_trees(orc_optimizer *o, const float *priors) {
+static int init_trees_impl(orc_optimizer *o, const float *priors, bool first);
+int orc_init_trees(orc_optimizer *o, const float *priors) { return init_trees_impl(o, priors, true); }
+// the tail of par_reset_trees (optimizer/mod.rs:340-359): as above, but argmin_data is left alone
+int orc_reinit_trees(orc_optimizer *o, const float *priors) { return init_trees_impl(o, priors, false); }
+static int init_trees_impl(orc_optimizer *o, const float *priors, bool first) {
     const Space &sp = o->space;
     std::fill(o->thread_err.begin(), o->thread_err.end(), 0);
     parallel_for(o->batch, o->n_threads, [&](uint32_t i, int t) {
@@ -1129,6 +1133,11 @@ int orc_init_trees(orc_optimizer *o, const float *priors) {
         add_actions(tr, root_id, sp, o->roots[i], priors + (size_t)i * sp.a_dim, o->thread_counters[t]);
         o->num_inspected_nodes[i] = 0;
     });
+    if (!first) {
+        for (int e : o->thread_err)
+            if (e) return e;
+        return 0;
+    }
     // :95-101 min_by over roots; first minimum (lowest index) on ties
     uint32_t best = 0;
     float best_e = sp.evaluate(o->costs[0]);
@@ -1145,6 +1154,78 @@ int orc_init_trees(orc_optimizer *o, const float *priors) {
     for (int e : o->thread_err)
         if (e) return e;
     return 0;
+}
+
+// par_reset_trees' first half (optimizer/mod.rs:284-339) with the example's modify_root (04-c21-tree.rs:172-206).
+// The reference draws from an unseeded thread_rng; the draws here come from the counter generator keyed by
+// (seed, epoch, global root index), and `n.choose(rng)` enumerates the candidates in node-index order (a uniform
+// choice does not depend on the enumeration order).  Returns 6 where the reference would panic.  The caller then
+// runs orc_init_trees (the shared tail :340-359).
+int orc_modify_roots(orc_optimizer *o, uint64_t seed, uint64_t epoch, uint64_t first_root, uint32_t k_min, uint32_t k_max) {
+    const Space &sp = o->space;
+    const uint32_t n = sp.n, a_dim = sp.a_dim;
+    int rc = 0;
+    for (uint32_t i = 0; i < o->batch; ++i) {
+        const SearchTree &t = o->trees[i];
+        State &root = o->roots[i];
+        uint64_t s = mix64(seed ^ mix64(first_root + i + 0x5851F42D4C957F2Dull) ^
+                           mix64(epoch * 0xA24BAED4963EE407ull + 0x9FB21C651E98DF25ull));
+        uint64_t ctr = 0;
+        auto next = [&]() { return mix64(s + (ctr++) * 0xD1342543DE82EF95ull); };
+        auto randomize = [&](uint32_t num) {  // modify_parent_once.rs:27-37 (choose_multiple as partial Fisher-Yates)
+            std::vector<uint32_t> perm(a_dim);
+            for (uint32_t q = 0; q < a_dim; ++q) perm[q] = q;
+            root.permitted.fill(0);
+            for (uint32_t q = 0; q < num; ++q) {
+                uint32_t j = q + bounded(next(), a_dim - q);
+                std::swap(perm[q], perm[j]);
+                mask_set(root.permitted.data(), perm[q]);
+            }
+        };
+        auto move_to = [&](uint32_t node) {  // p.actions_taken().for_each(|a| space.act(state, a))
+            for (uint16_t a : t.node_keys[node]) space_act(n, root, a);
+        };
+        const float c_root = t.nodes[0].w.c, c_star = t.nodes[0].w.c_t_star;  // n[0]: the empty path sorts first
+        uint32_t kcur = 0;
+        for (uint32_t w = 0; w < sp.words; ++w) kcur += (uint32_t)__builtin_popcount(root.permitted[w]);
+        std::vector<uint32_t> cands;
+        if (c_root == c_star) {
+            if (kcur < k_min || kcur > k_max) {  // unreachable!()
+                rc = 6;
+                continue;
+            }
+            if (kcur == k_max) {
+                uint32_t num = k_min + bounded(next(), k_max - k_min + 1);
+                for (uint32_t v = 0; v < n; ++v) root.parents[v] = 0;
+                for (uint32_t v = 2; v + 1 < n; ++v) root.parents[v] = (uint8_t)bounded(next(), v);
+                randomize(num);
+            } else {
+                for (uint32_t q = 0; q < t.nodes.size(); ++q)
+                    if (t.nodes[q].w.c == c_root) cands.push_back(q);
+                move_to(cands[bounded(next(), (uint32_t)cands.size())]);
+                randomize(kcur + bounded(next(), k_max - kcur + 1));
+            }
+        } else {
+            const float thr = (c_root + 3.0f * c_star) / 4.0f;
+            for (uint32_t q = 0; q < t.nodes.size(); ++q)
+                if (t.nodes[q].w.c <= thr) cands.push_back(q);
+            if (cands.empty()) {
+                rc = 6;
+                continue;
+            }
+            move_to(cands[bounded(next(), (uint32_t)cands.size())]);
+            randomize(k_min + bounded(next(), k_max - k_min + 1));
+        }
+    }
+    return rc;
+}
+
+void orc_get_roots(orc_optimizer *o, uint8_t *parents, uint32_t *mask) {
+    uint32_t n = o->space.n, w = o->space.words;
+    for (uint32_t i = 0; i < o->batch; ++i) {
+        std::memcpy(parents + (size_t)i * n, o->roots[i].parents.data(), n);
+        std::memcpy(mask + (size_t)i * w, o->roots[i].permitted.data(), (size_t)w * 4);
+    }
 }
 
 void orc_root_vecs(orc_optimizer *o, float *state_vecs) {

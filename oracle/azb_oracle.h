@@ -88,6 +88,12 @@ void orc_destroy(orc_optimizer *o);
 void orc_set_roots(orc_optimizer *o, const uint8_t *parents, const uint32_t *permitted_mask);
 /* tail of par_new (optimizer/mod.rs:62-101): costs, root node, add_actions(root, priors), argmin over roots */
 int orc_init_trees(orc_optimizer *o, const float *priors);
+/* par_reset_trees' modify_root half with the example's policy (optimizer/mod.rs:284-339; 04-c21-tree.rs:172-206);
+ * counter-generator draws keyed by (seed, epoch, global root). Follow with orc_init_trees. Returns 6 on the reference's panics */
+int orc_modify_roots(orc_optimizer *o, uint64_t seed, uint64_t epoch, uint64_t first_root, uint32_t k_min, uint32_t k_max);
+void orc_get_roots(orc_optimizer *o, uint8_t *parents, uint32_t *permitted_mask);
+/* tail of par_reset_trees (optimizer/mod.rs:340-359): like orc_init_trees but argmin_data is kept */
+int orc_reinit_trees(orc_optimizer *o, const float *priors);
 /* write_vec of every root state (optimizer/mod.rs:65-70) */
 void orc_root_vecs(orc_optimizer *o, float *state_vecs);
 /* first parallel region of par_roll_out_episodes (optimizer/mod.rs:159-174); state_vecs may be NULL */

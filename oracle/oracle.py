@@ -78,6 +78,11 @@ def lib():
     L.orc_init_trees.restype = C.c_int
     L.orc_init_trees.argtypes = [C.c_void_p, f32p]
     L.orc_root_vecs.argtypes = [C.c_void_p, f32p]
+    L.orc_reinit_trees.restype = C.c_int
+    L.orc_reinit_trees.argtypes = [C.c_void_p, f32p]
+    L.orc_modify_roots.restype = C.c_int
+    L.orc_modify_roots.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+    L.orc_get_roots.argtypes = [C.c_void_p, u8p, u32p]
     L.orc_rollout.restype = C.c_int
     L.orc_rollout.argtypes = [C.c_void_p, f32p]
     L.orc_add_actions.restype = C.c_int
@@ -243,6 +248,25 @@ class Optimizer:
         rc = lib().orc_init_trees(self._h, _p(pr, C.c_float))
         if rc:
             raise RuntimeError(f"orc_init_trees rc={rc}")
+
+    def reinit_trees(self, priors):
+        pr = np.ascontiguousarray(priors, dtype=np.float32)
+        assert pr.shape == (self.b, self.a)
+        rc = lib().orc_reinit_trees(self._h, _p(pr, C.c_float))
+        if rc:
+            raise RuntimeError(f"orc_reinit_trees rc={rc}")
+
+    def modify_roots(self, seed, epoch, first_root=0, k_min=5, k_max=None):
+        """par_reset_trees' modify_root half (example policy); follow with reinit_trees."""
+        rc = lib().orc_modify_roots(self._h, seed, epoch, first_root, k_min, self.a // 2 if k_max is None else k_max)
+        if rc:
+            raise RuntimeError(f"orc_modify_roots rc={rc}")
+
+    def get_roots(self):
+        p = np.zeros((self.b, self.n), dtype=np.uint8)
+        m = np.zeros((self.b, self.w), dtype=np.uint32)
+        lib().orc_get_roots(self._h, _p(p, C.c_uint8), _p(m, C.c_uint32))
+        return p, m
 
     def root_vecs(self):
         v = np.zeros((self.b, 2 * self.a), dtype=np.float32)

@@ -96,3 +96,47 @@ def test_update_model_on_device_trees(capi, orc, mode):
         loss2 = h.update_model(tol)
         assert abs(loss2 - want_loss2) <= 2e-5 * abs(want_loss2)
         assert np.abs(h.mlp_get_params() - want2).max() <= 2e-6
+
+
+def _cmp_trees(orc_opt, h, b):
+    for i in range(b):
+        d_o, d_g = orc_opt.dump_tree(i), h.dump_tree(i)
+        for k in ("nodes", "keys", "preds", "arcs"):
+            assert d_o[k].shape == d_g[k].shape and np.array_equal(d_o[k], d_g[k]), f"tree {i} {k}"
+
+
+@pytest.mark.parametrize("n,k_max", [(19, 9), (12, 0), (33, 0)])
+def test_reset_trees_policy_matches_oracle(capi, orc, n, k_max):
+    """azb_reset_trees (device modify_root + init) against the oracle with the same counter draws: the re-selected
+    roots, the rebuilt trees and the next epoch's search are bit-exact, over several epochs."""
+    b, steps = 72, 30
+    a = orc.action_dim(n)
+    kmx = k_max or a // 2
+    parents, masks = orc.generate_roots(3, 0, b, n, k_min=5, k_max=kmx)
+    o = orc.Optimizer(n, b, lambda_method=orc.LAMBDA_MULTISECTION)
+    o.set_roots(parents, masks)
+    o.init_trees(orc.hash_priors(5, 0, b, a, 0))
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_HASH, prior_seed=5, max_steps=steps) as h:
+        h.set_roots(parents, masks)
+        h.init_trees()
+        moved = 0
+        for epoch in range(3):
+            h.step(steps)
+            o.steps_hash(5, 0, 1, steps)
+            _cmp_trees(o, h, b)
+            h.reset_trees(21, 5, kmx)
+            o.modify_roots(21, epoch, 0, 5, kmx)
+            pg, mg = h.get_roots()
+            po, mo = o.get_roots()
+            assert np.array_equal(pg, po) and np.array_equal(mg, mo)
+            moved += int((pg != parents).any(axis=1).sum())
+            parents = pg
+            o.reinit_trees(orc.hash_priors(5, 0, b, a, 0))
+            _cmp_trees(o, h, b)
+            ag, ao = h.argmin(), o.argmin()
+            assert ag["eval"] == ao["eval"] and np.array_equal(ag["parents"], ao["parents"])
+        h.step(steps)
+        o.steps_hash(5, 0, 1, steps)
+        _cmp_trees(o, h, b)
+        assert h.argmin()["eval"] == o.argmin()["eval"]
+        assert moved > b  # roots really move
