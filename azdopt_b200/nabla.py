@@ -58,6 +58,9 @@ class TrivialModel:
     def write_predictions(self, states: np.ndarray, predictions: np.ndarray) -> None:
         return None
 
+    def update_model(self, states: np.ndarray, observations: np.ndarray, action_weights: np.ndarray) -> float:
+        return 0.0
+
 
 @dataclasses.dataclass
 class ArgminData:  # log.rs:1-11
@@ -161,9 +164,26 @@ class NablaOptimizer:
         (root state vectors, observations, action weights)."""
         return self.h.write_observations(n_obs_tol)
 
-    def par_reset_trees(self, new_roots):
-        """optimizer/mod.rs:284-360 with the root re-selection done by the caller: ``new_roots`` as in par_new."""
-        self._seed_roots(new_roots)
+    def par_update_model(self, n_obs_tol: int) -> float:
+        """optimizer/mod.rs:249-281: root vectors + observations + NablaModel::update_model; returns the loss.
+        ActionModel: fused on the device (f32 forward/backward + Adam, NCCL all-reduce if a communicator is
+        attached).  Any other model: its own ``update_model(states, observations, action_weights)`` on host arrays."""
+        if isinstance(self.model, ActionModel):
+            return self.h.update_model(n_obs_tol)
+        sv, obs, w = self.h.write_observations(n_obs_tol)
+        return float(self.model.update_model(sv, obs, w))
+
+    def par_reset_trees(self, new_roots=None, *, seed: int = 0, num_permitted_actions_range=None):
+        """optimizer/mod.rs:284-360.  ``new_roots=None``: the example's modify_root policy (04-c21-tree.rs:172-206)
+        on the device, draws keyed by (seed, reset count, global root index).  Otherwise the caller re-selected the
+        roots itself: ``new_roots`` as in par_new."""
+        if new_roots is not None:
+            self._seed_roots(new_roots)
+            return
+        lo, hi = num_permitted_actions_range or (0, 0)
+        if not isinstance(self.model, ActionModel):
+            raise TypeError("device-side root re-selection needs the device model (priors of the new roots)")
+        self.h.reset_trees(seed, lo, hi)
 
     def get_trees(self):  # optimizer/mod.rs:34-36, as canonical dumps
         return [self.h.dump_tree(i) for i in range(self.batch)]

@@ -1,7 +1,7 @@
 // c21_epoch.cpp — the epoch loop of graph-state/examples/04-c21-tree.rs:106-208 over the C++ mirror
 // (include/azb_nabla.hpp): par_new, `episodes` fused steps per epoch, argmin logging, observation pass.
-// Training (update_model) and the modify_root policy are "next" rows, so every epoch re-seeds fresh
-// synthetic roots.   build: g++ -O2 -std=c++17 -Iinclude examples/c21_epoch.cpp -Lazdopt_b200/lib -lazb -o c21_epoch
+// The whole loop runs on the device: fused search steps, the training step (par_update_model) and the example's
+// modify_root policy (par_reset_trees).   build: g++ -O2 -std=c++17 -Iinclude examples/c21_epoch.cpp -Lazdopt_b200/lib -lazb -o c21_epoch
 #include <cstdio>
 #include <cstdlib>
 
@@ -27,13 +27,9 @@ int main(int argc, char **argv) {
             best = opt.argmin_data();
             printf("%12g\tlambda_1=%.6f mu=%u\n", best.eval, best.lambda_1, best.mu);
             if (best.eval < goal) break;
-            std::vector<float> sv, obs, wts;
-            opt.observations(n_obs_tol, sv, obs, wts);
-            double wsum = 0;
-            for (float x : wts) wsum += x;
-            printf("epoch %u: %.0f observed root actions\n", epoch, wsum);
-            azb_generate_roots(epoch, 0, batch, n, 5, a / 2, parents.data(), permitted.data());
-            opt.par_reset_trees(parents, permitted);
+            const float loss = opt.par_update_model(n_obs_tol);                  // 04-c21-tree.rs:163
+            printf("epoch %u: loss %g\n", epoch, loss);
+            opt.par_reset_trees(/*seed=*/1234);                                  // 04-c21-tree.rs:172-207
         }
     } catch (const azb::Error &e) {
         fprintf(stderr, "azb error %d: %s\n", e.code, e.what());

@@ -34,6 +34,9 @@ struct ArgminData {  // log.rs:1-11
 struct NablaModel {
     virtual ~NablaModel() = default;
     virtual void write_predictions(const std::vector<float> &states, std::vector<float> &predictions) = 0;
+    // nabla/model/mod.rs:7: returns the loss
+    virtual float update_model(const std::vector<float> & /*states*/, const std::vector<float> & /*observations*/,
+                               const std::vector<float> & /*action_weights*/) { return 0.f; }
 };
 // nabla/model/mod.rs:10-23
 struct TrivialModel : NablaModel {
@@ -115,6 +118,22 @@ class NablaOptimizer {
         w.resize(obs.size());
         ck(azb_write_observations(h_, n_obs_tol, state_vecs.data(), obs.data(), w.data()));
     }
+    // par_update_model (optimizer/mod.rs:249-281) with the built-in ActionModel: root vectors, observations, f32
+    // forward/backward and the Adam step on the device (all-reduced if a communicator is attached); returns the loss
+    float par_update_model(uint32_t n_obs_tol) {
+        float loss = 0.f;
+        if (!model_) {
+            ck(azb_update_model(h_, n_obs_tol, &loss));
+        } else {
+            std::vector<float> sv, obs, w;
+            observations(n_obs_tol, sv, obs, w);
+            loss = model_->update_model(sv, obs, w);
+        }
+        return loss;
+    }
+    // par_reset_trees (optimizer/mod.rs:284-360) with the example's modify_root policy (04-c21-tree.rs:172-206) on the
+    // device; k_min/k_max = num_permitted_actions_range (0,0 = 5..=ACTION/2)
+    void par_reset_trees(uint64_t seed, uint32_t k_min = 0, uint32_t k_max = 0) { ck(azb_reset_trees(h_, seed, k_min, k_max)); }
     // par_reset_trees (optimizer/mod.rs:284-360) with the caller's modify_root already applied to the roots
     void par_reset_trees(const std::vector<uint8_t> &root_parents, const std::vector<uint32_t> &root_permitted) {
         reseed(root_parents, root_permitted);
