@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("n_as_tol", C.c_uint32 * MAX_TOL), ("n_as_tol_len", C.c_uint32), ("n_as_tol_default", C.c_uint32),
         ("mlp_hidden", C.c_uint32 * 3), ("mlp_mode", C.c_uint32), ("prior_mode", C.c_uint32),
         ("prior_seed", C.c_uint64), ("max_steps", C.c_uint32), ("cap_nodes", C.c_uint32), ("cap_preds", C.c_uint32),
-        ("cap_parents", C.c_uint32), ("max_episodes", C.c_uint32), ("n_groups", C.c_uint32), ("reserved", C.c_uint32 * 6),
+        ("cap_parents", C.c_uint32), ("max_episodes", C.c_uint32), ("n_groups", C.c_uint32), ("async_workers", C.c_uint32), ("reserved", C.c_uint32 * 5),
     ]
 
 

@@ -22,6 +22,7 @@
 #include "azb_mlp_tc.cuh"
 #include "azb_tree.cuh"
 #include "azb_train.cuh"
+#include "azb_async.cuh"
 
 #include <dlfcn.h>
 
@@ -55,6 +56,13 @@ struct azb_handle {
     uint32_t adam_t;
     uint64_t epoch;              // azb_reset_trees calls so far (keys the root re-selection draws)
     AzbAdam adam;
+    // asynchronous search kernel (azb_async.cuh)
+    bool async_ready, async_ran;
+    AzbAsyncParams asP;
+    AzbAsyncMaps asM;
+    int async_grid;
+    size_t async_smem;
+    void *async_bufs[12];
     // epoch-boundary collectives (NCCL, loaded on demand)
     void *nccl_lib, *nccl_comm;
     int comm_rank, comm_world;
@@ -176,6 +184,8 @@ int azb_destroy(azb_handle *h) {
     for (uint32_t g = 0; g < 64; ++g)
         if (h->ggraph[g]) cudaGraphExecDestroy(h->ggraph[g]);
     if (h->nccl_comm) azb_comm_destroy_impl(h);
+    for (void *p : h->async_bufs)
+        if (p) cudaFree(p);
     void *ptrs[] = {h->grad, h->adam_m, h->adam_v, h->tr_p, h->tr_dz[0], h->tr_dz[1], h->tr_x, h->tr_scal, h->tr_part, h->comm_buf,
                     h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
                     h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
@@ -586,7 +596,11 @@ static int launch_tree(azb_handle *h, uint32_t flags, uint32_t target_step, int 
 
 static int read_globals(azb_handle *h, AzbGlobals *g) {
     CK(cudaMemcpyAsync(g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    uint32_t as_abort = 0;
+    if (h->async_ran) CK(cudaMemcpyAsync(&as_abort, &h->asP.st->abort, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->async_ran = false;
+    if (as_abort == 1u) return fail(h, AZB_ERR_CUDA, "async search kernel: watchdog expired (no progress)");
     if (g->err)
         return fail(h, (int)g->err, "%s (tree %u, step %u)", azb_strerror((int)g->err), g->err_tree, g->err_step);
     return AZB_OK;
@@ -664,6 +678,129 @@ int azb_init_trees(azb_handle *h) {
     return AZB_OK;
 }
 
+
+}  // extern "C"
+
+// ---- the asynchronous search kernel (azb_async.cuh): set-up and launch -------------------------------------------
+template <int D, bool C>
+static int async_prepare_kernel(azb_handle *h, int *blocks_per_sm) {
+    CK(cudaFuncSetAttribute(azb_async_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->async_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, azb_async_kernel<D, C>, AS_THREADS, h->async_smem));
+    return AZB_OK;
+}
+
+static int async_create(azb_handle *h) {
+    if (h->async_ready) return AZB_OK;
+    if (h->cfg.prior_mode != AZB_PRIOR_MLP || h->cfg.mlp_mode != AZB_MLP_TC || !h->tc.ready)
+        return fail(h, AZB_ERR_INVALID, "async_workers needs AZB_PRIOR_MLP with AZB_MLP_TC");
+    if (h->cfg.max_episodes || h->n_groups > 1) return fail(h, AZB_ERR_INVALID, "async_workers excludes max_episodes / n_groups");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
+    if (!coop) return fail(h, AZB_ERR_CUDA, "cooperative launch not supported");
+    const uint32_t W = h->cfg.async_workers, B = h->L.B;
+    const size_t tree_smem = (size_t)AS_WARPS * h->smem_words_per_warp * 4 + ((h->A + 15) & ~15u);
+    const size_t mlp_smem = (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2 + 1024;
+    h->async_smem = std::max(tree_smem, mlp_smem);
+    int nb = 0, nb2 = 0, rc;
+    switch (azb_stack_depth(h->N)) {
+        case 3: rc = async_prepare_kernel<3, false>(h, &nb); if (!rc) rc = async_prepare_kernel<3, true>(h, &nb2); break;
+        case 4: rc = async_prepare_kernel<4, false>(h, &nb); if (!rc) rc = async_prepare_kernel<4, true>(h, &nb2); break;
+        default: rc = async_prepare_kernel<5, false>(h, &nb); if (!rc) rc = async_prepare_kernel<5, true>(h, &nb2); break;
+    }
+    if (rc) return rc;
+    nb = std::min(nb, nb2);
+    if (nb < 1) return fail(h, AZB_ERR_CUDA, "the async kernel does not fit on an SM (%zu bytes of shared memory)", h->async_smem);
+    h->async_grid = nb * prop.multiProcessorCount;
+    if ((int)W >= prop.multiProcessorCount || (int)W >= h->async_grid) return fail(h, AZB_ERR_INVALID, "async_workers >= SM count");
+    const uint32_t NW = (uint32_t)(h->async_grid - (int)W) * AS_WARPS;
+    if (B > 32u * NW) return fail(h, AZB_ERR_INVALID, "async mode holds at most %u trees per GPU", 32u * NW);
+    AzbAsyncParams &P = h->asP;
+    memset(&P, 0, sizeof(P));
+    P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
+    P.n_workers = W;
+    P.smem_words_per_warp = h->smem_words_per_warp;
+    P.ring_ld = h->tc.kpad[0];
+    P.timeout_ns = 30ull * 1000000000ull;
+    P.flush_ns = 4000ull;
+    if (const char *e = getenv("AZB_ASYNC_FLUSH_NS")) P.flush_ns = strtoull(e, nullptr, 10);
+    for (int l = 0; l < 4; ++l) {
+        P.kpad[l] = h->tc.kpad[l];
+        P.npad[l] = h->tc.npad[l];
+        P.bias[l] = h->tc.bias[l];
+    }
+    int nbuf = 0;
+    auto alloc = [&](void **p, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) {
+            h->dev_bytes += bytes;
+            h->async_bufs[nbuf++] = *p;
+            e = cudaMemsetAsync(*p, 0, bytes, h->stream);
+        }
+        return e;
+    };
+    CK(alloc((void **)&P.st, sizeof(AzbAsyncState)));
+    CK(alloc((void **)&P.tile_count, (size_t)P.NT * 4));
+    CK(alloc((void **)&P.tile_retired, (size_t)P.NT * 4));
+    CK(alloc((void **)&P.slot_tree, (size_t)P.NT * AS_TILE * 4));
+    CK(alloc((void **)&P.h_flag, (size_t)B * 4));
+    CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
+    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * h->tc.kpad[l + 1] * 2));
+    azb_encode_fn enc = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres) != cudaSuccess || !enc)
+        return fail(h, AZB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    const char *why = azb_tc_make_map(enc, &h->asM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
+    for (int l = 0; l < 3 && !why; ++l)
+        why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
+    for (int l = 0; l < 4 && !why; ++l)
+        why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], 128);
+    if (why) return fail(h, AZB_ERR_CUDA, "async tensor maps: %s", why);
+    CK(cudaStreamSynchronize(h->stream));
+    h->async_ready = true;
+    return AZB_OK;
+}
+
+template <int D, bool C>
+static cudaError_t async_launch(azb_handle *h) {
+    void *args[] = {(void *)&h->L, (void *)&h->asP, (void *)&h->asM};
+    return cudaLaunchCooperativeKernel((const void *)azb_async_kernel<D, C>, dim3(h->async_grid), dim3(AS_THREADS), args,
+                                       h->async_smem, h->stream);
+}
+
+// n_steps of every tree in one persistent kernel, then one batched forward over the rows of the last step (whose
+// add_actions is fused into the next launch, like the lock step's)
+static int run_async(azb_handle *h, uint32_t n_steps) {
+    int rc = async_create(h);
+    if (rc) return rc;
+    AzbAsyncParams &P = h->asP;
+    CK(cudaMemsetAsync(P.st, 0, sizeof(AzbAsyncState), h->stream));
+    CK(cudaMemsetAsync(P.tile_count, 0, (size_t)P.NT * 4, h->stream));
+    CK(cudaMemsetAsync(P.tile_retired, 0, (size_t)P.NT * 4, h->stream));
+    CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
+    P.target_step = h->steps_done + n_steps;
+    cudaError_t ce;
+    switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
+        case 6: ce = async_launch<3, false>(h); break;
+        case 7: ce = async_launch<3, true>(h); break;
+        case 8: ce = async_launch<4, false>(h); break;
+        case 9: ce = async_launch<4, true>(h); break;
+        case 10: ce = async_launch<5, false>(h); break;
+        default: ce = async_launch<5, true>(h); break;
+    }
+    if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
+    h->launches += 1;
+    h->async_ran = true;
+    rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
+    if (rc) return rc;
+    h->steps_done = P.target_step;
+    h->pending_add = true;
+    return AZB_OK;
+}
+
+extern "C" {
+
 // one launch = every tree below the target advances by at most one step; then the model forward over the batch
 static int enqueue_launch(azb_handle *h, uint32_t flags, uint32_t target) {
     int rc = launch_tree(h, flags, target);
@@ -677,6 +814,7 @@ static int enqueue_steps(azb_handle *h, uint32_t n_steps, uint32_t flags) {
     if (h->steps_done + n_steps > h->L.cap_steps)
         return fail(h, AZB_ERR_CAPACITY, "%u steps since azb_init_trees exceed max_steps", h->steps_done + n_steps);
     const uint32_t target = h->steps_done + n_steps;
+    if (h->cfg.async_workers && n_steps >= 2 && flags == (AZB_F_ADD | AZB_F_ROLLOUT)) return run_async(h, n_steps);
     if (h->cfg.max_episodes == 0 && n_steps) {
         // Lock-step launches (every tree advances exactly one step per launch).  Groups of trees advance on their own
         // streams: a group's launch only waits for its own slowest tree and its model forward overlaps the other

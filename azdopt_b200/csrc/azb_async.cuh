@@ -1,0 +1,454 @@
+// azb_async.cuh — the asynchronous form of the batched search step: ONE persistent, cooperative kernel in which
+// trees never wait for each other.
+//
+// The reference's step (NablaOptimizer::par_roll_out_episodes, az-discrete-opt/src/nabla/optimizer/mod.rs:121-191) is
+// a barrier: every tree walks until it has one new node, then ONE model call answers all of them.  Trees are
+// independent (each rayon task touches only its own row, :159-189), so the barrier is an artefact of batching the
+// model call, and it costs the GPU dearly: a launch lasts as long as its slowest tree (7-12 episodes) while the
+// average tree needs 1.9 (profiles/README.md).  Here
+//   * a TREE warp owns a fixed set of trees (tree = warp + k * n_warps).  It advances whichever of its trees has its
+//     priors, packs the new state vector into the next free row of a ring of 128-row tiles, and moves on; it polls a
+//     per-tree flag for the answer.  Ownership is static, so a tree's arena is only ever touched through one SM's L1
+//     (no cross-SM staleness inside the kernel); the priors, written by other SMs, are read with ld.cg.
+//   * an MLP worker CTA (one per SM, `n_workers` of them) takes the next full tile, runs the four Linear layers
+//     on the tensor cores (TMA -> 3-stage smem ring -> tcgen05.mma, two TMEM accumulators so the epilogue of one
+//     128-column block overlaps the MMAs of the next; hidden activations round-trip through an L2-resident scratch),
+//     scatters the sigmoid rows to the owning trees' prior rows and raises their flags.  A tile that stays partial
+//     for `flush_ns` is topped up with dummy rows and run anyway (tail of the run, tiny batches).
+// Results are identical to the lock-step path: a tree's walk depends only on its own priors, and a row's forward
+// pass does not depend on which tile it rides in (same K order per dot product).  Per-tree step clocks and the
+// cand[step][tree] table make the argmin pass indifferent to the interleaving.
+// Every spin loop has a watchdog on %globaltimer; on expiry the kernel sets `abort` and drains.
+#pragma once
+#include "azb_mlp_tc.cuh"
+#include "azb_tree.cuh"
+
+#define AS_THREADS 512
+#define AS_WARPS 16
+#define AS_STAGES 3
+#define AS_TILE 128
+#define AS_NONE 0xffffffffu
+
+struct AzbAsyncState {  // device memory, zeroed before every launch
+    uint32_t sm_flag[1024];  // first CTA to arrive on each SM (indexed by %smid)
+    uint32_t mlp_claims, tree_claims;
+    uint32_t row_tail;    // ring slots handed out
+    uint32_t tile_head;   // tile tickets handed to MLP workers
+    uint32_t tiles_done;
+    uint32_t done_trees;
+    uint32_t abort;       // 1 watchdog, 2 tree error
+    uint32_t rows_real, rows_dummy;
+};
+
+struct AzbAsyncMaps {
+    CUtensorMap ring;    // layer-0 input: [NT*128 rows][kpad0] bf16
+    CUtensorMap act[3];  // hidden activations of the workers: [n_workers*128 rows][kpad[l+1]]
+    CUtensorMap w[4];    // weights [rows padded to 128][kpad[l]], box 64 x 128
+};
+
+struct AzbAsyncParams {
+    AzbAsyncState *st;
+    uint32_t *tile_count;  // [NT] rows published into the tile, summed over its generations
+    uint32_t *slot_tree;   // [NT*128] owner of every ring row (AS_NONE = dummy)
+    uint32_t *tile_retired;  // [NT] generations of this ring tile the workers have finished
+    uint32_t *h_flag;      // [B] rows of this tree the model has answered since the launch began
+    uint16_t *ring;        // [NT*128][kpad0]
+    __nv_bfloat16 *act[3];
+    const float *bias[4];
+    uint32_t kpad[4], npad[4];
+    uint32_t NT, n_workers, target_step, smem_words_per_warp, ring_ld;
+    unsigned long long timeout_ns, flush_ns;
+};
+
+__device__ __forceinline__ unsigned long long as_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t as_ld_acquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t as_ld_volatile(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void as_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void as_named_bar(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// MLP worker: warps 0 (TMA producer), 1 (MMA issuer, TMEM owner), 2-5 (epilogue); the CTA's other warps have left.
+__device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
+                                 const uint32_t worker, uint8_t *smem) {
+    __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot, s_tile, s_epi_count;
+    __shared__ uint32_t s_rowtree[AS_TILE];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t MLP_THREADS = 6 * 32;
+    AzbAsyncState *st = P.st;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < AS_STAGES; ++s) {
+            tc_mbar_init(&full_bar[s], 1);
+            tc_mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc_mbar_init(&acc_full[a], 1);
+            tc_mbar_init(&acc_empty[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
+        for (int l = 0; l < 4; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w[l]) : "memory");
+        for (int l = 0; l < 3; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.act[l]) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, MLP_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t stage_bytes = 2u * AS_TILE * TC_BK * 2u;  // A tile + B tile, 16 KB each
+    const unsigned long long t_start = as_now();
+    uint32_t kbc = 0, ntc = 0;  // ring / accumulator counters (each role keeps its own copy in step)
+
+    for (;;) {
+        if (warp == 0 && lane == 0) {
+            // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
+            uint32_t q = atomicAdd(&st->tile_head, 1u);
+            const uint32_t *cnt_p = P.tile_count + (q % P.NT);
+            const uint32_t want = AS_TILE * (q / P.NT + 1u);
+            unsigned long long t_partial = 0;
+            bool flushed = false;
+            for (uint32_t spins = 0;; ++spins) {
+                if (as_ld_acquire(cnt_p) >= want) break;
+                if (as_ld_volatile(&st->abort) || as_ld_volatile(&st->done_trees) >= L.B) {
+                    q = AS_NONE;
+                    break;
+                }
+                const uint32_t tail = as_ld_volatile(&st->row_tail);
+                if (!flushed && tail > q * AS_TILE && tail < (q + 1u) * AS_TILE) {
+                    const unsigned long long now = as_now();
+                    if (t_partial == 0) t_partial = now;
+                    if (now - t_partial > P.flush_ns) {
+                        const uint32_t k = (q + 1u) * AS_TILE - tail;
+                        const uint32_t old = atomicAdd(&st->row_tail, k);
+                        for (uint32_t i = 0; i < k; ++i) P.slot_tree[(old + i) % (P.NT * AS_TILE)] = AS_NONE;
+                        __threadfence();
+                        for (uint32_t i = 0; i < k; ++i) atomicAdd(P.tile_count + (((old + i) / AS_TILE) % P.NT), 1u);
+                        atomicAdd(&st->rows_dummy, k);
+                        flushed = true;
+                    }
+                }
+                __nanosleep(128);
+                if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
+                    atomicExch(&st->abort, 1u);
+                    q = AS_NONE;
+                    break;
+                }
+            }
+            s_tile = q;
+            s_epi_count = 0u;
+        }
+        as_named_bar(1, MLP_THREADS);
+        const uint32_t q = s_tile;
+        if (q == AS_NONE) break;
+        const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
+
+        if (warp == 0) {
+            // ===== TMA producer =====
+            if (lane == 0) {
+                as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
+                uint32_t need = 0;
+                for (uint32_t l = 0; l < 4; ++l) {
+                    const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
+                    if (l > 0) {  // this layer's input is the previous layer's output: wait for all its epilogues
+                        need += 4u * ((P.npad[l - 1] + 127u) / 128u);
+                        while (*((volatile uint32_t *)&s_epi_count) < need) {}
+                        as_fence_proxy_async();
+                    }
+                    const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
+                    const int arow = (int)(l == 0 ? ring_row0 : worker * AS_TILE);
+                    for (uint32_t nt = 0; nt < n_tiles; ++nt)
+                        for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
+                            const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                            tc_mbar_wait(&empty_bar[s], ph ^ 1u);
+                            uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + stage_bytes / 2;
+                            tc_mbar_expect_tx(&full_bar[s], stage_bytes);
+                            tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
+                            tc_tma_load_2d(b_dst, &M.w[l], &full_bar[s], (int)(kb * TC_BK), (int)(nt * 128u));
+                        }
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer =====
+            for (uint32_t l = 0; l < 4; ++l) {
+                const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
+                for (uint32_t nt = 0; nt < n_tiles; ++nt, ++ntc) {
+                    const uint32_t a = ntc & 1u;
+                    tc_mbar_wait(&acc_empty[a], ((ntc >> 1) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
+                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
+                    const uint32_t tmem_d = tmem_base + a * 128u;
+                    for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
+                        const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                        tc_mbar_wait(&full_bar[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (lane == 0) {
+                            const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + stage_bytes / 2;
+#pragma unroll
+                            for (uint32_t k = 0; k < TC_BK / 16; ++k)
+                                tc_umma_f16(tmem_d, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u), idesc,
+                                            (kb | k) != 0u ? 1u : 0u);
+                            tc_umma_commit(&empty_bar[s]);
+                            if (kb + 1 == k_blocks) tc_umma_commit(&acc_full[a]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        } else {
+            // ===== epilogue (warps 2..5): TMEM -> registers -> bias + activation -> scratch / prior rows =====
+            const uint32_t q4 = warp & 3u, row = q4 * 32u + lane;
+            s_rowtree[threadIdx.x - 64u] = __ldcg(P.slot_tree + ring_row0 + (threadIdx.x - 64u));
+            as_named_bar(2, 128);
+            const uint32_t my_tree = s_rowtree[row];
+            for (uint32_t l = 0; l < 4; ++l) {
+                const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
+                const float *bias = P.bias[l];
+                for (uint32_t nt = 0; nt < n_tiles; ++nt, ++ntc) {
+                    const uint32_t a = ntc & 1u;
+                    tc_mbar_wait(&acc_full[a], (ntc >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
+                    for (uint32_t c0 = 0; c0 < bn; c0 += 32) {
+                        uint32_t r[32];
+                        tc_tmem_ld32(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
+                        const uint32_t nb = nt * 128u + c0;
+                        if (l < 3) {
+                            __nv_bfloat16 *dst = P.act[l] + (size_t)(worker * AS_TILE + row) * P.kpad[l + 1] + nb;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    float v0 = __uint_as_float(r[j + 2 * t]) + bias[nb + j + 2 * t];
+                                    float v1 = __uint_as_float(r[j + 2 * t + 1]) + bias[nb + j + 2 * t + 1];
+                                    v0 = v0 > 0.f ? v0 : 0.f;
+                                    v1 = v1 > 0.f ? v1 : 0.f;
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                                    pk[t] = *reinterpret_cast<uint32_t *>(&h2);
+                                }
+                                if (nb + j < P.kpad[l + 1]) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                        } else if (my_tree != AS_NONE) {
+                            float *dst = L.h + (size_t)my_tree * L.h_ld;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const uint32_t n = nb + j;
+                                if (n < L.A) {
+                                    const float v = __uint_as_float(r[j]) + bias[n];
+                                    dst[n] = __fdividef(1.0f, 1.0f + __expf(-v));
+                                }
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
+                    __syncwarp();
+                    if (lane == 0) {
+                        as_mbar_arrive(&acc_empty[a]);
+                        if (l < 3) atomicAdd(&s_epi_count, 1u);
+                    }
+                }
+            }
+            // the tile is answered: make the prior rows visible, then raise the owners' flags
+            __threadfence();
+            as_named_bar(2, 128);
+            if (my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
+            if (threadIdx.x == 64u) {
+                atomicAdd(P.tile_retired + (q % P.NT), 1u);
+                atomicAdd(&st->tiles_done, 1u);
+            }
+        }
+        as_named_bar(1, MLP_THREADS);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, MLP_THREADS);
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tree worker warp: owns trees gw, gw + NW, gw + 2 NW, ... (at most 32: lane k keeps the bookkeeping of tree k).
+template <int DEPTH, bool COUNT>
+__device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, const uint32_t tree_cta,
+                                  const uint32_t n_tree_ctas, uint32_t *smem) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xffffffffu;
+    AzbAsyncState *st = P.st;
+    uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)AS_WARPS * P.smem_words_per_warp);
+    for (uint32_t a = threadIdx.x; 4u * a < L.A; a += blockDim.x)
+        reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
+    __syncthreads();
+    uint32_t *base = smem + (size_t)warp * P.smem_words_per_warp;
+    WarpCtx cx;
+    cx.lane = lane;
+    cx.err = 0;
+    cx.full_count = COUNT;
+    cx.n_ins = cx.n_live = cx.n_noop = 0u;
+    cx.lut = lut;
+    cx.wk = base;
+    cx.par = (uint8_t *)(base + WK_HDR);
+    cx.perm = base + WK_HDR + L.PW;
+    cx.keym = cx.perm + L.W;
+    cx.rpar = (uint8_t *)(cx.keym + L.W);
+    cx.rperm = cx.keym + L.W + L.PW;
+    uint32_t *p = base + ((L.WS + 3u) & ~3u);
+    cx.cur = p;
+    p += 64;
+    cx.pfx = p;
+    p += 64;
+    cx.ct = p;
+    p += 32;
+    cx.lbuf = (float *)p;
+    cx.fr = p;
+    cx.cs = reinterpret_cast<CostScratch *>(p);
+    cx.ct[lane] = 0u;
+    __syncwarp();
+
+    const uint32_t NW = n_tree_ctas * AS_WARPS, gw = tree_cta * AS_WARPS + warp;
+    const uint32_t my_tree = gw + (uint32_t)lane * NW;
+    uint32_t my_state = my_tree < L.B ? 0u : 2u;  // 0 runnable, 1 waiting for priors, 2 done
+    uint32_t my_sub = 0;                          // rows this tree has submitted
+    const unsigned long long t_start = as_now();
+    uint32_t err_tree = 0, idle = 0;
+    const uint32_t ring_rows = P.NT * AS_TILE;
+    for (;;) {
+        if (my_state == 1u && as_ld_acquire(P.h_flag + my_tree) >= my_sub) my_state = 0u;
+        const uint32_t runnable = __ballot_sync(FULL, my_state == 0u);
+        if (__ballot_sync(FULL, my_state != 2u) == 0u) break;
+        if (as_ld_volatile(&st->abort)) break;
+        if (runnable == 0u) {
+            __nanosleep(200);
+            if ((++idle & 1023u) == 0u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+            continue;
+        }
+        const int k = __ffs(runnable) - 1;
+        const uint32_t tree = gw + (uint32_t)k * NW;
+        // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
+        cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
+        cx.blk = L.blk + (size_t)tree * L.cap_blk;
+        cx.blk4 = reinterpret_cast<uint4 *>(cx.blk);
+        cx.inl = L.inl + (size_t)tree * L.cap_in;
+        cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
+        cx.hash = L.hash + (size_t)tree * L.cap_hash;
+        uint32_t *gwk = L.walker + (size_t)tree * L.WS;
+        for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gwk[i];
+        __syncwarp();
+        if (cx.wk[WK_FLAGS] & 1u) tree_add_actions(L, cx, tree);
+        if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) tree_rollout<DEPTH>(L, cx, tree, 0u);
+        uint32_t new_state = 0u;
+        const bool pending = (cx.wk[WK_FLAGS] & 1u) != 0u, at_target = cx.wk[WK_STEP] >= P.target_step;
+        if (cx.err) {
+            new_state = 2u;
+            err_tree = tree;
+        } else if (pending && !at_target) {
+            // the new node needs priors: next ring row
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(&st->row_tail, 1u);
+            slot = __shfl_sync(FULL, slot, 0);
+            // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
+            {
+                const uint32_t q = slot / AS_TILE;
+                while (as_ld_acquire(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
+            }
+            const uint32_t pos = slot % ring_rows;
+            tree_pack(L, cx, tree, P.ring + (size_t)pos * P.ring_ld);
+            if (lane == 0) P.slot_tree[pos] = tree;
+            __threadfence();
+            as_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
+            new_state = 1u;
+        } else if (at_target) {
+            // last step of this launch: the row goes to the tree's own slot; the host runs one batched forward over them
+            if (pending) tree_pack(L, cx, tree);
+            new_state = 2u;
+        }
+        __syncwarp();
+        const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
+        for (uint32_t i = lane; i < live_words; i += 32) gwk[i] = cx.wk[i];
+        if (lane == k) {
+            my_state = new_state;
+            if (new_state == 1u) my_sub += 1u;
+        }
+        if (new_state == 2u && lane == 0) {
+            __threadfence();
+            atomicAdd(&st->done_trees, 1u);
+        }
+        if (cx.err) {
+            if (lane == 0) {
+                if (atomicCAS(&L.g->err, 0u, cx.err) == 0u) {
+                    L.g->err_tree = err_tree;
+                    L.g->err_step = cx.wk[WK_STEP];
+                }
+                atomicExch(&st->abort, 2u);
+            }
+            break;
+        }
+        __syncwarp();
+    }
+    if (lane < 16) {
+        uint32_t v = COUNT ? cx.ct[lane] : 0u;
+        if (lane == CT_INS) v = cx.n_ins;
+        if (lane == CT_LIVE) v = cx.n_live;
+        if (lane == CT_NOOP) v = cx.n_noop;
+        if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
+    }
+    {
+        const uint32_t rows = warp_sum_u32(my_sub);
+        if (lane == 0 && rows) atomicAdd(&st->rows_real, rows);
+    }
+}
+
+template <int DEPTH, bool COUNT>
+__global__ void __launch_bounds__(AS_THREADS, 2)
+    azb_async_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
+    extern __shared__ __align__(1024) uint8_t as_smem[];
+    __shared__ uint32_t s_role, s_idx;
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        uint32_t role = 0, idx = 0;
+        if (atomicCAS(&P.st->sm_flag[smid & 1023u], 0u, 1u) == 0u) {  // first CTA on this SM: may become its MLP worker
+            const uint32_t m = atomicAdd(&P.st->mlp_claims, 1u);
+            if (m < P.n_workers) {
+                role = 1;
+                idx = m;
+            }
+        }
+        if (!role) idx = atomicAdd(&P.st->tree_claims, 1u);
+        s_role = role;
+        s_idx = idx;
+    }
+    __syncthreads();
+    if (s_role) {
+        if (threadIdx.x >= 6 * 32) return;
+        uint8_t *smem = (uint8_t *)(((uintptr_t)as_smem + 1023) & ~(uintptr_t)1023);
+        async_mlp_worker(L, P, M, s_idx, smem);
+    } else {
+        async_tree_worker<DEPTH, COUNT>(L, P, s_idx, gridDim.x - P.n_workers, reinterpret_cast<uint32_t *>(as_smem));
+    }
+}

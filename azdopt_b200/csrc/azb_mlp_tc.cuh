@@ -296,11 +296,13 @@ static inline const char *azb_mlp_tc_create(AzbMlpTc &t, uint32_t rows, const ui
         }
     }
     for (int l = 0; l < 4; ++l) {
-        const size_t abytes = (size_t)t.rows_pad * t.kpad[l] * 2, wbytes = (size_t)t.npad[l] * t.kpad[l] * 2;
+        // weight rows are padded (zeros) to a multiple of 128 so that a 128-row TMA box never leaves the tensor
+        const size_t abytes = (size_t)t.rows_pad * t.kpad[l] * 2, wbytes = (size_t)((t.npad[l] + 127u) / 128u * 128u) * t.kpad[l] * 2;
         if (cudaMalloc((void **)&t.act[l], abytes) != cudaSuccess) return "cudaMalloc (activations) failed";
         if (cudaMalloc((void **)&t.w[l], wbytes) != cudaSuccess) return "cudaMalloc (weights) failed";
         if (cudaMalloc((void **)&t.bias[l], (size_t)t.npad[l] * 4) != cudaSuccess) return "cudaMalloc (bias) failed";
         cudaMemset(t.act[l], 0, abytes);
+        cudaMemset(t.w[l], 0, wbytes);
         if (dev_bytes) *dev_bytes += abytes + wbytes + (size_t)t.npad[l] * 4;
         const char *why = azb_tc_make_map(enc, &t.map_x[l], t.act[l], t.rows_pad, t.kpad[l], TC_BM);
         if (why) return why;

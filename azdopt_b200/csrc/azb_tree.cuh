@@ -150,7 +150,7 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
     const bool hashed = L.prior_mode == 1;
     if (!hashed) {
         const float *hrow = L.h + (size_t)tree * L.h_ld;
-        for (uint32_t a = lane; a < L.A; a += 32) cx.lbuf[a] = hrow[a];
+        for (uint32_t a = lane; a < L.A; a += 32) cx.lbuf[a] = __ldcg(hrow + a);  // written by other SMs in the async kernel
     }
     build_cur_mask(L, cx);
     // legal = permitted minus current edges (space.rs:75-89); counts per word -> exclusive prefix
@@ -691,11 +691,11 @@ __device__ __forceinline__ uint32_t pack_bit(const AzbLayout &L, const WarpCtx &
     const uint32_t word = i < L.A ? cx.cur[j >> 5] : cx.perm[j >> 5];
     return (word >> (j & 31)) & 1u;
 }
-__device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
+__device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint16_t *row_override = nullptr) {
     if (L.sv16) {
         // tensor-core MLP: the row goes out as bf16 (1.0 = 0x3F80), eight entries per 128-bit store; the row pitch is
         // a multiple of 64 entries and the tail beyond 2A stays zero
-        uint16_t *row = L.sv16 + (size_t)tree * L.sv16_ld;
+        uint16_t *row = row_override ? row_override : L.sv16 + (size_t)tree * L.sv16_ld;
         for (uint32_t i = 8u * cx.lane; i < 2 * L.A; i += 256) {
             uint32_t w[4];
 #pragma unroll

@@ -83,7 +83,11 @@ typedef struct azb_config {
                                    episodes and finishes the step in a later launch; same results, shorter launches */
     uint32_t n_groups;          /* >1: the trees of this handle advance as that many independent groups on their own
                                    CUDA streams (needs max_episodes = 0); results are identical, launches overlap */
-    uint32_t reserved[6];
+    uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as ONE persistent kernel in
+                                   which trees never wait for each other — tree warps advance whichever of their trees has
+                                   its priors, that many tensor-core worker CTAs answer state vectors in 128-row tiles as
+                                   they fill.  Same results as the lock step (trees are independent). 0 = lock step. */
+    uint32_t reserved[5];
 } azb_config;
 
 typedef struct azb_counters {   /* workload counters; definitions in oracle/azb_oracle.h and DESIGN.md */
