@@ -62,7 +62,7 @@ struct azb_handle {
     AzbAsyncMaps asM;
     int async_grid;
     size_t async_smem;
-    void *async_bufs[12];
+    void *async_bufs[16];
     // epoch-boundary collectives (NCCL, loaded on demand)
     void *nccl_lib, *nccl_comm;
     int comm_rank, comm_world;
@@ -701,7 +701,9 @@ static int async_create(azb_handle *h) {
     if (!coop) return fail(h, AZB_ERR_CUDA, "cooperative launch not supported");
     const uint32_t W = h->cfg.async_workers, B = h->L.B;
     const size_t tree_smem = (size_t)AS_WARPS * h->smem_words_per_warp * 4 + ((h->A + 15) & ~15u);
-    const size_t mlp_smem = (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2 + 1024;
+    size_t bias_bytes = 0;
+    for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
+    const size_t mlp_smem = (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2 + 1024 + bias_bytes;
     h->async_smem = std::max(tree_smem, mlp_smem);
     int nb = 0, nb2 = 0, rc;
     switch (azb_stack_depth(h->N)) {
@@ -725,6 +727,7 @@ static int async_create(azb_handle *h) {
     P.timeout_ns = 30ull * 1000000000ull;
     P.flush_ns = 4000ull;
     if (const char *e = getenv("AZB_ASYNC_FLUSH_NS")) P.flush_ns = strtoull(e, nullptr, 10);
+    if (const char *e = getenv("AZB_ASYNC_DBG")) P.dbg_flags = (uint32_t)strtoul(e, nullptr, 10);
     for (int l = 0; l < 4; ++l) {
         P.kpad[l] = h->tc.kpad[l];
         P.npad[l] = h->tc.npad[l];
@@ -745,6 +748,7 @@ static int async_create(azb_handle *h) {
     CK(alloc((void **)&P.tile_retired, (size_t)P.NT * 4));
     CK(alloc((void **)&P.slot_tree, (size_t)P.NT * AS_TILE * 4));
     CK(alloc((void **)&P.h_flag, (size_t)B * 4));
+    CK(alloc((void **)&P.dbg, 16 * 8));
     CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
     for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * h->tc.kpad[l + 1] * 2));
     azb_encode_fn enc = nullptr;
@@ -779,6 +783,7 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     CK(cudaMemsetAsync(P.tile_count, 0, (size_t)P.NT * 4, h->stream));
     CK(cudaMemsetAsync(P.tile_retired, 0, (size_t)P.NT * 4, h->stream));
     CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
+    CK(cudaMemsetAsync(P.dbg, 0, 16 * 8, h->stream));
     P.target_step = h->steps_done + n_steps;
     cudaError_t ce;
     switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
@@ -1323,6 +1328,19 @@ extern "C" int azb_debug_tree_prof(azb_handle *h, uint32_t *out4, uint32_t ntree
     return AZB_OK;
 }
 #endif
+
+// cycle counters of the async kernel's MLP workers (last launch) + its row statistics: out[0..14] counters,
+// out[15] = real rows << 32 | dummy rows
+extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {
+    if (!h || !out16 || !h->async_ready) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out16, h->asP.dbg, 16 * 8, cudaMemcpyDeviceToHost));
+    AzbAsyncState st;
+    CK(cudaMemcpy(&st, h->asP.st, sizeof(st), cudaMemcpyDeviceToHost));
+    out16[15] = ((unsigned long long)st.rows_real << 32) | st.rows_dummy;
+    return AZB_OK;
+}
 
 int azb_reset_counters(azb_handle *h) {
     if (!h) return AZB_ERR_INVALID;

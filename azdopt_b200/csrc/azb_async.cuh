@@ -10,7 +10,7 @@
 //     priors, packs the new state vector into the next free row of a ring of 128-row tiles, and moves on; it polls a
 //     per-tree flag for the answer.  Ownership is static, so a tree's arena is only ever touched through one SM's L1
 //     (no cross-SM staleness inside the kernel); the priors, written by other SMs, are read with ld.cg.
-//   * an MLP worker CTA (one per SM, `n_workers` of them) takes the next full tile, runs the four Linear layers
+//   * an MLP worker CTA (a whole SM, `n_workers` of them) takes the next full tile, runs the four Linear layers
 //     on the tensor cores (TMA -> 3-stage smem ring -> tcgen05.mma, two TMEM accumulators so the epilogue of one
 //     128-column block overlaps the MMAs of the next; hidden activations round-trip through an L2-resident scratch),
 //     scatters the sigmoid rows to the owning trees' prior rows and raises their flags.  A tile that stays partial
@@ -23,8 +23,10 @@
 #include "azb_mlp_tc.cuh"
 #include "azb_tree.cuh"
 
-#define AS_THREADS 512
-#define AS_WARPS 16
+#define AS_THREADS 1024
+#define AS_WARPS 32
+#define AS_EPI_WARPS 8   // two per TMEM lane quadrant, each taking half of a 128-column block
+#define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)
 #define AS_STAGES 3
 #define AS_TILE 128
 #define AS_NONE 0xffffffffu
@@ -58,6 +60,8 @@ struct AzbAsyncParams {
     uint32_t kpad[4], npad[4];
     uint32_t NT, n_workers, target_step, smem_words_per_warp, ring_ld;
     unsigned long long timeout_ns, flush_ns;
+    uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
+    unsigned long long *dbg;  // optional [16] cycle counters of the MLP workers (tools/async_probe.py); null = off
 };
 
 __device__ __forceinline__ unsigned long long as_now() {
@@ -84,14 +88,14 @@ __device__ __forceinline__ void as_named_bar(uint32_t id, uint32_t threads) {
 __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// MLP worker: warps 0 (TMA producer), 1 (MMA issuer, TMEM owner), 2-5 (epilogue); the CTA's other warps have left.
+// MLP worker: warps 0 (TMA producer), 1 (MMA issuer, TMEM owner), 2-9 (epilogue); the CTA's other warps have left.
 __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
                                  const uint32_t worker, uint8_t *smem) {
     __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_slot, s_tile, s_epi_count;
     __shared__ uint32_t s_rowtree[AS_TILE];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t MLP_THREADS = 6 * 32;
+    const uint32_t MLP_THREADS = AS_MLP_THREADS;
     AzbAsyncState *st = P.st;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < AS_STAGES; ++s) {
@@ -100,7 +104,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
         }
         for (int a = 0; a < 2; ++a) {
             tc_mbar_init(&acc_full[a], 1);
-            tc_mbar_init(&acc_empty[a], 4);
+            tc_mbar_init(&acc_empty[a], AS_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
@@ -112,6 +116,17 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // all biases into shared memory (behind the operand ring): the epilogue's only global traffic is its output
+    float *s_bias = reinterpret_cast<float *>(smem + (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2);
+    uint32_t bias_off[4];
+    {
+        uint32_t o = 0;
+        for (int l = 0; l < 4; ++l) {
+            bias_off[l] = o;
+            for (uint32_t i = threadIdx.x; i < P.npad[l]; i += MLP_THREADS) s_bias[o + i] = P.bias[l][i];
+            o += (P.npad[l] + 31u) & ~31u;
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     as_named_bar(1, MLP_THREADS);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -119,10 +134,12 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
     const uint32_t stage_bytes = 2u * AS_TILE * TC_BK * 2u;  // A tile + B tile, 16 KB each
     const unsigned long long t_start = as_now();
     uint32_t kbc = 0, ntc = 0;  // ring / accumulator counters (each role keeps its own copy in step)
+    long long d_acq = 0, d_w0 = 0, d_w1 = 0, d_busy = 0, d_tiles = 0;  // debug cycle counters (P.dbg)
 
     for (;;) {
         if (warp == 0 && lane == 0) {
             // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
+            const long long tq0 = clock64();
             uint32_t q = atomicAdd(&st->tile_head, 1u);
             const uint32_t *cnt_p = P.tile_count + (q % P.NT);
             const uint32_t want = AS_TILE * (q / P.NT + 1u);
@@ -157,6 +174,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             }
             s_tile = q;
             s_epi_count = 0u;
+            d_acq += clock64() - tq0;
         }
         as_named_bar(1, MLP_THREADS);
         const uint32_t q = s_tile;
@@ -166,13 +184,17 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
         if (warp == 0) {
             // ===== TMA producer =====
             if (lane == 0) {
+                const long long tt0 = clock64();
+                d_tiles += 1;
                 as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
                 uint32_t need = 0;
                 for (uint32_t l = 0; l < 4; ++l) {
                     const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
                     if (l > 0) {  // this layer's input is the previous layer's output: wait for all its epilogues
-                        need += 4u * ((P.npad[l - 1] + 127u) / 128u);
+                        need += AS_EPI_WARPS * ((P.npad[l - 1] + 127u) / 128u);
+                        const long long tw = clock64();
                         while (*((volatile uint32_t *)&s_epi_count) < need) {}
+                        d_w1 += clock64() - tw;
                         as_fence_proxy_async();
                     }
                     const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
@@ -180,13 +202,16 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     for (uint32_t nt = 0; nt < n_tiles; ++nt)
                         for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                             const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                            const long long tw = clock64();
                             tc_mbar_wait(&empty_bar[s], ph ^ 1u);
+                            d_w0 += clock64() - tw;
                             uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + stage_bytes / 2;
                             tc_mbar_expect_tx(&full_bar[s], stage_bytes);
                             tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
                             tc_tma_load_2d(b_dst, &M.w[l], &full_bar[s], (int)(kb * TC_BK), (int)(nt * 128u));
                         }
                 }
+                d_busy += clock64() - tt0;
             }
         } else if (warp == 1) {
             // ===== MMA issuer =====
@@ -194,14 +219,18 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
                 for (uint32_t nt = 0; nt < n_tiles; ++nt, ++ntc) {
                     const uint32_t a = ntc & 1u;
+                    long long tw = clock64();
                     tc_mbar_wait(&acc_empty[a], ((ntc >> 1) & 1u) ^ 1u);
+                    d_w1 += clock64() - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
                     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
                     const uint32_t tmem_d = tmem_base + a * 128u;
                     for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                        tw = clock64();
                         tc_mbar_wait(&full_bar[s], ph);
+                        d_w0 += clock64() - tw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (lane == 0) {
                             const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + stage_bytes / 2;
@@ -217,22 +246,30 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 }
             }
         } else {
-            // ===== epilogue (warps 2..5): TMEM -> registers -> bias + activation -> scratch / prior rows =====
-            const uint32_t q4 = warp & 3u, row = q4 * 32u + lane;
-            s_rowtree[threadIdx.x - 64u] = __ldcg(P.slot_tree + ring_row0 + (threadIdx.x - 64u));
-            as_named_bar(2, 128);
+            // ===== epilogue (warps 2..9): TMEM -> registers -> bias + activation -> scratch / prior rows =====
+            // warp w reads TMEM lanes 32 (w % 4) ..; the two warps of a quadrant split each 128-column block in halves
+            const uint32_t q4 = warp & 3u, half = (warp - 2u) >> 2, row = q4 * 32u + lane;
+            const uint32_t et = threadIdx.x - 64u;
+            if (et < AS_TILE) s_rowtree[et] = __ldcg(P.slot_tree + ring_row0 + et);
+            as_named_bar(2, AS_EPI_WARPS * 32);
             const uint32_t my_tree = s_rowtree[row];
             for (uint32_t l = 0; l < 4; ++l) {
                 const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
-                const float *bias = P.bias[l];
+                const float *bias = s_bias + bias_off[l];
                 for (uint32_t nt = 0; nt < n_tiles; ++nt, ++ntc) {
                     const uint32_t a = ntc & 1u;
+                    const long long tw = clock64();
                     tc_mbar_wait(&acc_full[a], (ntc >> 1) & 1u);
+                    const long long tb = clock64();
+                    d_w0 += tb - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
-                    for (uint32_t c0 = 0; c0 < bn; c0 += 32) {
+                    for (uint32_t c0 = half * 64u; c0 < min(bn, half * 64u + 64u); c0 += 32) {
                         uint32_t r[32];
-                        tc_tmem_ld32(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
+                        const long long tl0 = clock64();
+                        if (!(P.dbg_flags & 2u)) tc_tmem_ld32(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
+                        else for (int j = 0; j < 32; ++j) r[j] = j + lane;
+                        d_acq += clock64() - tl0;
                         const uint32_t nb = nt * 128u + c0;
                         if (l < 3) {
                             __nv_bfloat16 *dst = P.act[l] + (size_t)(worker * AS_TILE + row) * P.kpad[l + 1] + nb;
@@ -248,7 +285,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                     __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
                                     pk[t] = *reinterpret_cast<uint32_t *>(&h2);
                                 }
-                                if (nb + j < P.kpad[l + 1]) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                if (!(P.dbg_flags & 1u)) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
                         } else if (my_tree != AS_NONE) {
                             float *dst = L.h + (size_t)my_tree * L.h_ld;
@@ -262,25 +299,37 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                             }
                         }
                     }
+                    const long long tf0 = clock64();
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
+                    // the next layer reads this layer's stores through TMA: one cross-proxy fence per layer
+                    if (l < 3 && nt + 1 == n_tiles) as_fence_proxy_async();
                     __syncwarp();
+                    d_w1 += clock64() - tf0;
                     if (lane == 0) {
                         as_mbar_arrive(&acc_empty[a]);
                         if (l < 3) atomicAdd(&s_epi_count, 1u);
                     }
+                    d_busy += clock64() - tb;
                 }
             }
             // the tile is answered: make the prior rows visible, then raise the owners' flags
             __threadfence();
-            as_named_bar(2, 128);
-            if (my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
+            as_named_bar(2, AS_EPI_WARPS * 32);
+            if (half == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
             if (threadIdx.x == 64u) {
                 atomicAdd(P.tile_retired + (q % P.NT), 1u);
                 atomicAdd(&st->tiles_done, 1u);
             }
         }
         as_named_bar(1, MLP_THREADS);
+    }
+    if (P.dbg && lane == 0 && (warp <= 2)) {
+        unsigned long long *d = P.dbg + warp * 5;  // producer: acquire, wait empty, wait layer, tile busy, tiles
+        atomicAdd(d + 0, (unsigned long long)d_acq);   // MMA: -, wait full, wait acc_empty;  epilogue (warp 2): -, wait acc_full, -, busy
+        atomicAdd(d + 1, (unsigned long long)d_w0);
+        atomicAdd(d + 2, (unsigned long long)d_w1);
+        atomicAdd(d + 3, (unsigned long long)d_busy);
+        atomicAdd(d + 4, (unsigned long long)d_tiles);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     as_named_bar(1, MLP_THREADS);
@@ -424,7 +473,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
 }
 
 template <int DEPTH, bool COUNT>
-__global__ void __launch_bounds__(AS_THREADS, 2)
+__global__ void __launch_bounds__(AS_THREADS, 1)
     azb_async_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
     extern __shared__ __align__(1024) uint8_t as_smem[];
     __shared__ uint32_t s_role, s_idx;
@@ -445,7 +494,7 @@ __global__ void __launch_bounds__(AS_THREADS, 2)
     }
     __syncthreads();
     if (s_role) {
-        if (threadIdx.x >= 6 * 32) return;
+        if (threadIdx.x >= AS_MLP_THREADS) return;
         uint8_t *smem = (uint8_t *)(((uintptr_t)as_smem + 1023) & ~(uintptr_t)1023);
         async_mlp_worker(L, P, M, s_idx, smem);
     } else {
