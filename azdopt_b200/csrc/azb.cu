@@ -722,6 +722,9 @@ static int async_create(azb_handle *h) {
     memset(&P, 0, sizeof(P));
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
     P.n_workers = W;
+    P.group = 2;  // worker SMs per tile (profiles/README.md: 2 is robust across arena sizes; 1 is the most SM-efficient)
+    if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
+    if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
     P.smem_words_per_warp = h->smem_words_per_warp;
     P.ring_ld = h->tc.kpad[0];
     P.timeout_ns = 30ull * 1000000000ull;
@@ -748,7 +751,7 @@ static int async_create(azb_handle *h) {
     CK(alloc((void **)&P.tile_retired, (size_t)P.NT * 4));
     CK(alloc((void **)&P.slot_tree, (size_t)P.NT * AS_TILE * 4));
     CK(alloc((void **)&P.h_flag, (size_t)B * 4));
-    CK(alloc((void **)&P.dbg, 16 * 8));
+    CK(alloc((void **)&P.dbg, 24 * 8));
     CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
     for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * h->tc.kpad[l + 1] * 2));
     azb_encode_fn enc = nullptr;
@@ -783,7 +786,7 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     CK(cudaMemsetAsync(P.tile_count, 0, (size_t)P.NT * 4, h->stream));
     CK(cudaMemsetAsync(P.tile_retired, 0, (size_t)P.NT * 4, h->stream));
     CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
-    CK(cudaMemsetAsync(P.dbg, 0, 16 * 8, h->stream));
+    CK(cudaMemsetAsync(P.dbg, 0, 24 * 8, h->stream));
     P.target_step = h->steps_done + n_steps;
     cudaError_t ce;
     switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
@@ -1331,11 +1334,11 @@ extern "C" int azb_debug_tree_prof(azb_handle *h, uint32_t *out4, uint32_t ntree
 
 // cycle counters of the async kernel's MLP workers (last launch) + its row statistics: out[0..14] counters,
 // out[15] = real rows << 32 | dummy rows
-extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {
+extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {  // out: 24 entries
     if (!h || !out16 || !h->async_ready) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out16, h->asP.dbg, 16 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out16, h->asP.dbg, 24 * 8, cudaMemcpyDeviceToHost));
     AzbAsyncState st;
     CK(cudaMemcpy(&st, h->asP.st, sizeof(st), cudaMemcpyDeviceToHost));
     out16[15] = ((unsigned long long)st.rows_real << 32) | st.rows_dummy;

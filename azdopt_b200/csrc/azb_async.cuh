@@ -30,6 +30,12 @@
 #define AS_STAGES 3
 #define AS_TILE 128
 #define AS_NONE 0xffffffffu
+// cycle counters of the workers (tools/async_probe.py): only in the -DAZB_PROFILE flavour
+#ifdef AZB_PROFILE
+#define AS_CLK() clock64()
+#else
+#define AS_CLK() 0ll
+#endif
 
 struct AzbAsyncState {  // device memory, zeroed before every launch
     uint32_t sm_flag[1024];  // first CTA to arrive on each SM (indexed by %smid)
@@ -40,6 +46,8 @@ struct AzbAsyncState {  // device memory, zeroed before every launch
     uint32_t done_trees;
     uint32_t abort;       // 1 watchdog, 2 tree error
     uint32_t rows_real, rows_dummy;
+    // worker groups (AS_MAX_GROUPS): the leader's tile mailbox and the group's monotonic barriers
+    uint32_t grp_seq[64], grp_tile[64], grp_done[64], grp_layer[64 * 4];
 };
 
 struct AzbAsyncMaps {
@@ -58,7 +66,7 @@ struct AzbAsyncParams {
     __nv_bfloat16 *act[3];
     const float *bias[4];
     uint32_t kpad[4], npad[4];
-    uint32_t NT, n_workers, target_step, smem_words_per_warp, ring_ld;
+    uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
     unsigned long long timeout_ns, flush_ns;
     uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
     unsigned long long *dbg;  // optional [16] cycle counters of the MLP workers (tools/async_probe.py); null = off
@@ -84,6 +92,20 @@ __device__ __forceinline__ void as_mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ void as_named_bar(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// TMA load with an L2 eviction-priority hint: the 2.5 MB of weights are re-read by every tile while gigabytes of tree
+// arenas stream through the same L2, so the weight tiles are loaded evict_last
+__device__ __forceinline__ uint64_t as_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void as_tma_load_2d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            tc_smem_u32(dst)),
+        "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
 }
 __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -136,108 +158,132 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
     uint32_t kbc = 0, ntc = 0;  // ring / accumulator counters (each role keeps its own copy in step)
     long long d_acq = 0, d_w0 = 0, d_w1 = 0, d_busy = 0, d_tiles = 0;  // debug cycle counters (P.dbg)
 
+    // A GROUP of G worker SMs answers one tile together: member m computes the 128-column blocks nt = m, m + G, ...
+    // of every layer (a quarter of the weights streams through each SM's shared memory, which is what bounds a
+    // 128-row tile), the hidden activations meet in the group's L2-resident scratch, and the members synchronise at
+    // the three layer boundaries through monotonic counters in global memory.  The leader (m = 0) takes the tile.
+    const uint32_t G = P.group, grp = worker / G, mem = worker % G;
+    uint32_t seq = 0;  // tiles this group has taken
     for (;;) {
         if (warp == 0 && lane == 0) {
-            // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
-            const long long tq0 = clock64();
-            uint32_t q = atomicAdd(&st->tile_head, 1u);
-            const uint32_t *cnt_p = P.tile_count + (q % P.NT);
-            const uint32_t want = AS_TILE * (q / P.NT + 1u);
-            unsigned long long t_partial = 0;
-            bool flushed = false;
-            for (uint32_t spins = 0;; ++spins) {
-                if (as_ld_acquire(cnt_p) >= want) break;
-                if (as_ld_volatile(&st->abort) || as_ld_volatile(&st->done_trees) >= L.B) {
-                    q = AS_NONE;
-                    break;
-                }
-                const uint32_t tail = as_ld_volatile(&st->row_tail);
-                if (!flushed && tail > q * AS_TILE && tail < (q + 1u) * AS_TILE) {
-                    const unsigned long long now = as_now();
-                    if (t_partial == 0) t_partial = now;
-                    if (now - t_partial > P.flush_ns) {
-                        const uint32_t k = (q + 1u) * AS_TILE - tail;
-                        const uint32_t old = atomicAdd(&st->row_tail, k);
-                        for (uint32_t i = 0; i < k; ++i) P.slot_tree[(old + i) % (P.NT * AS_TILE)] = AS_NONE;
-                        __threadfence();
-                        for (uint32_t i = 0; i < k; ++i) atomicAdd(P.tile_count + (((old + i) / AS_TILE) % P.NT), 1u);
-                        atomicAdd(&st->rows_dummy, k);
-                        flushed = true;
+            const long long tq0 = AS_CLK();
+            uint32_t q;
+            if (mem == 0) {
+                // ---- the previous tile must be finished by every member before its scratch is reused
+                while (as_ld_acquire(&st->grp_done[grp]) < G * seq && !as_ld_volatile(&st->abort)) {}
+                // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
+                q = atomicAdd(&st->tile_head, 1u);
+                const uint32_t *cnt_p = P.tile_count + (q % P.NT);
+                const uint32_t want = AS_TILE * (q / P.NT + 1u);
+                unsigned long long t_partial = 0;
+                bool flushed = false;
+                for (uint32_t spins = 0;; ++spins) {
+                    if (as_ld_acquire(cnt_p) >= want) break;
+                    if (as_ld_volatile(&st->abort) || as_ld_volatile(&st->done_trees) >= L.B) {
+                        q = AS_NONE;
+                        break;
+                    }
+                    const uint32_t tail = as_ld_volatile(&st->row_tail);
+                    if (!flushed && tail > q * AS_TILE && tail < (q + 1u) * AS_TILE) {
+                        const unsigned long long now = as_now();
+                        if (t_partial == 0) t_partial = now;
+                        if (now - t_partial > P.flush_ns) {
+                            const uint32_t k = (q + 1u) * AS_TILE - tail;
+                            const uint32_t old = atomicAdd(&st->row_tail, k);
+                            for (uint32_t i = 0; i < k; ++i) P.slot_tree[(old + i) % (P.NT * AS_TILE)] = AS_NONE;
+                            __threadfence();
+                            for (uint32_t i = 0; i < k; ++i) atomicAdd(P.tile_count + (((old + i) / AS_TILE) % P.NT), 1u);
+                            atomicAdd(&st->rows_dummy, k);
+                            flushed = true;
+                        }
+                    }
+                    __nanosleep(64);
+                    if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
+                        atomicExch(&st->abort, 1u);
+                        q = AS_NONE;
+                        break;
                     }
                 }
-                __nanosleep(128);
-                if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
-                    atomicExch(&st->abort, 1u);
-                    q = AS_NONE;
-                    break;
+                st->grp_tile[grp] = q;
+                __threadfence();
+                atomicAdd(&st->grp_seq[grp], 1u);
+            } else {
+                for (uint32_t spins = 0; as_ld_acquire(&st->grp_seq[grp]) <= seq; ++spins) {
+                    if ((spins & 4095u) == 4095u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+                    if (as_ld_volatile(&st->abort)) break;
                 }
+                q = as_ld_volatile(&st->abort) ? AS_NONE : as_ld_volatile(&st->grp_tile[grp]);
             }
             s_tile = q;
-            s_epi_count = 0u;
-            d_acq += clock64() - tq0;
+            d_acq += AS_CLK() - tq0;
         }
         as_named_bar(1, MLP_THREADS);
         const uint32_t q = s_tile;
         if (q == AS_NONE) break;
         const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
+        const uint32_t arrive_target = G * (seq + 1u);  // value of the group's counters once every member has arrived
 
         if (warp == 0) {
             // ===== TMA producer =====
             if (lane == 0) {
-                const long long tt0 = clock64();
+                const long long tt0 = AS_CLK();
                 d_tiles += 1;
+                const uint64_t w_policy = as_policy_evict_last();
                 as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
-                uint32_t need = 0;
                 for (uint32_t l = 0; l < 4; ++l) {
                     const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
-                    if (l > 0) {  // this layer's input is the previous layer's output: wait for all its epilogues
-                        need += AS_EPI_WARPS * ((P.npad[l - 1] + 127u) / 128u);
-                        const long long tw = clock64();
-                        while (*((volatile uint32_t *)&s_epi_count) < need) {}
-                        d_w1 += clock64() - tw;
+                    if (l > 0) {  // this layer's input is the previous layer's output, written by all members
+                        const long long tw = AS_CLK();
+                        while (as_ld_acquire(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
+                        d_w1 += AS_CLK() - tw;
                         as_fence_proxy_async();
                     }
                     const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
-                    const int arow = (int)(l == 0 ? ring_row0 : worker * AS_TILE);
-                    for (uint32_t nt = 0; nt < n_tiles; ++nt)
+                    const int arow = (int)(l == 0 ? ring_row0 : grp * AS_TILE);
+                    for (uint32_t nt = mem; nt < n_tiles; nt += G)
                         for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                             const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
-                            const long long tw = clock64();
+                            const long long tw = AS_CLK();
                             tc_mbar_wait(&empty_bar[s], ph ^ 1u);
-                            d_w0 += clock64() - tw;
+                            d_w0 += AS_CLK() - tw;
                             uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + stage_bytes / 2;
+                            if (P.dbg_flags & 4u) {  // timing experiment: no loads, the MMAs run on stale operands
+                                as_mbar_arrive(&full_bar[s]);
+                                continue;
+                            }
                             tc_mbar_expect_tx(&full_bar[s], stage_bytes);
                             tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
-                            tc_tma_load_2d(b_dst, &M.w[l], &full_bar[s], (int)(kb * TC_BK), (int)(nt * 128u));
+                            as_tma_load_2d_hint(b_dst, &M.w[l], &full_bar[s], (int)(kb * TC_BK), (int)(nt * 128u), w_policy);
                         }
                 }
-                d_busy += clock64() - tt0;
+                d_busy += AS_CLK() - tt0;
             }
         } else if (warp == 1) {
             // ===== MMA issuer =====
             for (uint32_t l = 0; l < 4; ++l) {
                 const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
-                for (uint32_t nt = 0; nt < n_tiles; ++nt, ++ntc) {
+                for (uint32_t nt = mem; nt < n_tiles; nt += G, ++ntc) {
                     const uint32_t a = ntc & 1u;
-                    long long tw = clock64();
+                    long long tw = AS_CLK();
                     tc_mbar_wait(&acc_empty[a], ((ntc >> 1) & 1u) ^ 1u);
-                    d_w1 += clock64() - tw;
+                    d_w1 += AS_CLK() - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
                     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
                     const uint32_t tmem_d = tmem_base + a * 128u;
                     for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
-                        tw = clock64();
+                        tw = AS_CLK();
                         tc_mbar_wait(&full_bar[s], ph);
-                        d_w0 += clock64() - tw;
+                        d_w0 += AS_CLK() - tw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (lane == 0) {
                             const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + stage_bytes / 2;
 #pragma unroll
                             for (uint32_t k = 0; k < TC_BK / 16; ++k)
-                                tc_umma_f16(tmem_d, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u), idesc,
-                                            (kb | k) != 0u ? 1u : 0u);
+                                if (!(P.dbg_flags & 8u))  // timing experiment: loads only
+                                    tc_umma_f16(tmem_d, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u), idesc,
+                                                (kb | k) != 0u ? 1u : 0u);
                             tc_umma_commit(&empty_bar[s]);
                             if (kb + 1 == k_blocks) tc_umma_commit(&acc_full[a]);
                         }
@@ -256,23 +302,23 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             for (uint32_t l = 0; l < 4; ++l) {
                 const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
                 const float *bias = s_bias + bias_off[l];
-                for (uint32_t nt = 0; nt < n_tiles; ++nt, ++ntc) {
+                for (uint32_t nt = mem; nt < n_tiles; nt += G, ++ntc) {
                     const uint32_t a = ntc & 1u;
-                    const long long tw = clock64();
+                    const long long tw = AS_CLK();
                     tc_mbar_wait(&acc_full[a], (ntc >> 1) & 1u);
-                    const long long tb = clock64();
+                    const long long tb = AS_CLK();
                     d_w0 += tb - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
                     for (uint32_t c0 = half * 64u; c0 < min(bn, half * 64u + 64u); c0 += 32) {
                         uint32_t r[32];
-                        const long long tl0 = clock64();
+                        const long long tl0 = AS_CLK();
                         if (!(P.dbg_flags & 2u)) tc_tmem_ld32(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
                         else for (int j = 0; j < 32; ++j) r[j] = j + lane;
-                        d_acq += clock64() - tl0;
+                        d_acq += AS_CLK() - tl0;
                         const uint32_t nb = nt * 128u + c0;
                         if (l < 3) {
-                            __nv_bfloat16 *dst = P.act[l] + (size_t)(worker * AS_TILE + row) * P.kpad[l + 1] + nb;
+                            __nv_bfloat16 *dst = P.act[l] + (size_t)(grp * AS_TILE + row) * P.kpad[l + 1] + nb;
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
                                 uint32_t pk[4];
@@ -299,28 +345,39 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                             }
                         }
                     }
-                    const long long tf0 = clock64();
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    // the next layer reads this layer's stores through TMA: one cross-proxy fence per layer
-                    if (l < 3 && nt + 1 == n_tiles) as_fence_proxy_async();
                     __syncwarp();
-                    d_w1 += clock64() - tf0;
-                    if (lane == 0) {
-                        as_mbar_arrive(&acc_empty[a]);
-                        if (l < 3) atomicAdd(&s_epi_count, 1u);
+                    if (lane == 0) as_mbar_arrive(&acc_empty[a]);
+                    d_busy += AS_CLK() - tb;
+                }
+                // ---- layer boundary: this member's share of the layer is stored; tell the group
+                const long long tf0 = AS_CLK();
+                if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
+                __threadfence();
+                as_named_bar(2, AS_EPI_WARPS * 32);
+                if (threadIdx.x == 64u) {
+                    if (l < 3) {
+                        atomicAdd(&st->grp_layer[grp * 4 + l], 1u);
+                    } else if (atomicAdd(&st->grp_done[grp], 1u) + 1u == arrive_target) {
+                        s_epi_count = 1u;  // this member is the last of the group to finish the tile
+                    } else {
+                        s_epi_count = 0u;
                     }
-                    d_busy += clock64() - tb;
+                }
+                d_w1 += AS_CLK() - tf0;
+            }
+            // the tile is answered once every member is done: the last one raises the owners' flags
+            as_named_bar(2, AS_EPI_WARPS * 32);
+            if (s_epi_count) {
+                __threadfence();
+                if (half == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
+                if (threadIdx.x == 64u) {
+                    atomicAdd(P.tile_retired + (q % P.NT), 1u);
+                    atomicAdd(&st->tiles_done, 1u);
                 }
             }
-            // the tile is answered: make the prior rows visible, then raise the owners' flags
-            __threadfence();
-            as_named_bar(2, AS_EPI_WARPS * 32);
-            if (half == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
-            if (threadIdx.x == 64u) {
-                atomicAdd(P.tile_retired + (q % P.NT), 1u);
-                atomicAdd(&st->tiles_done, 1u);
-            }
         }
+        seq += 1u;
         as_named_bar(1, MLP_THREADS);
     }
     if (P.dbg && lane == 0 && (warp <= 2)) {
@@ -381,6 +438,8 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     const uint32_t my_tree = gw + (uint32_t)lane * NW;
     uint32_t my_state = my_tree < L.B ? 0u : 2u;  // 0 runnable, 1 waiting for priors, 2 done
     uint32_t my_sub = 0;                          // rows this tree has submitted
+    long long my_run = 0;                         // cycles spent advancing this tree (P.dbg)
+    const long long t_k0 = AS_CLK();
     const unsigned long long t_start = as_now();
     uint32_t err_tree = 0, idle = 0;
     const uint32_t ring_rows = P.NT * AS_TILE;
@@ -396,6 +455,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         }
         const int k = __ffs(runnable) - 1;
         const uint32_t tree = gw + (uint32_t)k * NW;
+        const long long t_run0 = AS_CLK();
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
         cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
         cx.blk = L.blk + (size_t)tree * L.cap_blk;
@@ -442,6 +502,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (lane == k) {
             my_state = new_state;
             if (new_state == 1u) my_sub += 1u;
+            my_run += AS_CLK() - t_run0;
         }
         if (new_state == 2u && lane == 0) {
             __threadfence();
@@ -465,6 +526,11 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (lane == CT_LIVE) v = cx.n_live;
         if (lane == CT_NOOP) v = cx.n_noop;
         if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
+    }
+    if (P.dbg && my_tree < L.B) {
+        atomicAdd(P.dbg + 16, (unsigned long long)my_run);
+        atomicMax(P.dbg + 17, (unsigned long long)my_run);
+        if (my_tree == 0) P.dbg[18] = (unsigned long long)(AS_CLK() - t_k0);
     }
     {
         const uint32_t rows = warp_sum_u32(my_sub);

@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--max-episodes", type=int, default=int(os.environ.get("AZB_MAX_EPISODES", "0")))
     ap.add_argument("--groups", type=int, default=int(os.environ.get("AZB_GROUPS", "1")),
                     help="concurrent tree groups per GPU (own CUDA stream each); needs --max-episodes 0")
+    ap.add_argument("--async-workers", type=int, default=int(os.environ.get("AZB_ASYNC_WORKERS", "-1")),
+                    help="tensor-core worker SMs of the asynchronous search kernel; 0 = lock step; -1 = auto")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-baseline-roots", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -188,10 +190,14 @@ def main():
     a = capi.action_dim(n)
     total_steps = args.warmup + args.steps
     prof_steps = min(args.steps, 100)
+    aw = args.async_workers
+    if aw < 0:  # auto: 40 (48 above 4096 roots) of the 148 SMs answer state vectors in pairs, the others walk trees
+        ok = args.mlp == "tc" and not args.max_episodes and args.groups == 1 and b >= 1024
+        aw = (40 if b <= 4096 else 48) if ok else 0
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
                               mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
-                              n_groups=1 if args.max_episodes else args.groups)
+                              n_groups=1 if args.max_episodes else args.groups, async_workers=aw)
     parents, masks = capi.generate_roots(args.seed, rank * b, b, n)
     mlp_note = args.mlp
     try:
@@ -200,6 +206,7 @@ def main():
         if args.mlp != "tc":
             raise
         cfg.mlp_mode = capi.MLP_FP32
+        cfg.async_workers = aw = 0
         h = capi.Handle(cfg)
         mlp_note = f"fp32 (tensor-core path unavailable: {e})"
         args.mlp = "fp32"
@@ -243,27 +250,37 @@ def main():
     noops = allreduce(float(k["n_noop"]), dist.ReduceOp.SUM if world > 1 else None)
     value = sims / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel (the search kernel): per-launch events over a continuation of the run
+    # ---- roofline of the dominant kernel (the search kernel): events over a continuation of the run with all
+    #      workload counters on.  Lock step: one launch per step, per-launch events.  Asynchronous kernel: ONE launch
+    #      runs all prof_steps steps (search + in-kernel model forward), so "per launch" is that whole launch.
     h.reset_counters()
-    tree_ms, mlp_ms = h.step_profile(prof_steps)
-    kp = h.counters()
     hbm_peak, peak_src = _peaks()
-    bytes_per_launch = algorithmic_bytes(kp, n) / prof_steps
-    tree_launch_s = tree_ms * 1e-3 / prof_steps
+    if aw:
+        prof_ms, _ = h.step_timed(prof_steps)
+        kp = h.counters()
+        tree_ms, mlp_ms = prof_ms, 0.0
+        bytes_per_launch = algorithmic_bytes(kp, n)
+        tree_launch_s = prof_ms * 1e-3
+    else:
+        tree_ms, mlp_ms = h.step_profile(prof_steps)
+        kp = h.counters()
+        bytes_per_launch = algorithmic_bytes(kp, n) / prof_steps
+        tree_launch_s = tree_ms * 1e-3 / prof_steps
     achieved = bytes_per_launch / tree_launch_s / 1e9
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full, profiles/)
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tr = json.load(f)
-        if tr.get("roots") == b and tr.get("vertices") == n:
-            traffic = tr["dram_bytes_per_launch"]
+        if tr.get("roots") == b and tr.get("vertices") == n and tr.get("kernel") == ("azb_async_kernel" if aw else "azb_tree_kernel"):
+            traffic = tr["dram_bytes_per_launch"] * (tr.get("steps_per_launch", 1) and prof_steps / tr.get("steps_per_launch", 1) if aw else 1)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "azb_tree_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "azb_async_kernel" if aw else "azb_tree_kernel", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_us": tree_launch_s * 1e6,
-                "mlp_us_per_step": mlp_ms * 1e3 / prof_steps,
-                "tree_share_of_step": tree_ms / max(tree_ms + mlp_ms, 1e-9)}
+                "steps_per_launch": prof_steps if aw else 1,
+                "mlp_us_per_step": None if aw else mlp_ms * 1e3 / prof_steps,
+                "tree_share_of_step": None if aw else tree_ms / max(tree_ms + mlp_ms, 1e-9)}
     dev_bytes = h.device_bytes()
 
     # ---- e2e: a whole epoch through the C ABI with HOST buffers: roots H2D (set_roots), init, K per-step calls each
@@ -274,8 +291,7 @@ def main():
     h2.set_roots(parents, masks)
     h2.init_trees()
     n_live_before = h2.counters()["n_live"]
-    for _ in range(args.steps):
-        h2.step(1, cap=4)
+    n_imp, imp_log = h2.step(args.steps, cap=args.steps)  # the epoch's K steps in one call, improvement log to the host
     am = h2.argmin()
     torch.cuda.synchronize()
     e1 = time.perf_counter()
@@ -284,10 +300,27 @@ def main():
     e2e_sims = allreduce(float(e2e_sims), dist.ReduceOp.SUM if world > 1 else None)
     roots_bytes = parents.nbytes + masks.nbytes
     e2e = {"value": e2e_sims / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": roots_bytes / args.steps + 4,
-           "d2h_bytes_per_step": 40 + 16 + (n + 4 * capi.mask_words(n) + 16) / args.steps,
-           "what": "azb_set_roots(host) + azb_init_trees + K x azb_step(1 step, improvement log to host) + "
-                   "azb_get_argmin(host), wall clock, max over ranks"}
+           "h2d_bytes_per_step": roots_bytes / args.steps,
+           "d2h_bytes_per_step": (48 + 16 * min(n_imp, args.steps) + n + 4 * capi.mask_words(n) + 16) / args.steps,
+           "what": "one epoch through the C ABI with host buffers: azb_set_roots(host roots, H2D) + azb_init_trees + "
+                   "azb_step(K steps, per-step improvement log D2H) + azb_get_argmin(D2H); wall clock, max over ranks"}
+    # the same epoch driven one step per call, like the reference's loop body (04-c21-tree.rs:143): every call
+    # synchronises and reads the step's improvement record back
+    barrier()
+    p0 = time.perf_counter()
+    h2.set_roots(parents, masks)
+    h2.init_trees()
+    n_live_before = h2.counters()["n_live"]
+    for _ in range(args.steps):
+        h2.step(1, cap=4)
+    am1 = h2.argmin()
+    torch.cuda.synchronize()
+    p1 = time.perf_counter()
+    ps_sims = allreduce(float(h2.counters()["n_live"] - n_live_before), dist.ReduceOp.SUM if world > 1 else None)
+    ps_s = allreduce(p1 - p0, dist.ReduceOp.MAX if world > 1 else None)
+    e2e["per_step_calls"] = {"value": ps_sims / ps_s, "unit": UNIT,
+                             "what": "same, K x azb_step(1) (one CUDA-graph launch + sync + read-back per step)",
+                             "same_argmin": bool(am1["eval"] == am["eval"])}
     h.close()
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
@@ -309,6 +342,8 @@ def main():
             "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
                        "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": mlp_note, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
+                       "search": (f"asynchronous persistent kernel: {aw} tensor-core worker SMs + tree warps, one launch per "
+                                  "azb_step call" if aw else "lock step: one search launch + model forward per step"),
                        "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
                        "simulations_in_timed_region": sims, "noop_root_steps": noops,
                        "cost_evals_per_sec": evals / (ms_max * 1e-3)},
