@@ -272,7 +272,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tr = json.load(f)
         if tr.get("roots") == b and tr.get("vertices") == n and tr.get("kernel") == ("azb_async_kernel" if aw else "azb_tree_kernel"):
-            traffic = tr["dram_bytes_per_launch"] * (tr.get("steps_per_launch", 1) and prof_steps / tr.get("steps_per_launch", 1) if aw else 1)
+            traffic = tr["dram_bytes_per_launch"] * (prof_steps / tr.get("steps_per_launch", prof_steps) if aw else 1)
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "azb_async_kernel" if aw else "azb_tree_kernel", "achieved": achieved,
