@@ -700,7 +700,10 @@ static int async_create(azb_handle *h) {
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
     if (!coop) return fail(h, AZB_ERR_CUDA, "cooperative launch not supported");
     const uint32_t W = h->cfg.async_workers, B = h->L.B;
-    const size_t tree_smem = (size_t)AS_WARPS * h->smem_words_per_warp * 4 + ((h->A + 15) & ~15u);
+    // tree warps per CTA: 32, fewer when a large N needs more shared memory per warp (at most ~160 KB per SM, the rest is L1)
+    const size_t lut_bytes = (h->A + 15) & ~15u, per_warp = (size_t)h->smem_words_per_warp * 4;
+    const uint32_t tree_warps = (uint32_t)std::max<size_t>(4, std::min<size_t>(AS_WARPS, (160 * 1024 - lut_bytes) / per_warp));
+    const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
     const size_t mlp_smem = (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2 + 1024 + bias_bytes;
@@ -716,12 +719,13 @@ static int async_create(azb_handle *h) {
     if (nb < 1) return fail(h, AZB_ERR_CUDA, "the async kernel does not fit on an SM (%zu bytes of shared memory)", h->async_smem);
     h->async_grid = nb * prop.multiProcessorCount;
     if ((int)W >= prop.multiProcessorCount || (int)W >= h->async_grid) return fail(h, AZB_ERR_INVALID, "async_workers >= SM count");
-    const uint32_t NW = (uint32_t)(h->async_grid - (int)W) * AS_WARPS;
+    const uint32_t NW = (uint32_t)(h->async_grid - (int)W) * tree_warps;
     if (B > 32u * NW) return fail(h, AZB_ERR_INVALID, "async mode holds at most %u trees per GPU", 32u * NW);
     AzbAsyncParams &P = h->asP;
     memset(&P, 0, sizeof(P));
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
     P.n_workers = W;
+    P.tree_warps = tree_warps;
     P.group = 2;  // worker SMs per tile (profiles/README.md: 2 is robust across arena sizes; 1 is the most SM-efficient)
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);

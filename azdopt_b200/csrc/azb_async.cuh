@@ -38,13 +38,14 @@
 #endif
 
 struct AzbAsyncState {  // device memory, zeroed before every launch
+    uint32_t abort;       // 1 watchdog, 2 tree error.  Polled by every waiting warp: alone in its 128-byte line, away
+    uint32_t pad0[31];    // from the counters the atomics below keep invalidating
     uint32_t sm_flag[1024];  // first CTA to arrive on each SM (indexed by %smid)
     uint32_t mlp_claims, tree_claims;
     uint32_t row_tail;    // ring slots handed out
     uint32_t tile_head;   // tile tickets handed to MLP workers
     uint32_t tiles_done;
     uint32_t done_trees;
-    uint32_t abort;       // 1 watchdog, 2 tree error
     uint32_t rows_real, rows_dummy;
     // worker groups (AS_MAX_GROUPS): the leader's tile mailbox and the group's monotonic barriers
     uint32_t grp_seq[64], grp_tile[64], grp_done[64], grp_layer[64 * 4];
@@ -67,6 +68,7 @@ struct AzbAsyncParams {
     const float *bias[4];
     uint32_t kpad[4], npad[4];
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
+    uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
     unsigned long long timeout_ns, flush_ns;
     uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
     unsigned long long *dbg;  // optional [16] cycle counters of the MLP workers (tools/async_probe.py); null = off
@@ -197,7 +199,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                             flushed = true;
                         }
                     }
-                    __nanosleep(64);
+                    __nanosleep(100);
                     if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
                         atomicExch(&st->abort, 1u);
                         q = AS_NONE;
@@ -404,10 +406,11 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
     AzbAsyncState *st = P.st;
-    uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)AS_WARPS * P.smem_words_per_warp);
+    uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)P.tree_warps * P.smem_words_per_warp);
     for (uint32_t a = threadIdx.x; 4u * a < L.A; a += blockDim.x)
         reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
     __syncthreads();
+    if ((uint32_t)warp >= P.tree_warps) return;
     uint32_t *base = smem + (size_t)warp * P.smem_words_per_warp;
     WarpCtx cx;
     cx.lane = lane;
@@ -434,7 +437,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     cx.ct[lane] = 0u;
     __syncwarp();
 
-    const uint32_t NW = n_tree_ctas * AS_WARPS, gw = tree_cta * AS_WARPS + warp;
+    const uint32_t NW = n_tree_ctas * P.tree_warps, gw = tree_cta * P.tree_warps + warp;
     const uint32_t my_tree = gw + (uint32_t)lane * NW;
     uint32_t my_state = my_tree < L.B ? 0u : 2u;  // 0 runnable, 1 waiting for priors, 2 done
     uint32_t my_sub = 0;                          // rows this tree has submitted
@@ -447,10 +450,12 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (my_state == 1u && as_ld_acquire(P.h_flag + my_tree) >= my_sub) my_state = 0u;
         const uint32_t runnable = __ballot_sync(FULL, my_state == 0u);
         if (__ballot_sync(FULL, my_state != 2u) == 0u) break;
-        if (as_ld_volatile(&st->abort)) break;
-        if (runnable == 0u) {
+        if (runnable == 0u) {  // every tree of this warp waits for its priors (the round trip is tens of microseconds)
             __nanosleep(200);
-            if ((++idle & 1023u) == 0u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+            if ((++idle & 31u) == 0u) {
+                if (as_ld_volatile(&st->abort)) break;
+                if ((idle & 2047u) == 0u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+            }
             continue;
         }
         const int k = __ffs(runnable) - 1;

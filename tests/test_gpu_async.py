@@ -26,7 +26,7 @@ def _same(ha, hb, b):
     assert ha.counters() == hb.counters()
 
 
-@pytest.mark.parametrize("n,b,workers", [(19, 300, 4), (19, 1024, 8), (12, 77, 4), (33, 160, 4)])
+@pytest.mark.parametrize("n,b,workers", [(19, 300, 4), (19, 1024, 8), (12, 77, 4), (33, 160, 4), (64, 96, 4)])
 def test_async_equals_lock_step(capi, n, b, workers):
     steps = 36
     parents, masks = capi.generate_roots(5, 0, b, n)
