@@ -441,13 +441,17 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     const uint32_t my_tree = gw + (uint32_t)lane * NW;
     uint32_t my_state = my_tree < L.B ? 0u : 2u;  // 0 runnable, 1 waiting for priors, 2 done
     uint32_t my_sub = 0;                          // rows this tree has submitted
-    long long my_run = 0;                         // cycles spent advancing this tree (P.dbg)
+    uint32_t my_steps = 0;                        // times this tree has been advanced
+    long long my_run = 0, my_wait = 0, my_t0 = 0;  // cycles spent advancing this tree / waiting for its priors (P.dbg)
     const long long t_k0 = AS_CLK();
     const unsigned long long t_start = as_now();
     uint32_t err_tree = 0, idle = 0;
     const uint32_t ring_rows = P.NT * AS_TILE;
     for (;;) {
-        if (my_state == 1u && as_ld_acquire(P.h_flag + my_tree) >= my_sub) my_state = 0u;
+        if (my_state == 1u && as_ld_acquire(P.h_flag + my_tree) >= my_sub) {
+            my_state = 0u;
+            my_wait += AS_CLK() - my_t0;
+        }
         const uint32_t runnable = __ballot_sync(FULL, my_state == 0u);
         if (__ballot_sync(FULL, my_state != 2u) == 0u) break;
         if (runnable == 0u) {  // every tree of this warp waits for its priors (the round trip is tens of microseconds)
@@ -458,7 +462,9 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
             }
             continue;
         }
-        const int k = __ffs(runnable) - 1;
+        // among this warp's runnable trees take the one that is furthest behind: the run ends when its slowest tree does
+        const uint32_t behind = __reduce_min_sync(FULL, my_state == 0u ? my_steps : 0xffffffffu);
+        const int k = __ffs(__ballot_sync(FULL, my_state == 0u && my_steps == behind)) - 1;
         const uint32_t tree = gw + (uint32_t)k * NW;
         const long long t_run0 = AS_CLK();
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
@@ -507,7 +513,9 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (lane == k) {
             my_state = new_state;
             if (new_state == 1u) my_sub += 1u;
-            my_run += AS_CLK() - t_run0;
+            my_steps += 1u;
+            my_t0 = AS_CLK();
+            my_run += my_t0 - t_run0;
         }
         if (new_state == 2u && lane == 0) {
             __threadfence();
@@ -535,6 +543,9 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     if (P.dbg && my_tree < L.B) {
         atomicAdd(P.dbg + 16, (unsigned long long)my_run);
         atomicMax(P.dbg + 17, (unsigned long long)my_run);
+        atomicAdd(P.dbg + 19, (unsigned long long)my_wait);
+        atomicMax(P.dbg + 20, (unsigned long long)my_wait);
+        atomicMax(P.dbg + 21, (unsigned long long)(my_wait + my_run));
         if (my_tree == 0) P.dbg[18] = (unsigned long long)(AS_CLK() - t_k0);
     }
     {

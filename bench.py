@@ -228,7 +228,20 @@ def main():
     # ---- device-resident timing: inputs in HBM, W warm-up steps, K timed steps
     h.set_roots(parents, masks)
     h.init_trees()
-    h.step(args.warmup)
+    try:
+        h.step(args.warmup)
+    except capi.AzbError as e:
+        if not aw:
+            raise
+        # the persistent kernel could not run here (e.g. no cooperative launch): same path, lock-step launches
+        sys.stderr.write(f"bench: asynchronous kernel unavailable ({e}); falling back to the lock step\n")
+        h.close()
+        cfg.async_workers = aw = 0
+        h = capi.Handle(cfg)
+        h.mlp_init(args.seed + 1)
+        h.set_roots(parents, masks)
+        h.init_trees()
+        h.step(args.warmup)
     h.reset_counters()
     h.set_counter_mode(False)  # timed pass: only n_live / n_noop / n_ins are counted
     launches0 = h.kernel_launches()

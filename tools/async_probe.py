@@ -36,4 +36,5 @@ for w in workers:
                   f"MMA wait-full {us(d[6]):6.1f} wait-acc {us(d[7]):6.1f} | epilogue wait-acc {us(d[11]):6.1f} busy {us(d[13]):6.1f} (tmem-ld {us(d[10]):6.1f} fence {us(d[12]):6.1f}) | "
                   f"tiles {d[4]} rows real {d[15] >> 32} dummy {d[15] & 0xffffffff}", flush=True)
             print(f"      trees: kernel {d[18]/1965e3:.1f} ms; cycles advancing a tree: mean {d[16]/b/1965e3:.1f} ms, max {d[17]/1965e3:.1f} ms "
-                  f"(per step: mean {d[16]/b/steps/1965:.1f} us, slowest tree {d[17]/steps/1965:.1f} us)", flush=True)
+                  f"(per step: mean {d[16]/b/steps/1965:.1f} us, slowest tree {d[17]/steps/1965:.1f} us); waiting for priors per step: "
+                  f"mean {d[19]/b/steps/1965:.1f} us, max tree {d[20]/steps/1965:.1f} us; max (run+wait) {d[21]/1965e3:.1f} ms", flush=True)
