@@ -67,3 +67,45 @@ def test_async_then_training_and_reset(capi):
         assert out[0] == out[1]
         assert np.array_equal(lock.mlp_get_params(), asy.mlp_get_params())
         _same(lock, asy, b)
+
+
+@pytest.mark.parametrize("b", [1, 129])
+def test_async_ragged_batch_sizes(capi, b):
+    """One root, and one more than a tile: partial tiles are flushed with dummy rows, nothing hangs, same trees."""
+    n, steps = 19, 25
+    parents, masks = capi.generate_roots(2, 0, b, n)
+    kw = dict(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=steps)
+    with _mk(capi, n, b, **kw) as lock, _mk(capi, n, b, async_workers=2, **kw) as asy:
+        for h in (lock, asy):
+            h.mlp_init(9)
+            h.set_roots(parents, masks)
+            h.init_trees()
+            h.step(steps)
+        _same(lock, asy, b)
+
+
+def test_async_reports_capacity_overflow_instead_of_hanging(capi):
+    """A tree that overflows its arena inside the persistent kernel raises the abort flag: every spin loop drains and
+    the call returns AZB_ERR_CAPACITY (the lock step reports the same error)."""
+    n, b = 19, 200
+    parents, masks = capi.generate_roots(3, 0, b, n)
+    for workers in (0, 4):
+        with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=200, cap_nodes=24,
+                 async_workers=workers) as h:
+            h.mlp_init(1)
+            h.set_roots(parents, masks)
+            h.init_trees()
+            with pytest.raises(capi.AzbError) as e:
+                h.step(150)
+            assert e.value.code == capi.ERR_CAPACITY
+
+
+def test_async_needs_the_tensor_core_model(capi):
+    n, b = 19, 64
+    parents, masks = capi.generate_roots(3, 0, b, n)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_HASH, async_workers=4, max_steps=20) as h:
+        h.set_roots(parents, masks)
+        h.init_trees()
+        with pytest.raises(capi.AzbError) as e:
+            h.step(10)
+        assert e.value.code == capi.ERR_INVALID
