@@ -29,12 +29,17 @@
 #define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)
 #define AS_STAGES 3
 #define AS_TILE 128
+#ifndef AS_COMMIT_PAIRS
+#define AS_COMMIT_PAIRS 0
+#endif
 #define AS_NONE 0xffffffffu
 // cycle counters of the workers (tools/async_probe.py): only in the -DAZB_PROFILE flavour
 #ifdef AZB_PROFILE
 #define AS_CLK() clock64()
+#define AS_DBG(bit) ((P.dbg_flags & (bit)) != 0u)  // timing experiments (AZB_ASYNC_DBG): profile flavour only
 #else
 #define AS_CLK() 0ll
+#define AS_DBG(bit) false
 #endif
 
 struct AzbAsyncState {  // device memory, zeroed before every launch
@@ -92,6 +97,22 @@ __device__ __forceinline__ uint32_t as_ld_volatile(const uint32_t *p) {
 __device__ __forceinline__ void as_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
+// spin on test_wait (no suspend): the worker owns its SM, and try_wait's suspend/wake-up costs more than the
+// wait itself at this granularity (one barrier round trip per 64-deep k-block)
+__device__ __forceinline__ void as_mbar_spin(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(tc_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void as_named_bar(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -108,6 +129,15 @@ __device__ __forceinline__ void as_tma_load_2d_hint(void *dst, const CUtensorMap
             tc_smem_u32(dst)),
         "l"(map), "r"(tc_smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
+}
+__device__ __forceinline__ void as_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -224,6 +254,22 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
         if (q == AS_NONE) break;
         const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
         const uint32_t arrive_target = G * (seq + 1u);  // value of the group's counters once every member has arrived
+        if (AS_DBG(16u)) {  // timing experiment: answer the tile at once with whatever the prior rows hold
+            if (warp >= 2) {
+                const uint32_t et = threadIdx.x - 64u;
+                if (mem == 0 && et < AS_TILE) {
+                    const uint32_t t = __ldcg(P.slot_tree + ring_row0 + et);
+                    if (t != AS_NONE) atomicAdd(P.h_flag + t, 1u);
+                }
+                if (threadIdx.x == 64u) {
+                    if (mem == 0) atomicAdd(P.tile_retired + (q % P.NT), 1u);
+                    atomicAdd(&st->grp_done[grp], 1u);
+                }
+            }
+            seq += 1u;
+            as_named_bar(1, MLP_THREADS);
+            continue;
+        }
 
         if (warp == 0) {
             // ===== TMA producer =====
@@ -246,10 +292,10 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                         for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                             const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
                             const long long tw = AS_CLK();
-                            tc_mbar_wait(&empty_bar[s], ph ^ 1u);
+                            as_mbar_spin(&empty_bar[s], ph ^ 1u);
                             d_w0 += AS_CLK() - tw;
                             uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + stage_bytes / 2;
-                            if (P.dbg_flags & 4u) {  // timing experiment: no loads, the MMAs run on stale operands
+                            if (AS_DBG(4u)) {  // timing experiment: no loads, the MMAs run on stale operands
                                 as_mbar_arrive(&full_bar[s]);
                                 continue;
                             }
@@ -267,7 +313,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 for (uint32_t nt = mem; nt < n_tiles; nt += G, ++ntc) {
                     const uint32_t a = ntc & 1u;
                     long long tw = AS_CLK();
-                    tc_mbar_wait(&acc_empty[a], ((ntc >> 1) & 1u) ^ 1u);
+                    as_mbar_spin(&acc_empty[a], ((ntc >> 1) & 1u) ^ 1u);
                     d_w1 += AS_CLK() - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
@@ -276,17 +322,25 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
                         tw = AS_CLK();
-                        tc_mbar_wait(&full_bar[s], ph);
+                        as_mbar_spin(&full_bar[s], ph);
                         d_w0 += AS_CLK() - tw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (lane == 0) {
                             const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + stage_bytes / 2;
 #pragma unroll
                             for (uint32_t k = 0; k < TC_BK / 16; ++k)
-                                if (!(P.dbg_flags & 8u))  // timing experiment: loads only
+                                if (!AS_DBG(8u))  // timing experiment: loads only
                                     tc_umma_f16(tmem_d, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u), idesc,
                                                 (kb | k) != 0u ? 1u : 0u);
+#if AS_COMMIT_PAIRS
+                            // release ring slots two at a time: 8 MMAs go out back to back between commits
+                            if ((kb & 1u) || kb + 1 == k_blocks) {
+                                if (kb & 1u) tc_umma_commit(&empty_bar[(kbc - 1u) % AS_STAGES]);
+                                tc_umma_commit(&empty_bar[s]);
+                            }
+#else
                             tc_umma_commit(&empty_bar[s]);
+#endif
                             if (kb + 1 == k_blocks) tc_umma_commit(&acc_full[a]);
                         }
                         __syncwarp();
@@ -307,42 +361,62 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 for (uint32_t nt = mem; nt < n_tiles; nt += G, ++ntc) {
                     const uint32_t a = ntc & 1u;
                     const long long tw = AS_CLK();
-                    tc_mbar_wait(&acc_full[a], (ntc >> 1) & 1u);
+                    as_mbar_spin(&acc_full[a], (ntc >> 1) & 1u);
                     const long long tb = AS_CLK();
                     d_w0 += tb - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
-                    for (uint32_t c0 = half * 64u; c0 < min(bn, half * 64u + 64u); c0 += 32) {
-                        uint32_t r[32];
+                    // 16 columns at a time: the accumulator slice and its biases (four 128-bit shared-memory loads issued
+                    // together) stay inside the 64-register budget, so nothing serialises on shared-memory latency
+                    for (uint32_t c0 = half * 64u; c0 < min(bn, half * 64u + 64u); c0 += 16) {
+                        uint32_t r[16];
                         const long long tl0 = AS_CLK();
-                        if (!(P.dbg_flags & 2u)) tc_tmem_ld32(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
-                        else for (int j = 0; j < 32; ++j) r[j] = j + lane;
+                        as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
                         d_acq += AS_CLK() - tl0;
                         const uint32_t nb = nt * 128u + c0;
+                        float b[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4 *>(bias + nb + j);
+                            b[j] = b4.x;
+                            b[j + 1] = b4.y;
+                            b[j + 2] = b4.z;
+                            b[j + 3] = b4.w;
+                        }
                         if (l < 3) {
                             __nv_bfloat16 *dst = P.act[l] + (size_t)(grp * AS_TILE + row) * P.kpad[l + 1] + nb;
+                            uint32_t pk[8];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    float v0 = __uint_as_float(r[j + 2 * t]) + bias[nb + j + 2 * t];
-                                    float v1 = __uint_as_float(r[j + 2 * t + 1]) + bias[nb + j + 2 * t + 1];
-                                    v0 = v0 > 0.f ? v0 : 0.f;
-                                    v1 = v1 > 0.f ? v1 : 0.f;
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-                                    pk[t] = *reinterpret_cast<uint32_t *>(&h2);
-                                }
-                                if (!(P.dbg_flags & 1u)) *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            for (int t = 0; t < 8; ++t) {
+                                float v0 = __uint_as_float(r[2 * t]) + b[2 * t];
+                                float v1 = __uint_as_float(r[2 * t + 1]) + b[2 * t + 1];
+                                v0 = v0 > 0.f ? v0 : 0.f;
+                                v1 = v1 > 0.f ? v1 : 0.f;
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                                pk[t] = *reinterpret_cast<uint32_t *>(&h2);
+                            }
+                            if (!AS_DBG(1u)) {
+                                *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                *reinterpret_cast<uint4 *>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                             }
                         } else if (my_tree != AS_NONE) {
                             float *dst = L.h + (size_t)my_tree * L.h_ld;
+                            const bool vec = (L.h_ld & 3u) == 0u;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
+                            for (int j = 0; j < 16; j += 4) {
+                                float o[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    const float v = __uint_as_float(r[j + t]) + b[j + t];
+                                    o[t] = __fdividef(1.0f, 1.0f + __expf(-v));
+                                }
                                 const uint32_t n = nb + j;
-                                if (n < L.A) {
-                                    const float v = __uint_as_float(r[j]) + bias[n];
-                                    dst[n] = __fdividef(1.0f, 1.0f + __expf(-v));
+                                if (vec && n + 3u < L.A) {
+                                    *reinterpret_cast<float4 *>(dst + n) = make_float4(o[0], o[1], o[2], o[3]);
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t)
+                                        if (n + t < L.A) dst[n + t] = o[t];
                                 }
                             }
                         }

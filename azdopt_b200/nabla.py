@@ -185,6 +185,19 @@ class NablaOptimizer:
             raise TypeError("device-side root re-selection needs the device model (priors of the new roots)")
         self.h.reset_trees(seed, lo, hi)
 
+    # ---- the example's on-disk outputs (04-c21-tree.rs:118-123,153-157; azdopt_b200/observe.py)
+    def argmin_graph6(self) -> bytes:
+        """graph6 of the best tree found so far (connected_bitset_graph/graph6.rs:11-39)."""
+        from . import observe
+
+        return observe.graph6_of_state(self.argmin_data().parents)
+
+    def tree_dot(self, i: int) -> str:
+        """Graphviz DOT of search DAG `i` with the reference's labels (nabla/tree/graphviz.rs:9-51)."""
+        from . import observe
+
+        return observe.search_tree_dot(self.h.dump_tree(i))
+
     def get_trees(self):  # optimizer/mod.rs:34-36, as canonical dumps
         return [self.h.dump_tree(i) for i in range(self.batch)]
 
