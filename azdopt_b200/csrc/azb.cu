@@ -706,7 +706,7 @@ static int async_create(azb_handle *h) {
     const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
-    const size_t mlp_smem = (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2 + 1024 + bias_bytes;
+    const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes;
     h->async_smem = std::max(tree_smem, mlp_smem);
     int nb = 0, nb2 = 0, rc;
     switch (azb_stack_depth(h->N)) {
@@ -726,7 +726,8 @@ static int async_create(azb_handle *h) {
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
     P.n_workers = W;
     P.tree_warps = tree_warps;
-    P.group = 2;  // worker SMs per tile (profiles/README.md: 2 is robust across arena sizes; 1 is the most SM-efficient)
+    // worker SMs per tile: one when few SMs serve the model (every tree keeps its own warp at 4096 roots), pairs otherwise
+    P.group = W <= 24 ? 1 : 2;
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
     P.smem_words_per_warp = h->smem_words_per_warp;

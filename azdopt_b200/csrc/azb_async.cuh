@@ -27,11 +27,9 @@
 #define AS_WARPS 32
 #define AS_EPI_WARPS 8   // two per TMEM lane quadrant, each taking half of a 128-column block
 #define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)
-#define AS_STAGES 3
+#define AS_STAGES 2
+#define AS_ACC 4          // 128-column blocks per pass: one A k-block is reused by up to four TMEM accumulators
 #define AS_TILE 128
-#ifndef AS_COMMIT_PAIRS
-#define AS_COMMIT_PAIRS 0
-#endif
 #define AS_NONE 0xffffffffu
 // cycle counters of the workers (tools/async_probe.py): only in the -DAZB_PROFILE flavour
 #ifdef AZB_PROFILE
@@ -145,7 +143,7 @@ __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.pro
 // MLP worker: warps 0 (TMA producer), 1 (MMA issuer, TMEM owner), 2-9 (epilogue); the CTA's other warps have left.
 __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
                                  const uint32_t worker, uint8_t *smem) {
-    __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full, acc_empty;
     __shared__ uint32_t tmem_slot, s_tile, s_epi_count;
     __shared__ uint32_t s_rowtree[AS_TILE];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,22 +154,20 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             tc_mbar_init(&full_bar[s], 1);
             tc_mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            tc_mbar_init(&acc_full[a], 1);
-            tc_mbar_init(&acc_empty[a], AS_EPI_WARPS);
-        }
+        tc_mbar_init(&acc_full, 1);
+        tc_mbar_init(&acc_empty, AS_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
         for (int l = 0; l < 4; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w[l]) : "memory");
         for (int l = 0; l < 3; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.act[l]) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(256u)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // all biases into shared memory (behind the operand ring): the epilogue's only global traffic is its output
-    float *s_bias = reinterpret_cast<float *>(smem + (size_t)AS_STAGES * 2 * AS_TILE * TC_BK * 2);
+    float *s_bias = reinterpret_cast<float *>(smem + (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2);
     uint32_t bias_off[4];
     {
         uint32_t o = 0;
@@ -185,9 +181,10 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
     as_named_bar(1, MLP_THREADS);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t stage_bytes = 2u * AS_TILE * TC_BK * 2u;  // A tile + B tile, 16 KB each
+    const uint32_t tile_bytes = AS_TILE * TC_BK * 2u;             // one 128 x 64 bf16 operand tile, 16 KB
+    const uint32_t stage_bytes = (1u + AS_ACC) * tile_bytes;      // [A | B0 | B1 | B2 | B3]
     const unsigned long long t_start = as_now();
-    uint32_t kbc = 0, ntc = 0;  // ring / accumulator counters (each role keeps its own copy in step)
+    uint32_t kbc = 0, ntc = 0;  // ring stage / pass counters (each role keeps its own copy in step)
     long long d_acq = 0, d_w0 = 0, d_w1 = 0, d_busy = 0, d_tiles = 0;  // debug cycle counters (P.dbg)
 
     // A GROUP of G worker SMs answers one tile together: member m computes the 128-column blocks nt = m, m + G, ...
@@ -288,21 +285,28 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     }
                     const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
                     const int arow = (int)(l == 0 ? ring_row0 : grp * AS_TILE);
-                    for (uint32_t nt = mem; nt < n_tiles; nt += G)
+                    // this member's blocks nt = mem, mem + G, ... in passes of up to AS_ACC: per k-block ONE A tile and the
+                    // pass's B tiles, so a tile's activations are read once per pass instead of once per block
+                    const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
+                    for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC) {
+                        const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                         for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                             const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
                             const long long tw = AS_CLK();
                             as_mbar_spin(&empty_bar[s], ph ^ 1u);
                             d_w0 += AS_CLK() - tw;
-                            uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + stage_bytes / 2;
+                            uint8_t *a_dst = smem + (size_t)s * stage_bytes;
                             if (AS_DBG(4u)) {  // timing experiment: no loads, the MMAs run on stale operands
                                 as_mbar_arrive(&full_bar[s]);
                                 continue;
                             }
-                            tc_mbar_expect_tx(&full_bar[s], stage_bytes);
+                            tc_mbar_expect_tx(&full_bar[s], (1u + np) * tile_bytes);
                             tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
-                            as_tma_load_2d_hint(b_dst, &M.w[l], &full_bar[s], (int)(kb * TC_BK), (int)(nt * 128u), w_policy);
+                            for (uint32_t j = 0; j < np; ++j)
+                                as_tma_load_2d_hint(a_dst + (1u + j) * tile_bytes, &M.w[l], &full_bar[s], (int)(kb * TC_BK),
+                                                    (int)((mem + (p0 + j) * G) * 128u), w_policy);
                         }
+                    }
                 }
                 d_busy += AS_CLK() - tt0;
             }
@@ -310,15 +314,13 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             // ===== MMA issuer =====
             for (uint32_t l = 0; l < 4; ++l) {
                 const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
-                for (uint32_t nt = mem; nt < n_tiles; nt += G, ++ntc) {
-                    const uint32_t a = ntc & 1u;
+                const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
+                for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
+                    const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                     long long tw = AS_CLK();
-                    as_mbar_spin(&acc_empty[a], ((ntc >> 1) & 1u) ^ 1u);
+                    as_mbar_spin(&acc_empty, (ntc & 1u) ^ 1u);  // the epilogue has drained the previous pass
                     d_w1 += AS_CLK() - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
-                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
-                    const uint32_t tmem_d = tmem_base + a * 128u;
                     for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
                         tw = AS_CLK();
@@ -326,22 +328,20 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                         d_w0 += AS_CLK() - tw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (lane == 0) {
-                            const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + stage_bytes / 2;
+                            const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes);
+                            for (uint32_t j = 0; j < np; ++j) {
+                                const uint32_t nt = mem + (p0 + j) * G;
+                                const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
+                                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
+                                const uint32_t b_addr = a_addr + (1u + j) * tile_bytes;
 #pragma unroll
-                            for (uint32_t k = 0; k < TC_BK / 16; ++k)
-                                if (!AS_DBG(8u))  // timing experiment: loads only
-                                    tc_umma_f16(tmem_d, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u), idesc,
-                                                (kb | k) != 0u ? 1u : 0u);
-#if AS_COMMIT_PAIRS
-                            // release ring slots two at a time: 8 MMAs go out back to back between commits
-                            if ((kb & 1u) || kb + 1 == k_blocks) {
-                                if (kb & 1u) tc_umma_commit(&empty_bar[(kbc - 1u) % AS_STAGES]);
-                                tc_umma_commit(&empty_bar[s]);
+                                for (uint32_t k = 0; k < TC_BK / 16; ++k)
+                                    if (!AS_DBG(8u))  // timing experiment: loads only
+                                        tc_umma_f16(tmem_base + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
+                                                    idesc, (kb | k) != 0u ? 1u : 0u);
                             }
-#else
                             tc_umma_commit(&empty_bar[s]);
-#endif
-                            if (kb + 1 == k_blocks) tc_umma_commit(&acc_full[a]);
+                            if (kb + 1 == k_blocks) tc_umma_commit(&acc_full);
                         }
                         __syncwarp();
                     }
@@ -358,20 +358,23 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             for (uint32_t l = 0; l < 4; ++l) {
                 const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
                 const float *bias = s_bias + bias_off[l];
-                for (uint32_t nt = mem; nt < n_tiles; nt += G, ++ntc) {
-                    const uint32_t a = ntc & 1u;
-                    const long long tw = AS_CLK();
-                    as_mbar_spin(&acc_full[a], (ntc >> 1) & 1u);
-                    const long long tb = AS_CLK();
-                    d_w0 += tb - tw;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
+                for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
+                  const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
+                  const long long tw = AS_CLK();
+                  as_mbar_spin(&acc_full, ntc & 1u);
+                  const long long tb = AS_CLK();
+                  d_w0 += tb - tw;
+                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                  for (uint32_t ja = 0; ja < np; ++ja) {
+                    const uint32_t nt = mem + (p0 + ja) * G;
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
                     // 16 columns at a time: the accumulator slice and its biases (four 128-bit shared-memory loads issued
                     // together) stay inside the 64-register budget, so nothing serialises on shared-memory latency
                     for (uint32_t c0 = half * 64u; c0 < min(bn, half * 64u + 64u); c0 += 16) {
                         uint32_t r[16];
                         const long long tl0 = AS_CLK();
-                        as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + a * 128u + c0, r);
+                        as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + ja * 128u + c0, r);
                         d_acq += AS_CLK() - tl0;
                         const uint32_t nb = nt * 128u + c0;
                         float b[16];
@@ -421,10 +424,11 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                             }
                         }
                     }
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) as_mbar_arrive(&acc_empty[a]);
-                    d_busy += AS_CLK() - tb;
+                  }
+                  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                  __syncwarp();
+                  if (lane == 0) as_mbar_arrive(&acc_empty);
+                  d_busy += AS_CLK() - tb;
                 }
                 // ---- layer boundary: this member's share of the layer is stored; tell the group
                 const long long tf0 = AS_CLK();
@@ -468,7 +472,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
     as_named_bar(1, MLP_THREADS);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 

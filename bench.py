@@ -191,9 +191,10 @@ def main():
     total_steps = args.warmup + args.steps
     prof_steps = min(args.steps, 100)
     aw = args.async_workers
-    if aw < 0:  # auto: 40 (48 above 4096 roots) of the 148 SMs answer state vectors in pairs, the others walk trees
-        ok = args.mlp == "tc" and not args.max_episodes and args.groups == 1 and b >= 1024
-        aw = (40 if b <= 4096 else 48) if ok else 0
+    if aw < 0:  # auto: 20 of the 148 SMs answer state vectors (128 x 32 warps walk: one tree per warp at 4096 roots);
+        # above 4096 roots 48 SMs in pairs
+        ok = args.mlp == "tc" and not args.max_episodes and args.groups == 1 and 1024 <= b <= 100000
+        aw = (20 if b <= 4096 else 48) if ok else 0
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
                               mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,

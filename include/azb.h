@@ -85,8 +85,8 @@ typedef struct azb_config {
                                    CUDA streams (needs max_episodes = 0); results are identical, launches overlap */
     uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as ONE persistent kernel in
                                    which trees never wait for each other — tree warps advance whichever of their trees has
-                                   its priors, that many tensor-core worker CTAs answer state vectors in 128-row tiles as
-                                   they fill.  Same results as the lock step (trees are independent). 0 = lock step. */
+                                   its priors, that many tensor-core worker SMs (20 at 4096 roots; in pairs per tile above
+                                   24) answer state vectors in 128-row tiles as they fill.  Same results as the lock step (trees are independent). 0 = lock step. */
     uint32_t reserved[5];
 } azb_config;
 
