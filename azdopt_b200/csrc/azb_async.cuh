@@ -82,11 +82,11 @@ __device__ __forceinline__ unsigned long long as_now() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ uint32_t as_ld_acquire(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
+// Polls use ld.volatile (served by L2, where the atomics land), never ld.acquire.gpu: an acquire load comes with
+// CCTL.IVALL — it invalidates the SM's whole L1 — and a waiting warp polls every microsecond beside 31 warps whose
+// walks live on L1 hits (ncu: 160 M CCTL per 100 steps; phase cycles of the walkers 1.6-2x the lock step's).  What a
+// poll guards is read afterwards through L2 anyway (ld.cg prior rows, TMA operand tiles, __ldcg slot owners) and was
+// published behind a __threadfence, so observing the flag in L2 is enough.
 __device__ __forceinline__ uint32_t as_ld_volatile(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -199,7 +199,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             uint32_t q;
             if (mem == 0) {
                 // ---- the previous tile must be finished by every member before its scratch is reused
-                while (as_ld_acquire(&st->grp_done[grp]) < G * seq && !as_ld_volatile(&st->abort)) {}
+                while (as_ld_volatile(&st->grp_done[grp]) < G * seq && !as_ld_volatile(&st->abort)) {}
                 // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
                 q = atomicAdd(&st->tile_head, 1u);
                 const uint32_t *cnt_p = P.tile_count + (q % P.NT);
@@ -207,7 +207,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 unsigned long long t_partial = 0;
                 bool flushed = false;
                 for (uint32_t spins = 0;; ++spins) {
-                    if (as_ld_acquire(cnt_p) >= want) break;
+                    if (as_ld_volatile(cnt_p) >= want) break;
                     if (as_ld_volatile(&st->abort) || as_ld_volatile(&st->done_trees) >= L.B) {
                         q = AS_NONE;
                         break;
@@ -237,7 +237,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 __threadfence();
                 atomicAdd(&st->grp_seq[grp], 1u);
             } else {
-                for (uint32_t spins = 0; as_ld_acquire(&st->grp_seq[grp]) <= seq; ++spins) {
+                for (uint32_t spins = 0; as_ld_volatile(&st->grp_seq[grp]) <= seq; ++spins) {
                     if ((spins & 4095u) == 4095u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
                     if (as_ld_volatile(&st->abort)) break;
                 }
@@ -279,7 +279,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
                     if (l > 0) {  // this layer's input is the previous layer's output, written by all members
                         const long long tw = AS_CLK();
-                        while (as_ld_acquire(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
+                        while (as_ld_volatile(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
                         d_w1 += AS_CLK() - tw;
                         as_fence_proxy_async();
                     }
@@ -523,17 +523,21 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     long long my_run = 0, my_wait = 0, my_t0 = 0;  // cycles spent advancing this tree / waiting for its priors (P.dbg)
     const long long t_k0 = AS_CLK();
     const unsigned long long t_start = as_now();
-    uint32_t err_tree = 0, idle = 0;
+    uint32_t err_tree = 0, idle = 0, naps = 0;
     const uint32_t ring_rows = P.NT * AS_TILE;
     for (;;) {
-        if (my_state == 1u && as_ld_acquire(P.h_flag + my_tree) >= my_sub) {
+        if (my_state == 1u && as_ld_volatile(P.h_flag + my_tree) >= my_sub) {
             my_state = 0u;
             my_wait += AS_CLK() - my_t0;
         }
         const uint32_t runnable = __ballot_sync(FULL, my_state == 0u);
         if (__ballot_sync(FULL, my_state != 2u) == 0u) break;
-        if (runnable == 0u) {  // every tree of this warp waits for its priors (the round trip is tens of microseconds)
-            __nanosleep(200);
+        if (runnable == 0u) {
+            // every tree of this warp waits for its priors.  The round trip is tens of microseconds, so the first sleeps
+            // after a walk are long and only then does the warp poll every microsecond: waiting warps would otherwise
+            // take issue slots and LSU bandwidth from the walking ones (phase cycles 91 K -> 74 K per tree-step)
+            __nanosleep(naps < 6u ? 5000u : 1000u);
+            ++naps;
             if ((++idle & 31u) == 0u) {
                 if (as_ld_volatile(&st->abort)) break;
                 if ((idle & 2047u) == 0u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
@@ -545,6 +549,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         const int k = __ffs(__ballot_sync(FULL, my_state == 0u && my_steps == behind)) - 1;
         const uint32_t tree = gw + (uint32_t)k * NW;
         const long long t_run0 = AS_CLK();
+        naps = 0;
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
         cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
         cx.blk = L.blk + (size_t)tree * L.cap_blk;
@@ -570,7 +575,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
             // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
             {
                 const uint32_t q = slot / AS_TILE;
-                while (as_ld_acquire(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
+                while (as_ld_volatile(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
             }
             const uint32_t pos = slot % ring_rows;
             tree_pack(L, cx, tree, P.ring + (size_t)pos * P.ring_ld);
@@ -618,6 +623,12 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (lane == CT_NOOP) v = cx.n_noop;
         if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
     }
+#ifdef AZB_PROFILE
+    if (lane >= 16) {  // per-phase lane-0 cycles of this warp's walks (tools/phase_probe.py)
+        const uint32_t v = cx.ct[lane];
+        if (v) atomicAdd(&L.g->prof[lane - 16], (unsigned long long)v);
+    }
+#endif
     if (P.dbg && my_tree < L.B) {
         atomicAdd(P.dbg + 16, (unsigned long long)my_run);
         atomicMax(P.dbg + 17, (unsigned long long)my_run);

@@ -5,17 +5,21 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["AZB_LIB"] = os.path.join(ROOT, "azdopt_b200", "lib", "libazb_prof.so")
+os.environ["AZB_LIB"] = os.environ.get("PROF_LIB", os.path.join(ROOT, "azdopt_b200", "lib", "libazb_prof.so"))
 from azdopt_b200 import capi  # noqa: E402
 
 PH = ["sel", "cur", "probe", "arc", "cascade", "cost", "insert", "reset", "add", "pack", "load", "store"]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 19
+aw = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # > 0: the asynchronous kernel with that many worker SMs (MLP priors)
 L = capi.lib()
 L.azb_debug_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-for b in (1, 4096):
-    cfg = capi.default_config(n, b, prior_mode=capi.PRIOR_HASH, max_steps=400)
+for b in ((int(os.environ.get("PROBE_B", "4096")),) if aw else (1, 4096)):
+    cfg = (capi.default_config(n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=400, async_workers=aw) if aw
+           else capi.default_config(n, b, prior_mode=capi.PRIOR_HASH, max_steps=400))
     p, m = capi.generate_roots(0, 0, b, n)
     with capi.Handle(cfg) as h:
+        if aw:
+            h.mlp_init(1)
         h.set_roots(p, m)
         h.init_trees()
         h.step(50)
