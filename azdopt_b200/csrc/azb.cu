@@ -6,6 +6,7 @@
 //
 // This file never includes, links or loads anything under oracle/.
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -215,12 +216,29 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     if (cfg.n_vertices < 5 || cfg.n_vertices > AZB_MAX_VERTICES || cfg.n_roots == 0) return AZB_ERR_INVALID;
     if (cfg.n_as_tol_len > AZB_MAX_TOL) return AZB_ERR_INVALID;
     if (cfg.prior_mode > AZB_PRIOR_INJECTED || cfg.mlp_mode > AZB_MLP_TC) return AZB_ERR_INVALID;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg.device < 0 || cfg.device >= ndev) return AZB_ERR_CUDA;
     azb_handle *h = new azb_handle();
     memset((void *)h, 0, sizeof(*h));
     h->err[0] = 0;
     *out = h;  // returned even on failure so that azb_last_error can be read; the caller destroys it
+    {
+        // a device in exclusive-process mode refuses a new context while the previous process is still being torn
+        // down (seen between back-to-back benchmark processes): retry for a few seconds before giving up
+        int ndev = 0;
+        cudaError_t ce = cudaSuccess;
+        for (int attempt = 0; attempt < 50; ++attempt) {
+            ce = cudaGetDeviceCount(&ndev);
+            if (ce == cudaSuccess && cfg.device >= 0 && cfg.device < ndev) {
+                ce = cudaSetDevice(cfg.device);
+                if (ce == cudaSuccess) ce = cudaFree(nullptr);
+            }
+            if (ce == cudaSuccess || ce == cudaErrorNoDevice || ce == cudaErrorInsufficientDriver) break;
+            cudaGetLastError();
+            struct timespec ts = {0, 100 * 1000 * 1000};
+            nanosleep(&ts, nullptr);
+        }
+        if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "no usable CUDA device: %s", cudaGetErrorString(ce));
+        if (cfg.device < 0 || cfg.device >= ndev) return fail(h, AZB_ERR_CUDA, "device %d of %d", cfg.device, ndev);
+    }
     const uint32_t N = cfg.n_vertices, A = action_dim(N), W = (A + 31) / 32, PW = (N + 3) / 4, B = cfg.n_roots;
     if (cfg.c_upper == 0.0f) cfg.c_upper = (float)(isqrt_ceil(N - 1) + (N + 1) / 2);  // 04-c21-tree.rs:59-68
     if (!(cfg.c_upper > cfg.c_lower)) return fail(h, AZB_ERR_INVALID, "c_upper must exceed c_lower");

@@ -491,27 +491,8 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     if ((uint32_t)warp >= P.tree_warps) return;
     uint32_t *base = smem + (size_t)warp * P.smem_words_per_warp;
     WarpCtx cx;
-    cx.lane = lane;
-    cx.err = 0;
     cx.full_count = COUNT;
-    cx.n_ins = cx.n_live = cx.n_noop = 0u;
-    cx.lut = lut;
-    cx.wk = base;
-    cx.par = (uint8_t *)(base + WK_HDR);
-    cx.perm = base + WK_HDR + L.PW;
-    cx.keym = cx.perm + L.W;
-    cx.rpar = (uint8_t *)(cx.keym + L.W);
-    cx.rperm = cx.keym + L.W + L.PW;
-    uint32_t *p = base + ((L.WS + 3u) & ~3u);
-    cx.cur = p;
-    p += 64;
-    cx.pfx = p;
-    p += 64;
-    cx.ct = p;
-    p += 32;
-    cx.lbuf = (float *)p;
-    cx.fr = p;
-    cx.cs = reinterpret_cast<CostScratch *>(p);
+    ctx_bind_smem(L, cx, base, lut, lane);
     cx.ct[lane] = 0u;
     __syncwarp();
 
@@ -551,12 +532,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         const long long t_run0 = AS_CLK();
         naps = 0;
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
-        cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
-        cx.blk = L.blk + (size_t)tree * L.cap_blk;
-        cx.blk4 = reinterpret_cast<uint4 *>(cx.blk);
-        cx.inl = L.inl + (size_t)tree * L.cap_in;
-        cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
-        cx.hash = L.hash + (size_t)tree * L.cap_hash;
+        ctx_bind_tree(L, cx, tree);
         uint32_t *gwk = L.walker + (size_t)tree * L.WS;
         for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gwk[i];
         __syncwarp();

@@ -72,6 +72,40 @@ struct WarpCtx {
     uint32_t n_ins, n_live, n_noop;
 };
 
+// carve a warp's shared-memory region: walker block | cur mask | prefix | counters | one region shared by the
+// children's c* (selection), the cascade work lists and the cost scratch (never live together)
+__device__ __forceinline__ void ctx_bind_smem(const AzbLayout &L, WarpCtx &cx, uint32_t *base, const uint8_t *lut, int lane) {
+    cx.lane = lane;
+    cx.err = 0;
+    cx.n_ins = cx.n_live = cx.n_noop = 0u;
+    cx.lut = lut;
+    cx.wk = base;
+    cx.par = (uint8_t *)(base + WK_HDR);
+    cx.perm = base + WK_HDR + L.PW;
+    cx.keym = cx.perm + L.W;
+    cx.rpar = (uint8_t *)(cx.keym + L.W);
+    cx.rperm = cx.keym + L.W + L.PW;
+    uint32_t *p = base + ((L.WS + 3u) & ~3u);
+    cx.cur = p;
+    p += 64;
+    cx.pfx = p;
+    p += 64;
+    cx.ct = p;
+    p += 32;
+    cx.lbuf = (float *)p;
+    cx.fr = p;
+    cx.cs = reinterpret_cast<CostScratch *>(p);
+}
+// point a WarpCtx at one tree's slabs
+__device__ __forceinline__ void ctx_bind_tree(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
+    cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
+    cx.blk = L.blk + (size_t)tree * L.cap_blk;
+    cx.blk4 = reinterpret_cast<uint4 *>(cx.blk);
+    cx.inl = L.inl + (size_t)tree * L.cap_in;
+    cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
+    cx.hash = L.hash + (size_t)tree * L.cap_hash;
+}
+
 __device__ __forceinline__ void count(WarpCtx &cx, int which, uint32_t n) {
     if (cx.full_count && cx.lane == 0) cx.ct[which] += n;
 }
@@ -479,6 +513,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                         ov = azb_f2ord(v);
                     } else {
                         float cur = 0.f;
+#pragma unroll 2
                         for (int t = (int)n_out - 1; t >= 0; --t)  // newest first, left fold (:79-82)
                             cur = __fadd_rn(cur, __fsqrt_rn(fabsf(__fsub_rn(cx.lbuf[t], v))));
                         if (cur != cur) cx.err = 4;
@@ -560,7 +595,9 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             cx.err = 3;
             break;
         }
-        bool reset = false;
+        bool reset = false, casc_old = false;
+        float casc_c = 0.f;
+        uint32_t casc_n = 0u, casc_e = 0u;
         if (hit >= 0) {  // transposition (tree/mod.rs:172-179)
             count(cx, CT_HIT, 1);
             uint4 *rec = cx.node + (size_t)hit * 4;
@@ -585,8 +622,10 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
             __syncwarp();
             PROF_ADD(cx, PH_ARC);
-            tree_cascade(L, cx, pos, depth, __uint_as_float(q0.y), q0.z, act_o ? 0u : 1u, true);
-            PROF_ADD(cx, PH_CASCADE);
+            casc_c = __uint_as_float(q0.y);
+            casc_n = q0.z;
+            casc_e = act_o ? 0u : 1u;
+            casc_old = true;
             reset = true;
         } else {
             // ---- new node (tree/mod.rs:181-216)
@@ -647,8 +686,10 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             PROF_ADD(cx, PH_INSERT);
             if (!any) {
                 count(cx, CT_TERM, 1);
-                tree_cascade(L, cx, pos, depth, c_new, 0u, 1u, false);
-                PROF_ADD(cx, PH_CASCADE);
+                casc_c = c_new;
+                casc_n = 0u;
+                casc_e = 1u;
+                casc_old = false;
                 reset = true;
             } else {
                 pos = nn;
@@ -667,6 +708,9 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
         }
         if (reset) {
+            // one call site for both cascades (transposition arc / new terminal node): the body is 9 KB of code
+            tree_cascade(L, cx, pos, depth, casc_c, casc_n, casc_e, casc_old);
+            PROF_ADD(cx, PH_CASCADE);
             walker_reset(L, cx);
             pos = 0;
             depth = 0;
@@ -735,35 +779,10 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
     uint32_t *base = smem + (size_t)warp * smem_words_per_warp;
     if (tree < tree_end) {
         WarpCtx cx;
-        cx.lane = lane;
-        cx.err = 0;
         cx.full_count = COUNT;
-        cx.n_ins = cx.n_live = cx.n_noop = 0u;
-        cx.lut = lut;
-        cx.wk = base;
-        cx.par = (uint8_t *)(base + WK_HDR);
-        cx.perm = base + WK_HDR + L.PW;
-        cx.keym = cx.perm + L.W;
-        cx.rpar = (uint8_t *)(cx.keym + L.W);
-        cx.rperm = cx.keym + L.W + L.PW;
-        uint32_t *p = base + ((L.WS + 3u) & ~3u);
-        cx.cur = p;
-        p += 64;
-        cx.pfx = p;
-        p += 64;
-        cx.ct = p;
-        p += 32;
-        // children's c* (selection), cascade frontiers and the cost scratch are never live together: one region
-        cx.lbuf = (float *)p;
-        cx.fr = p;
-        cx.cs = reinterpret_cast<CostScratch *>(p);
+        ctx_bind_smem(L, cx, base, lut, lane);
         (void)lcap;
-        cx.node = L.node + (size_t)tree * L.cap_nodes * 4;
-        cx.blk = L.blk + (size_t)tree * L.cap_blk;
-        cx.blk4 = reinterpret_cast<uint4 *>(cx.blk);
-        cx.inl = L.inl + (size_t)tree * L.cap_in;
-        cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
-        cx.hash = L.hash + (size_t)tree * L.cap_hash;
+        ctx_bind_tree(L, cx, tree);
         uint32_t *gw = L.walker + (size_t)tree * L.WS;
         PROF_T0();
         cx.ct[lane] = 0u;

@@ -194,7 +194,7 @@ def main():
     if aw < 0:  # auto: 20 of the 148 SMs answer state vectors (128 x 32 warps walk: one tree per warp at 4096 roots);
         # above 4096 roots 48 SMs in pairs
         ok = args.mlp == "tc" and not args.max_episodes and args.groups == 1 and 1024 <= b <= 100000
-        aw = (20 if b <= 4096 else 48) if ok else 0
+        aw = (40 if b < 4096 else 20 if b == 4096 else 48) if ok else 0
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
                               mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
