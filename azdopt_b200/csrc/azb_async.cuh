@@ -543,28 +543,32 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (cx.err) {
             new_state = 2u;
             err_tree = tree;
-        } else if (pending && !at_target) {
-            // the new node needs priors: next ring row
-            uint32_t slot = 0;
-            if (lane == 0) slot = atomicAdd(&st->row_tail, 1u);
-            slot = __shfl_sync(FULL, slot, 0);
-            // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
-            {
+        } else {
+            // a new node needs priors: its state vector goes to the next ring row — or, on the last step of this launch,
+            // to the tree's own row (the host runs one batched forward over those)
+            const bool to_ring = pending && !at_target;
+            uint32_t slot = 0, pos = 0;
+            uint16_t *row = nullptr;
+            if (to_ring) {
+                if (lane == 0) slot = atomicAdd(&st->row_tail, 1u);
+                slot = __shfl_sync(FULL, slot, 0);
+                // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
                 const uint32_t q = slot / AS_TILE;
                 while (as_ld_volatile(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
+                pos = slot % ring_rows;
+                row = P.ring + (size_t)pos * P.ring_ld;
             }
-            const uint32_t pos = slot % ring_rows;
-            tree_pack(L, cx, tree, P.ring + (size_t)pos * P.ring_ld);
-            if (lane == 0) P.slot_tree[pos] = tree;
-            __threadfence();
-            as_fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
-            new_state = 1u;
-        } else if (at_target) {
-            // last step of this launch: the row goes to the tree's own slot; the host runs one batched forward over them
-            if (pending) tree_pack(L, cx, tree);
-            new_state = 2u;
+            if (pending) tree_pack(L, cx, tree, row);
+            if (to_ring) {
+                if (lane == 0) P.slot_tree[pos] = tree;
+                __threadfence();
+                as_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
+                new_state = 1u;
+            } else if (at_target) {
+                new_state = 2u;
+            }
         }
         __syncwarp();
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;

@@ -740,14 +740,26 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
         // tensor-core MLP: the row goes out as bf16 (1.0 = 0x3F80), eight entries per 128-bit store; the row pitch is
         // a multiple of 64 entries and the tail beyond 2A stays zero
         uint16_t *row = row_override ? row_override : L.sv16 + (size_t)tree * L.sv16_ld;
-        for (uint32_t i = 8u * cx.lane; i < 2 * L.A; i += 256) {
+        const uint32_t n2 = 2 * L.A;
+#pragma unroll 1
+        for (uint32_t i = 8u * cx.lane; i < n2; i += 256) {
+            // eight consecutive entries = eight mask bits: taken with one 64-bit shift when the chunk lies inside one
+            // half of the vector (always, when A is a multiple of 8), bit by bit otherwise
+            uint32_t bits = 0;
+            if (i + 8u <= L.A || (i >= L.A && i + 8u <= n2)) {
+                const uint32_t *m = i < L.A ? cx.cur : cx.perm;
+                const uint32_t j = i < L.A ? i : i - L.A;
+                const uint32_t w0 = m[j >> 5], w1 = ((j & 31u) > 24u) ? m[(j >> 5) + 1u] : 0u;
+                bits = (uint32_t)((((unsigned long long)w1 << 32) | w0) >> (j & 31u)) & 0xffu;
+            } else {
+#pragma unroll 1
+                for (uint32_t q = 0; q < 8u; ++q)
+                    if (i + q < n2) bits |= pack_bit(L, cx, i + q) << q;
+            }
             uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t lo = (i + 2 * q < 2 * L.A && pack_bit(L, cx, i + 2 * q)) ? 0x3F80u : 0u;
-                const uint32_t hi = (i + 2 * q + 1 < 2 * L.A && pack_bit(L, cx, i + 2 * q + 1)) ? 0x3F80u : 0u;
-                w[q] = lo | (hi << 16);
-            }
+            for (int q = 0; q < 4; ++q)
+                w[q] = (((bits >> (2 * q)) & 1u) * 0x3F80u) | (((bits >> (2 * q + 1)) & 1u) * 0x3F800000u);
             *reinterpret_cast<uint4 *>(row + i) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         return;
