@@ -77,7 +77,8 @@ class NablaOptimizer:
 
     @classmethod
     def par_new(cls, space: ROTModifyParentsOnce, init_states, model, batch: int, *, n_as_tol=(200, 50, 50),
-                n_as_tol_default=25, device: int = 0, first_root: int = 0, max_steps: int = 800) -> "NablaOptimizer":
+                n_as_tol_default=25, device: int = 0, first_root: int = 0, max_steps: int = 800,
+                async_workers: Optional[int] = None) -> "NablaOptimizer":
         """optimizer/mod.rs:39-118.  ``init_states`` is either ``(parents[B,N] u8, permitted[B,W] u32)`` or a callable
         ``i -> (parents[N], iterable of permitted action ids)`` (the reference's closure draws from thread_rng)."""
         self = object.__new__(cls)
@@ -88,9 +89,15 @@ class NablaOptimizer:
             hidden = tuple(model.hidden)
         else:
             prior, mlp, hidden = capi.PRIOR_INJECTED, capi.MLP_FP32, (512, 1024, 512)
+        if async_workers is None:
+            # the asynchronous search kernel (same results) wherever it applies: the tensor-core device model and
+            # enough roots to fill tiles; 20 worker SMs keep one warp per tree at 4096 roots
+            ok = mlp == capi.MLP_TC and prior == capi.PRIOR_MLP and 1024 <= batch <= 100000
+            async_workers = (40 if batch < 4096 else 20 if batch == 4096 else 48) if ok else 0
         cfg = capi.default_config(space.n, batch, device=device, first_root=first_root, c_lower=space.c_lower,
                                   c_upper=space.c_upper, n_as_tol=n_as_tol, n_as_tol_default=n_as_tol_default,
-                                  prior_mode=prior, mlp_mode=mlp, mlp_hidden=hidden, max_steps=max_steps)
+                                  prior_mode=prior, mlp_mode=mlp, mlp_hidden=hidden, max_steps=max_steps,
+                                  async_workers=async_workers)
         self.h = capi.Handle(cfg)
         if isinstance(model, ActionModel):
             if model.params is not None:

@@ -140,3 +140,30 @@ def test_reset_trees_policy_matches_oracle(capi, orc, n, k_max):
         _cmp_trees(o, h, b)
         assert h.argmin()["eval"] == o.argmin()["eval"]
         assert moved > b  # roots really move
+
+
+def test_python_mirror_runs_the_examples_epoch_loop(capi, orc):
+    """NablaOptimizer (azdopt_b200/nabla.py) with the reference's method names: par_new, the fused steps,
+    par_update_model, par_reset_trees, argmin_data — two epochs equal the same calls made on the raw handle."""
+    from azdopt_b200 import nabla, observe
+
+    n, b, steps = 19, 64, 40
+    roots = capi.generate_roots(4, 0, b, n)
+    opt = nabla.NablaOptimizer.par_new(nabla.ROTModifyParentsOnce(n=n), roots, nabla.ActionModel(seed=5, arithmetic="tc"),
+                                       b, max_steps=steps)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=steps) as h:
+        h.mlp_init(5)
+        h.set_roots(*roots)
+        h.init_trees()
+        for epoch in range(2):
+            imp = opt.roll_out(steps)
+            n_imp, log = h.step(steps, cap=steps)
+            assert [tuple(x) for x in imp] == [tuple(x) for x in log]
+            assert opt.par_update_model(3) == h.update_model(3)
+            opt.par_reset_trees(seed=9)
+            h.reset_trees(9)
+            a, g = opt.argmin_data(), h.argmin()
+            assert a.eval == g["eval"] and a.mu == g["mu"] and np.array_equal(a.parents, g["parents"])
+        assert opt.argmin_graph6() == observe.graph6_of_state(g["parents"])
+        assert opt.tree_dot(0).startswith("graph search_tree {")
+    opt.close()
