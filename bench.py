@@ -102,10 +102,12 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
-def cpu_reference_run(n, roots, steps, warmup, seed, threads):
+def cpu_reference_run(n, roots, steps, warmup, seed, threads, budget_s=None):
     """The restated reference (oracle/azb_oracle.cpp: dense eigensolve, leaf-stripping matching, ordered maps) on
     the host cores.  Tree + state + cost are timed; priors are the counter hash (the reference evaluates its MLP on
-    a GPU through dfdx — nabla/model/dfdx.rs:81-83 — so no CPU forward is part of its CPU path)."""
+    a GPU through dfdx — nabla/model/dfdx.rs:81-83 — so no CPU forward is part of its CPU path).
+    With `budget_s` the steps run in chunks of 50 and the run stops after the chunk that crosses the budget (a
+    bounded sample: the steps actually run are returned)."""
     from oracle import oracle
 
     oracle.build()
@@ -118,9 +120,16 @@ def cpu_reference_run(n, roots, steps, warmup, seed, threads):
         o.steps_hash(seed, 0, 1, warmup)
     o.reset_counters()
     t0 = time.perf_counter()
-    o.steps_hash(seed, 0, 1 + warmup, steps)
+    done = 0
+    while done < steps:
+        c = min(50, steps - done) if budget_s else steps
+        o.steps_hash(seed, 0, 1 + warmup + done, c)
+        done += c
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
     k = o.counters()
+    k["steps_run"] = done
     return k["n_live"] / dt, dt, k
 
 
@@ -139,7 +148,8 @@ def main():
     ap.add_argument("--async-workers", type=int, default=int(os.environ.get("AZB_ASYNC_WORKERS", "-1")),
                     help="tensor-core worker SMs of the asynchronous search kernel; 0 = lock step; -1 = auto")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-baseline-roots", type=int, default=512)
+    ap.add_argument("--cpu-baseline-roots", type=int, default=4096)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0, help="time bound of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -155,16 +165,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample_roots = min(b, 1024)
-        val, dt, k = cpu_reference_run(n, sample_roots, args.steps, args.warmup, args.seed, host_threads)
+        sample_roots = b  # the whole per-GPU batch; bounded in time instead (a step = one pass over these roots)
+        val, dt, k = cpu_reference_run(n, sample_roots, args.steps, args.warmup, args.seed, host_threads, budget_s=60.0)
         line = {
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / k["steps_run"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": f"c21 N={n}, {sample_roots}-root sample of the {b}-roots-per-GPU batch, "
-                                   f"n_as_tol=[200,50,50]->25, hash priors", "vertices": n, "roots": sample_roots},
+            "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {sample_roots} roots (one GPU's batch), "
+                                   f"n_as_tol=[200,50,50]->25, hash priors", "vertices": n, "roots": sample_roots,
+                       "steps_run": k["steps_run"], "seconds": dt},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads, "kind": "port",
-                             "sample": f"{sample_roots} roots x {args.steps} steps after {args.warmup} warm-up; the "
+                             "sample": f"{sample_roots} roots x {k['steps_run']} steps ({dt:.1f} s) after {args.warmup} warm-up; the "
                                        "reference is Rust and cannot be built here, so this is its C++ restatement "
                                        "(oracle/), tree+state+cost on all host threads, MLP forward excluded"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -341,10 +352,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = min(b, args.cpu_baseline_roots)
-        cs = min(args.steps, 200)
-        val, dt, _ = cpu_reference_run(n, cb, cs, 4, args.seed, host_threads)
+        val, dt, kc = cpu_reference_run(n, cb, args.steps, 4, args.seed, host_threads, budget_s=args.cpu_baseline_seconds)
         cpu = {"value": val, "unit": UNIT, "cores": host_threads, "kind": "port",
-               "sample": f"{cb} roots x {cs} steps ({dt:.1f} s); restated reference (C++ oracle), tree+state+cost on "
+               "sample": f"{cb} roots x {kc['steps_run']} steps ({dt:.1f} s); restated reference (C++ oracle), tree+state+cost on "
                          "all host threads, hash priors, MLP forward excluded"}
 
     if rank == 0:
