@@ -24,6 +24,7 @@
 #include "azb_tree.cuh"
 #include "azb_train.cuh"
 #include "azb_async.cuh"
+#include "azb_pipe.cuh"
 
 #include <dlfcn.h>
 
@@ -63,6 +64,11 @@ struct azb_handle {
     AzbAsyncMaps asM;
     int async_grid;
     size_t async_smem;
+    // weight-stationary model pipeline beside the tree kernel (azb_pipe.cuh)
+    bool pipe;
+    AzbPipeParams piQ;
+    AzbPipeMaps piM;
+    size_t pipe_smem;
     void *async_bufs[16];
     // epoch-boundary collectives (NCCL, loaded on demand)
     void *nccl_lib, *nccl_comm;
@@ -717,7 +723,54 @@ static int async_create(azb_handle *h) {
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->cfg.device));
     if (!coop) return fail(h, AZB_ERR_CUDA, "cooperative launch not supported");
-    const uint32_t W = h->cfg.async_workers, B = h->L.B;
+    uint32_t W = h->cfg.async_workers;
+    const uint32_t B = h->L.B;
+    // The model as a weight-stationary pipeline of SMs (azb_pipe.cuh) when every layer's weights fit in the shared
+    // memory of a few SMs: members per stage from the largest column block whose weights stay <= 160 KB.
+    AzbPipeParams &Q = h->piQ;
+    memset(&Q, 0, sizeof(Q));
+    h->pipe = false;
+    {
+        // Opt-in (AZB_ASYNC_PIPE=1): bit-identical results, a tile's latency falls to ~25 us, but every tile passes through
+        // every stage and the K = 1024 stage needs ~6 us per tile (16 k-blocks of barrier round trips per member), which
+        // caps the pipeline at ~20 M rows/s — below the in-kernel workers' 45 M (profiles/README.md, round 1 session 4)
+        bool want = false;
+        if (const char *e = getenv("AZB_ASYNC_PIPE")) want = atoi(e) != 0;
+        const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 4096;  // static barriers / row owners + alignment
+        uint32_t total = 0;
+        size_t need = 0;
+        for (int l = 0; l < 4 && want; ++l) {
+            const uint32_t kpad = h->tc.kpad[l], npad = h->tc.npad[l];
+            uint32_t bn = 256;
+            while (bn >= 32 && (size_t)bn * kpad * 2 > 160 * 1024) bn >>= 1;
+            if (bn < 32) { want = false; break; }
+            uint32_t members = (npad + bn - 1) / bn;
+            if (l == 3) {  // the head: at least two members (latency), columns split evenly in multiples of 16
+                members = std::max(members, 2u);
+                bn = ((npad + members - 1) / members + 15) / 16 * 16;
+            } else if (npad % bn) {  // hidden layers: the blocks must tile the next layer's K exactly
+                want = false;
+                break;
+            }
+            if (bn % 16 || bn > 256 || bn < 16) { want = false; break; }
+            Q.BN[l] = bn;
+            Q.S[l] = members;
+            Q.first_cta[l] = total;
+            total += Q.S[l];
+            const size_t wbytes = (size_t)bn * kpad * 2, bias = (size_t)((bn + 31) & ~31u) * 4;
+            size_t ns = (budget - wbytes - bias) / (AS_TILE * TC_BK * 2);
+            ns = std::min<size_t>(ns, PIPE_MAX_STAGES);
+            if (ns < 2) { want = false; break; }
+            Q.stages[l] = (uint32_t)ns;
+            need = std::max(need, wbytes + bias + ns * AS_TILE * TC_BK * 2 + 1024);
+        }
+        if (want && total >= 4 && total <= 40 && (int)total < prop.multiProcessorCount / 2) {
+            Q.n_ctas = total;
+            h->pipe = true;
+            h->pipe_smem = need;
+            W = total;  // SMs the model takes
+        }
+    }
     // tree warps per CTA: 32, fewer when a large N needs more shared memory per warp (at most ~160 KB per SM, the rest is L1)
     const size_t lut_bytes = (h->A + 15) & ~15u, per_warp = (size_t)h->smem_words_per_warp * 4;
     const uint32_t tree_warps = (uint32_t)std::max<size_t>(4, std::min<size_t>(AS_WARPS, (160 * 1024 - lut_bytes) / per_warp));
@@ -725,7 +778,7 @@ static int async_create(azb_handle *h) {
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
     const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes;
-    h->async_smem = std::max(tree_smem, mlp_smem);
+    h->async_smem = h->pipe ? tree_smem : std::max(tree_smem, mlp_smem);
     int nb = 0, nb2 = 0, rc;
     switch (azb_stack_depth(h->N)) {
         case 3: rc = async_prepare_kernel<3, false>(h, &nb); if (!rc) rc = async_prepare_kernel<3, true>(h, &nb2); break;
@@ -742,11 +795,12 @@ static int async_create(azb_handle *h) {
     AzbAsyncParams &P = h->asP;
     memset(&P, 0, sizeof(P));
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
-    P.n_workers = W;
+    P.n_workers = h->pipe ? 0u : W;  // in-kernel workers; the pipeline is its own kernel
     P.tree_warps = tree_warps;
     // worker SMs per tile: one when few SMs serve the model (every tree keeps its own warp at 4096 roots), pairs otherwise
     P.group = W <= 24 ? 1 : 2;
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
+    if (h->pipe) P.group = 1;
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
     P.smem_words_per_warp = h->smem_words_per_warp;
     P.ring_ld = h->tc.kpad[0];
@@ -774,9 +828,10 @@ static int async_create(azb_handle *h) {
     CK(alloc((void **)&P.tile_retired, (size_t)P.NT * 4));
     CK(alloc((void **)&P.slot_tree, (size_t)P.NT * AS_TILE * 4));
     CK(alloc((void **)&P.h_flag, (size_t)B * 4));
-    CK(alloc((void **)&P.dbg, 24 * 8));
+    CK(alloc((void **)&P.dbg, 64 * 8));
     CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
-    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * h->tc.kpad[l + 1] * 2));
+    const uint32_t act_tiles = h->pipe ? PIPE_D : W;
+    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)act_tiles * AS_TILE * h->tc.kpad[l + 1] * 2));
     azb_encode_fn enc = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres) != cudaSuccess || !enc)
@@ -786,6 +841,16 @@ static int async_create(azb_handle *h) {
         why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
     for (int l = 0; l < 4 && !why; ++l)
         why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], 128);
+    if (h->pipe) {
+        why = why ? why : azb_tc_make_map(enc, &h->piM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
+        for (int l = 0; l < 3 && !why; ++l)
+            why = azb_tc_make_map(enc, &h->piM.act[l], P.act[l], (uint64_t)PIPE_D * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
+        for (int l = 0; l < 4 && !why; ++l)
+            why = azb_tc_make_map(enc, &h->piM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], Q.BN[l]);
+        CK(cudaFuncSetAttribute(azb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+        if (!h->gstream[0]) CK(cudaStreamCreateWithFlags(&h->gstream[0], cudaStreamNonBlocking));
+        if (!h->gevent[0]) CK(cudaEventCreateWithFlags(&h->gevent[0], cudaEventDisableTiming));
+    }
     if (why) return fail(h, AZB_ERR_CUDA, "async tensor maps: %s", why);
     CK(cudaStreamSynchronize(h->stream));
     h->async_ready = true;
@@ -795,7 +860,8 @@ static int async_create(azb_handle *h) {
 template <int D, bool C>
 static cudaError_t async_launch(azb_handle *h) {
     void *args[] = {(void *)&h->L, (void *)&h->asP, (void *)&h->asM};
-    return cudaLaunchCooperativeKernel((const void *)azb_async_kernel<D, C>, dim3(h->async_grid), dim3(AS_THREADS), args,
+    const int grid = h->pipe ? h->async_grid - (int)h->piQ.n_ctas : h->async_grid;
+    return cudaLaunchCooperativeKernel((const void *)azb_async_kernel<D, C>, dim3(grid), dim3(AS_THREADS), args,
                                        h->async_smem, h->stream);
 }
 
@@ -809,9 +875,20 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     CK(cudaMemsetAsync(P.tile_count, 0, (size_t)P.NT * 4, h->stream));
     CK(cudaMemsetAsync(P.tile_retired, 0, (size_t)P.NT * 4, h->stream));
     CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
-    CK(cudaMemsetAsync(P.dbg, 0, 24 * 8, h->stream));
+    CK(cudaMemsetAsync(P.dbg, 0, 64 * 8, h->stream));
     P.target_step = h->steps_done + n_steps;
     cudaError_t ce;
+    if (h->pipe) {
+        // the model pipeline runs beside the tree kernel on its own stream: it takes piQ.n_ctas whole SMs (its shared
+        // memory excludes a tree CTA), the tree kernel the rest; both end when every tree has reached the target step
+        CK(cudaEventRecord(h->fork_event, h->stream));
+        CK(cudaStreamWaitEvent(h->gstream[0], h->fork_event, 0));
+        azb_pipe_kernel<<<h->piQ.n_ctas, PIPE_THREADS, h->pipe_smem, h->gstream[0]>>>(h->L, P, h->piQ, h->piM);
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "model pipeline launch: %s", cudaGetErrorString(ce));
+        CK(cudaEventRecord(h->gevent[0], h->gstream[0]));
+        h->launches += 1;
+    }
     switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
         case 6: ce = async_launch<3, false>(h); break;
         case 7: ce = async_launch<3, true>(h); break;
@@ -820,7 +897,15 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
         case 10: ce = async_launch<5, false>(h); break;
         default: ce = async_launch<5, true>(h); break;
     }
-    if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
+    if (ce != cudaSuccess) {
+        if (h->pipe) {  // the pipeline is already waiting for tiles: tell it to drain
+            const uint32_t one = 1;
+            cudaMemcpy(&P.st->abort, &one, 4, cudaMemcpyHostToDevice);
+            cudaStreamSynchronize(h->gstream[0]);
+        }
+        return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
+    }
+    if (h->pipe) CK(cudaStreamWaitEvent(h->stream, h->gevent[0], 0));
     h->launches += 1;
     h->async_ran = true;
     rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
@@ -1365,6 +1450,17 @@ extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {  // o
     AzbAsyncState st;
     CK(cudaMemcpy(&st, h->asP.st, sizeof(st), cudaMemcpyDeviceToHost));
     out16[15] = ((unsigned long long)st.rows_real << 32) | st.rows_dummy;
+    return AZB_OK;
+}
+
+// cycle counters of the model pipeline's stages (azb_pipe.cuh, profile flavour): out[l*8 + i], 32 entries; i = producer
+// wait-input, wait-empty, tiles (summed over members), MMA wait-acc, wait-full, epilogue wait, busy, MMA wait-first-block
+extern "C" int azb_debug_pipe(azb_handle *h, unsigned long long *out32, unsigned int *members4) {
+    if (!h || !out32 || !h->async_ready || !h->pipe) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out32, h->asP.dbg + 24, 40 * 8, cudaMemcpyDeviceToHost));
+    if (members4) for (int l = 0; l < 4; ++l) members4[l] = h->piQ.S[l];
     return AZB_OK;
 }
 

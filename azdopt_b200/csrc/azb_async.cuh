@@ -52,6 +52,10 @@ struct AzbAsyncState {  // device memory, zeroed before every launch
     uint32_t rows_real, rows_dummy;
     // worker groups (AS_MAX_GROUPS): the leader's tile mailbox and the group's monotonic barriers
     uint32_t grp_seq[64], grp_tile[64], grp_done[64], grp_layer[64 * 4];
+    // weight-stationary pipeline (azb_pipe.cuh): first tile that will not be processed + 1 (0 = not known yet), and
+    // per stage and activation slot the number of members that have stored their columns (monotonic over generations)
+    uint32_t final_q1;
+    uint32_t pipe_done[4 * 8];
 };
 
 struct AzbAsyncMaps {
@@ -270,7 +274,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
 
         if (warp == 0) {
             // ===== TMA producer =====
-            if (lane == 0) {
+            if (tc_elect_one()) {
                 const long long tt0 = AS_CLK();
                 d_tiles += 1;
                 const uint64_t w_policy = as_policy_evict_last();
@@ -327,7 +331,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                         as_mbar_spin(&full_bar[s], ph);
                         d_w0 += AS_CLK() - tw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (lane == 0) {
+                        if (tc_elect_one()) {
                             const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes);
                             for (uint32_t j = 0; j < np; ++j) {
                                 const uint32_t nt = mem + (p0 + j) * G;

@@ -65,6 +65,20 @@ __device__ __forceinline__ void tc_umma_f16(uint32_t tmem_d, uint64_t adesc, uin
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One elected lane of a converged warp.  `if (lane == 0)` makes the issue block a divergent region, and ptxas then
+// feeds every tcgen05.mma through a waterfall loop (ELECT + 7 R2UR.BROADCAST + branch per instruction, ~100 cycles
+// each: the issue thread, not the tensor pipe, bounds small-N MMAs); with elect.sync it knows the block is uniform.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void tc_umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
@@ -134,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (tc_elect_one()) {
             for (uint32_t kb = 0; kb < k_blocks; ++kb) {
                 const uint32_t s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1u;
                 tc_mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -152,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const uint32_t s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1u;
             tc_mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+            if (tc_elect_one()) {
                 const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + a_bytes;
 #pragma unroll
                 for (uint32_t k = 0; k < TC_BK / 16; ++k) {
