@@ -65,7 +65,8 @@ struct azb_handle {
     int async_grid;
     size_t async_smem;
     // weight-stationary model pipeline beside the tree kernel (azb_pipe.cuh)
-    bool pipe;
+    bool pipe, split;
+    size_t worker_smem;
     AzbPipeParams piQ;
     AzbPipeMaps piM;
     size_t pipe_smem;
@@ -777,8 +778,13 @@ static int async_create(azb_handle *h) {
     const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
-    const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes;
-    h->async_smem = h->pipe ? tree_smem : std::max(tree_smem, mlp_smem);
+    const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
+    // the model (workers or pipeline) is its own kernel beside the tree kernel; AZB_ASYNC_SPLIT=0 folds the workers into
+    // the tree kernel (one launch: what ncu can capture, since it serialises kernels)
+    h->split = !h->pipe;
+    if (const char *e = getenv("AZB_ASYNC_SPLIT")) h->split = !h->pipe && atoi(e) != 0;
+    h->worker_smem = mlp_smem;
+    h->async_smem = (h->pipe || h->split) ? tree_smem : std::max(tree_smem, mlp_smem);
     int nb = 0, nb2 = 0, rc;
     switch (azb_stack_depth(h->N)) {
         case 3: rc = async_prepare_kernel<3, false>(h, &nb); if (!rc) rc = async_prepare_kernel<3, true>(h, &nb2); break;
@@ -795,7 +801,8 @@ static int async_create(azb_handle *h) {
     AzbAsyncParams &P = h->asP;
     memset(&P, 0, sizeof(P));
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
-    P.n_workers = h->pipe ? 0u : W;  // in-kernel workers; the pipeline is its own kernel
+    P.n_workers = h->pipe ? 0u : W;  // worker SMs; the pipeline is its own kernel
+    P.split = (h->pipe || h->split) ? 1u : 0u;
     P.tree_warps = tree_warps;
     // worker SMs per tile: one when few SMs serve the model (every tree keeps its own warp at 4096 roots), pairs otherwise
     P.group = W <= 24 ? 1 : 2;
@@ -848,6 +855,9 @@ static int async_create(azb_handle *h) {
         for (int l = 0; l < 4 && !why; ++l)
             why = azb_tc_make_map(enc, &h->piM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], Q.BN[l]);
         CK(cudaFuncSetAttribute(azb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+    }
+    if (h->split) CK(cudaFuncSetAttribute(azb_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->worker_smem));
+    if (h->pipe || h->split) {
         if (!h->gstream[0]) CK(cudaStreamCreateWithFlags(&h->gstream[0], cudaStreamNonBlocking));
         if (!h->gevent[0]) CK(cudaEventCreateWithFlags(&h->gevent[0], cudaEventDisableTiming));
     }
@@ -860,7 +870,7 @@ static int async_create(azb_handle *h) {
 template <int D, bool C>
 static cudaError_t async_launch(azb_handle *h) {
     void *args[] = {(void *)&h->L, (void *)&h->asP, (void *)&h->asM};
-    const int grid = h->pipe ? h->async_grid - (int)h->piQ.n_ctas : h->async_grid;
+    const int grid = h->pipe ? h->async_grid - (int)h->piQ.n_ctas : h->split ? h->async_grid - (int)h->asP.n_workers : h->async_grid;
     return cudaLaunchCooperativeKernel((const void *)azb_async_kernel<D, C>, dim3(grid), dim3(AS_THREADS), args,
                                        h->async_smem, h->stream);
 }
@@ -878,17 +888,21 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     CK(cudaMemsetAsync(P.dbg, 0, 64 * 8, h->stream));
     P.target_step = h->steps_done + n_steps;
     cudaError_t ce;
-    if (h->pipe) {
-        // the model pipeline runs beside the tree kernel on its own stream: it takes piQ.n_ctas whole SMs (its shared
-        // memory excludes a tree CTA), the tree kernel the rest; both end when every tree has reached the target step
+    if (h->pipe || h->split) {
+        // the model runs beside the tree kernel on its own stream: its CTAs take whole SMs (their shared memory excludes
+        // a tree CTA), the tree kernel the rest; both end when every tree has reached the target step
         CK(cudaEventRecord(h->fork_event, h->stream));
         CK(cudaStreamWaitEvent(h->gstream[0], h->fork_event, 0));
-        azb_pipe_kernel<<<h->piQ.n_ctas, PIPE_THREADS, h->pipe_smem, h->gstream[0]>>>(h->L, P, h->piQ, h->piM);
+        if (h->pipe)
+            azb_pipe_kernel<<<h->piQ.n_ctas, PIPE_THREADS, h->pipe_smem, h->gstream[0]>>>(h->L, P, h->piQ, h->piM);
+        else
+            azb_worker_kernel<<<P.n_workers, AS_MLP_THREADS, h->worker_smem, h->gstream[0]>>>(h->L, P, h->asM);
         ce = cudaGetLastError();
         if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "model pipeline launch: %s", cudaGetErrorString(ce));
         CK(cudaEventRecord(h->gevent[0], h->gstream[0]));
         h->launches += 1;
     }
+    const bool two = h->pipe || h->split;
     switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
         case 6: ce = async_launch<3, false>(h); break;
         case 7: ce = async_launch<3, true>(h); break;
@@ -898,14 +912,14 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
         default: ce = async_launch<5, true>(h); break;
     }
     if (ce != cudaSuccess) {
-        if (h->pipe) {  // the pipeline is already waiting for tiles: tell it to drain
+        if (two) {  // the model kernel is already waiting for tiles: tell it to drain
             const uint32_t one = 1;
             cudaMemcpy(&P.st->abort, &one, 4, cudaMemcpyHostToDevice);
             cudaStreamSynchronize(h->gstream[0]);
         }
         return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
     }
-    if (h->pipe) CK(cudaStreamWaitEvent(h->stream, h->gevent[0], 0));
+    if (two) CK(cudaStreamWaitEvent(h->stream, h->gevent[0], 0));
     h->launches += 1;
     h->async_ran = true;
     rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);

@@ -25,7 +25,11 @@
 
 #define AS_THREADS 1024
 #define AS_WARPS 32
-#define AS_EPI_WARPS 8   // two per TMEM lane quadrant, each taking half of a 128-column block
+#define AS_EPI_WARPS 8   // two per TMEM lane quadrant, each taking AS_EPI_COLS columns of a 128-column block
+#define AS_EPI_COLS (128 / (AS_EPI_WARPS / 4))      // 64
+#define AS_EPI_SLICES (AS_EPI_COLS / 16)            // 16-column TMEM slices per warp and block
+#define AS_EPI_CHUNKS (AS_EPI_COLS / 8)             // 16-byte chunks per staged row
+#define AS_EPI_STG_BYTES (32 * AS_EPI_COLS * 2)     // staging tile per warp: [32 rows x AS_EPI_COLS bf16]
 #define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)
 #define AS_STAGES 2
 #define AS_ACC 4          // 128-column blocks per pass: one A k-block is reused by up to four TMEM accumulators
@@ -75,6 +79,7 @@ struct AzbAsyncParams {
     const float *bias[4];
     uint32_t kpad[4], npad[4];
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
+    uint32_t split;          // 1: the model is its own kernel (azb_worker_kernel / azb_pipe_kernel) beside the tree kernel
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
     unsigned long long timeout_ns, flush_ns;
     uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
@@ -141,6 +146,24 @@ __device__ __forceinline__ void as_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) 
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void as_tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {  // no wait: batch several, then wait::ld
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// explicit shared-space accesses: the workers' shared memory arrives as a generic pointer, and ptxas then emits generic
+// LD.E / ST.E for the biases and the staging tile
+__device__ __forceinline__ uint4 as_lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void as_sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -181,6 +204,8 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             o += (P.npad[l] + 31u) & ~31u;
         }
     }
+    // per epilogue warp a staging tile behind the biases (coalesced activation stores)
+    uint8_t *stg = reinterpret_cast<uint8_t *>(s_bias + bias_off[3] + ((P.npad[3] + 31u) & ~31u)) + (warp >= 2 ? warp - 2u : 0u) * AS_EPI_STG_BYTES;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     as_named_bar(1, MLP_THREADS);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -354,7 +379,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
         } else {
             // ===== epilogue (warps 2..9): TMEM -> registers -> bias + activation -> scratch / prior rows =====
             // warp w reads TMEM lanes 32 (w % 4) ..; the two warps of a quadrant split each 128-column block in halves
-            const uint32_t q4 = warp & 3u, half = (warp - 2u) >> 2, row = q4 * 32u + lane;
+            const uint32_t q4 = warp & 3u, part = (warp - 2u) >> 2, col0 = part * AS_EPI_COLS, row = q4 * 32u + lane;
             const uint32_t et = threadIdx.x - 64u;
             if (et < AS_TILE) s_rowtree[et] = __ldcg(P.slot_tree + ring_row0 + et);
             as_named_bar(2, AS_EPI_WARPS * 32);
@@ -373,9 +398,47 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                   for (uint32_t ja = 0; ja < np; ++ja) {
                     const uint32_t nt = mem + (p0 + ja) * G;
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
-                    // 16 columns at a time: the accumulator slice and its biases (four 128-bit shared-memory loads issued
-                    // together) stay inside the 64-register budget, so nothing serialises on shared-memory latency
-                    for (uint32_t c0 = half * 64u; c0 < min(bn, half * 64u + 64u); c0 += 16) {
+                    if (l < 3) {
+                        // this warp's 64 columns of the block: four 16-column TMEM slices in flight at once, bias + ReLU,
+                        // bf16 pairs into the warp's staging tile [32 rows x 128 B]; 16-byte chunks XOR-swizzled by row,
+                        // so these stores and the row-wise reads below are both bank-conflict free
+                        if (col0 < bn) {
+                            uint32_t r[AS_EPI_SLICES][16];
+                            const long long tl0 = AS_CLK();
+#pragma unroll
+                            for (uint32_t sl = 0; sl < AS_EPI_SLICES; ++sl)
+                                as_tmem_ld16_issue(tmem_base + ((q4 * 32u) << 16) + ja * 128u + col0 + sl * 16u, r[sl]);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            d_acq += AS_CLK() - tl0;
+                            const uint32_t srow = tc_smem_u32(stg) + lane * (AS_EPI_COLS * 2u);
+                            const uint32_t bias_s = tc_smem_u32(bias + nt * 128u + col0);
+                            const uint32_t sw = AS_EPI_CHUNKS == 8 ? (lane & 7u) : ((lane >> 1) & 3u);  // chunk swizzle of this row
+#pragma unroll
+                            for (uint32_t sl = 0; sl < AS_EPI_SLICES; ++sl) {
+                                uint32_t pk[8];
+#pragma unroll
+                                for (int t = 0; t < 8; t += 2) {
+                                    const uint4 b4 = as_lds128(bias_s + (sl * 16u + 2u * t) * 4u);
+                                    float v0 = __uint_as_float(r[sl][2 * t]) + __uint_as_float(b4.x);
+                                    float v1 = __uint_as_float(r[sl][2 * t + 1]) + __uint_as_float(b4.y);
+                                    float v2 = __uint_as_float(r[sl][2 * t + 2]) + __uint_as_float(b4.z);
+                                    float v3 = __uint_as_float(r[sl][2 * t + 3]) + __uint_as_float(b4.w);
+                                    v0 = fmaxf(v0, 0.f);
+                                    v1 = fmaxf(v1, 0.f);
+                                    v2 = fmaxf(v2, 0.f);
+                                    v3 = fmaxf(v3, 0.f);
+                                    __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+                                    pk[t] = *reinterpret_cast<uint32_t *>(&h01);
+                                    pk[t + 1] = *reinterpret_cast<uint32_t *>(&h23);
+                                }
+                                const uint32_t ch = 2u * sl;  // this slice's two 16-byte chunks in the staged row
+                                as_sts128(srow + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                                as_sts128(srow + (((ch + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+                            }
+                        }
+                    } else {
+                      // the Sigmoid head: f32 rows scattered to the owning trees' prior rows, 16 columns at a time
+                      for (uint32_t c0 = col0; c0 < min(bn, col0 + (uint32_t)AS_EPI_COLS); c0 += 16) {
                         uint32_t r[16];
                         const long long tl0 = AS_CLK();
                         as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + ja * 128u + c0, r);
@@ -390,23 +453,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                             b[j + 2] = b4.z;
                             b[j + 3] = b4.w;
                         }
-                        if (l < 3) {
-                            __nv_bfloat16 *dst = P.act[l] + (size_t)(grp * AS_TILE + row) * P.kpad[l + 1] + nb;
-                            uint32_t pk[8];
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                float v0 = __uint_as_float(r[2 * t]) + b[2 * t];
-                                float v1 = __uint_as_float(r[2 * t + 1]) + b[2 * t + 1];
-                                v0 = v0 > 0.f ? v0 : 0.f;
-                                v1 = v1 > 0.f ? v1 : 0.f;
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-                                pk[t] = *reinterpret_cast<uint32_t *>(&h2);
-                            }
-                            if (!AS_DBG(1u)) {
-                                *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                *reinterpret_cast<uint4 *>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                            }
-                        } else if (my_tree != AS_NONE) {
+                        if (my_tree != AS_NONE) {
                             float *dst = L.h + (size_t)my_tree * L.h_ld;
                             const bool vec = (L.h_ld & 3u) == 0u;
 #pragma unroll
@@ -427,6 +474,23 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                 }
                             }
                         }
+                      }
+                    }
+                    if (l < 3 && col0 < bn) {
+                        // the warp's [32 rows x AS_EPI_COLS columns] go out as contiguous row pieces: AS_EPI_CHUNKS lanes per
+                        // row (a store per thread and row touched 32 lines per instruction and held the epilogue to ~0.4 us
+                        // per 16-column slice on the LSU)
+                        __syncwarp();
+                        const uint32_t rr = lane / AS_EPI_CHUNKS, cc = lane % AS_EPI_CHUNKS;
+                        __nv_bfloat16 *dst0 = P.act[l] + (size_t)(grp * AS_TILE + q4 * 32u) * P.kpad[l + 1] + nt * 128u + col0 + cc * 8u;
+#pragma unroll
+                        for (uint32_t it = 0; it < AS_EPI_CHUNKS; ++it) {
+                            const uint32_t rw = it * (32u / AS_EPI_CHUNKS) + rr;
+                            const uint32_t sw = AS_EPI_CHUNKS == 8 ? (rw & 7u) : ((rw >> 1) & 3u);
+                            const uint4 v = as_lds128(tc_smem_u32(stg) + rw * (AS_EPI_COLS * 2u) + ((cc ^ sw) << 4));
+                            if (!AS_DBG(1u)) *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * P.kpad[l + 1]) = v;
+                        }
+                        __syncwarp();
                     }
                   }
                   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -454,7 +518,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
             as_named_bar(2, AS_EPI_WARPS * 32);
             if (s_epi_count) {
                 __threadfence();
-                if (half == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
+                if (part == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
                 if (threadIdx.x == 64u) {
                     atomicAdd(P.tile_retired + (q % P.NT), 1u);
                     atomicAdd(&st->tiles_done, 1u);
@@ -631,12 +695,18 @@ template <int DEPTH, bool COUNT>
 __global__ void __launch_bounds__(AS_THREADS, 1)
     azb_async_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
     extern __shared__ __align__(1024) uint8_t as_smem[];
+    if (P.split) {  // the model runs in its own kernel beside this one (the default): every CTA walks
+        async_tree_worker<DEPTH, COUNT>(L, P, blockIdx.x, gridDim.x, reinterpret_cast<uint32_t *>(as_smem));
+        return;
+    }
+    // One-kernel form (AZB_ASYNC_SPLIT=0; what a kernel-serialising profiler such as ncu can capture): the first CTA on
+    // each of n_workers SMs becomes that SM's MLP worker (compiled under this kernel's 64 registers: slower epilogue)
     __shared__ uint32_t s_role, s_idx;
     if (threadIdx.x == 0) {
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         uint32_t role = 0, idx = 0;
-        if (atomicCAS(&P.st->sm_flag[smid & 1023u], 0u, 1u) == 0u) {  // first CTA on this SM: may become its MLP worker
+        if (atomicCAS(&P.st->sm_flag[smid & 1023u], 0u, 1u) == 0u) {
             const uint32_t m = atomicAdd(&P.st->mlp_claims, 1u);
             if (m < P.n_workers) {
                 role = 1;
@@ -655,4 +725,14 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
     } else {
         async_tree_worker<DEPTH, COUNT>(L, P, s_idx, gridDim.x - P.n_workers, reinterpret_cast<uint32_t *>(as_smem));
     }
+}
+
+// The MLP workers are a kernel of their own, launched beside the tree kernel on a second stream, one CTA per worker SM
+// (their shared memory excludes a tree CTA from the SM).  The tree kernel then asks only for its own shared memory and
+// the workers are not held to its 64 registers per thread (the epilogue keeps four TMEM slices in flight).
+__global__ void __launch_bounds__(AS_MLP_THREADS, 1)
+    azb_worker_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
+    extern __shared__ __align__(1024) uint8_t as_wsmem[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)as_wsmem + 1023) & ~(uintptr_t)1023);
+    async_mlp_worker(L, P, M, blockIdx.x, smem);
 }
