@@ -358,16 +358,32 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (tc_elect_one()) {
                             const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes);
-                            for (uint32_t j = 0; j < np; ++j) {
-                                const uint32_t nt = mem + (p0 + j) * G;
-                                const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
-                                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
-                                const uint32_t b_addr = a_addr + (1u + j) * tile_bytes;
+                            if (G == 1u) {
+                                // adjacent 128-column blocks are adjacent in the stage and in TMEM: one N <= 256 MMA per
+                                // pair reads the A tile once for both (a 128x128x16 SS-MMA is shared-memory bound)
+                                for (uint32_t j = 0; j < np; j += 2) {
+                                    const uint32_t nt = p0 + j;
+                                    const uint32_t bn = min(256u, P.npad[l] - nt * 128u);
+                                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
+                                    const uint32_t b_addr = a_addr + (1u + j) * tile_bytes;
 #pragma unroll
-                                for (uint32_t k = 0; k < TC_BK / 16; ++k)
-                                    if (!AS_DBG(8u))  // timing experiment: loads only
-                                        tc_umma_f16(tmem_base + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
-                                                    idesc, (kb | k) != 0u ? 1u : 0u);
+                                    for (uint32_t k = 0; k < TC_BK / 16; ++k)
+                                        if (!AS_DBG(8u))
+                                            tc_umma_f16(tmem_base + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
+                                                        idesc, (kb | k) != 0u ? 1u : 0u);
+                                }
+                            } else {
+                                for (uint32_t j = 0; j < np; ++j) {
+                                    const uint32_t nt = mem + (p0 + j) * G;
+                                    const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
+                                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
+                                    const uint32_t b_addr = a_addr + (1u + j) * tile_bytes;
+#pragma unroll
+                                    for (uint32_t k = 0; k < TC_BK / 16; ++k)
+                                        if (!AS_DBG(8u))  // timing experiment: loads only
+                                            tc_umma_f16(tmem_base + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
+                                                        idesc, (kb | k) != 0u ? 1u : 0u);
+                                }
                             }
                             tc_umma_commit(&empty_bar[s]);
                             if (kb + 1 == k_blocks) tc_umma_commit(&acc_full);
