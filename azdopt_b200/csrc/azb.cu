@@ -805,7 +805,7 @@ static int async_create(azb_handle *h) {
     P.split = (h->pipe || h->split) ? 1u : 0u;
     P.tree_warps = tree_warps;
     // worker SMs per tile: one when few SMs serve the model (every tree keeps its own warp at 4096 roots), pairs otherwise
-    P.group = W <= 24 ? 1 : 2;
+    P.group = W < 40 ? 1 : 2;
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
     if (h->pipe) P.group = 1;
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);

@@ -203,9 +203,9 @@ def main():
     prof_steps = min(args.steps, 100)
     aw = args.async_workers
     if aw < 0:  # auto: 20 of the 148 SMs answer state vectors (128 x 32 warps walk: one tree per warp at 4096 roots);
-        # above 4096 roots 48 SMs in pairs
+        # 48 SMs in pairs up to 16 K roots, 32 single SMs beyond (profiles/README.md, worker sweeps)
         ok = args.mlp == "tc" and not args.max_episodes and args.groups == 1 and 1024 <= b <= 100000
-        aw = (40 if b < 4096 else 20 if b == 4096 else 48) if ok else 0
+        aw = (40 if b < 4096 else 20 if b == 4096 else 48 if b < 16384 else 32) if ok else 0
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
                               mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
@@ -366,8 +366,9 @@ def main():
             "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
                        "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": mlp_note, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
-                       "search": (f"asynchronous persistent kernel: {aw} tensor-core worker SMs + tree warps, one launch per "
-                                  "azb_step call" if aw else "lock step: one search launch + model forward per step"),
+                       "search": (f"asynchronous: persistent tree kernel ({148 - aw} SMs) beside a persistent tensor-core model "
+                                  f"kernel ({aw} SMs), one launch of each per azb_step call" if aw
+                                  else "lock step: one search launch + model forward per step"),
                        "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
                        "simulations_in_timed_region": sims, "noop_root_steps": noops,
                        "cost_evals_per_sec": evals / (ms_max * 1e-3)},

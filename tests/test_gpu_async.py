@@ -1,6 +1,8 @@
-"""The asynchronous search kernel (azb_config.async_workers > 0: persistent tree warps + in-kernel tensor-core MLP
-workers, azb_async.cuh) must give exactly what the lock step gives: trees are independent and a row's forward pass
-does not depend on the tile it rides in.  Bit-exact trees, walkers, priors, improvement log, argmin, counters."""
+"""The asynchronous search step (azb_config.async_workers > 0: a persistent tree kernel beside a persistent tensor-core
+model kernel, azb_async.cuh) must give exactly what the lock step gives: trees are independent and a row's forward pass
+does not depend on the tile it rides in.  Bit-exact trees, walkers, priors, improvement log, argmin, counters — in the
+default two-kernel form, the one-kernel form (AZB_ASYNC_SPLIT=0, what ncu captures) and the weight-stationary model
+pipeline (AZB_ASYNC_PIPE=1, azb_pipe.cuh)."""
 import numpy as np
 import pytest
 
@@ -43,6 +45,25 @@ def test_async_equals_lock_step(capi, n, b, workers):
         # mixed calls: a single step (the CUDA-graph path) between two asynchronous runs
         for h in (lock, asy):
             h.step(1)
+            h.step(steps)
+        _same(lock, asy, b)
+
+
+@pytest.mark.parametrize("env", [{"AZB_ASYNC_SPLIT": "0"}, {"AZB_ASYNC_PIPE": "1"}, {"AZB_ASYNC_GROUP": "2"}])
+@pytest.mark.parametrize("n,b,workers", [(19, 1024, 8), (12, 77, 4)])
+def test_async_variants_equal_lock_step(capi, monkeypatch, env, n, b, workers):
+    """The other forms of the model side (read from the environment when the handle first runs asynchronously)."""
+    steps = 30
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    parents, masks = capi.generate_roots(6, 0, b, n)
+    kw = dict(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=2 * steps + 2)
+    with _mk(capi, n, b, **kw) as lock, _mk(capi, n, b, async_workers=workers, **kw) as asy:
+        for h in (lock, asy):
+            h.mlp_init(4)
+            h.set_roots(parents, masks)
+            h.init_trees()
+            h.step(steps)
             h.step(steps)
         _same(lock, asy, b)
 
