@@ -170,7 +170,7 @@ __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.pro
 // MLP worker: warps 0 (TMA producer), 1 (MMA issuer, TMEM owner), 2-9 (epilogue); the CTA's other warps have left.
 __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
                                  const uint32_t worker, uint8_t *smem) {
-    __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full, acc_empty;
+    __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full, acc_empty, layer_bar;
     __shared__ uint32_t tmem_slot, s_tile, s_epi_count;
     __shared__ uint32_t s_rowtree[AS_TILE];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -183,6 +183,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
         }
         tc_mbar_init(&acc_full, 1);
         tc_mbar_init(&acc_empty, AS_EPI_WARPS);
+        tc_mbar_init(&layer_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
         for (int l = 0; l < 4; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w[l]) : "memory");
@@ -222,6 +223,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
     // the three layer boundaries through monotonic counters in global memory.  The leader (m = 0) takes the tile.
     const uint32_t G = P.group, grp = worker / G, mem = worker % G;
     uint32_t seq = 0;  // tiles this group has taken
+    uint32_t lbc = 0;  // layer boundaries passed (G == 1: phase of layer_bar)
     for (;;) {
         if (warp == 0 && lane == 0) {
             const long long tq0 = AS_CLK();
@@ -308,7 +310,12 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
                     if (l > 0) {  // this layer's input is the previous layer's output, written by all members
                         const long long tw = AS_CLK();
-                        while (as_ld_volatile(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
+                        if (G == 1u) {  // a single worker: the layer boundary is a shared-memory barrier, not an L2 round trip
+                            as_mbar_spin(&layer_bar, lbc & 1u);
+                            ++lbc;
+                        } else {
+                            while (as_ld_volatile(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
+                        }
                         d_w1 += AS_CLK() - tw;
                         as_fence_proxy_async();
                     }
@@ -521,7 +528,8 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 as_named_bar(2, AS_EPI_WARPS * 32);
                 if (threadIdx.x == 64u) {
                     if (l < 3) {
-                        atomicAdd(&st->grp_layer[grp * 4 + l], 1u);
+                        if (G == 1u) as_mbar_arrive(&layer_bar);
+                        else atomicAdd(&st->grp_layer[grp * 4 + l], 1u);
                     } else if (atomicAdd(&st->grp_done[grp], 1u) + 1u == arrive_target) {
                         s_epi_count = 1u;  // this member is the last of the group to finish the tile
                     } else {
