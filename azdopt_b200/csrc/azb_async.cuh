@@ -308,7 +308,24 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
                 for (uint32_t l = 0; l < 4; ++l) {
                     const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
+                    // this member's blocks nt = mem, mem + G, ... in passes of up to AS_ACC: per k-block ONE A tile and the
+                    // pass's B tiles, so a tile's activations are read once per pass instead of once per block
+                    const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
+                    uint32_t pre = 0;  // k-blocks of the first pass whose weight tiles were requested ahead of the layer barrier
                     if (l > 0) {  // this layer's input is the previous layer's output, written by all members
+                        // the weights do not depend on it: while the epilogue warps still drain the previous layer, the
+                        // ring's stages are free, so the first stages' B tiles go out now and only their A tiles wait
+                        const uint32_t np0 = min((uint32_t)AS_ACC, mine);
+                        if (!AS_DBG(4u))
+                            for (; np0 && pre < min((uint32_t)AS_STAGES, k_blocks); ++pre) {
+                                const uint32_t kc = kbc + pre, s = kc % AS_STAGES, ph = (kc / AS_STAGES) & 1u;
+                                as_mbar_spin(&empty_bar[s], ph ^ 1u);
+                                uint8_t *a_dst = smem + (size_t)s * stage_bytes;
+                                tc_mbar_expect_tx(&full_bar[s], (1u + np0) * tile_bytes);
+                                for (uint32_t j = 0; j < np0; ++j)
+                                    as_tma_load_2d_hint(a_dst + (1u + j) * tile_bytes, &M.w[l], &full_bar[s], (int)(pre * TC_BK),
+                                                        (int)((mem + j * G) * 128u), w_policy);
+                            }
                         const long long tw = AS_CLK();
                         if (G == 1u) {  // a single worker: the layer boundary is a shared-memory barrier, not an L2 round trip
                             as_mbar_spin(&layer_bar, lbc & 1u);
@@ -321,17 +338,18 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     }
                     const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
                     const int arow = (int)(l == 0 ? ring_row0 : grp * AS_TILE);
-                    // this member's blocks nt = mem, mem + G, ... in passes of up to AS_ACC: per k-block ONE A tile and the
-                    // pass's B tiles, so a tile's activations are read once per pass instead of once per block
-                    const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
                     for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC) {
                         const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                         for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                             const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                            uint8_t *a_dst = smem + (size_t)s * stage_bytes;
+                            if (p0 == 0u && kb < pre) {  // stage claimed and its B tiles requested above: only the A tile is left
+                                tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
+                                continue;
+                            }
                             const long long tw = AS_CLK();
                             as_mbar_spin(&empty_bar[s], ph ^ 1u);
                             d_w0 += AS_CLK() - tw;
-                            uint8_t *a_dst = smem + (size_t)s * stage_bytes;
                             if (AS_DBG(4u)) {  // timing experiment: no loads, the MMAs run on stale operands
                                 as_mbar_arrive(&full_bar[s]);
                                 continue;
