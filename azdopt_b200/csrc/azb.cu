@@ -778,7 +778,7 @@ static int async_create(azb_handle *h) {
     const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
-    const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
+    const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + 1024 + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
     // the model (workers or pipeline) is its own kernel beside the tree kernel; AZB_ASYNC_SPLIT=0 folds the workers into
     // the tree kernel (one launch: what ncu can capture, since it serialises kernels)
     h->split = !h->pipe;
@@ -846,6 +846,8 @@ static int async_create(azb_handle *h) {
     const char *why = azb_tc_make_map(enc, &h->asM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
     for (int l = 0; l < 3 && !why; ++l)
         why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
+    for (int l = 0; l < 3 && !why; ++l)
+        why = azb_tc_make_map(enc, &h->asM.act_st[l], P.act[l], (uint64_t)act_tiles * AS_TILE, h->tc.kpad[l + 1], 32);
     for (int l = 0; l < 4 && !why; ++l)
         why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], 128);
     if (h->pipe) {

@@ -30,6 +30,11 @@
 #define AS_EPI_SLICES (AS_EPI_COLS / 16)            // 16-column TMEM slices per warp and block
 #define AS_EPI_CHUNKS (AS_EPI_COLS / 8)             // 16-byte chunks per staged row
 #define AS_EPI_STG_BYTES (32 * AS_EPI_COLS * 2)     // staging tile per warp: [32 rows x AS_EPI_COLS bf16]
+// The staged tile is exactly a SWIZZLE_128B box, so one TMA store could replace the row-piece stores.  Measured: slower
+// (epilogue 15.8 -> 21.0 us per tile, 32.7 -> 31.3 M simulations/s): with ONE staging tile per warp every block waits
+// for the previous store to have read it (wait_group.read) behind a proxy fence, and there is no shared memory left for
+// a second tile (160 KB operand ring + 32 KB staging + biases).  Kept switchable.
+#define AS_EPI_TMA_STORE 0
 #define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)
 #define AS_STAGES 2
 #define AS_ACC 4          // 128-column blocks per pass: one A k-block is reused by up to four TMEM accumulators
@@ -65,6 +70,7 @@ struct AzbAsyncState {  // device memory, zeroed before every launch
 struct AzbAsyncMaps {
     CUtensorMap ring;    // layer-0 input: [NT*128 rows][kpad0] bf16
     CUtensorMap act[3];  // hidden activations of the workers: [n_workers*128 rows][kpad[l+1]]
+    CUtensorMap act_st[3];  // the same buffers with a 64 x 32 box: an epilogue warp's staged rows leave as one TMA store
     CUtensorMap w[4];    // weights [rows padded to 128][kpad[l]], box 64 x 128
 };
 
@@ -206,7 +212,8 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
         }
     }
     // per epilogue warp a staging tile behind the biases (coalesced activation stores)
-    uint8_t *stg = reinterpret_cast<uint8_t *>(s_bias + bias_off[3] + ((P.npad[3] + 31u) & ~31u)) + (warp >= 2 ? warp - 2u : 0u) * AS_EPI_STG_BYTES;
+    uint8_t *stg = reinterpret_cast<uint8_t *>(s_bias + bias_off[3] + ((P.npad[3] + 31u) & ~31u));
+    stg = (uint8_t *)(((uintptr_t)stg + 1023) & ~(uintptr_t)1023) + (warp >= 2 ? warp - 2u : 0u) * AS_EPI_STG_BYTES;  // swizzle atoms: 1 KB
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     as_named_bar(1, MLP_THREADS);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -451,6 +458,10 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                 as_tmem_ld16_issue(tmem_base + ((q4 * 32u) << 16) + ja * 128u + col0 + sl * 16u, r[sl]);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                             d_acq += AS_CLK() - tl0;
+                            if (AS_EPI_TMA_STORE) {  // the previous TMA store of this warp must have read the staging tile
+                                if (tc_elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                                __syncwarp();
+                            }
                             const uint32_t srow = tc_smem_u32(stg) + lane * (AS_EPI_COLS * 2u);
                             const uint32_t bias_s = tc_smem_u32(bias + nt * 128u + col0);
                             const uint32_t sw = AS_EPI_CHUNKS == 8 ? (lane & 7u) : ((lane >> 1) & 3u);  // chunk swizzle of this row
@@ -517,7 +528,17 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                         }
                       }
                     }
-                    if (l < 3 && col0 < bn) {
+                    if (AS_EPI_TMA_STORE && l < 3 && col0 < bn) {
+                        // the staged [32 rows x 64 columns] is a SWIZZLE_128B box: one TMA store (no LSU work at all)
+                        as_fence_proxy_async();  // the staging writes, for the async proxy
+                        __syncwarp();
+                        if (tc_elect_one() && !AS_DBG(1u)) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&M.act_st[l]),
+                                         "r"(tc_smem_u32(stg)), "r"((int)(nt * 128u + col0)), "r"((int)(grp * AS_TILE + q4 * 32u))
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else if (l < 3 && col0 < bn) {
                         // the warp's [32 rows x AS_EPI_COLS columns] go out as contiguous row pieces: AS_EPI_CHUNKS lanes per
                         // row (a store per thread and row touched 32 lines per instruction and held the epilogue to ~0.4 us
                         // per 16-column slice on the LSU)
@@ -541,7 +562,12 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                 }
                 // ---- layer boundary: this member's share of the layer is stored; tell the group
                 const long long tf0 = AS_CLK();
-                if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
+                if (AS_EPI_TMA_STORE) {
+                    if (l < 3 && tc_elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's stores are done
+                    __syncwarp();
+                } else if (l < 3) {
+                    as_fence_proxy_async();  // the next layer reads these stores through TMA
+                }
                 __threadfence();
                 as_named_bar(2, AS_EPI_WARPS * 32);
                 if (threadIdx.x == 64u) {
