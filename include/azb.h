@@ -83,10 +83,13 @@ typedef struct azb_config {
                                    episodes and finishes the step in a later launch; same results, shorter launches */
     uint32_t n_groups;          /* >1: the trees of this handle advance as that many independent groups on their own
                                    CUDA streams (needs max_episodes = 0); results are identical, launches overlap */
-    uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as ONE persistent kernel in
-                                   which trees never wait for each other — tree warps advance whichever of their trees has
-                                   its priors, that many tensor-core worker SMs (20 at 4096 roots; in pairs per tile above
-                                   24) answer state vectors in 128-row tiles as they fill.  Same results as the lock step (trees are independent). 0 = lock step. */
+    uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as two persistent kernels side
+                                   by side in which trees never wait for each other — tree warps advance whichever of their
+                                   trees has its priors, that many tensor-core worker SMs (20 at 4096 roots, 32 from 16 K roots;
+                                   in pairs per tile from 40) answer state vectors in 128-row tiles as they fill.  Same
+                                   results as the lock step (trees are independent).  0 = lock step.  Environment, read when
+                                   the handle first runs this way: AZB_ASYNC_SPLIT=0 (one kernel, for ncu), AZB_ASYNC_GROUP=g,
+                                   AZB_ASYNC_PIPE=1 (weight-stationary model pipeline), AZB_ASYNC_FLUSH_NS. */
     uint32_t reserved[5];
 } azb_config;
 

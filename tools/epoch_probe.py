@@ -8,7 +8,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 b = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 epochs = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 800
-aw = int(sys.argv[5]) if len(sys.argv) > 5 else (20 if b <= 4096 else 48)  # 0 = lock step
+aw = int(sys.argv[5]) if len(sys.argv) > 5 else (20 if b <= 4096 else 48 if b < 16384 else 32)  # 0 = lock step
 cfg = capi.default_config(n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=steps, async_workers=aw)
 p, m = capi.generate_roots(0, 0, b, n)
 with capi.Handle(cfg) as h:
