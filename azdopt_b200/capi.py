@@ -76,6 +76,7 @@ SIGNATURES = {
     "azb_init_trees": (C.c_int, [C.c_void_p]),
     "azb_step": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(Improvement), C.c_uint32, u32p]),
     "azb_step_enqueue": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "azb_step_poll": (C.c_int, [C.c_void_p, C.POINTER(Improvement), C.POINTER(C.c_int)]),
     "azb_step_timed": (C.c_int, [C.c_void_p, C.c_uint32, f32p, u32p]),
     "azb_step_profile": (C.c_int, [C.c_void_p, C.c_uint32, f32p, f32p]),
     "azb_rollout_host": (C.c_int, [C.c_void_p, f32p]),
@@ -279,6 +280,13 @@ class Handle:
 
     def step_enqueue(self, n_steps):
         self._ck(self._L.azb_step_enqueue(self._h, n_steps))
+
+    def step_poll(self):
+        """Result of the next enqueued step (azb_step_poll): (improved, (step, tree, node, eval))."""
+        imp = Improvement()
+        flag = C.c_int()
+        self._ck(self._L.azb_step_poll(self._h, C.byref(imp), C.byref(flag)))
+        return bool(flag.value), (imp.step, imp.tree, imp.node, np.float32(imp.eval))
 
     def step_timed(self, n_steps):
         ms = C.c_float()

@@ -67,6 +67,13 @@ struct azb_handle {
     // weight-stationary model pipeline beside the tree kernel (azb_pipe.cuh)
     bool pipe, split;
     size_t worker_smem;
+    // azb_step_poll: per-step results of enqueued steps while they still run (copies on their own stream)
+    cudaStream_t poll_stream;
+    uint2 *poll_pin;          // pinned: one candidate row [B]
+    uint32_t *poll_word;      // pinned: best_c at the start of the batch
+    uint32_t poll_next;       // next candidate slot to report (slot s = step s - 1)
+    uint32_t poll_best;       // running best, order-preserving bits
+    bool poll_best_valid;
     AzbPipeParams piQ;
     AzbPipeMaps piM;
     size_t pipe_smem;
@@ -207,6 +214,9 @@ int azb_destroy(azb_handle *h) {
     }
     if (h->fork_event) cudaEventDestroy(h->fork_event);
     if (h->pin_g) cudaFreeHost(h->pin_g);
+    if (h->poll_pin) cudaFreeHost(h->poll_pin);
+    if (h->poll_word) cudaFreeHost(h->poll_word);
+    if (h->poll_stream) cudaStreamDestroy(h->poll_stream);
     if (h->pin_log) cudaFreeHost(h->pin_log);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -647,6 +657,8 @@ static int run_argmin(azb_handle *h, uint32_t slot_hi) {
     h->launches += 2;
     CK(cudaGetLastError());
     h->argmin_from = slot_hi;
+    h->poll_next = slot_hi;
+    h->poll_best_valid = false;
     return AZB_OK;
 }
 
@@ -689,6 +701,8 @@ int azb_init_trees(azb_handle *h) {
     h->pending_add = false;
     h->steps_done = 0;
     h->argmin_from = first ? 0u : 1u;
+    h->poll_next = 1u;
+    h->poll_best_valid = false;
     if (first) {  // par_new's silent argmin over the roots (optimizer/mod.rs:95-101)
         rc = run_argmin(h, 1);
         if (rc) return rc;
@@ -1066,6 +1080,8 @@ static int step_once_graph(azb_handle *h, azb_improvement *improvements, uint32_
     h->launches += 2 + (mlp ? 4 : 0);
     h->steps_done += 1;
     h->argmin_from = h->steps_done + 1;
+    h->poll_next = h->argmin_from;
+    h->poll_best_valid = false;
     h->pending_add = true;
     CK(cudaStreamSynchronize(h->stream));
     const AzbGlobals &g = *h->pin_g;
@@ -1110,7 +1126,74 @@ int azb_step_enqueue(azb_handle *h, uint32_t n_steps) {
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
     if (h->cfg.max_episodes) return fail(h, AZB_ERR_INVALID, "azb_step_enqueue needs max_episodes = 0");
     CK(cudaSetDevice(h->cfg.device));
+    if (h->steps_done + n_steps > h->L.cap_steps)
+        return fail(h, AZB_ERR_CAPACITY, "%u steps since azb_init_trees exceed max_steps", h->steps_done + n_steps);
+    // candidate rows of these steps: "not written yet" (a tree's entry is (ord(c), node) once it has finished the step,
+    // (0xffffffff, 0) for an exhausted root) — what azb_step_poll waits on
+    if (n_steps)
+        CK(cudaMemsetAsync(h->L.cand + (size_t)(h->steps_done + 1) * h->L.B, 0xff, (size_t)n_steps * h->L.B * sizeof(uint2), h->stream));
     return enqueue_steps(h, n_steps, AZB_F_ADD | AZB_F_ROLLOUT);
+}
+
+// The result of the next enqueued step that has not been reported yet, as soon as EVERY tree has finished that step —
+// while later steps are still running (trees are independent, so on the asynchronous path they run ahead of the
+// caller).  This is par_roll_out_episodes' per-step return value (optimizer/mod.rs:121-191, ArgminImprovement) at the
+// speed of the fused loop: the host reads the step's candidate row (8 B per tree) on a copy stream and applies
+// par_update_argmmim_data's rule itself (first minimum over trees, strictly below the running best: :194-246).
+// After the last step azb_step(h, 0, ...) completes the batch (device-side argmin state, log, error check); the
+// improvements it logs are exactly the ones reported here.
+int azb_step_poll(azb_handle *h, azb_improvement *out, int *improved) {
+    if (!h || !improved) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    if (h->poll_next > h->steps_done || h->poll_next < h->argmin_from)
+        return fail(h, AZB_ERR_STATE, "no enqueued step is waiting to be reported (azb_step_enqueue first)");
+    CK(cudaSetDevice(h->cfg.device));
+    const uint32_t B = h->L.B;
+    if (!h->poll_stream) CK(cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking));
+    if (!h->poll_pin) CK(cudaMallocHost((void **)&h->poll_pin, (size_t)B * sizeof(uint2)));
+    if (!h->poll_word) CK(cudaMallocHost((void **)&h->poll_word, 16));
+    if (!h->poll_best_valid) {  // the running best is only rewritten by the argmin pass that ends a batch
+        CK(cudaMemcpyAsync(h->poll_word, &h->L.g->best_c, 4, cudaMemcpyDeviceToHost, h->poll_stream));
+        CK(cudaStreamSynchronize(h->poll_stream));
+        h->poll_best = h->poll_word[0];
+        h->poll_best_valid = true;
+    }
+    const uint2 *src = h->L.cand + (size_t)h->poll_next * B;
+    bool finished = false;  // the enqueued work has ended: one more look at the row decides
+    for (;;) {
+        CK(cudaMemcpyAsync(h->poll_pin, src, (size_t)B * sizeof(uint2), cudaMemcpyDeviceToHost, h->poll_stream));
+        CK(cudaStreamSynchronize(h->poll_stream));
+        bool complete = true;
+        for (uint32_t t = 0; t < B; ++t)
+            if (h->poll_pin[t].y == 0xffffffffu) {
+                complete = false;
+                break;
+            }
+        if (complete) break;
+        if (finished) {  // a tree stopped before this step (capacity, NaN, watchdog): report what the device says
+            int rc = check_device_error(h);
+            return rc ? rc : fail(h, AZB_ERR_CUDA, "step %u was not finished by every tree", h->poll_next - 1u);
+        }
+        const cudaError_t q = cudaStreamQuery(h->stream);
+        if (q == cudaSuccess) finished = true;
+        else if (q != cudaErrorNotReady) return fail(h, AZB_ERR_CUDA, "%s", cudaGetErrorString(q));
+    }
+    unsigned long long m = ~0ull;
+    for (uint32_t t = 0; t < B; ++t) {
+        const unsigned long long k = ((unsigned long long)h->poll_pin[t].x << 32) | t;
+        m = k < m ? k : m;
+    }
+    const uint32_t oc = (uint32_t)(m >> 32), tree = (uint32_t)m;
+    *improved = oc < h->poll_best ? 1 : 0;
+    if (*improved) h->poll_best = oc;
+    if (out) {
+        out->step = h->poll_next - 1u;
+        out->tree = tree;
+        out->node = h->poll_pin[tree].y;
+        out->eval = azb_ord2f(oc);
+    }
+    h->poll_next += 1u;
+    return AZB_OK;
 }
 
 int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_improved) {

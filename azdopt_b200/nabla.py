@@ -162,6 +162,19 @@ class NablaOptimizer:
             raise TypeError("the fused loop needs the device model")
         return self.h.step(n_steps, cap=max(64, n_steps))[1]
 
+    def roll_out_ahead(self, n_steps: int):
+        """The per-step loop of the example (04-c21-tree.rs:140-150: one par_roll_out_episodes per step, log when it
+        improved) with the trees running ahead of the caller: yields (step, improved, (step, tree, node, eval)) for each
+        of the n_steps as soon as every tree has finished that step (azb_step_enqueue + azb_step_poll), then completes
+        the batch, so argmin_data() afterwards is what n_steps calls of par_roll_out_episodes would have left."""
+        if not isinstance(self.model, ActionModel):
+            raise TypeError("the fused loop needs the device model")
+        self.h.step_enqueue(n_steps)
+        for _ in range(n_steps):
+            improved, rec = self.h.step_poll()
+            yield rec[0], improved, rec
+        self.h.step(0)
+
     def argmin_data(self) -> ArgminData:  # optimizer/mod.rs:361-363
         a = self.h.argmin()
         return ArgminData(a["parents"], a["permitted"], a["lambda1"], a["mu"], a["eval"])

@@ -346,6 +346,28 @@ def main():
     e2e["per_step_calls"] = {"value": ps_sims / ps_s, "unit": UNIT,
                              "what": "same, K x azb_step(1) (one CUDA-graph launch + sync + read-back per step)",
                              "same_argmin": bool(am1["eval"] == am["eval"])}
+    # ... and with the trees running ahead of the caller: azb_step_enqueue(K), then one azb_step_poll per step (the
+    # step's ArgminImprovement as soon as every tree has finished it), azb_step(0) to complete
+    barrier()
+    q0 = time.perf_counter()
+    h2.set_roots(parents, masks)
+    h2.init_trees()
+    n_live_before = h2.counters()["n_live"]
+    h2.step_enqueue(args.steps)
+    n_pol = 0
+    for _ in range(args.steps):
+        n_pol += 1 if h2.step_poll()[0] else 0
+    h2.step(0)
+    am2 = h2.argmin()
+    torch.cuda.synchronize()
+    q1 = time.perf_counter()
+    pq_sims = allreduce(float(h2.counters()["n_live"] - n_live_before), dist.ReduceOp.SUM if world > 1 else None)
+    pq_s = allreduce(q1 - q0, dist.ReduceOp.MAX if world > 1 else None)
+    e2e["per_step_polled"] = {"value": pq_sims / pq_s, "unit": UNIT,
+                              "what": "same, azb_step_enqueue(K) + K x azb_step_poll (each step's improvement record read back "
+                                      "as soon as every tree has finished it, later steps still running) + azb_step(0)",
+                              "d2h_bytes_per_step": 8 * b, "same_argmin": bool(am2["eval"] == am["eval"]),
+                              "same_improvements": bool(n_pol == n_imp)}
     h.close()
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores

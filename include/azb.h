@@ -149,6 +149,14 @@ int azb_step(azb_handle *h, uint32_t n_steps, azb_improvement *improvements, uin
 /* enqueue only (no wait, no read-back; needs max_episodes = 0): lets several handles share one GPU concurrently.
  * azb_step(h, 0, ...) or any reading call completes the work and reports errors. */
 int azb_step_enqueue(azb_handle *h, uint32_t n_steps);
+/* par_roll_out_episodes' per-step return value (ArgminImprovement, optimizer/mod.rs:24-27,121-191) for steps enqueued
+ * with azb_step_enqueue, one step per call in order, as soon as EVERY tree has finished that step — later steps keep
+ * running (with async_workers > 0 the trees run ahead of the caller, so a loop of one call per step advances at the
+ * speed of the fused loop).  *improved = 1 and *out = the record (may be null) when the step lowered the best cost
+ * (the reference's rule: first minimum over trees, strictly below the running best, optimizer/mod.rs:194-246).
+ * azb_step(h, 0, ...) after the last step completes the batch; it logs exactly the improvements reported here.
+ * AZB_ERR_STATE when no enqueued step is left to report. */
+int azb_step_poll(azb_handle *h, azb_improvement *out, int *improved);
 /* same as azb_step, timed with CUDA events on the library's stream; *ms = device time of the n_steps */
 int azb_step_timed(azb_handle *h, uint32_t n_steps, float *ms, uint32_t *n_improved);
 

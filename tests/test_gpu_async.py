@@ -130,3 +130,36 @@ def test_async_needs_the_tensor_core_model(capi):
         with pytest.raises(capi.AzbError) as e:
             h.step(10)
         assert e.value.code == capi.ERR_INVALID
+
+
+@pytest.mark.parametrize("workers", [0, 4])
+def test_step_poll_reports_each_step_while_later_steps_run(capi, workers):
+    """azb_step_enqueue + one azb_step_poll per step: the per-step ArgminImprovement of par_roll_out_episodes, read while
+    the trees run ahead.  The polled improvements are exactly the log azb_step(h, 0) then returns, and exactly what one
+    blocking azb_step(K) gives."""
+    n, b, steps = 19, 300, 40
+    parents, masks = capi.generate_roots(11, 0, b, n)
+    kw = dict(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=2 * steps, async_workers=workers)
+    with _mk(capi, n, b, **kw) as ref, _mk(capi, n, b, **kw) as h:
+        for x in (ref, h):
+            x.mlp_init(5)
+            x.set_roots(parents, masks)
+            x.init_trees()
+        with pytest.raises(capi.AzbError) as e:
+            h.step_poll()
+        assert e.value.code == capi.ERR_STATE
+        for rnd in range(2):  # two batches: the running best carries over
+            n_ref, log_ref = ref.step(steps, cap=256)
+            h.step_enqueue(steps)
+            polled = []
+            for s in range(steps):
+                improved, rec = h.step_poll()
+                assert rec[0] == rnd * steps + s
+                if improved:
+                    polled.append(tuple(rec))
+            with pytest.raises(capi.AzbError):
+                h.step_poll()  # nothing left
+            n_end, log_end = h.step(0, cap=256)
+            assert n_end == n_ref == len(polled)
+            assert [tuple(x) for x in log_end] == polled == [tuple(x) for x in log_ref]
+        _same(ref, h, b)
