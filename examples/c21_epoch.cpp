@@ -10,6 +10,7 @@
 int main(int argc, char **argv) {
     const uint32_t n = 19, batch = argc > 1 ? (uint32_t)atoi(argv[1]) : 512;  // 04-c21-tree.rs:33,54
     const uint32_t epochs = argc > 2 ? (uint32_t)atoi(argv[2]) : 2, episodes = 800, n_obs_tol = 200;  // :133-135
+    const bool per_step = argc > 3 && atoi(argv[3]) != 0;  // the example's loop shape: one result per step, as it completes
     azb_config cfg;
     if (azb_config_default(&cfg, n, batch) != AZB_OK) return 1;
     const uint32_t a = (n - 1) * (n - 2) / 2 - 1, w = (a + 31) / 32;
@@ -22,8 +23,13 @@ int main(int argc, char **argv) {
         printf("%12g\tlambda_1=%.6f mu=%u\n", best.eval, best.lambda_1, best.mu);
         const float goal = (5.2f - 2.0f) / 13.0f;  // squish(5.2), 04-c21-tree.rs:117
         for (uint32_t epoch = 1; epoch <= epochs; ++epoch) {
-            for (const auto &imp : opt.roll_out(episodes))
-                printf("epoch %u step %u: tree %u node %u eval %g\n", epoch, imp.step, imp.tree, imp.node, imp.eval);
+            if (per_step)
+                opt.roll_out_ahead(episodes, [&](uint32_t step, bool improved, const azb_improvement &imp) {
+                    if (improved) printf("epoch %u step %u: tree %u node %u eval %g\n", epoch, step, imp.tree, imp.node, imp.eval);
+                });
+            else
+                for (const auto &imp : opt.roll_out(episodes))
+                    printf("epoch %u step %u: tree %u node %u eval %g\n", epoch, imp.step, imp.tree, imp.node, imp.eval);
             best = opt.argmin_data();
             printf("%12g\tlambda_1=%.6f mu=%u\n", best.eval, best.lambda_1, best.mu);
             if (best.eval < goal) break;

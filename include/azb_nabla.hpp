@@ -104,6 +104,21 @@ class NablaOptimizer {
         log.resize(n < log.size() ? n : log.size());
         return log;
     }
+    // The example's per-step loop (04-c21-tree.rs:140-150) with the trees running ahead of the caller: on_step(step,
+    // improved, record) for each of the n_steps as soon as every tree has finished that step, then the batch is
+    // completed, so argmin_data() afterwards is what n_steps calls of par_roll_out_episodes would have left.
+    template <class F>
+    void roll_out_ahead(uint32_t n_steps, F &&on_step) {
+        ck(azb_step_enqueue(h_, n_steps));
+        for (uint32_t s = 0; s < n_steps; ++s) {
+            azb_improvement rec{};
+            int improved = 0;
+            ck(azb_step_poll(h_, &rec, &improved));
+            on_step(rec.step, improved != 0, rec);
+        }
+        uint32_t n = 0;
+        ck(azb_step(h_, 0, nullptr, 0, &n));
+    }
     ArgminData argmin_data() {  // optimizer/mod.rs:361-363
         ArgminData d;
         d.parents.resize(cfg_.n_vertices);

@@ -349,6 +349,10 @@ def test_cpp_host_mirror_example_runs(capi):
     out = subprocess.run([exe, "64", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert "epoch 1: loss" in out.stdout  # the whole loop ran: steps, par_update_model, par_reset_trees
+    # the per-step form of the loop (roll_out_ahead: azb_step_enqueue + azb_step_poll) prints the same epoch
+    out2 = subprocess.run([exe, "64", "1", "1"], capture_output=True, text=True, timeout=300)
+    assert out2.returncode == 0, out2.stderr
+    assert out2.stdout == out.stdout
 
 
 @pytest.mark.parametrize("max_episodes", [1, 2, 5])
