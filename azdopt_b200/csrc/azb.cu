@@ -904,6 +904,9 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
     CK(cudaMemsetAsync(P.dbg, 0, 64 * 8, h->stream));
     P.target_step = h->steps_done + n_steps;
+    // watchdog: measured from the start of the launch, so it grows with the work (a step takes ~0.1-1 ms at the supported
+    // sizes; 5 ms per step on top of 30 s never fires on a healthy run of any length)
+    P.timeout_ns = 30ull * 1000000000ull + (unsigned long long)n_steps * 5000000ull;
     cudaError_t ce;
     if (h->pipe || h->split) {
         // the model runs beside the tree kernel on its own stream: its CTAs take whole SMs (their shared memory excludes
