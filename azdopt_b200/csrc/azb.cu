@@ -19,6 +19,7 @@
 #include "../../include/azb.h"
 #include "azb_common.cuh"
 #include "azb_cost.cuh"
+#include "azb_graph.cuh"
 #include "azb_mlp.cuh"
 #include "azb_mlp_tc.cuh"
 #include "azb_tree.cuh"
@@ -1355,6 +1356,66 @@ int azb_eval_costs(azb_handle *h, const uint8_t *parents, uint32_t m, double *la
                 return fail(h, AZB_ERR_INVALID, "tree %u: parents[%u] is not < %u", i, v, v);
     CK(cudaSetDevice(h->cfg.device));
     return eval_costs_dev(h, parents, m, lambda1, mu, c, ms);
+}
+
+// ---- stand-alone cost + action kinds of connected bitset graphs ----
+int azb_eval_graph_costs(azb_handle *h, const uint32_t *nbr, uint32_t m, uint32_t n, double *lambda1, uint32_t *mu,
+                         uint32_t *kinds, float *ms) {
+    if (!h || !nbr || m == 0) return AZB_ERR_INVALID;
+    if (n < 2 || n > 32) return fail(h, AZB_ERR_INVALID, "graphs have 2..32 vertices (B32 neighbourhoods), got %u", n);
+    const uint32_t full = n == 32 ? 0xffffffffu : (1u << n) - 1u;
+    for (uint32_t i = 0; i < m; ++i) {  // what BitsetGraph::try_from + to_connected (bitset_graph/mod.rs) accept
+        const uint32_t *g = nbr + (size_t)i * n;
+        for (uint32_t v = 0; v < n; ++v) {
+            if ((g[v] & ~full) || (g[v] >> v & 1u)) return fail(h, AZB_ERR_INVALID, "graph %u: vertex %u has a loop or a neighbour >= N", i, v);
+            for (uint32_t r = g[v]; r; r &= r - 1)
+                if (!(g[__builtin_ctz(r)] >> v & 1u)) return fail(h, AZB_ERR_INVALID, "graph %u: neighbourhoods are not symmetric at %u", i, v);
+        }
+        uint32_t seen = 1u, fresh = 1u;
+        while (fresh) {
+            uint32_t next = 0u;
+            for (uint32_t r = fresh; r; r &= r - 1) next |= g[__builtin_ctz(r)];
+            fresh = next & ~seen;
+            seen |= fresh;
+        }
+        if (seen != full) return fail(h, AZB_ERR_INVALID, "graph %u is not connected", i);
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    const uint32_t kw = (n * (n - 1) + 31) / 32;
+    uint32_t *d_nbr = nullptr, *d_mu = nullptr, *d_kinds = nullptr, *d_err = nullptr;
+    double *d_l1 = nullptr;
+    auto release = [&]() {
+        cudaFree(d_nbr);
+        cudaFree(d_mu);
+        cudaFree(d_kinds);
+        cudaFree(d_err);
+        cudaFree(d_l1);
+    };
+    cudaError_t ce = cudaMalloc((void **)&d_nbr, (size_t)m * n * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_mu, (size_t)m * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_kinds, (size_t)m * kw * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_err, 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_l1, (size_t)m * 8);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_nbr, nbr, (size_t)m * n * 4, cudaMemcpyHostToDevice, h->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_err, 0, 4, h->stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev0, h->stream);
+    if (ce == cudaSuccess) {
+        azb_graph_cost_kernel<<<(m + AZG_WARPS - 1) / AZG_WARPS, AZG_WARPS * 32, 0, h->stream>>>(d_nbr, m, n, kw, d_l1, d_mu, d_kinds, d_err);
+        h->launches += 1;
+        ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev1, h->stream);
+    uint32_t err = 0;
+    if (ce == cudaSuccess && lambda1) ce = cudaMemcpyAsync(lambda1, d_l1, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess && mu) ce = cudaMemcpyAsync(mu, d_mu, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess && kinds) ce = cudaMemcpyAsync(kinds, d_kinds, (size_t)m * kw * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+    if (ce == cudaSuccess && ms) ce = cudaEventElapsedTime(ms, h->ev0, h->ev1);
+    release();
+    if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "azb_eval_graph_costs: %s", cudaGetErrorString(ce));
+    if (err) return fail(h, (int)err, "%s", azb_strerror((int)err));
+    return AZB_OK;
 }
 
 // ---- results ----

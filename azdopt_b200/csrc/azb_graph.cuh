@@ -1,0 +1,259 @@
+// azb_graph.cuh -- SURVEY 8(f) row 3: the c21 cost and the action kinds of CONNECTED GRAPHS held as neighbourhood
+// bit sets (`ConnectedBitsetGraph<N, B32>`, graph-state/src/simple_graph/connected_bitset_graph/mod.rs), batched.
+// One warp per graph, lane v = vertex v (N <= 32), everything in shared memory and registers:
+//   * action kinds (`action_kinds` :134-154 over `is_cut_edge` :45-71) in the index space of
+//     `AddOrDeleteEdge::action_index` (bitset_graph/space/action.rs:10-19): one lane per vertex pair, bit-set BFS;
+//   * matching number (`maximum_matching` :226-317 is a branch and bound; only its SIZE is read, so any exact
+//     algorithm gives the same number): greedy start + Edmonds' blossom augmentation, serial on lane 0;
+//   * lambda_1 (`adjacency_matrix` :200-216 with its 1e-4 diagonal, `conjecture_2_1_cost` :319-337 takes the
+//     largest eigenvalue): warp-parallel Householder tridiagonalisation in f64 (lane = row), then the largest
+//     eigenvalue by Sturm counts on a 32-point section per round (lane = section point).
+// The snapshot has no NablaStateActionSpace over these graphs, so this is the stand-alone cost row only.
+#pragma once
+#include <cstdint>
+
+#define AZG_WARPS 4
+#define AZG_LD 33  // row stride of the dense matrix (f64 words)
+
+struct AzgWarpScratch {
+    double a[32 * AZG_LD];
+    double u[32], w[32], d[32], e[32];
+    uint32_t nbr[32];
+    uint32_t kinds[32];
+    int8_t match[32], par[32], base[32], queue[32];
+};
+
+__device__ __forceinline__ double azg_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double azg_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// connected_bitset_graph/mod.rs:45-71
+__device__ __forceinline__ bool azg_is_cut_edge(const uint32_t *nbr, uint32_t v, uint32_t u) {
+    uint32_t fresh = nbr[v] ^ (1u << u), explored = 1u << v;
+    while (fresh) {
+        if (fresh >> u & 1u) return false;
+        explored |= fresh;
+        uint32_t next = 0u;
+        for (uint32_t r = fresh; r; r &= r - 1) next |= nbr[__ffs(r) - 1];
+        fresh = next & ~explored;
+    }
+    return true;
+}
+
+// Edmonds' blossom algorithm (array form), serial; match/par/base/queue live in the warp's shared scratch
+__device__ uint32_t azg_matching_number(AzgWarpScratch &s, uint32_t n) {
+    int8_t *match = s.match, *par = s.par, *base = s.base, *queue = s.queue;
+    uint32_t size = 0;
+    for (uint32_t v = 0; v < n; ++v) match[v] = -1;
+    for (uint32_t v = 0; v < n; ++v) {  // greedy start
+        if (match[v] >= 0) continue;
+        for (uint32_t r = s.nbr[v]; r; r &= r - 1) {
+            const int t = __ffs(r) - 1;
+            if (match[t] < 0) {
+                match[v] = (int8_t)t;
+                match[t] = (int8_t)v;
+                ++size;
+                break;
+            }
+        }
+    }
+    for (uint32_t root = 0; root < n; ++root) {
+        if (match[root] >= 0) continue;
+        for (uint32_t i = 0; i < n; ++i) {
+            par[i] = -1;
+            base[i] = (int8_t)i;
+        }
+        uint32_t used = 1u << root, qh = 0, qt = 0;
+        queue[qt++] = (int8_t)root;
+        int found = -1;
+        while (qh < qt && found < 0) {
+            const int v = queue[qh++];
+            for (uint32_t r = s.nbr[v]; r && found < 0; r &= r - 1) {
+                int to = __ffs(r) - 1;
+                if (base[v] == base[to] || match[v] == to) continue;
+                if (to == (int)root || (match[to] >= 0 && par[match[to]] >= 0)) {
+                    // an odd cycle: contract it onto the lowest common ancestor of v and to
+                    uint32_t seen = 0u;
+                    int a = v, b = to, cur;
+                    for (;;) {
+                        a = base[a];
+                        seen |= 1u << a;
+                        if (match[a] < 0) break;
+                        a = par[match[a]];
+                    }
+                    for (;;) {
+                        b = base[b];
+                        if (seen >> b & 1u) break;
+                        b = par[match[b]];
+                    }
+                    cur = b;
+                    uint32_t blossom = 0u;
+                    for (int side = 0; side < 2; ++side) {
+                        int x = side ? to : v, child = side ? v : to;
+                        while (base[x] != cur) {
+                            blossom |= 1u << base[x];
+                            blossom |= 1u << base[match[x]];
+                            par[x] = (int8_t)child;
+                            child = match[x];
+                            x = par[match[x]];
+                        }
+                    }
+                    for (uint32_t i = 0; i < n; ++i)
+                        if (blossom >> base[i] & 1u) {
+                            base[i] = (int8_t)cur;
+                            if (!(used >> i & 1u)) {
+                                used |= 1u << i;
+                                queue[qt++] = (int8_t)i;
+                            }
+                        }
+                } else if (par[to] < 0) {
+                    par[to] = (int8_t)v;
+                    if (match[to] < 0) {
+                        found = to;
+                    } else {
+                        to = match[to];
+                        used |= 1u << to;
+                        queue[qt++] = (int8_t)to;
+                    }
+                }
+            }
+        }
+        if (found >= 0) {
+            ++size;
+            for (int v = found; v >= 0;) {
+                const int pv = par[v], ppv = match[pv];
+                match[v] = (int8_t)pv;
+                match[pv] = (int8_t)v;
+                v = ppv;
+            }
+        }
+    }
+    return size;
+}
+
+// number of eigenvalues of the symmetric tridiagonal (d, e) below x equals n  <=>  x > lambda_max
+__device__ __forceinline__ bool azg_above_all(const double *d, const double *e, uint32_t n, double x, double tiny) {
+    double q = __dsub_rn(d[0], x);
+    bool all = q < 0.0;
+    for (uint32_t i = 1; i < n && all; ++i) {
+        if (fabs(q) < tiny) q = -tiny;
+        q = __dsub_rn(__dsub_rn(d[i], x), __ddiv_rn(__dmul_rn(e[i - 1], e[i - 1]), q));
+        all = q < 0.0;
+    }
+    return all;
+}
+
+__global__ void __launch_bounds__(AZG_WARPS * 32)
+azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n, uint32_t kw, double *__restrict__ l1_out,
+                      uint32_t *__restrict__ mu_out, uint32_t *__restrict__ kinds_out, uint32_t *err) {
+    __shared__ AzgWarpScratch scratch[AZG_WARPS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * AZG_WARPS + warp;
+    if (g >= m) return;
+    AzgWarpScratch &s = scratch[warp];
+    const uint32_t mine = lane < n ? nbr_g[(size_t)g * n + lane] : 0u;
+    s.nbr[lane] = mine;
+    s.kinds[lane] = 0u;
+    __syncwarp();
+
+    // ---- action kinds: pair p = colex(v, u) = v (v - 1) / 2 + u, 32 pairs per round
+    const uint32_t e2 = n * (n - 1) / 2;
+    for (uint32_t p0 = 0; p0 < e2; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        bool add = false, del = false;
+        if (p < e2) {
+            uint32_t v = (uint32_t)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+            while (v * (v - 1) / 2 > p) --v;
+            while (v * (v + 1) / 2 <= p) ++v;
+            const uint32_t u = p - v * (v - 1) / 2;
+            if (s.nbr[v] >> u & 1u) del = !azg_is_cut_edge(s.nbr, v, u);
+            else add = true;
+        }
+        const uint32_t wa = __ballot_sync(0xffffffffu, add), wd = __ballot_sync(0xffffffffu, del);
+        if (lane == 0) {
+            s.kinds[p0 >> 5] |= wa;
+            const uint32_t bit = e2 + p0, sh = bit & 31u;
+            s.kinds[bit >> 5] |= wd << sh;
+            if (sh && (wd >> (32u - sh))) s.kinds[(bit >> 5) + 1] |= wd >> (32u - sh);
+        }
+        __syncwarp();
+    }
+    if (kinds_out && lane < kw) kinds_out[(size_t)g * kw + lane] = s.kinds[lane];
+
+    // ---- matching number
+    uint32_t mu = 0;
+    if (lane == 0) mu = azg_matching_number(s, n);
+    __syncwarp();
+
+    // ---- lambda_1 of A + 1e-4 I
+    for (uint32_t j = 0; j < n; ++j) s.a[lane * AZG_LD + j] = lane == j ? 0.0001 : ((mine >> j & 1u) ? 1.0 : 0.0);
+    __syncwarp();
+    for (uint32_t k = 0; k + 2 < n; ++k) {
+        const bool act = lane > k && lane < n;
+        const double x = act ? s.a[lane * AZG_LD + k] : 0.0;
+        const double norm2 = azg_warp_sum(__dmul_rn(x, x));
+        const double x0 = __shfl_sync(0xffffffffu, x, k + 1);
+        const double rest2 = azg_warp_sum(lane == k + 1 ? 0.0 : __dmul_rn(x, x));
+        if (rest2 == 0.0) {  // the column is already tridiagonal
+            if (lane == 0) s.e[k] = x0;
+            continue;
+        }
+        const double alpha = x0 > 0.0 ? -__dsqrt_rn(norm2) : __dsqrt_rn(norm2);
+        double u = lane == k + 1 ? __dsub_rn(x, alpha) : x;
+        const double un2 = azg_warp_sum(__dmul_rn(u, u));
+        u = __dmul_rn(u, __ddiv_rn(1.0, __dsqrt_rn(un2)));
+        s.u[lane] = u;
+        __syncwarp();
+        double q = 0.0;
+        if (act)
+            for (uint32_t j = k + 1; j < n; ++j) q = __dadd_rn(q, __dmul_rn(s.a[lane * AZG_LD + j], s.u[j]));
+        const double uq = azg_warp_sum(__dmul_rn(u, q));
+        const double w = __dsub_rn(q, __dmul_rn(uq, u));
+        s.w[lane] = w;
+        __syncwarp();
+        if (act)
+            for (uint32_t j = k + 1; j < n; ++j) {
+                const double t = __dadd_rn(__dmul_rn(u, s.w[j]), __dmul_rn(w, s.u[j]));
+                s.a[lane * AZG_LD + j] = __dsub_rn(s.a[lane * AZG_LD + j], __dmul_rn(2.0, t));
+            }
+        if (lane == 0) s.e[k] = alpha;
+        __syncwarp();
+    }
+    if (lane < n) s.d[lane] = s.a[lane * AZG_LD + lane];
+    if (lane == 0 && n >= 2) s.e[n - 2] = s.a[(n - 1) * AZG_LD + n - 2];
+    __syncwarp();
+    // Gershgorin bracket of the spectrum, then 33-fold sections of [lo, hi] with  not above(lo), above(hi)
+    double rad = 0.0, dd = -1e300;
+    if (lane < n) {
+        dd = s.d[lane];
+        rad = (lane > 0 ? fabs(s.e[lane - 1]) : 0.0) + (lane + 1 < n ? fabs(s.e[lane]) : 0.0);
+    }
+    double hi = azg_warp_max(lane < n ? dd + rad : -1e300), lo = -azg_warp_max(lane < n ? rad - dd : -1e300);
+    const double scale = fmax(fabs(hi), fabs(lo));
+    const double tiny = fmax(scale, 1.0) * 1e-300;
+    hi = hi + fmax(scale, 1.0) * 1e-9;
+    for (int round = 0; round < 16; ++round) {
+        const double step = __ddiv_rn(__dsub_rn(hi, lo), 33.0);
+        const double x = __dadd_rn(lo, __dmul_rn(step, (double)(lane + 1)));
+        const uint32_t above = __ballot_sync(0xffffffffu, azg_above_all(s.d, s.e, n, x, tiny));
+        const int first = above ? __ffs(above) - 1 : 32;
+        const double nlo = first > 0 ? __shfl_sync(0xffffffffu, x, first - 1) : lo;
+        const double nhi = first < 32 ? __shfl_sync(0xffffffffu, x, first & 31) : hi;
+        lo = nlo;
+        hi = nhi;
+        if (!(__dsub_rn(hi, lo) > 4.0 * 2.220446049250313e-16 * fmax(fabs(hi), fabs(lo)))) break;
+    }
+    const double l1 = __dmul_rn(0.5, __dadd_rn(lo, hi));
+    if (lane == 0) {
+        l1_out[g] = l1;
+        mu_out[g] = mu;
+        if (!(l1 > 1.4)) atomicMax(err, 5u);  // connected_bitset_graph/mod.rs:333 `assert!(lambda_1 > 1.4)`
+    }
+}

@@ -196,6 +196,17 @@ int azb_get_priors(azb_handle *h, float *priors /*[B*A]*/);
 int azb_eval_costs(azb_handle *h, const uint8_t *parents /*[M*N]*/, uint32_t m, double *lambda1, uint32_t *mu,
                    float *c, float *ms);
 
+/* ---- the same cost for CONNECTED GRAPHS held as neighbourhood bit sets
+ *      (ConnectedBitsetGraph<N, B32>: simple_graph/connected_bitset_graph/mod.rs).  nbr[g*n + v] = neighbours of v.
+ *      lambda1 = largest eigenvalue of A + 1e-4 I (adjacency_matrix :200-216, conjecture_2_1_cost :319-337),
+ *      mu = matching_number (:218-317), kinds[g][ceil(n(n-1)/32)] = action_kinds (:134-154) in the index space of
+ *      AddOrDeleteEdge::action_index (bitset_graph/space/action.rs:10-19): bit colex(e) set <=> Add(e) is available,
+ *      bit n(n-1)/2 + colex(e) set <=> Delete(e) is (e is an edge and not a cut edge, is_cut_edge :45-71).
+ *      AZB_ERR_INVALID for n outside 2..32, loops, asymmetric or disconnected input (what try_from / to_connected
+ *      reject); AZB_ERR_LAMBDA where the reference asserts lambda_1 > 1.4.  Any output pointer may be NULL. ---- */
+int azb_eval_graph_costs(azb_handle *h, const uint32_t *nbr /*[M*n]*/, uint32_t m, uint32_t n, double *lambda1,
+                         uint32_t *mu, uint32_t *kinds, float *ms);
+
 /* ---- epoch boundary ("next" rows): par_update_model's observation pass (tree/mod.rs:242-264,
  *      optimizer/mod.rs:262-278) ---- */
 int azb_write_observations(azb_handle *h, uint32_t n_obs_tol, float *state_vecs, float *observations,

@@ -236,6 +236,7 @@ double lambda1_dense(uint32_t n, const uint8_t *parents) {
 }
 
 // independent cross-check: cyclic Jacobi
+double jacobi_max_eigenvalue(uint32_t n, double (*a)[MAXN]);
 double lambda1_jacobi(uint32_t n, const uint8_t *parents) {
     double a[MAXN][MAXN];
     for (uint32_t i = 0; i < n; ++i)
@@ -244,6 +245,10 @@ double lambda1_jacobi(uint32_t n, const uint8_t *parents) {
         a[i][parents[i]] = 1.0;
         a[parents[i]][i] = 1.0;
     }
+    return jacobi_max_eigenvalue(n, a);
+}
+
+double jacobi_max_eigenvalue(uint32_t n, double (*a)[MAXN]) {
     for (int sweep = 0; sweep < 100; ++sweep) {
         double off = 0.0;
         for (uint32_t p = 0; p < n; ++p)
@@ -951,6 +956,88 @@ void parallel_for(uint32_t n, int n_threads, F f) {
     for (auto &t : ts) t.join();
 }
 
+
+// ----------------------------------------------------------------------------
+// the c21 cost and the action kinds of a connected graph held as neighbourhood bit sets
+// (simple_graph/connected_bitset_graph/mod.rs; B32: one u32 per vertex, N <= 32)
+// ----------------------------------------------------------------------------
+
+// connected_bitset_graph/mod.rs:45-71: breadth-first search from v in G - vu; a cut edge never reaches u
+bool graph_is_cut_edge(const uint32_t *nbr, uint32_t v, uint32_t u) {
+    uint32_t new_vertices = nbr[v] ^ (1u << u);  // :52-55 add_or_remove(u)
+    uint32_t explored = 1u << v;                 // :56-57
+    while (new_vertices) {                       // :58
+        if (new_vertices >> u & 1u) return false;  // :59-61
+        explored |= new_vertices;                // :62
+        uint32_t recent = new_vertices;          // :63
+        new_vertices = 0u;                       // :64
+        for (uint32_t r = recent; r; r &= r - 1) new_vertices |= nbr[__builtin_ctz(r)];  // :65-67
+        new_vertices &= ~explored;               // :68
+    }
+    return true;  // :70
+}
+
+// connected_bitset_graph/mod.rs:134-154 in the index space of AddOrDeleteEdge::action_index
+// (bitset_graph/space/action.rs:10-19): bit colex(e) = Add(e) is available, bit C(N,2) + colex(e) = Delete(e) is
+void graph_action_kinds(uint32_t n, const uint32_t *nbr, uint32_t *kinds) {
+    const uint32_t e2 = n * (n - 1) / 2;
+    for (uint32_t w = 0; w < (2 * e2 + 31) / 32; ++w) kinds[w] = 0u;
+    for (uint32_t v = 0; v < n; ++v)
+        for (uint32_t u = 0; u < v; ++u) {  // :139-140
+            const uint32_t pos = colex_position(v, u);
+            if (nbr[v] >> u & 1u) {                                          // :141
+                if (!graph_is_cut_edge(nbr, v, u)) mask_set(kinds, e2 + pos);  // :143-147 (None for a cut edge)
+            } else {
+                mask_set(kinds, pos);  // :149
+            }
+        }
+}
+
+// connected_bitset_graph/mod.rs:226-317: depth-first branch and bound over (matched edges, unvisited vertices);
+// only the size of the matching is ever read on this path, so the edge lists are kept as counts
+uint32_t graph_matching_number(uint32_t n, const uint32_t *nbr) {
+    if (n == 0) return 0;  // :235-237
+    struct Search {
+        uint32_t edges, unvisited;
+    };
+    std::vector<Search> queue;  // a VecDeque used as a stack: push_back / pop_back (:242-246)
+    queue.push_back({0u, n >= 32 ? 0xffffffffu : (1u << n) - 1u});  // :238-243
+    uint32_t matching_number = 0;                                   // :244
+    while (!queue.empty()) {
+        Search m = queue.back();
+        queue.pop_back();
+        uint32_t unvisited = m.unvisited;
+        uint32_t max_future = (uint32_t)__builtin_popcount(unvisited) / 2;  // :261
+        if (m.edges + max_future <= matching_number) continue;               // :262-264
+        const uint32_t next_v = 31u - (uint32_t)__builtin_clz(unvisited);    // :269 max_unchecked
+        unvisited ^= 1u << next_v;                                           // :274
+        max_future = (uint32_t)__builtin_popcount(unvisited) / 2;            // :275
+        if (m.edges + max_future > matching_number) queue.push_back({m.edges, unvisited});  // :279-285
+        for (uint32_t nb = unvisited & nbr[next_v]; nb; nb &= nb - 1) {      // :286-288 ascending
+            const uint32_t next_u = (uint32_t)__builtin_ctz(nb);
+            const uint32_t new_edges = m.edges + 1;                          // :289-290
+            const uint32_t new_unvisited = unvisited ^ (1u << next_u);       // :291-296
+            if (new_edges > matching_number) matching_number = new_edges;    // :297-300
+            max_future = (uint32_t)__builtin_popcount(new_unvisited) / 2;    // :302
+            if (new_edges + max_future > matching_number) queue.push_back({new_edges, new_unvisited});  // :303-309
+        }
+    }
+    return matching_number;
+}
+
+// connected_bitset_graph/mod.rs:200-216 + :324-333: the largest real part of the eigenvalues of A + 1e-4 I.  faer's
+// general `eigenvalues()` is un-vendored; the matrix is symmetric, so its spectrum is real and any backward-stable
+// symmetric solver gives the same lambda_1 to ~1e-15 (cyclic Jacobi here)
+double graph_lambda1(uint32_t n, const uint32_t *nbr) {
+    double a[MAXN][MAXN];
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < n; ++j) a[i][j] = 0.0;
+    for (uint32_t i = 0; i < n; ++i) a[i][i] = 0.0001;  // :205-209 "ZERO"
+    for (uint32_t v = 0; v < n; ++v)
+        for (uint32_t r = nbr[v]; r; r &= r - 1) a[v][__builtin_ctz(r)] = 1.0;  // :210-214
+    return jacobi_max_eigenvalue(n, a);
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------
@@ -1006,6 +1093,21 @@ int orc_cost(uint32_t n, const uint8_t *parents, int method, float c_lower, floa
     *mu = k.mu;
     *c = sp.evaluate(k);
     return bad ? 1 : 0;
+}
+
+
+/* ---- connected bitset graphs (connected_bitset_graph/mod.rs) ---- */
+int orc_graph_is_cut_edge(uint32_t n, const uint32_t *nbr, uint32_t v, uint32_t u) {
+    (void)n;
+    return graph_is_cut_edge(nbr, v, u) ? 1 : 0;
+}
+void orc_graph_action_kinds(uint32_t n, const uint32_t *nbr, uint32_t *kinds) { graph_action_kinds(n, nbr, kinds); }
+uint32_t orc_graph_matching_number(uint32_t n, const uint32_t *nbr) { return graph_matching_number(n, nbr); }
+/* conjecture_2_1_cost (:319-337): returns 1 where the reference's `assert!(lambda_1 > 1.4)` would abort */
+int orc_graph_cost(uint32_t n, const uint32_t *nbr, double *lambda1, uint32_t *mu) {
+    *lambda1 = graph_lambda1(n, nbr);
+    *mu = graph_matching_number(n, nbr);
+    return *lambda1 > 1.4 ? 0 : 1;
 }
 
 uint32_t orc_matching_greedy(uint32_t n, const uint8_t *parents) { return matching_greedy(n, parents); }

@@ -61,6 +61,11 @@ uint32_t orc_c_upper(uint32_t n);                                       /* 04-c2
 /* cost of one tree: lambda_1 (f64), mu, squished eval c (f32). returns 0, or 1 if lambda_1 < 1.4 (ordered_edge.rs:79 panics) */
 int orc_cost(uint32_t n, const uint8_t *parents, int method, float c_lower, float c_upper,
              double *lambda1, uint32_t *mu, float *c);
+/* SURVEY 8(f) row 3 -- connected graphs as neighbourhood bit sets (B32, N <= 32; connected_bitset_graph/mod.rs) */
+int orc_graph_is_cut_edge(uint32_t n, const uint32_t *nbr, uint32_t v, uint32_t u);          /* :45-71 */
+void orc_graph_action_kinds(uint32_t n, const uint32_t *nbr, uint32_t *kinds /*[ceil(N(N-1)/32)]*/); /* :134-154, action.rs:10-19 */
+uint32_t orc_graph_matching_number(uint32_t n, const uint32_t *nbr);                         /* :218-317 */
+int orc_graph_cost(uint32_t n, const uint32_t *nbr, double *lambda1, uint32_t *mu);          /* :200-216, :319-337 */
 uint32_t orc_matching_greedy(uint32_t n, const uint8_t *parents);       /* independent O(N) matching for cross-checks */
 uint32_t orc_matching_poly(uint32_t n, const uint8_t *parents);         /* degree of the matching polynomial (N <= 22) */
 /* legal actions of (parents, permitted mask) ascending; returns count (space.rs:75-89) */

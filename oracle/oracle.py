@@ -60,6 +60,13 @@ def lib():
     L.orc_c_upper.argtypes = [C.c_uint32]
     L.orc_cost.restype = C.c_int
     L.orc_cost.argtypes = [C.c_uint32, u8p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_double), u32p, f32p]
+    L.orc_graph_is_cut_edge.restype = C.c_int
+    L.orc_graph_is_cut_edge.argtypes = [C.c_uint32, u32p, C.c_uint32, C.c_uint32]
+    L.orc_graph_action_kinds.argtypes = [C.c_uint32, u32p, u32p]
+    L.orc_graph_matching_number.restype = C.c_uint32
+    L.orc_graph_matching_number.argtypes = [C.c_uint32, u32p]
+    L.orc_graph_cost.restype = C.c_int
+    L.orc_graph_cost.argtypes = [C.c_uint32, u32p, C.POINTER(C.c_double), u32p]
     L.orc_matching_greedy.restype = C.c_uint32
     L.orc_matching_greedy.argtypes = [C.c_uint32, u8p]
     L.orc_matching_poly.restype = C.c_uint32
@@ -135,6 +142,46 @@ def cost(parents, method=LAMBDA_DENSE, c_lower=2.0, c_up=None):
     lam, mu, c = C.c_double(), C.c_uint32(), C.c_float()
     rc = lib().orc_cost(n, _p(p, C.c_uint8), method, c_lower, float(c_up), C.byref(lam), C.byref(mu), C.byref(c))
     return lam.value, mu.value, np.float32(c.value), rc
+
+
+# ---- connected graphs as neighbourhood bit sets (connected_bitset_graph/mod.rs) ----
+def graph_from_edges(n, edges):
+    """Neighbourhood masks u32[n] of an edge list (try_from.rs: BitsetGraph from &[(usize, usize)])."""
+    nbr = np.zeros(n, dtype=np.uint32)
+    for u, v in edges:
+        nbr[u] |= np.uint32(1 << v)
+        nbr[v] |= np.uint32(1 << u)
+    return nbr
+
+
+def graph_kind_words(n: int) -> int:
+    return (n * (n - 1) + 31) // 32
+
+
+def graph_is_cut_edge(nbr, v, u) -> bool:
+    a = np.ascontiguousarray(nbr, dtype=np.uint32)
+    return bool(lib().orc_graph_is_cut_edge(a.shape[0], _p(a, C.c_uint32), v, u))
+
+
+def graph_action_kinds(nbr):
+    """Bit colex(e): Add(e) available; bit C(n,2)+colex(e): Delete(e) available (mod.rs:134-154, action.rs:10-19)."""
+    a = np.ascontiguousarray(nbr, dtype=np.uint32)
+    out = np.zeros(graph_kind_words(a.shape[0]), dtype=np.uint32)
+    lib().orc_graph_action_kinds(a.shape[0], _p(a, C.c_uint32), _p(out, C.c_uint32))
+    return out
+
+
+def graph_matching_number(nbr) -> int:
+    a = np.ascontiguousarray(nbr, dtype=np.uint32)
+    return int(lib().orc_graph_matching_number(a.shape[0], _p(a, C.c_uint32)))
+
+
+def graph_cost(nbr):
+    """(lambda_1 of A + 1e-4 I, mu, rc) for one connected graph (mod.rs:319-337)."""
+    a = np.ascontiguousarray(nbr, dtype=np.uint32)
+    lam, mu = C.c_double(), C.c_uint32()
+    rc = lib().orc_graph_cost(a.shape[0], _p(a, C.c_uint32), C.byref(lam), C.byref(mu))
+    return lam.value, mu.value, rc
 
 
 def matching_greedy(parents):
