@@ -1400,7 +1400,7 @@ int azb_eval_graph_costs(azb_handle *h, const uint32_t *nbr, uint32_t m, uint32_
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d_err, 0, 4, h->stream);
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev0, h->stream);
     if (ce == cudaSuccess) {
-        azb_graph_cost_kernel<<<(m + AZG_WARPS - 1) / AZG_WARPS, AZG_WARPS * 32, 0, h->stream>>>(d_nbr, m, n, kw, d_l1, d_mu, d_kinds, d_err);
+        azb_graph_cost_kernel<<<(m + AZG_WARPS - 1) / AZG_WARPS, AZG_WARPS * 32, AZG_WARPS * azg_warp_bytes(n), h->stream>>>(d_nbr, m, n, kw, d_l1, d_mu, d_kinds, d_err);
         h->launches += 1;
         ce = cudaGetLastError();
     }

@@ -13,15 +13,15 @@
 #include <cstdint>
 
 #define AZG_WARPS 4
-#define AZG_LD 33  // row stride of the dense matrix (f64 words)
 
-struct AzgWarpScratch {
-    double a[32 * AZG_LD];
-    double u[32], w[32], d[32], e[32];
-    uint32_t nbr[32];
-    uint32_t kinds[32];
-    int8_t match[32], par[32], base[32], queue[32];
+struct AzgWarpScratch {  // one per warp, carved out of dynamic shared memory: the matrix is n rows of (n | 1) doubles
+    double *a;
+    double *u, *w, *d, *e;
+    uint32_t *nbr, *kinds;
+    int8_t *match, *par, *base, *queue;
 };
+__host__ __device__ inline uint32_t azg_ld(uint32_t n) { return n | 1u; }  // odd row stride: rows start in different banks
+__host__ __device__ inline uint32_t azg_warp_bytes(uint32_t n) { return 8u * n * azg_ld(n) + 4u * 32u * 8u + 2u * 32u * 4u + 4u * 32u; }
 
 __device__ __forceinline__ double azg_warp_sum(double v) {
 #pragma unroll
@@ -48,7 +48,7 @@ __device__ __forceinline__ bool azg_is_cut_edge(const uint32_t *nbr, uint32_t v,
 }
 
 // Edmonds' blossom algorithm (array form), serial; match/par/base/queue live in the warp's shared scratch
-__device__ uint32_t azg_matching_number(AzgWarpScratch &s, uint32_t n) {
+__device__ uint32_t azg_matching_number(const AzgWarpScratch &s, uint32_t n) {
     int8_t *match = s.match, *par = s.par, *base = s.base, *queue = s.queue;
     uint32_t size = 0;
     for (uint32_t v = 0; v < n; ++v) match[v] = -1;
@@ -138,14 +138,17 @@ __device__ uint32_t azg_matching_number(AzgWarpScratch &s, uint32_t n) {
     return size;
 }
 
-// number of eigenvalues of the symmetric tridiagonal (d, e) below x equals n  <=>  x > lambda_max
-__device__ __forceinline__ bool azg_above_all(const double *d, const double *e, uint32_t n, double x, double tiny) {
-    double q = __dsub_rn(d[0], x);
-    bool all = q < 0.0;
+// x > lambda_max of the symmetric tridiagonal (d, e)  <=>  every leading principal minor of x I - T is positive:
+// p_0 = 1, p_1 = x - d_0, p_i = (x - d_{i-1}) p_{i-1} - e_{i-2}^2 p_{i-2}.  No division; |p_i| <= (2 ||T||)^32 < 1e60.
+__device__ __forceinline__ bool azg_above_all(const double *d, const double *e, uint32_t n, double x) {
+    double pm = 1.0, p = __dsub_rn(x, d[0]);
+    bool all = p > 0.0;
     for (uint32_t i = 1; i < n && all; ++i) {
-        if (fabs(q) < tiny) q = -tiny;
-        q = __dsub_rn(__dsub_rn(d[i], x), __ddiv_rn(__dmul_rn(e[i - 1], e[i - 1]), q));
-        all = q < 0.0;
+        const double ee = __dmul_rn(e[i - 1], e[i - 1]);
+        const double pn = __dsub_rn(__dmul_rn(__dsub_rn(x, d[i]), p), __dmul_rn(ee, pm));
+        pm = p;
+        p = pn;
+        all = p > 0.0;
     }
     return all;
 }
@@ -153,11 +156,26 @@ __device__ __forceinline__ bool azg_above_all(const double *d, const double *e, 
 __global__ void __launch_bounds__(AZG_WARPS * 32)
 azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n, uint32_t kw, double *__restrict__ l1_out,
                       uint32_t *__restrict__ mu_out, uint32_t *__restrict__ kinds_out, uint32_t *err) {
-    __shared__ AzgWarpScratch scratch[AZG_WARPS];
+    extern __shared__ __align__(16) uint8_t azg_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x * AZG_WARPS + warp;
     if (g >= m) return;
-    AzgWarpScratch &s = scratch[warp];
+    const uint32_t AZG_LD = azg_ld(n);
+    AzgWarpScratch s;
+    {
+        uint8_t *base = azg_smem + (size_t)warp * azg_warp_bytes(n);
+        s.a = reinterpret_cast<double *>(base);
+        s.u = s.a + n * AZG_LD;
+        s.w = s.u + 32;
+        s.d = s.w + 32;
+        s.e = s.d + 32;
+        s.nbr = reinterpret_cast<uint32_t *>(s.e + 32);
+        s.kinds = s.nbr + 32;
+        s.match = reinterpret_cast<int8_t *>(s.kinds + 32);
+        s.par = s.match + 32;
+        s.base = s.par + 32;
+        s.queue = s.base + 32;
+    }
     const uint32_t mine = lane < n ? nbr_g[(size_t)g * n + lane] : 0u;
     s.nbr[lane] = mine;
     s.kinds[lane] = 0u;
@@ -193,7 +211,8 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     __syncwarp();
 
     // ---- lambda_1 of A + 1e-4 I
-    for (uint32_t j = 0; j < n; ++j) s.a[lane * AZG_LD + j] = lane == j ? 0.0001 : ((mine >> j & 1u) ? 1.0 : 0.0);
+    if (lane < n)
+        for (uint32_t j = 0; j < n; ++j) s.a[lane * AZG_LD + j] = lane == j ? 0.0001 : ((mine >> j & 1u) ? 1.0 : 0.0);
     __syncwarp();
     for (uint32_t k = 0; k + 2 < n; ++k) {
         const bool act = lane > k && lane < n;
@@ -237,12 +256,11 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     }
     double hi = azg_warp_max(lane < n ? dd + rad : -1e300), lo = -azg_warp_max(lane < n ? rad - dd : -1e300);
     const double scale = fmax(fabs(hi), fabs(lo));
-    const double tiny = fmax(scale, 1.0) * 1e-300;
     hi = hi + fmax(scale, 1.0) * 1e-9;
     for (int round = 0; round < 16; ++round) {
         const double step = __ddiv_rn(__dsub_rn(hi, lo), 33.0);
         const double x = __dadd_rn(lo, __dmul_rn(step, (double)(lane + 1)));
-        const uint32_t above = __ballot_sync(0xffffffffu, azg_above_all(s.d, s.e, n, x, tiny));
+        const uint32_t above = __ballot_sync(0xffffffffu, azg_above_all(s.d, s.e, n, x));
         const int first = above ? __ffs(above) - 1 : 32;
         const double nlo = first > 0 ? __shfl_sync(0xffffffffu, x, first - 1) : lo;
         const double nhi = first < 32 ? __shfl_sync(0xffffffffu, x, first & 31) : hi;
