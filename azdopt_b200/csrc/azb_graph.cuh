@@ -47,14 +47,16 @@ __device__ __forceinline__ bool azg_is_cut_edge(const uint32_t *nbr, uint32_t v,
     return true;
 }
 
-// Edmonds' blossom algorithm (array form), serial; match/par/base/queue live in the warp's shared scratch
-__device__ uint32_t azg_matching_number(const AzgWarpScratch &s, uint32_t n) {
+// Edmonds' blossom algorithm (array form), serial, on the vertices of `alive` with neighbourhoods nbr[] (already
+// restricted to `alive`); match/par/base/queue live in the warp's shared scratch
+__device__ uint32_t azg_matching_number(const AzgWarpScratch &s, const uint32_t *nbr, uint32_t alive, uint32_t n) {
     int8_t *match = s.match, *par = s.par, *base = s.base, *queue = s.queue;
     uint32_t size = 0;
     for (uint32_t v = 0; v < n; ++v) match[v] = -1;
-    for (uint32_t v = 0; v < n; ++v) {  // greedy start
+    for (uint32_t av = alive; av; av &= av - 1) {  // greedy start
+        const uint32_t v = __ffs(av) - 1;
         if (match[v] >= 0) continue;
-        for (uint32_t r = s.nbr[v]; r; r &= r - 1) {
+        for (uint32_t r = nbr[v]; r; r &= r - 1) {
             const int t = __ffs(r) - 1;
             if (match[t] < 0) {
                 match[v] = (int8_t)t;
@@ -64,7 +66,8 @@ __device__ uint32_t azg_matching_number(const AzgWarpScratch &s, uint32_t n) {
             }
         }
     }
-    for (uint32_t root = 0; root < n; ++root) {
+    for (uint32_t ar = alive; ar; ar &= ar - 1) {
+        const uint32_t root = __ffs(ar) - 1;
         if (match[root] >= 0) continue;
         for (uint32_t i = 0; i < n; ++i) {
             par[i] = -1;
@@ -75,7 +78,7 @@ __device__ uint32_t azg_matching_number(const AzgWarpScratch &s, uint32_t n) {
         int found = -1;
         while (qh < qt && found < 0) {
             const int v = queue[qh++];
-            for (uint32_t r = s.nbr[v]; r && found < 0; r &= r - 1) {
+            for (uint32_t r = nbr[v]; r && found < 0; r &= r - 1) {
                 int to = __ffs(r) - 1;
                 if (base[v] == base[to] || match[v] == to) continue;
                 if (to == (int)root || (match[to] >= 0 && par[match[to]] >= 0)) {
@@ -205,9 +208,29 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     }
     if (kinds_out && lane < kw) kinds_out[(size_t)g * kw + lane] = s.kinds[lane];
 
-    // ---- matching number
-    uint32_t mu = 0;
-    if (lane == 0) mu = azg_matching_number(s, n);
+    // ---- matching number: pendant edges first (some maximum matching contains any given pendant edge, so matching a
+    // leaf with its neighbour and deleting both is exact), one ballot per leaf; what is left has minimum degree 2 and
+    // goes through the blossom search on lane 0.  A tree never gets there.
+    uint32_t mu = 0, alive = n == 32 ? 0xffffffffu : (1u << n) - 1u;
+    for (;;) {
+        const bool me = alive >> lane & 1u;
+        const uint32_t mynb = mine & alive;
+        const uint32_t leaves = __ballot_sync(0xffffffffu, me && __popc(mynb) == 1);
+        alive &= ~__ballot_sync(0xffffffffu, me && mynb == 0u);
+        if (!leaves) break;
+        const int v = __ffs(leaves) - 1;
+        const int t = __ffs(__shfl_sync(0xffffffffu, mynb, v)) - 1;
+        alive &= ~((1u << v) | (1u << t));
+        ++mu;
+    }
+    if (alive) {
+        __syncwarp();
+        s.kinds[lane] = (alive >> lane & 1u) ? (mine & alive) : 0u;  // the kinds are out: their words hold the core now
+        __syncwarp();
+        uint32_t core = 0;
+        if (lane == 0) core = azg_matching_number(s, s.kinds, alive, n);
+        mu += __shfl_sync(0xffffffffu, core, 0);
+    }
     __syncwarp();
 
     // ---- lambda_1 of A + 1e-4 I
@@ -217,31 +240,44 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     for (uint32_t k = 0; k + 2 < n; ++k) {
         const bool act = lane > k && lane < n;
         const double x = act ? s.a[lane * AZG_LD + k] : 0.0;
-        const double norm2 = azg_warp_sum(__dmul_rn(x, x));
         const double x0 = __shfl_sync(0xffffffffu, x, k + 1);
         const double rest2 = azg_warp_sum(lane == k + 1 ? 0.0 : __dmul_rn(x, x));
+        const double norm2 = __dadd_rn(rest2, __dmul_rn(x0, x0));
         if (rest2 == 0.0) {  // the column is already tridiagonal
             if (lane == 0) s.e[k] = x0;
             continue;
         }
         const double alpha = x0 > 0.0 ? -__dsqrt_rn(norm2) : __dsqrt_rn(norm2);
         double u = lane == k + 1 ? __dsub_rn(x, alpha) : x;
-        const double un2 = azg_warp_sum(__dmul_rn(u, u));
+        const double u0 = __dsub_rn(x0, alpha);
+        const double un2 = __dadd_rn(rest2, __dmul_rn(u0, u0));
         u = __dmul_rn(u, __ddiv_rn(1.0, __dsqrt_rn(un2)));
         s.u[lane] = u;
         __syncwarp();
-        double q = 0.0;
-        if (act)
-            for (uint32_t j = k + 1; j < n; ++j) q = __dadd_rn(q, __dmul_rn(s.a[lane * AZG_LD + j], s.u[j]));
+        double *__restrict__ arow = s.a + lane * AZG_LD;
+        const double *__restrict__ uu = s.u;
+        double q = 0.0, q1 = 0.0;
+        if (act) {
+            uint32_t j = k + 1;
+            for (; j + 1 < n; j += 2) {  // two partial sums: half the dependent additions
+                q = __dadd_rn(q, __dmul_rn(arow[j], uu[j]));
+                q1 = __dadd_rn(q1, __dmul_rn(arow[j + 1], uu[j + 1]));
+            }
+            if (j < n) q = __dadd_rn(q, __dmul_rn(arow[j], uu[j]));
+            q = __dadd_rn(q, q1);
+        }
         const double uq = azg_warp_sum(__dmul_rn(u, q));
         const double w = __dsub_rn(q, __dmul_rn(uq, u));
         s.w[lane] = w;
         __syncwarp();
-        if (act)
+        const double *__restrict__ ww = s.w;
+        if (act) {
+#pragma unroll 4
             for (uint32_t j = k + 1; j < n; ++j) {
-                const double t = __dadd_rn(__dmul_rn(u, s.w[j]), __dmul_rn(w, s.u[j]));
-                s.a[lane * AZG_LD + j] = __dsub_rn(s.a[lane * AZG_LD + j], __dmul_rn(2.0, t));
+                const double t = __dadd_rn(__dmul_rn(u, ww[j]), __dmul_rn(w, uu[j]));
+                arow[j] = __dsub_rn(arow[j], __dmul_rn(2.0, t));
             }
+        }
         if (lane == 0) s.e[k] = alpha;
         __syncwarp();
     }
