@@ -1400,7 +1400,9 @@ int azb_eval_graph_costs(azb_handle *h, const uint32_t *nbr, uint32_t m, uint32_
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d_err, 0, 4, h->stream);
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev0, h->stream);
     if (ce == cudaSuccess) {
-        azb_graph_cost_kernel<<<(m + AZG_WARPS - 1) / AZG_WARPS, AZG_WARPS * 32, AZG_WARPS * azg_warp_bytes(n), h->stream>>>(d_nbr, m, n, kw, d_l1, d_mu, d_kinds, d_err);
+        const uint32_t blocks = (m + AZG_WARPS - 1) / AZG_WARPS, smem = AZG_WARPS * azg_warp_bytes(n);
+        if (azg_packed(n)) azb_graph_cost_kernel<true><<<blocks, AZG_WARPS * 32, smem, h->stream>>>(d_nbr, m, n, kw, d_l1, d_mu, d_kinds, d_err);
+        else azb_graph_cost_kernel<false><<<blocks, AZG_WARPS * 32, smem, h->stream>>>(d_nbr, m, n, kw, d_l1, d_mu, d_kinds, d_err);
         h->launches += 1;
         ce = cudaGetLastError();
     }

@@ -14,14 +14,18 @@
 
 #define AZG_WARPS 4
 
-struct AzgWarpScratch {  // one per warp, carved out of dynamic shared memory: the matrix is n rows of (n | 1) doubles
+struct AzgWarpScratch {  // one per warp, carved out of dynamic shared memory: the matrix is a packed lower triangle
     double *a;
     double *u, *w, *d, *e;
     uint32_t *nbr, *kinds;
     int8_t *match, *par, *base, *queue;
 };
-__host__ __device__ inline uint32_t azg_ld(uint32_t n) { return n | 1u; }  // odd row stride: rows start in different banks
-__host__ __device__ inline uint32_t azg_warp_bytes(uint32_t n) { return 8u * n * azg_ld(n) + 4u * 32u * 8u + 2u * 32u * 4u + 4u * 32u; }
+__host__ __device__ inline uint32_t azg_tri(uint32_t n) { return (n * (n + 1) / 2 + 1u) & ~1u; }  // doubles, 16 B multiple
+__host__ __device__ inline uint32_t azg_ld(uint32_t n) { return n | 1u; }  // square layout: odd row stride
+__host__ __device__ inline bool azg_packed(uint32_t n) { return n > 22u; }  // the triangle costs index arithmetic and a
+// divergent second loop in A u; it pays once the square would hold the kernel below ~40 resident warps per SM
+__host__ __device__ inline uint32_t azg_mat_doubles(uint32_t n) { return azg_packed(n) ? azg_tri(n) : n * azg_ld(n); }
+__host__ __device__ inline uint32_t azg_warp_bytes(uint32_t n) { return 8u * azg_mat_doubles(n) + 4u * 32u * 8u + 2u * 32u * 4u + 4u * 32u; }
 
 __device__ __forceinline__ double azg_warp_sum(double v) {
 #pragma unroll
@@ -143,12 +147,11 @@ __device__ uint32_t azg_matching_number(const AzgWarpScratch &s, const uint32_t 
 
 // x > lambda_max of the symmetric tridiagonal (d, e)  <=>  every leading principal minor of x I - T is positive:
 // p_0 = 1, p_1 = x - d_0, p_i = (x - d_{i-1}) p_{i-1} - e_{i-2}^2 p_{i-2}.  No division; |p_i| <= (2 ||T||)^32 < 1e60.
-__device__ __forceinline__ bool azg_above_all(const double *d, const double *e, uint32_t n, double x) {
+__device__ __forceinline__ bool azg_above_all(const double *d, const double *e2, uint32_t n, double x) {
     double pm = 1.0, p = __dsub_rn(x, d[0]);
     bool all = p > 0.0;
     for (uint32_t i = 1; i < n && all; ++i) {
-        const double ee = __dmul_rn(e[i - 1], e[i - 1]);
-        const double pn = __dsub_rn(__dmul_rn(__dsub_rn(x, d[i]), p), __dmul_rn(ee, pm));
+        const double pn = __fma_rn(__dsub_rn(x, d[i]), p, -__dmul_rn(e2[i - 1], pm));
         pm = p;
         p = pn;
         all = p > 0.0;
@@ -156,6 +159,7 @@ __device__ __forceinline__ bool azg_above_all(const double *d, const double *e, 
     return all;
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(AZG_WARPS * 32)
 azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n, uint32_t kw, double *__restrict__ l1_out,
                       uint32_t *__restrict__ mu_out, uint32_t *__restrict__ kinds_out, uint32_t *err) {
@@ -163,12 +167,11 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = blockIdx.x * AZG_WARPS + warp;
     if (g >= m) return;
-    const uint32_t AZG_LD = azg_ld(n);
     AzgWarpScratch s;
     {
         uint8_t *base = azg_smem + (size_t)warp * azg_warp_bytes(n);
         s.a = reinterpret_cast<double *>(base);
-        s.u = s.a + n * AZG_LD;
+        s.u = s.a + azg_mat_doubles(n);
         s.w = s.u + 32;
         s.d = s.w + 32;
         s.e = s.d + 32;
@@ -233,16 +236,20 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     }
     __syncwarp();
 
-    // ---- lambda_1 of A + 1e-4 I
+    // ---- lambda_1 of A + 1e-4 I.  The matrix is symmetric: lane i keeps the lower-triangle row i (entries j <= i) at
+    // a + i (i + 1) / 2; the upper part of a row is read down its column (consecutive words across lanes).
+    // (n <= 22: plain square rows of n | 1 doubles, every row whole -- fewer instructions, and it fits anyway)
+    double *__restrict__ arow = s.a + (PACKED ? lane * (lane + 1) / 2 : lane * azg_ld(n));
+    const uint32_t jmax = PACKED ? lane : n - 1;  // last column this lane stores
     if (lane < n)
-        for (uint32_t j = 0; j < n; ++j) s.a[lane * AZG_LD + j] = lane == j ? 0.0001 : ((mine >> j & 1u) ? 1.0 : 0.0);
+        for (uint32_t j = 0; j <= jmax; ++j) arow[j] = lane == j ? 0.0001 : ((mine >> j & 1u) ? 1.0 : 0.0);
     __syncwarp();
     for (uint32_t k = 0; k + 2 < n; ++k) {
         const bool act = lane > k && lane < n;
-        const double x = act ? s.a[lane * AZG_LD + k] : 0.0;
+        const double x = act ? arow[k] : 0.0;
         const double x0 = __shfl_sync(0xffffffffu, x, k + 1);
         const double rest2 = azg_warp_sum(lane == k + 1 ? 0.0 : __dmul_rn(x, x));
-        const double norm2 = __dadd_rn(rest2, __dmul_rn(x0, x0));
+        const double norm2 = __fma_rn(x0, x0, rest2);
         if (rest2 == 0.0) {  // the column is already tridiagonal
             if (lane == 0) s.e[k] = x0;
             continue;
@@ -250,39 +257,50 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
         const double alpha = x0 > 0.0 ? -__dsqrt_rn(norm2) : __dsqrt_rn(norm2);
         double u = lane == k + 1 ? __dsub_rn(x, alpha) : x;
         const double u0 = __dsub_rn(x0, alpha);
-        const double un2 = __dadd_rn(rest2, __dmul_rn(u0, u0));
+        const double un2 = __fma_rn(u0, u0, rest2);
         u = __dmul_rn(u, __ddiv_rn(1.0, __dsqrt_rn(un2)));
         s.u[lane] = u;
         __syncwarp();
-        double *__restrict__ arow = s.a + lane * AZG_LD;
         const double *__restrict__ uu = s.u;
         double q = 0.0, q1 = 0.0;
         if (act) {
             uint32_t j = k + 1;
-            for (; j + 1 < n; j += 2) {  // two partial sums: half the dependent additions
-                q = __dadd_rn(q, __dmul_rn(arow[j], uu[j]));
-                q1 = __dadd_rn(q1, __dmul_rn(arow[j + 1], uu[j + 1]));
+            for (; j + 1 <= jmax; j += 2) {  // own row (up to the diagonal when packed), two partial sums
+                q = __fma_rn(arow[j], uu[j], q);
+                q1 = __fma_rn(arow[j + 1], uu[j + 1], q1);
             }
-            if (j < n) q = __dadd_rn(q, __dmul_rn(arow[j], uu[j]));
+            if (j <= jmax) q = __fma_rn(arow[j], uu[j], q);
+            if (PACKED) {
+                const double *col = s.a + lane;  // A[i][j] = A[j][i] for j > i: row j starts at j (j + 1) / 2
+                j = lane + 1;
+                uint32_t off = j * (j + 1) / 2;
+                for (; j + 1 < n; j += 2) {
+                    q = __fma_rn(col[off], uu[j], q);
+                    off += j + 1;
+                    q1 = __fma_rn(col[off], uu[j + 1], q1);
+                    off += j + 2;
+                }
+                if (j < n) q = __fma_rn(col[off], uu[j], q);
+            }
             q = __dadd_rn(q, q1);
         }
         const double uq = azg_warp_sum(__dmul_rn(u, q));
-        const double w = __dsub_rn(q, __dmul_rn(uq, u));
+        const double w = __fma_rn(-uq, u, q);
         s.w[lane] = w;
-        __syncwarp();
+        __syncwarp();  // also: every column read of this step is done before the rows change
         const double *__restrict__ ww = s.w;
         if (act) {
+            const double u2 = __dmul_rn(-2.0, u), w2 = __dmul_rn(-2.0, w);  // A' = A - 2 u w^T - 2 w u^T
 #pragma unroll 4
-            for (uint32_t j = k + 1; j < n; ++j) {
-                const double t = __dadd_rn(__dmul_rn(u, ww[j]), __dmul_rn(w, uu[j]));
-                arow[j] = __dsub_rn(arow[j], __dmul_rn(2.0, t));
-            }
+            for (uint32_t j = k + 1; j <= jmax; ++j) arow[j] = __fma_rn(u2, ww[j], __fma_rn(w2, uu[j], arow[j]));
         }
         if (lane == 0) s.e[k] = alpha;
         __syncwarp();
     }
-    if (lane < n) s.d[lane] = s.a[lane * AZG_LD + lane];
-    if (lane == 0 && n >= 2) s.e[n - 2] = s.a[(n - 1) * AZG_LD + n - 2];
+    if (lane < n) s.d[lane] = arow[lane];
+    if (lane == n - 1 && n >= 2) s.e[n - 2] = arow[n - 2];
+    __syncwarp();
+    if (lane + 1 < n) s.u[lane] = __dmul_rn(s.e[lane], s.e[lane]);  // squared off-diagonal, once
     __syncwarp();
     // Gershgorin bracket of the spectrum, then 33-fold sections of [lo, hi] with  not above(lo), above(hi)
     double rad = 0.0, dd = -1e300;
@@ -296,7 +314,7 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     for (int round = 0; round < 16; ++round) {
         const double step = __ddiv_rn(__dsub_rn(hi, lo), 33.0);
         const double x = __dadd_rn(lo, __dmul_rn(step, (double)(lane + 1)));
-        const uint32_t above = __ballot_sync(0xffffffffu, azg_above_all(s.d, s.e, n, x));
+        const uint32_t above = __ballot_sync(0xffffffffu, azg_above_all(s.d, s.u, n, x));
         const int first = above ? __ffs(above) - 1 : 32;
         const double nlo = first > 0 ? __shfl_sync(0xffffffffu, x, first - 1) : lo;
         const double nhi = first < 32 ? __shfl_sync(0xffffffffu, x, first & 31) : hi;
