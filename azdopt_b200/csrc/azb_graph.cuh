@@ -2,7 +2,8 @@
 // bit sets (`ConnectedBitsetGraph<N, B32>`, graph-state/src/simple_graph/connected_bitset_graph/mod.rs), batched.
 // One warp per graph, lane v = vertex v (N <= 32), everything in shared memory and registers:
 //   * action kinds (`action_kinds` :134-154 over `is_cut_edge` :45-71) in the index space of
-//     `AddOrDeleteEdge::action_index` (bitset_graph/space/action.rs:10-19): one lane per vertex pair, bit-set BFS;
+//     `AddOrDeleteEdge::action_index` (bitset_graph/space/action.rs:10-19): the bit-set BFS test on the N - 1 edges
+//     of a spanning tree (the only possible cut edges), then one lane per vertex pair;
 //   * matching number (`maximum_matching` :226-317 is a branch and bound; only its SIZE is read, so any exact
 //     algorithm gives the same number): greedy start + Edmonds' blossom augmentation, serial on lane 0;
 //   * lambda_1 (`adjacency_matrix` :200-216 with its 1e-4 diagonal, `conjecture_2_1_cost` :319-337 takes the
@@ -187,6 +188,26 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     s.kinds[lane] = 0u;
     __syncwarp();
 
+    // ---- cut edges.  Only the N - 1 edges of a spanning tree can be cut edges (any other edge closes a cycle with
+    // the tree), so: a breadth-first spanning tree by ballots (lane v learns its parent), then ONE round of the
+    // reference's test (`is_cut_edge`), lane v on the edge to its parent, instead of one test per edge of the graph.
+    uint32_t *brg = reinterpret_cast<uint32_t *>(s.u);  // brg[v]: bit u <=> vu is a cut edge (the doubles are free here)
+    brg[lane] = 0u;
+    int parent = -1;
+    for (uint32_t seen = 1u, frontier = 1u; frontier;) {
+        const uint32_t cand = mine & frontier;
+        const bool join = lane < n && !(seen >> lane & 1u) && cand;
+        if (join) parent = __ffs(cand) - 1;
+        frontier = __ballot_sync(0xffffffffu, join);
+        seen |= frontier;
+    }
+    __syncwarp();
+    if (parent >= 0 && azg_is_cut_edge(s.nbr, lane, (uint32_t)parent)) {
+        atomicOr(&brg[lane], 1u << parent);
+        atomicOr(&brg[parent], 1u << lane);
+    }
+    __syncwarp();
+
     // ---- action kinds: pair p = colex(v, u) = v (v - 1) / 2 + u, 32 pairs per round
     const uint32_t e2 = n * (n - 1) / 2;
     for (uint32_t p0 = 0; p0 < e2; p0 += 32) {
@@ -197,7 +218,7 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
             while (v * (v - 1) / 2 > p) --v;
             while (v * (v + 1) / 2 <= p) ++v;
             const uint32_t u = p - v * (v - 1) / 2;
-            if (s.nbr[v] >> u & 1u) del = !azg_is_cut_edge(s.nbr, v, u);
+            if (s.nbr[v] >> u & 1u) del = !(brg[v] >> u & 1u);
             else add = true;
         }
         const uint32_t wa = __ballot_sync(0xffffffffu, add), wd = __ballot_sync(0xffffffffu, del);
