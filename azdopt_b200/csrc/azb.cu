@@ -51,6 +51,8 @@ struct azb_handle {
     float *cost_c;
     uint32_t *cost_err;
     uint32_t cost_cap;
+    uint8_t *graph_buf;  // azb_eval_graph_costs: one grow-only slab [l1 | nbr | mu | kinds | err]
+    size_t graph_cap;
     // observations scratch
     float *obs, *obs_w;
     // training step (azb_train.cuh): gradient (parameter order), Adam moments, predictions, two dZ buffers, scalars
@@ -205,7 +207,7 @@ int azb_destroy(azb_handle *h) {
     void *ptrs[] = {h->grad, h->adam_m, h->adam_v, h->tr_p, h->tr_dz[0], h->tr_dz[1], h->tr_x, h->tr_scal, h->tr_part, h->comm_buf,
                     h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
                     h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
-                    h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf};
+                    h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf, h->graph_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     azb_mlp_tc_destroy(h->tc);
@@ -1363,41 +1365,27 @@ int azb_eval_graph_costs(azb_handle *h, const uint32_t *nbr, uint32_t m, uint32_
                          uint32_t *kinds, float *ms) {
     if (!h || !nbr || m == 0) return AZB_ERR_INVALID;
     if (n < 2 || n > 32) return fail(h, AZB_ERR_INVALID, "graphs have 2..32 vertices (B32 neighbourhoods), got %u", n);
-    const uint32_t full = n == 32 ? 0xffffffffu : (1u << n) - 1u;
-    for (uint32_t i = 0; i < m; ++i) {  // what BitsetGraph::try_from + to_connected (bitset_graph/mod.rs) accept
-        const uint32_t *g = nbr + (size_t)i * n;
-        for (uint32_t v = 0; v < n; ++v) {
-            if ((g[v] & ~full) || (g[v] >> v & 1u)) return fail(h, AZB_ERR_INVALID, "graph %u: vertex %u has a loop or a neighbour >= N", i, v);
-            for (uint32_t r = g[v]; r; r &= r - 1)
-                if (!(g[__builtin_ctz(r)] >> v & 1u)) return fail(h, AZB_ERR_INVALID, "graph %u: neighbourhoods are not symmetric at %u", i, v);
-        }
-        uint32_t seen = 1u, fresh = 1u;
-        while (fresh) {
-            uint32_t next = 0u;
-            for (uint32_t r = fresh; r; r &= r - 1) next |= g[__builtin_ctz(r)];
-            fresh = next & ~seen;
-            seen |= fresh;
-        }
-        if (seen != full) return fail(h, AZB_ERR_INVALID, "graph %u is not connected", i);
-    }
+    // loops, asymmetric neighbourhoods, neighbours >= N and disconnected inputs are found by the kernel itself
     CK(cudaSetDevice(h->cfg.device));
     const uint32_t kw = (n * (n - 1) + 31) / 32;
-    uint32_t *d_nbr = nullptr, *d_mu = nullptr, *d_kinds = nullptr, *d_err = nullptr;
-    double *d_l1 = nullptr;
-    auto release = [&]() {
-        cudaFree(d_nbr);
-        cudaFree(d_mu);
-        cudaFree(d_kinds);
-        cudaFree(d_err);
-        cudaFree(d_l1);
-    };
-    cudaError_t ce = cudaMalloc((void **)&d_nbr, (size_t)m * n * 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_mu, (size_t)m * 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_kinds, (size_t)m * kw * 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_err, 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void **)&d_l1, (size_t)m * 8);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_nbr, nbr, (size_t)m * n * 4, cudaMemcpyHostToDevice, h->stream);
-    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_err, 0, 4, h->stream);
+    // one slab on the handle, grown when a larger batch arrives (a cudaMalloc per call costs more than the kernel)
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_l1 = 0, o_nbr = o_l1 + up((size_t)m * 8), o_mu = o_nbr + up((size_t)m * n * 4), o_kinds = o_mu + up((size_t)m * 4),
+                 o_err = o_kinds + up((size_t)m * kw * 4), total = o_err + 256;
+    if (total > h->graph_cap) {
+        if (h->graph_buf) cudaFree(h->graph_buf);
+        h->graph_buf = nullptr;
+        h->graph_cap = 0;
+        CK(cudaMalloc((void **)&h->graph_buf, total));
+        h->graph_cap = total;
+    }
+    double *d_l1 = reinterpret_cast<double *>(h->graph_buf + o_l1);
+    uint32_t *d_nbr = reinterpret_cast<uint32_t *>(h->graph_buf + o_nbr), *d_mu = reinterpret_cast<uint32_t *>(h->graph_buf + o_mu),
+             *d_kinds = reinterpret_cast<uint32_t *>(h->graph_buf + o_kinds), *d_err = reinterpret_cast<uint32_t *>(h->graph_buf + o_err);
+    auto release = []() {};
+    cudaError_t ce = cudaMemcpyAsync(d_nbr, nbr, (size_t)m * n * 4, cudaMemcpyHostToDevice, h->stream);
+    const uint32_t err0[2] = {0u, 0xffffffffu};  // [0] bit AZB_ERR_* per kind of failure, [1] first rejected graph
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_err, err0, 8, cudaMemcpyHostToDevice, h->stream);
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev0, h->stream);
     if (ce == cudaSuccess) {
         const uint32_t blocks = (m + AZG_WARPS - 1) / AZG_WARPS, smem = AZG_WARPS * azg_warp_bytes(n);
@@ -1407,16 +1395,18 @@ int azb_eval_graph_costs(azb_handle *h, const uint32_t *nbr, uint32_t m, uint32_
         ce = cudaGetLastError();
     }
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev1, h->stream);
-    uint32_t err = 0;
+    uint32_t err[2] = {0u, 0u};
     if (ce == cudaSuccess && lambda1) ce = cudaMemcpyAsync(lambda1, d_l1, (size_t)m * 8, cudaMemcpyDeviceToHost, h->stream);
     if (ce == cudaSuccess && mu) ce = cudaMemcpyAsync(mu, d_mu, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream);
     if (ce == cudaSuccess && kinds) ce = cudaMemcpyAsync(kinds, d_kinds, (size_t)m * kw * 4, cudaMemcpyDeviceToHost, h->stream);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, h->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(err, d_err, 8, cudaMemcpyDeviceToHost, h->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
     if (ce == cudaSuccess && ms) ce = cudaEventElapsedTime(ms, h->ev0, h->ev1);
     release();
     if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "azb_eval_graph_costs: %s", cudaGetErrorString(ce));
-    if (err) return fail(h, (int)err, "%s", azb_strerror((int)err));
+    if (err[0] & (1u << AZB_ERR_INVALID))
+        return fail(h, AZB_ERR_INVALID, "graph %u is not a connected simple graph (a loop, a neighbour >= N, asymmetric neighbourhoods, or disconnected)", err[1]);
+    if (err[0] & (1u << AZB_ERR_LAMBDA)) return fail(h, AZB_ERR_LAMBDA, "%s", azb_strerror(AZB_ERR_LAMBDA));
     return AZB_OK;
 }
 

@@ -187,6 +187,14 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     s.nbr[lane] = mine;
     s.kinds[lane] = 0u;
     __syncwarp();
+    // ---- what BitsetGraph::try_from / to_connected accept: no loops, neighbours < N, symmetric (column v of the
+    // relation, gathered by ballots, must equal row v); connectedness falls out of the spanning tree below
+    const uint32_t full = n == 32 ? 0xffffffffu : (1u << n) - 1u;
+    bool bad = (mine & ~full) || (mine >> lane & 1u);
+    for (uint32_t v = 0; v < n; ++v) {
+        const uint32_t column = __ballot_sync(0xffffffffu, mine >> v & 1u);
+        if (lane == v) bad = bad || column != mine;
+    }
 
     // ---- cut edges.  Only the N - 1 edges of a spanning tree can be cut edges (any other edge closes a cycle with
     // the tree), so: a breadth-first spanning tree by ballots (lane v learns its parent), then ONE round of the
@@ -194,12 +202,22 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     uint32_t *brg = reinterpret_cast<uint32_t *>(s.u);  // brg[v]: bit u <=> vu is a cut edge (the doubles are free here)
     brg[lane] = 0u;
     int parent = -1;
-    for (uint32_t seen = 1u, frontier = 1u; frontier;) {
+    uint32_t seen = 1u;
+    for (uint32_t frontier = 1u; frontier;) {
         const uint32_t cand = mine & frontier;
         const bool join = lane < n && !(seen >> lane & 1u) && cand;
         if (join) parent = __ffs(cand) - 1;
         frontier = __ballot_sync(0xffffffffu, join);
         seen |= frontier;
+    }
+    if (__any_sync(0xffffffffu, bad) || seen != full) {  // not a connected simple graph: report the first such input
+        if (lane == 0) {
+            atomicOr(err, 1u << 1);
+            atomicMin(err + 1, g);
+            l1_out[g] = 0.0;
+            mu_out[g] = 0u;
+        }
+        return;
     }
     __syncwarp();
     if (parent >= 0 && azg_is_cut_edge(s.nbr, lane, (uint32_t)parent)) {
@@ -347,6 +365,6 @@ azb_graph_cost_kernel(const uint32_t *__restrict__ nbr_g, uint32_t m, uint32_t n
     if (lane == 0) {
         l1_out[g] = l1;
         mu_out[g] = mu;
-        if (!(l1 > 1.4)) atomicMax(err, 5u);  // connected_bitset_graph/mod.rs:333 `assert!(lambda_1 > 1.4)`
+        if (!(l1 > 1.4)) atomicOr(err, 1u << 5);  // connected_bitset_graph/mod.rs:333 `assert!(lambda_1 > 1.4)`
     }
 }

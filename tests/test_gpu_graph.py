@@ -55,6 +55,19 @@ def test_invalid_graphs_are_rejected(capi, orc):
             assert e.value.code == capi.ERR_INVALID
 
 
+def test_one_bad_graph_in_a_batch_is_named(capi, orc):
+    rng = np.random.default_rng(3)
+    graphs = np.stack([random_connected_graph(rng, 12, 0.2) for _ in range(64)])
+    graphs[37, 4] ^= np.uint32(1 << 9)  # one direction of an edge only
+    with _mk(capi) as h:
+        with pytest.raises(capi.AzbError) as e:
+            h.eval_graph_costs(graphs)
+        assert e.value.code == capi.ERR_INVALID and "graph 37" in str(e.value)
+        graphs[37, 4] ^= np.uint32(1 << 9)
+        l1, mu, _, _ = h.eval_graph_costs(graphs)  # the handle stays usable
+        assert mu[37] == orc.graph_matching_number(graphs[37])
+
+
 def test_full_size_properties(capi, orc):
     """65 536 graphs on 32 vertices: relabelling invariance (the cost is a graph invariant, the kinds permute with the
     vertices), counts of the kind masks, and the oracle on a sample."""
