@@ -151,11 +151,12 @@ __device__ uint32_t azg_matching_number(const AzgWarpScratch &s, const uint32_t 
 __device__ __forceinline__ bool azg_above_all(const double *d, const double *e2, uint32_t n, double x) {
     double pm = 1.0, p = __dsub_rn(x, d[0]);
     bool all = p > 0.0;
-    for (uint32_t i = 1; i < n && all; ++i) {
+    // no early exit: the warp runs as long as its highest section point anyway, and that one never leaves early
+    for (uint32_t i = 1; i < n; ++i) {
         const double pn = __fma_rn(__dsub_rn(x, d[i]), p, -__dmul_rn(e2[i - 1], pm));
         pm = p;
         p = pn;
-        all = p > 0.0;
+        all = all && p > 0.0;
     }
     return all;
 }
