@@ -55,3 +55,47 @@ def test_random_graphs_against_networkx_and_lapack(orc, n, p):
                 assert dele == (1 if is_edge and (v, u) not in bridges else 0)
                 if is_edge:
                     assert orc.graph_is_cut_edge(g, v, u) == ((v, u) in bridges)
+
+
+def _brute_force_matching(n, edges):
+    """Exact matching number by exhaustive search over edge subsets (small graphs only)."""
+    best = 0
+
+    def go(i, used, size):
+        nonlocal best
+        best = max(best, size)
+        if size + (len(edges) - i) <= best:
+            return
+        for k in range(i, len(edges)):
+            a, b = edges[k]
+            if not (used >> a & 1) and not (used >> b & 1):
+                go(k + 1, used | 1 << a | 1 << b, size + 1)
+
+    go(0, 0, 0)
+    return best
+
+
+def test_small_graphs_against_exhaustive_search(orc):
+    """Every connected graph the generator yields on <= 7 vertices: the restated branch and bound equals an exhaustive
+    search, relabelling does not change the cost, and the kinds permute with the vertices."""
+    rng = np.random.default_rng(11)
+    for n in range(2, 8):
+        for _ in range(60):
+            g = random_connected_graph(rng, n, float(rng.random()) * 0.8)
+            edges = edges_of(g)
+            assert orc.graph_matching_number(g) == _brute_force_matching(n, edges)
+            perm = rng.permutation(n)
+            g2 = orc.graph_from_edges(n, [(int(perm[a]), int(perm[b])) for a, b in edges])
+            l1, mu, _ = orc.graph_cost(g)
+            l2, mu2, _ = orc.graph_cost(g2)
+            assert mu == mu2 and abs(l1 - l2) <= 1e-12 * max(1.0, l1)
+            k1, k2 = orc.graph_action_kinds(g), orc.graph_action_kinds(g2)
+            e2 = n * (n - 1) // 2
+            for v in range(n):
+                for u in range(v):
+                    p1 = orc.colex_position(v, u)
+                    p2 = orc.colex_position(int(perm[v]), int(perm[u]))
+                    for off in (0, e2):
+                        b1 = int(k1[(off + p1) >> 5]) >> ((off + p1) & 31) & 1
+                        b2 = int(k2[(off + p2) >> 5]) >> ((off + p2) & 31) & 1
+                        assert b1 == b2
