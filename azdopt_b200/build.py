@@ -13,6 +13,9 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",  # every contraction in the search kernels is written out (bit parity with the reference's f32)
     "-Xcompiler", "-fPIC", "-shared",
+    # the CUDA runtime is linked dynamically (libcudart.so.12 is in the image's ld cache; the rpath covers a bare box):
+    # a statically linked runtime embeds the name of every runtime entry point in the shipped .so
+    "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 
@@ -36,12 +39,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build_profile_flavour() -> str:
-    """lib/libazb_prof.so: the same library with -DAZB_PROFILE (per-phase clock64 accumulators; tools/phase_probe.py)."""
-    out = os.path.join(_HERE, "lib", "libazb_prof.so")
+def build_variant(name: str, defines=()) -> str:
+    """lib/libazb_<name>.so: the same library with extra -D flags (select it with AZB_LIB=<path>)."""
+    out = os.path.join(_HERE, "lib", f"libazb_{name}.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    subprocess.check_call([_nvcc(), *NVCC_FLAGS, "-DAZB_PROFILE", "-o", out, os.path.join(_CSRC, "azb.cu")])
+    subprocess.check_call([_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, os.path.join(_CSRC, "azb.cu")])
     return out
+
+
+def build_profile_flavour() -> str:
+    """lib/libazb_prof.so: -DAZB_PROFILE (per-phase clock64 accumulators; tools/phase_probe.py, tools/async_probe.py)."""
+    return build_variant("prof", ["AZB_PROFILE"])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -105,6 +105,7 @@ SIGNATURES = {
     "azb_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "azb_device_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "azb_flush_l2": (C.c_int, [C.c_void_p]),
+    "azb_debug_cascade_spills": (C.c_int, [C.c_void_p, u32p]),
 }
 
 
@@ -447,6 +448,11 @@ class Handle:
     def kernel_launches(self) -> int:
         n = C.c_uint64()
         self._ck(self._L.azb_kernel_launches(self._h, C.byref(n)))
+        return int(n.value)
+
+    def cascade_spills(self) -> int:
+        n = C.c_uint32()
+        self._ck(self._L.azb_debug_cascade_spills(self._h, C.byref(n)))
         return int(n.value)
 
     def device_bytes(self) -> int:

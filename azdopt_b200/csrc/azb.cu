@@ -25,7 +25,6 @@
 #include "azb_tree.cuh"
 #include "azb_train.cuh"
 #include "azb_async.cuh"
-#include "azb_pipe.cuh"
 
 #include <dlfcn.h>
 
@@ -67,9 +66,7 @@ struct azb_handle {
     AzbAsyncMaps asM;
     int async_grid;
     size_t async_smem;
-    // weight-stationary model pipeline beside the tree kernel (azb_pipe.cuh)
-    bool pipe, split;
-    size_t worker_smem;
+    unsigned long long async_timeout_base_ns;
     // azb_step_poll: per-step results of enqueued steps while they still run (copies on their own stream)
     cudaStream_t poll_stream;
     uint2 *poll_pin;          // pinned: one candidate row [B]
@@ -77,9 +74,6 @@ struct azb_handle {
     uint32_t poll_next;       // next candidate slot to report (slot s = step s - 1)
     uint32_t poll_best;       // running best, order-preserving bits
     bool poll_best_valid;
-    AzbPipeParams piQ;
-    AzbPipeMaps piM;
-    size_t pipe_smem;
     void *async_bufs[16];
     // epoch-boundary collectives (NCCL, loaded on demand)
     void *nccl_lib, *nccl_comm;
@@ -205,7 +199,7 @@ int azb_destroy(azb_handle *h) {
     for (void *p : h->async_bufs)
         if (p) cudaFree(p);
     void *ptrs[] = {h->grad, h->adam_m, h->adam_v, h->tr_p, h->tr_dz[0], h->tr_dz[1], h->tr_x, h->tr_scal, h->tr_part, h->comm_buf,
-                    h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
+                    h->L.walker, h->L.node, h->L.blk, h->L.inl, h->L.key, h->L.hash, h->L.casc, h->L.cand, h->L.stepmin, (void *)h->L.lut, h->L.sv,
                     h->L.h, h->L.g, h->L.log, h->params, h->act[0], h->act[1], h->act[2], h->mlp_x, h->mlp_y,
                     h->cost_par, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err, h->obs, h->obs_w, h->flush_buf, h->graph_buf};
     for (void *p : ptrs)
@@ -339,6 +333,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     CK(dmalloc(h, &L.inl, (size_t)B * L.cap_in));
     CK(dmalloc(h, &L.key, (size_t)B * L.cap_nodes * W));
     CK(dmalloc(h, &L.hash, (size_t)B * L.cap_hash));
+    CK(dmalloc(h, &L.casc, (size_t)B * 2 * L.cap_nodes));
     CK(dmalloc(h, &L.cand, (size_t)(L.cap_steps + 1) * B));
     CK(dmalloc(h, &L.stepmin, (size_t)L.cap_steps + 1));
     {
@@ -743,52 +738,6 @@ static int async_create(azb_handle *h) {
     if (!coop) return fail(h, AZB_ERR_CUDA, "cooperative launch not supported");
     uint32_t W = h->cfg.async_workers;
     const uint32_t B = h->L.B;
-    // The model as a weight-stationary pipeline of SMs (azb_pipe.cuh) when every layer's weights fit in the shared
-    // memory of a few SMs: members per stage from the largest column block whose weights stay <= 160 KB.
-    AzbPipeParams &Q = h->piQ;
-    memset(&Q, 0, sizeof(Q));
-    h->pipe = false;
-    {
-        // Opt-in (AZB_ASYNC_PIPE=1): bit-identical results, a tile's latency falls to ~25 us, but every tile passes through
-        // every stage and the K = 1024 stage needs ~6 us per tile (16 k-blocks of barrier round trips per member), which
-        // caps the pipeline at ~20 M rows/s — below the in-kernel workers' 45 M (profiles/README.md, round 1 session 4)
-        bool want = false;
-        if (const char *e = getenv("AZB_ASYNC_PIPE")) want = atoi(e) != 0;
-        const size_t budget = (size_t)prop.sharedMemPerBlockOptin - 4096;  // static barriers / row owners + alignment
-        uint32_t total = 0;
-        size_t need = 0;
-        for (int l = 0; l < 4 && want; ++l) {
-            const uint32_t kpad = h->tc.kpad[l], npad = h->tc.npad[l];
-            uint32_t bn = 256;
-            while (bn >= 32 && (size_t)bn * kpad * 2 > 160 * 1024) bn >>= 1;
-            if (bn < 32) { want = false; break; }
-            uint32_t members = (npad + bn - 1) / bn;
-            if (l == 3) {  // the head: at least two members (latency), columns split evenly in multiples of 16
-                members = std::max(members, 2u);
-                bn = ((npad + members - 1) / members + 15) / 16 * 16;
-            } else if (npad % bn) {  // hidden layers: the blocks must tile the next layer's K exactly
-                want = false;
-                break;
-            }
-            if (bn % 16 || bn > 256 || bn < 16) { want = false; break; }
-            Q.BN[l] = bn;
-            Q.S[l] = members;
-            Q.first_cta[l] = total;
-            total += Q.S[l];
-            const size_t wbytes = (size_t)bn * kpad * 2, bias = (size_t)((bn + 31) & ~31u) * 4;
-            size_t ns = (budget - wbytes - bias) / (AS_TILE * TC_BK * 2);
-            ns = std::min<size_t>(ns, PIPE_MAX_STAGES);
-            if (ns < 2) { want = false; break; }
-            Q.stages[l] = (uint32_t)ns;
-            need = std::max(need, wbytes + bias + ns * AS_TILE * TC_BK * 2 + 1024);
-        }
-        if (want && total >= 4 && total <= 40 && (int)total < prop.multiProcessorCount / 2) {
-            Q.n_ctas = total;
-            h->pipe = true;
-            h->pipe_smem = need;
-            W = total;  // SMs the model takes
-        }
-    }
     // tree warps per CTA: 32, fewer when a large N needs more shared memory per warp (at most ~160 KB per SM, the rest is L1)
     const size_t lut_bytes = (h->A + 15) & ~15u, per_warp = (size_t)h->smem_words_per_warp * 4;
     uint32_t tree_warps = (uint32_t)std::max<size_t>(4, std::min<size_t>(AS_WARPS, (160 * 1024 - lut_bytes) / per_warp));
@@ -797,12 +746,8 @@ static int async_create(azb_handle *h) {
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
     const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + 1024 + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
-    // the model (workers or pipeline) is its own kernel beside the tree kernel; AZB_ASYNC_SPLIT=0 folds the workers into
-    // the tree kernel (one launch: what ncu can capture, since it serialises kernels)
-    h->split = !h->pipe;
-    if (const char *e = getenv("AZB_ASYNC_SPLIT")) h->split = !h->pipe && atoi(e) != 0;
-    h->worker_smem = mlp_smem;
-    h->async_smem = (h->pipe || h->split) ? tree_smem : std::max(tree_smem, mlp_smem);
+    // every CTA of the one cooperative launch asks for the larger of the two roles' shared memory
+    h->async_smem = std::max(tree_smem, mlp_smem);
     int nb = 0, nb2 = 0, rc;
     switch (azb_stack_depth(h->N)) {
         case 3: rc = async_prepare_kernel<3, false>(h, &nb); if (!rc) rc = async_prepare_kernel<3, true>(h, &nb2); break;
@@ -819,17 +764,17 @@ static int async_create(azb_handle *h) {
     AzbAsyncParams &P = h->asP;
     memset(&P, 0, sizeof(P));
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
-    P.n_workers = h->pipe ? 0u : W;  // worker SMs; the pipeline is its own kernel
-    P.split = (h->pipe || h->split) ? 1u : 0u;
+    P.n_workers = W;  // model CTAs (whole SMs)
     P.tree_warps = tree_warps;
     // worker SMs per tile: one when few SMs serve the model (every tree keeps its own warp at 4096 roots), pairs otherwise
     P.group = W < 40 ? 1 : 2;
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
-    if (h->pipe) P.group = 1;
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
     P.smem_words_per_warp = h->smem_words_per_warp;
     P.ring_ld = h->tc.kpad[0];
-    P.timeout_ns = 30ull * 1000000000ull;
+    h->async_timeout_base_ns = 2ull * 1000000000ull;
+    if (const char *e = getenv("AZB_ASYNC_TIMEOUT_MS")) h->async_timeout_base_ns = strtoull(e, nullptr, 10) * 1000000ull;
+    P.timeout_ns = h->async_timeout_base_ns;
     P.flush_ns = 4000ull;
     if (const char *e = getenv("AZB_ASYNC_FLUSH_NS")) P.flush_ns = strtoull(e, nullptr, 10);
     if (const char *e = getenv("AZB_ASYNC_DBG")) P.dbg_flags = (uint32_t)strtoul(e, nullptr, 10);
@@ -855,8 +800,7 @@ static int async_create(azb_handle *h) {
     CK(alloc((void **)&P.h_flag, (size_t)B * 4));
     CK(alloc((void **)&P.dbg, 64 * 8));
     CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
-    const uint32_t act_tiles = h->pipe ? PIPE_D : W;
-    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)act_tiles * AS_TILE * h->tc.kpad[l + 1] * 2));
+    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * h->tc.kpad[l + 1] * 2));
     azb_encode_fn enc = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres) != cudaSuccess || !enc)
@@ -864,23 +808,8 @@ static int async_create(azb_handle *h) {
     const char *why = azb_tc_make_map(enc, &h->asM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
     for (int l = 0; l < 3 && !why; ++l)
         why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
-    for (int l = 0; l < 3 && !why; ++l)
-        why = azb_tc_make_map(enc, &h->asM.act_st[l], P.act[l], (uint64_t)act_tiles * AS_TILE, h->tc.kpad[l + 1], 32);
     for (int l = 0; l < 4 && !why; ++l)
         why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], 128);
-    if (h->pipe) {
-        why = why ? why : azb_tc_make_map(enc, &h->piM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
-        for (int l = 0; l < 3 && !why; ++l)
-            why = azb_tc_make_map(enc, &h->piM.act[l], P.act[l], (uint64_t)PIPE_D * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
-        for (int l = 0; l < 4 && !why; ++l)
-            why = azb_tc_make_map(enc, &h->piM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], Q.BN[l]);
-        CK(cudaFuncSetAttribute(azb_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
-    }
-    if (h->split) CK(cudaFuncSetAttribute(azb_worker_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->worker_smem));
-    if (h->pipe || h->split) {
-        if (!h->gstream[0]) CK(cudaStreamCreateWithFlags(&h->gstream[0], cudaStreamNonBlocking));
-        if (!h->gevent[0]) CK(cudaEventCreateWithFlags(&h->gevent[0], cudaEventDisableTiming));
-    }
     if (why) return fail(h, AZB_ERR_CUDA, "async tensor maps: %s", why);
     CK(cudaStreamSynchronize(h->stream));
     h->async_ready = true;
@@ -890,13 +819,12 @@ static int async_create(azb_handle *h) {
 template <int D, bool C>
 static cudaError_t async_launch(azb_handle *h) {
     void *args[] = {(void *)&h->L, (void *)&h->asP, (void *)&h->asM};
-    const int grid = h->pipe ? h->async_grid - (int)h->piQ.n_ctas : h->split ? h->async_grid - (int)h->asP.n_workers : h->async_grid;
-    return cudaLaunchCooperativeKernel((const void *)azb_async_kernel<D, C>, dim3(grid), dim3(AS_THREADS), args,
+    return cudaLaunchCooperativeKernel((const void *)azb_async_kernel<D, C>, dim3(h->async_grid), dim3(AS_THREADS), args,
                                        h->async_smem, h->stream);
 }
 
-// n_steps of every tree in one persistent kernel, then one batched forward over the rows of the last step (whose
-// add_actions is fused into the next launch, like the lock step's)
+// n_steps of every tree in ONE persistent cooperative kernel (tree CTAs + model CTAs), then one batched forward over
+// the rows of the last step (whose add_actions is fused into the next launch, like the lock step's)
 static int run_async(azb_handle *h, uint32_t n_steps) {
     int rc = async_create(h);
     if (rc) return rc;
@@ -907,25 +835,10 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
     CK(cudaMemsetAsync(P.dbg, 0, 64 * 8, h->stream));
     P.target_step = h->steps_done + n_steps;
-    // watchdog: measured from the start of the launch, so it grows with the work (a step takes ~0.1-1 ms at the supported
-    // sizes; 5 ms per step on top of 30 s never fires on a healthy run of any length)
-    P.timeout_ns = 30ull * 1000000000ull + (unsigned long long)n_steps * 5000000ull;
+    // watchdog, measured from the start of the launch: a step takes 0.1-1.2 ms at the supported sizes, so 2 s plus
+    // 20 ms per step never fires on a healthy run, profiler replays included, and a stuck launch ends within seconds
+    P.timeout_ns = h->async_timeout_base_ns + (unsigned long long)n_steps * 20000000ull;
     cudaError_t ce;
-    if (h->pipe || h->split) {
-        // the model runs beside the tree kernel on its own stream: its CTAs take whole SMs (their shared memory excludes
-        // a tree CTA), the tree kernel the rest; both end when every tree has reached the target step
-        CK(cudaEventRecord(h->fork_event, h->stream));
-        CK(cudaStreamWaitEvent(h->gstream[0], h->fork_event, 0));
-        if (h->pipe)
-            azb_pipe_kernel<<<h->piQ.n_ctas, PIPE_THREADS, h->pipe_smem, h->gstream[0]>>>(h->L, P, h->piQ, h->piM);
-        else
-            azb_worker_kernel<<<P.n_workers, AS_MLP_THREADS, h->worker_smem, h->gstream[0]>>>(h->L, P, h->asM);
-        ce = cudaGetLastError();
-        if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "model pipeline launch: %s", cudaGetErrorString(ce));
-        CK(cudaEventRecord(h->gevent[0], h->gstream[0]));
-        h->launches += 1;
-    }
-    const bool two = h->pipe || h->split;
     switch (azb_stack_depth(h->N) * 2 + (h->count_full ? 1 : 0)) {
         case 6: ce = async_launch<3, false>(h); break;
         case 7: ce = async_launch<3, true>(h); break;
@@ -934,15 +847,7 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
         case 10: ce = async_launch<5, false>(h); break;
         default: ce = async_launch<5, true>(h); break;
     }
-    if (ce != cudaSuccess) {
-        if (two) {  // the model kernel is already waiting for tiles: tell it to drain
-            const uint32_t one = 1;
-            cudaMemcpy(&P.st->abort, &one, 4, cudaMemcpyHostToDevice);
-            cudaStreamSynchronize(h->gstream[0]);
-        }
-        return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
-    }
-    if (two) CK(cudaStreamWaitEvent(h->stream, h->gevent[0], 0));
+    if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
     h->launches += 1;
     h->async_ran = true;
     rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
@@ -1069,19 +974,29 @@ static int step_once_graph(azb_handle *h, azb_improvement *improvements, uint32_
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         int rc = launch_tree(h, flags, 0xffffffffu);
         if (rc == AZB_OK && mlp) rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
+        cudaError_t cc = cudaSuccess;  // first failure inside the capture region
         if (rc == AZB_OK) {
             azb_argmin1_kernel<<<1, 256, 0, h->stream>>>(h->L);
-            cudaMemcpyAsync(h->pin_g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream);
-            cudaMemcpyAsync(h->pin_log, h->L.log, sizeof(azb_improvement), cudaMemcpyDeviceToHost, h->stream);
+            cc = cudaGetLastError();
+            if (cc == cudaSuccess)
+                cc = cudaMemcpyAsync(h->pin_g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream);
+            if (cc == cudaSuccess)
+                cc = cudaMemcpyAsync(h->pin_log, h->L.log, sizeof(azb_improvement), cudaMemcpyDeviceToHost, h->stream);
         }
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
         h->launches = launches_before;
-        if (rc) return rc;
-        if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "stream capture: %s", cudaGetErrorString(ce));
+        if (rc || cc != cudaSuccess || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc) return rc;
+            return fail(h, AZB_ERR_CUDA, "stream capture of the single-step graph: %s", cudaGetErrorString(cc != cudaSuccess ? cc : ce));
+        }
         CK(cudaGraphInstantiate(&h->step_graph, graph, 0));
         cudaGraphDestroy(graph);
         h->step_graph_key = key;
     }
+    // stale pinned data must not read as a result: the graph's last node rewrites both words, or the check below fires
+    h->pin_g->err = 0xffffffffu;
+    h->pin_g->next_slot = 0xffffffffu;
     CK(cudaGraphLaunch(h->step_graph, h->stream));
     h->launches += 2 + (mlp ? 4 : 0);
     h->steps_done += 1;
@@ -1091,6 +1006,8 @@ static int step_once_graph(azb_handle *h, azb_improvement *improvements, uint32_
     h->pending_add = true;
     CK(cudaStreamSynchronize(h->stream));
     const AzbGlobals &g = *h->pin_g;
+    if (g.err == 0xffffffffu || g.next_slot != h->argmin_from)
+        return fail(h, AZB_ERR_CUDA, "the single-step graph did not deliver its result (a node of the graph failed)");
     if (g.err) return fail(h, (int)g.err, "%s (tree %u, step %u)", azb_strerror((int)g.err), g.err_tree, g.err_step);
     if (n_improved) *n_improved = g.n_improved;
     if (improvements && cap && g.n_improved) improvements[0] = *h->pin_log;
@@ -1609,14 +1526,13 @@ extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {  // o
     return AZB_OK;
 }
 
-// cycle counters of the model pipeline's stages (azb_pipe.cuh, profile flavour): out[l*8 + i], 32 entries; i = producer
-// wait-input, wait-empty, tiles (summed over members), MMA wait-acc, wait-full, epilogue wait, busy, MMA wait-first-block
-extern "C" int azb_debug_pipe(azb_handle *h, unsigned long long *out32, unsigned int *members4) {
-    if (!h || !out32 || !h->async_ready || !h->pipe) return AZB_ERR_INVALID;
+// cascade waves that outgrew the shared-memory work list and continued in global scratch since azb_create (diagnostic;
+// tests use it to prove that a dense transposition DAG really exercised that path)
+extern "C" int azb_debug_cascade_spills(azb_handle *h, uint32_t *out) {
+    if (!h || !out) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out32, h->asP.dbg + 24, 40 * 8, cudaMemcpyDeviceToHost));
-    if (members4) for (int l = 0; l < 4; ++l) members4[l] = h->piQ.S[l];
+    CK(cudaMemcpy(out, &h->L.g->casc_spills, 4, cudaMemcpyDeviceToHost));
     return AZB_OK;
 }
 
@@ -1755,6 +1671,17 @@ static int train_backward(azb_handle *h, const float *x, uint32_t ldx, const flo
     h->launches += 2;
     rc = comm_allreduce(h, h->tr_scal, 1, AZB_NCCL_FLOAT64);
     if (rc) return rc;
+    {
+        // The loss divides every weight by this sum (dfdx.rs:106-110).  With no observation at all (no root child is
+        // exhausted or has n_t >= n_obs_tol: short epochs) it is 0/0: the reference's step would write NaN into every
+        // parameter.  Here the step is refused before anything is computed; the sum is global, so every rank of a
+        // sharded run takes the same branch.
+        double wsum = 0.0;
+        CK(cudaMemcpyAsync(&wsum, h->tr_scal, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!(wsum > 0.0) || !std::isfinite(wsum))
+            return fail(h, AZB_ERR_STATE, "no observations: the action weights sum to %g, the model is left unchanged", wsum);
+    }
     // forward, f32 (dfdx.rs:115-116)
     {
         const float *in = x;
@@ -1807,6 +1734,10 @@ static int train_backward(azb_handle *h, const float *x, uint32_t ldx, const flo
     return comm_allreduce(h, h->tr_scal + 1, 1, AZB_NCCL_FLOAT64);
 }
 
+// reads the (global) loss and applies the Adam step, unless the loss is not finite: a NaN gradient would destroy the
+// parameters and both moment buffers for good (and, sharded, on every rank), so the step is refused and reported
+static int train_finish(azb_handle *h, float *loss);
+
 static int train_adam(azb_handle *h) {
     h->adam_t += 1;
     AzbAdam cfg = h->adam;
@@ -1829,6 +1760,19 @@ static int train_read_loss(azb_handle *h, float *loss) {
     CK(cudaStreamSynchronize(h->stream));
     if (loss) *loss = (float)l;
     return AZB_OK;
+}
+
+static int train_finish(azb_handle *h, float *loss) {
+    float l = 0.f;
+    int rc = train_read_loss(h, &l);
+    if (rc) return rc;
+    if (loss) *loss = l;
+    if (!std::isfinite(l)) {
+        CK(cudaMemsetAsync(h->grad, 0, h->n_params * 4, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return fail(h, AZB_ERR_NAN, "the loss is not finite (%g): Adam step refused, the model is left unchanged", (double)l);
+    }
+    return train_adam(h);
 }
 
 int azb_adam_config(azb_handle *h, float lr, float beta1, float beta2, float eps, float l2) {
@@ -1869,9 +1813,7 @@ int azb_model_update(azb_handle *h, const float *states, const float *observatio
     if (rc) return rc;
     rc = train_backward(h, h->tr_x, h->S, h->obs, h->obs_w, rows);
     if (rc) return rc;
-    rc = train_adam(h);
-    if (rc) return rc;
-    return train_read_loss(h, loss);
+    return train_finish(h, loss);
 }
 
 int azb_update_model(azb_handle *h, uint32_t n_obs_tol, float *loss) {
@@ -1888,9 +1830,7 @@ int azb_update_model(azb_handle *h, uint32_t n_obs_tol, float *loss) {
     CK(cudaGetLastError());
     rc = train_backward(h, h->L.sv, h->L.sv_ld, h->obs, h->obs_w, h->L.B);
     if (rc) return rc;
-    rc = train_adam(h);
-    if (rc) return rc;
-    rc = train_read_loss(h, loss);
+    rc = train_finish(h, loss);
     if (rc) return rc;
     return check_device_error(h);
 }

@@ -5,20 +5,30 @@
 // a barrier: every tree walks until it has one new node, then ONE model call answers all of them.  Trees are
 // independent (each rayon task touches only its own row, :159-189), so the barrier is an artefact of batching the
 // model call, and it costs the GPU dearly: a launch lasts as long as its slowest tree (7-12 episodes) while the
-// average tree needs 1.9 (profiles/README.md).  Here
-//   * a TREE warp owns a fixed set of trees (tree = warp + k * n_warps).  It advances whichever of its trees has its
-//     priors, packs the new state vector into the next free row of a ring of 128-row tiles, and moves on; it polls a
-//     per-tree flag for the answer.  Ownership is static, so a tree's arena is only ever touched through one SM's L1
-//     (no cross-SM staleness inside the kernel); the priors, written by other SMs, are read with ld.cg.
-//   * an MLP worker CTA (a whole SM, `n_workers` of them) takes the next full tile, runs the four Linear layers
-//     on the tensor cores (TMA -> 3-stage smem ring -> tcgen05.mma, two TMEM accumulators so the epilogue of one
-//     128-column block overlaps the MMAs of the next; hidden activations round-trip through an L2-resident scratch),
-//     scatters the sigmoid rows to the owning trees' prior rows and raises their flags.  A tile that stays partial
-//     for `flush_ns` is topped up with dummy rows and run anyway (tail of the run, tiny batches).
+// average tree needs 1.9 (profiles/README.md).  Here every CTA of ONE cooperative launch (one CTA per SM, all
+// co-resident by construction, so the waits below cannot deadlock) takes one of two roles:
+//   * TREE CTA (32 warps at the kernel's 64 registers).  A warp owns a fixed set of trees (tree = warp + k * n_warps).
+//     It advances whichever of its trees has its priors, packs the new state vector into the next free row of a ring
+//     of 128-row tiles, and moves on; it polls a per-tree flag for the answer.  Ownership is static, so a tree's arena
+//     is only ever touched through one SM's L1; the priors, written by other SMs, are read with ld.cg behind one
+//     acquire load of the flag.
+//   * MODEL CTA (the first CTA to arrive on each of `n_workers` SMs).  Its eight warpgroups re-divide the CTA's
+//     registers with setmaxnreg: warpgroup 0 (TMA producer warp + tcgen05.mma issuer warp) shrinks to 56, warpgroups
+//     1-2 (eight epilogue warps) grow to 168 — four 16-column TMEM slices in flight per warp without spilling —, and
+//     warpgroups 3-7 shrink to 24 and leave.  A worker takes the next full tile and runs the four Linear layers on
+//     the tensor cores in A-stationary passes (per 64-deep k-block ONE activation tile and the weight tiles of up to
+//     four 128-column blocks feed four TMEM accumulators; adjacent blocks as one N = 256 MMA), hidden activations
+//     round-trip through an L2-resident scratch, the Sigmoid head scatters f32 rows to the owning trees' prior rows
+//     and the last writer raises their flags.  A tile that stays partial for `flush_ns` is topped up with dummy rows
+//     and run anyway (tail of the run, tiny batches).
 // Results are identical to the lock-step path: a tree's walk depends only on its own priors, and a row's forward
 // pass does not depend on which tile it rides in (same K order per dot product).  Per-tree step clocks and the
 // cand[step][tree] table make the argmin pass indifferent to the interleaving.
 // Every spin loop has a watchdog on %globaltimer; on expiry the kernel sets `abort` and drains.
+//
+// Round 1 also had a two-kernel form (tree kernel + model kernel on two streams, spinning on each other) and a
+// weight-stationary model pipeline kernel.  Both are gone: separately launched kernels that wait for each other are
+// not guaranteed to run at the same time (B200_PROFILING.md), and they hung under anything that serialises kernels.
 #pragma once
 #include "azb_mlp_tc.cuh"
 #include "azb_tree.cuh"
@@ -26,20 +36,25 @@
 #define AS_THREADS 1024
 #define AS_WARPS 32
 #define AS_EPI_WARPS 8   // two per TMEM lane quadrant, each taking AS_EPI_COLS columns of a 128-column block
+#define AS_EPI_WARP0 4   // first epilogue warp: warpgroups 1 and 2 of a model CTA
 #define AS_EPI_COLS (128 / (AS_EPI_WARPS / 4))      // 64
 #define AS_EPI_SLICES (AS_EPI_COLS / 16)            // 16-column TMEM slices per warp and block
 #define AS_EPI_CHUNKS (AS_EPI_COLS / 8)             // 16-byte chunks per staged row
 #define AS_EPI_STG_BYTES (32 * AS_EPI_COLS * 2)     // staging tile per warp: [32 rows x AS_EPI_COLS bf16]
-// The staged tile is exactly a SWIZZLE_128B box, so one TMA store could replace the row-piece stores.  Measured: slower
-// (epilogue 15.8 -> 21.0 us per tile, 32.7 -> 31.3 M simulations/s): with ONE staging tile per warp every block waits
-// for the previous store to have read it (wait_group.read) behind a proxy fence, and there is no shared memory left for
-// a second tile (160 KB operand ring + 32 KB staging + biases).  Kept switchable.
-#define AS_EPI_TMA_STORE 0
-#define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)
+#define AS_MLP_THREADS ((2 + AS_EPI_WARPS) * 32)    // threads that meet at the model CTA's named barrier 1
+// register budgets of a model CTA's warpgroups (setmaxnreg; 128 x (56 + 2 x 168 + 5 x 24) = 65 536 = 1024 x 64)
+#define AS_REGS_FRONT 56
+#define AS_REGS_EPI 168
+#define AS_REGS_IDLE 24
 #define AS_STAGES 2
 #define AS_ACC 4          // 128-column blocks per pass: one A k-block is reused by up to four TMEM accumulators
 #define AS_TILE 128
 #define AS_NONE 0xffffffffu
+// one acquire load of a flag after the relaxed polls have seen it (PTX memory model: what the flag guards is read or
+// overwritten afterwards).  It costs one L1 invalidation (CCTL.IVALL) per tree-step; -DAS_ACQUIRE=0 measures without.
+#ifndef AS_ACQUIRE
+#define AS_ACQUIRE 1
+#endif
 // cycle counters of the workers (tools/async_probe.py): only in the -DAZB_PROFILE flavour
 #ifdef AZB_PROFILE
 #define AS_CLK() clock64()
@@ -61,16 +76,11 @@ struct AzbAsyncState {  // device memory, zeroed before every launch
     uint32_t rows_real, rows_dummy;
     // worker groups (AS_MAX_GROUPS): the leader's tile mailbox and the group's monotonic barriers
     uint32_t grp_seq[64], grp_tile[64], grp_done[64], grp_layer[64 * 4];
-    // weight-stationary pipeline (azb_pipe.cuh): first tile that will not be processed + 1 (0 = not known yet), and
-    // per stage and activation slot the number of members that have stored their columns (monotonic over generations)
-    uint32_t final_q1;
-    uint32_t pipe_done[4 * 8];
 };
 
 struct AzbAsyncMaps {
     CUtensorMap ring;    // layer-0 input: [NT*128 rows][kpad0] bf16
     CUtensorMap act[3];  // hidden activations of the workers: [n_workers*128 rows][kpad[l+1]]
-    CUtensorMap act_st[3];  // the same buffers with a 64 x 32 box: an epilogue warp's staged rows leave as one TMA store
     CUtensorMap w[4];    // weights [rows padded to 128][kpad[l]], box 64 x 128
 };
 
@@ -85,7 +95,6 @@ struct AzbAsyncParams {
     const float *bias[4];
     uint32_t kpad[4], npad[4];
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
-    uint32_t split;          // 1: the model is its own kernel (azb_worker_kernel / azb_pipe_kernel) beside the tree kernel
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
     unsigned long long timeout_ns, flush_ns;
     uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
@@ -99,12 +108,16 @@ __device__ __forceinline__ unsigned long long as_now() {
 }
 // Polls use ld.volatile (served by L2, where the atomics land), never ld.acquire.gpu: an acquire load comes with
 // CCTL.IVALL — it invalidates the SM's whole L1 — and a waiting warp polls every microsecond beside 31 warps whose
-// walks live on L1 hits (ncu: 160 M CCTL per 100 steps; phase cycles of the walkers 1.6-2x the lock step's).  What a
-// poll guards is read afterwards through L2 anyway (ld.cg prior rows, TMA operand tiles, __ldcg slot owners) and was
-// published behind a __threadfence, so observing the flag in L2 is enough.
+// walks live on L1 hits (ncu: 160 M CCTL per 100 steps; phase cycles of the walkers 1.6-2x the lock step's).  Once a
+// poll has seen its value, ONE as_ld_acquire of the same word orders what follows (AS_ACQUIRE).
 __device__ __forceinline__ uint32_t as_ld_volatile(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t as_ld_acquire(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void as_mbar_arrive(uint64_t *bar) {
@@ -173,66 +186,56 @@ __device__ __forceinline__ void as_sts128(uint32_t saddr, uint32_t a, uint32_t b
 __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// MLP worker: warps 0 (TMA producer), 1 (MMA issuer, TMEM owner), 2-9 (epilogue); the CTA's other warps have left.
-__device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
-                                 const uint32_t worker, uint8_t *smem) {
-    __shared__ __align__(8) uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full, acc_empty, layer_bar;
-    __shared__ uint32_t tmem_slot, s_tile, s_epi_count;
-    __shared__ uint32_t s_rowtree[AS_TILE];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t MLP_THREADS = AS_MLP_THREADS;
+// Model CTA.  Roles: warp 0 TMA producer and tile taker, warp 1 MMA issuer and TMEM owner (warpgroup 0, 56 registers),
+// warps 4-11 epilogue (warpgroups 1-2, 168 registers).  Each role is its own function with its own copy of the loop
+// over tiles, so that no code is shared between register budgets; they meet at named barrier 1 (AS_MLP_THREADS).
+struct AsWorkerShared {
+    uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full, acc_empty, layer_bar;
+    uint32_t tmem_slot, tile, epi_last;
+    uint32_t bias_off[4];  // first entry of layer l's biases in the shared-memory copy
+    uint32_t rowtree[AS_TILE];
+};
+
+// A GROUP of G worker SMs answers one tile together: member m computes the 128-column blocks nt = m, m + G, ... of
+// every layer (a 1/G share of the weights streams through each SM's shared memory, which is what bounds a 128-row
+// tile), the hidden activations meet in the group's L2-resident scratch, and the members synchronise at the three
+// layer boundaries through monotonic counters in global memory.  The leader (m = 0) takes the tile.
+struct AsWorkerId {
+    uint32_t G, grp, mem;
+};
+__device__ __forceinline__ uint32_t as_blocks_of_member(uint32_t npad, const AsWorkerId &id) {
+    const uint32_t n_tiles = (npad + 127u) / 128u;
+    return n_tiles > id.mem ? (n_tiles - id.mem + id.G - 1u) / id.G : 0u;
+}
+#define AS_TILE_BYTES (AS_TILE * TC_BK * 2u)              // one 128 x 64 bf16 operand tile, 16 KB
+#define AS_STAGE_BYTES ((1u + AS_ACC) * AS_TILE_BYTES)    // [A | B0 | B1 | B2 | B3]
+
+// ---- warp 0: takes tiles for the group, feeds the operand ring by TMA
+__device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M, const AsWorkerId id,
+                                      uint8_t *smem, AsWorkerShared &S) {
+    const uint32_t lane = threadIdx.x & 31;
     AzbAsyncState *st = P.st;
-    if (warp == 0 && lane == 0) {
+    if (lane == 0) {
         for (int s = 0; s < AS_STAGES; ++s) {
-            tc_mbar_init(&full_bar[s], 1);
-            tc_mbar_init(&empty_bar[s], 1);
+            tc_mbar_init(&S.full_bar[s], 1);
+            tc_mbar_init(&S.empty_bar[s], 1);
         }
-        tc_mbar_init(&acc_full, 1);
-        tc_mbar_init(&acc_empty, AS_EPI_WARPS);
-        tc_mbar_init(&layer_bar, 1);
+        tc_mbar_init(&S.acc_full, 1);
+        tc_mbar_init(&S.acc_empty, AS_EPI_WARPS);
+        tc_mbar_init(&S.layer_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
         for (int l = 0; l < 4; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w[l]) : "memory");
         for (int l = 0; l < 3; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.act[l]) : "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // all biases into shared memory (behind the operand ring): the epilogue's only global traffic is its output
-    float *s_bias = reinterpret_cast<float *>(smem + (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2);
-    uint32_t bias_off[4];
-    {
-        uint32_t o = 0;
-        for (int l = 0; l < 4; ++l) {
-            bias_off[l] = o;
-            for (uint32_t i = threadIdx.x; i < P.npad[l]; i += MLP_THREADS) s_bias[o + i] = P.bias[l][i];
-            o += (P.npad[l] + 31u) & ~31u;
-        }
-    }
-    // per epilogue warp a staging tile behind the biases (coalesced activation stores)
-    uint8_t *stg = reinterpret_cast<uint8_t *>(s_bias + bias_off[3] + ((P.npad[3] + 31u) & ~31u));
-    stg = (uint8_t *)(((uintptr_t)stg + 1023) & ~(uintptr_t)1023) + (warp >= 2 ? warp - 2u : 0u) * AS_EPI_STG_BYTES;  // swizzle atoms: 1 KB
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    as_named_bar(1, MLP_THREADS);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_slot;
-    const uint32_t tile_bytes = AS_TILE * TC_BK * 2u;             // one 128 x 64 bf16 operand tile, 16 KB
-    const uint32_t stage_bytes = (1u + AS_ACC) * tile_bytes;      // [A | B0 | B1 | B2 | B3]
+    __syncwarp();
+    as_named_bar(1, AS_MLP_THREADS);
     const unsigned long long t_start = as_now();
-    uint32_t kbc = 0, ntc = 0;  // ring stage / pass counters (each role keeps its own copy in step)
+    const uint32_t G = id.G, grp = id.grp, mem = id.mem;
+    uint32_t kbc = 0, seq = 0, lbc = 0;  // ring stage counter, tiles taken, layer boundaries passed (G == 1: phase of layer_bar)
     long long d_acq = 0, d_w0 = 0, d_w1 = 0, d_busy = 0, d_tiles = 0;  // debug cycle counters (P.dbg)
-
-    // A GROUP of G worker SMs answers one tile together: member m computes the 128-column blocks nt = m, m + G, ...
-    // of every layer (a quarter of the weights streams through each SM's shared memory, which is what bounds a
-    // 128-row tile), the hidden activations meet in the group's L2-resident scratch, and the members synchronise at
-    // the three layer boundaries through monotonic counters in global memory.  The leader (m = 0) takes the tile.
-    const uint32_t G = P.group, grp = worker / G, mem = worker % G;
-    uint32_t seq = 0;  // tiles this group has taken
-    uint32_t lbc = 0;  // layer boundaries passed (G == 1: phase of layer_bar)
     for (;;) {
-        if (warp == 0 && lane == 0) {
+        if (lane == 0) {
             const long long tq0 = AS_CLK();
             uint32_t q;
             if (mem == 0) {
@@ -271,6 +274,9 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                         break;
                     }
                 }
+#if AS_ACQUIRE
+                if (q != AS_NONE) (void)as_ld_acquire(cnt_p);  // the tile's rows and owners are read after this
+#endif
                 st->grp_tile[grp] = q;
                 __threadfence();
                 atomicAdd(&st->grp_seq[grp], 1u);
@@ -279,117 +285,135 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                     if ((spins & 4095u) == 4095u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
                     if (as_ld_volatile(&st->abort)) break;
                 }
+#if AS_ACQUIRE
+                (void)as_ld_acquire(&st->grp_seq[grp]);
+#endif
                 q = as_ld_volatile(&st->abort) ? AS_NONE : as_ld_volatile(&st->grp_tile[grp]);
             }
-            s_tile = q;
+            S.tile = q;
             d_acq += AS_CLK() - tq0;
         }
-        as_named_bar(1, MLP_THREADS);
-        const uint32_t q = s_tile;
+        __syncwarp();
+        as_named_bar(1, AS_MLP_THREADS);
+        const uint32_t q = S.tile;
         if (q == AS_NONE) break;
         const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
         const uint32_t arrive_target = G * (seq + 1u);  // value of the group's counters once every member has arrived
-        if (AS_DBG(16u)) {  // timing experiment: answer the tile at once with whatever the prior rows hold
-            if (warp >= 2) {
-                const uint32_t et = threadIdx.x - 64u;
-                if (mem == 0 && et < AS_TILE) {
-                    const uint32_t t = __ldcg(P.slot_tree + ring_row0 + et);
-                    if (t != AS_NONE) atomicAdd(P.h_flag + t, 1u);
-                }
-                if (threadIdx.x == 64u) {
-                    if (mem == 0) atomicAdd(P.tile_retired + (q % P.NT), 1u);
-                    atomicAdd(&st->grp_done[grp], 1u);
-                }
-            }
-            seq += 1u;
-            as_named_bar(1, MLP_THREADS);
-            continue;
-        }
-
-        if (warp == 0) {
-            // ===== TMA producer =====
-            if (tc_elect_one()) {
-                const long long tt0 = AS_CLK();
-                d_tiles += 1;
-                const uint64_t w_policy = as_policy_evict_last();
-                as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
-                for (uint32_t l = 0; l < 4; ++l) {
-                    const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
-                    // this member's blocks nt = mem, mem + G, ... in passes of up to AS_ACC: per k-block ONE A tile and the
-                    // pass's B tiles, so a tile's activations are read once per pass instead of once per block
-                    const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
-                    uint32_t pre = 0;  // k-blocks of the first pass whose weight tiles were requested ahead of the layer barrier
-                    if (l > 0) {  // this layer's input is the previous layer's output, written by all members
-                        // the weights do not depend on it: while the epilogue warps still drain the previous layer, the
-                        // ring's stages are free, so the first stages' B tiles go out now and only their A tiles wait
-                        const uint32_t np0 = min((uint32_t)AS_ACC, mine);
-                        if (!AS_DBG(4u))
-                            for (; np0 && pre < min((uint32_t)AS_STAGES, k_blocks); ++pre) {
-                                const uint32_t kc = kbc + pre, s = kc % AS_STAGES, ph = (kc / AS_STAGES) & 1u;
-                                as_mbar_spin(&empty_bar[s], ph ^ 1u);
-                                uint8_t *a_dst = smem + (size_t)s * stage_bytes;
-                                tc_mbar_expect_tx(&full_bar[s], (1u + np0) * tile_bytes);
-                                for (uint32_t j = 0; j < np0; ++j)
-                                    as_tma_load_2d_hint(a_dst + (1u + j) * tile_bytes, &M.w[l], &full_bar[s], (int)(pre * TC_BK),
-                                                        (int)((mem + j * G) * 128u), w_policy);
-                            }
-                        const long long tw = AS_CLK();
-                        if (G == 1u) {  // a single worker: the layer boundary is a shared-memory barrier, not an L2 round trip
-                            as_mbar_spin(&layer_bar, lbc & 1u);
-                            ++lbc;
-                        } else {
-                            while (as_ld_volatile(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
-                        }
-                        d_w1 += AS_CLK() - tw;
-                        as_fence_proxy_async();
-                    }
-                    const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
-                    const int arow = (int)(l == 0 ? ring_row0 : grp * AS_TILE);
-                    for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC) {
-                        const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
-                        for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
-                            const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
-                            uint8_t *a_dst = smem + (size_t)s * stage_bytes;
-                            if (p0 == 0u && kb < pre) {  // stage claimed and its B tiles requested above: only the A tile is left
-                                tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
-                                continue;
-                            }
-                            const long long tw = AS_CLK();
-                            as_mbar_spin(&empty_bar[s], ph ^ 1u);
-                            d_w0 += AS_CLK() - tw;
-                            if (AS_DBG(4u)) {  // timing experiment: no loads, the MMAs run on stale operands
-                                as_mbar_arrive(&full_bar[s]);
-                                continue;
-                            }
-                            tc_mbar_expect_tx(&full_bar[s], (1u + np) * tile_bytes);
-                            tc_tma_load_2d(a_dst, ma, &full_bar[s], (int)(kb * TC_BK), arow);
-                            for (uint32_t j = 0; j < np; ++j)
-                                as_tma_load_2d_hint(a_dst + (1u + j) * tile_bytes, &M.w[l], &full_bar[s], (int)(kb * TC_BK),
-                                                    (int)((mem + (p0 + j) * G) * 128u), w_policy);
-                        }
-                    }
-                }
-                d_busy += AS_CLK() - tt0;
-            }
-        } else if (warp == 1) {
-            // ===== MMA issuer =====
+        if (!AS_DBG(16u) && tc_elect_one()) {
+            const long long tt0 = AS_CLK();
+            d_tiles += 1;
+            const uint64_t w_policy = as_policy_evict_last();
+            as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
             for (uint32_t l = 0; l < 4; ++l) {
-                const uint32_t n_tiles = (P.npad[l] + 127u) / 128u, k_blocks = P.kpad[l] / TC_BK;
-                const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
+                const uint32_t k_blocks = P.kpad[l] / TC_BK;
+                // this member's blocks nt = mem, mem + G, ... in passes of up to AS_ACC: per k-block ONE A tile and the
+                // pass's B tiles, so a tile's activations are read once per pass instead of once per block
+                const uint32_t mine = as_blocks_of_member(P.npad[l], id);
+                uint32_t pre = 0;  // k-blocks of the first pass whose weight tiles were requested ahead of the layer barrier
+                if (l > 0) {  // this layer's input is the previous layer's output, written by all members
+                    // the weights do not depend on it: while the epilogue warps still drain the previous layer, the
+                    // ring's stages are free, so the first stages' B tiles go out now and only their A tiles wait
+                    const uint32_t np0 = min((uint32_t)AS_ACC, mine);
+                    if (!AS_DBG(4u))
+                        for (; np0 && pre < min((uint32_t)AS_STAGES, k_blocks); ++pre) {
+                            const uint32_t kc = kbc + pre, s = kc % AS_STAGES, ph = (kc / AS_STAGES) & 1u;
+                            as_mbar_spin(&S.empty_bar[s], ph ^ 1u);
+                            uint8_t *a_dst = smem + (size_t)s * AS_STAGE_BYTES;
+                            tc_mbar_expect_tx(&S.full_bar[s], (1u + np0) * AS_TILE_BYTES);
+                            for (uint32_t j = 0; j < np0; ++j)
+                                as_tma_load_2d_hint(a_dst + (1u + j) * AS_TILE_BYTES, &M.w[l], &S.full_bar[s], (int)(pre * TC_BK),
+                                                    (int)((mem + j * G) * 128u), w_policy);
+                        }
+                    const long long tw = AS_CLK();
+                    if (G == 1u) {  // a single worker: the layer boundary is a shared-memory barrier, not an L2 round trip
+                        as_mbar_spin(&S.layer_bar, lbc & 1u);
+                        ++lbc;
+                    } else {
+                        while (as_ld_volatile(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
+#if AS_ACQUIRE
+                        (void)as_ld_acquire(&st->grp_layer[grp * 4 + l - 1]);
+#endif
+                    }
+                    d_w1 += AS_CLK() - tw;
+                    as_fence_proxy_async();
+                }
+                const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
+                const int arow = (int)(l == 0 ? ring_row0 : grp * AS_TILE);
+                for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC) {
+                    const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
+                    for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
+                        const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                        uint8_t *a_dst = smem + (size_t)s * AS_STAGE_BYTES;
+                        if (p0 == 0u && kb < pre) {  // stage claimed and its B tiles requested above: only the A tile is left
+                            tc_tma_load_2d(a_dst, ma, &S.full_bar[s], (int)(kb * TC_BK), arow);
+                            continue;
+                        }
+                        const long long tw = AS_CLK();
+                        as_mbar_spin(&S.empty_bar[s], ph ^ 1u);
+                        d_w0 += AS_CLK() - tw;
+                        if (AS_DBG(4u)) {  // timing experiment: no loads, the MMAs run on stale operands
+                            as_mbar_arrive(&S.full_bar[s]);
+                            continue;
+                        }
+                        tc_mbar_expect_tx(&S.full_bar[s], (1u + np) * AS_TILE_BYTES);
+                        tc_tma_load_2d(a_dst, ma, &S.full_bar[s], (int)(kb * TC_BK), arow);
+                        for (uint32_t j = 0; j < np; ++j)
+                            as_tma_load_2d_hint(a_dst + (1u + j) * AS_TILE_BYTES, &M.w[l], &S.full_bar[s], (int)(kb * TC_BK),
+                                                (int)((mem + (p0 + j) * G) * 128u), w_policy);
+                    }
+                }
+            }
+            d_busy += AS_CLK() - tt0;
+        }
+        __syncwarp();
+        seq += 1u;
+        as_named_bar(1, AS_MLP_THREADS);
+    }
+    if (P.dbg && lane == 0) {  // producer: acquire, wait empty, wait layer, tile busy, tiles
+        atomicAdd(P.dbg + 0, (unsigned long long)d_acq);
+        atomicAdd(P.dbg + 1, (unsigned long long)d_w0);
+        atomicAdd(P.dbg + 2, (unsigned long long)d_w1);
+        atomicAdd(P.dbg + 3, (unsigned long long)d_busy);
+        atomicAdd(P.dbg + 4, (unsigned long long)d_tiles);
+    }
+    as_named_bar(1, AS_MLP_THREADS);
+}
+
+// ---- warp 1: owns TMEM, issues tcgen05.mma
+__device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const AsWorkerId id, uint8_t *smem, AsWorkerShared &S) {
+    const uint32_t lane = threadIdx.x & 31;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&S.tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, AS_MLP_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_slot;
+    const uint32_t G = id.G, mem = id.mem;
+    uint32_t kbc = 0, ntc = 0;
+    long long d_w0 = 0, d_w1 = 0;
+    for (;;) {
+        as_named_bar(1, AS_MLP_THREADS);
+        const uint32_t q = S.tile;
+        if (q == AS_NONE) break;
+        if (!AS_DBG(16u))
+            for (uint32_t l = 0; l < 4; ++l) {
+                const uint32_t k_blocks = P.kpad[l] / TC_BK;
+                const uint32_t mine = as_blocks_of_member(P.npad[l], id);
                 for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
                     const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                     long long tw = AS_CLK();
-                    as_mbar_spin(&acc_empty, (ntc & 1u) ^ 1u);  // the epilogue has drained the previous pass
+                    as_mbar_spin(&S.acc_empty, (ntc & 1u) ^ 1u);  // the epilogue has drained the previous pass
                     d_w1 += AS_CLK() - tw;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
                         tw = AS_CLK();
-                        as_mbar_spin(&full_bar[s], ph);
+                        as_mbar_spin(&S.full_bar[s], ph);
                         d_w0 += AS_CLK() - tw;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         if (tc_elect_one()) {
-                            const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * stage_bytes);
+                            const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * AS_STAGE_BYTES);
                             if (G == 1u) {
                                 // adjacent 128-column blocks are adjacent in the stage and in TMEM: one N <= 256 MMA per
                                 // pair reads the A tile once for both (a 128x128x16 SS-MMA is shared-memory bound)
@@ -397,7 +421,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                     const uint32_t nt = p0 + j;
                                     const uint32_t bn = min(256u, P.npad[l] - nt * 128u);
                                     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
-                                    const uint32_t b_addr = a_addr + (1u + j) * tile_bytes;
+                                    const uint32_t b_addr = a_addr + (1u + j) * AS_TILE_BYTES;
 #pragma unroll
                                     for (uint32_t k = 0; k < TC_BK / 16; ++k)
                                         if (!AS_DBG(8u))
@@ -409,7 +433,7 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                     const uint32_t nt = mem + (p0 + j) * G;
                                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
                                     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
-                                    const uint32_t b_addr = a_addr + (1u + j) * tile_bytes;
+                                    const uint32_t b_addr = a_addr + (1u + j) * AS_TILE_BYTES;
 #pragma unroll
                                     for (uint32_t k = 0; k < TC_BK / 16; ++k)
                                         if (!AS_DBG(8u))  // timing experiment: loads only
@@ -417,33 +441,83 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                                         idesc, (kb | k) != 0u ? 1u : 0u);
                                 }
                             }
-                            tc_umma_commit(&empty_bar[s]);
-                            if (kb + 1 == k_blocks) tc_umma_commit(&acc_full);
+                            tc_umma_commit(&S.empty_bar[s]);
+                            if (kb + 1 == k_blocks) tc_umma_commit(&S.acc_full);
                         }
                         __syncwarp();
                     }
                 }
             }
-        } else {
-            // ===== epilogue (warps 2..9): TMEM -> registers -> bias + activation -> scratch / prior rows =====
-            // warp w reads TMEM lanes 32 (w % 4) ..; the two warps of a quadrant split each 128-column block in halves
-            const uint32_t q4 = warp & 3u, part = (warp - 2u) >> 2, col0 = part * AS_EPI_COLS, row = q4 * 32u + lane;
-            const uint32_t et = threadIdx.x - 64u;
-            if (et < AS_TILE) s_rowtree[et] = __ldcg(P.slot_tree + ring_row0 + et);
-            as_named_bar(2, AS_EPI_WARPS * 32);
-            const uint32_t my_tree = s_rowtree[row];
-            for (uint32_t l = 0; l < 4; ++l) {
-                const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
-                const float *bias = s_bias + bias_off[l];
-                const uint32_t mine = n_tiles > mem ? (n_tiles - mem + G - 1u) / G : 0u;
-                for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
-                  const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
-                  const long long tw = AS_CLK();
-                  as_mbar_spin(&acc_full, ntc & 1u);
-                  const long long tb = AS_CLK();
-                  d_w0 += tb - tw;
-                  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                  for (uint32_t ja = 0; ja < np; ++ja) {
+        as_named_bar(1, AS_MLP_THREADS);
+    }
+    if (P.dbg && lane == 0) {  // MMA: -, wait full, wait acc_empty
+        atomicAdd(P.dbg + 5 + 1, (unsigned long long)d_w0);
+        atomicAdd(P.dbg + 5 + 2, (unsigned long long)d_w1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, AS_MLP_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// ---- warps 4-11: TMEM -> registers -> bias + activation -> scratch / prior rows
+__device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const AzbAsyncParams &P, const AsWorkerId id, uint8_t *smem,
+                                      AsWorkerShared &S) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t et = threadIdx.x - AS_EPI_WARP0 * 32u;  // 0 .. 255
+    AzbAsyncState *st = P.st;
+    // all biases into shared memory (behind the operand ring): the epilogue's only global traffic is its output
+    float *s_bias = reinterpret_cast<float *>(smem + (size_t)AS_STAGES * AS_STAGE_BYTES);
+    uint32_t bias_end = 0;
+    for (int l = 0; l < 4; ++l) {
+        if (et == 0u) S.bias_off[l] = bias_end;
+        for (uint32_t i = et; i < P.npad[l]; i += AS_EPI_WARPS * 32u) s_bias[bias_end + i] = P.bias[l][i];
+        bias_end += (P.npad[l] + 31u) & ~31u;
+    }
+    // per epilogue warp a staging tile behind the biases (coalesced activation stores)
+    uint8_t *stg = reinterpret_cast<uint8_t *>(s_bias + bias_end);
+    stg = (uint8_t *)(((uintptr_t)stg + 1023) & ~(uintptr_t)1023) + (warp - AS_EPI_WARP0) * AS_EPI_STG_BYTES;  // swizzle atoms: 1 KB
+    as_named_bar(1, AS_MLP_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_slot;
+    const uint32_t G = id.G, grp = id.grp, mem = id.mem;
+    // warp w may read TMEM lanes 32 (w % 4) ..; the two warps of a quadrant split each 128-column block in halves
+    const uint32_t q4 = warp & 3u, part = (warp - AS_EPI_WARP0) >> 2, col0 = part * AS_EPI_COLS, row = q4 * 32u + lane;
+    uint32_t ntc = 0, seq = 0;
+    long long d_acq = 0, d_w0 = 0, d_w1 = 0, d_busy = 0;
+    for (;;) {
+        as_named_bar(1, AS_MLP_THREADS);
+        const uint32_t q = S.tile;
+        if (q == AS_NONE) break;
+        const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
+        const uint32_t arrive_target = G * (seq + 1u);
+        if (AS_DBG(16u)) {  // timing experiment: answer the tile at once with whatever the prior rows hold
+            if (mem == 0 && et < AS_TILE) {
+                const uint32_t t = __ldcg(P.slot_tree + ring_row0 + et);
+                if (t != AS_NONE) atomicAdd(P.h_flag + t, 1u);
+            }
+            if (et == 0u) {
+                if (mem == 0) atomicAdd(P.tile_retired + (q % P.NT), 1u);
+                atomicAdd(&st->grp_done[grp], 1u);
+            }
+            seq += 1u;
+            as_named_bar(1, AS_MLP_THREADS);
+            continue;
+        }
+        if (et < AS_TILE) S.rowtree[et] = __ldcg(P.slot_tree + ring_row0 + et);
+        as_named_bar(2, AS_EPI_WARPS * 32);
+        const uint32_t my_tree = S.rowtree[row];
+        for (uint32_t l = 0; l < 4; ++l) {
+            const float *bias = s_bias + S.bias_off[l];
+            const uint32_t mine = as_blocks_of_member(P.npad[l], id);
+            for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
+                const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
+                const long long tw = AS_CLK();
+                as_mbar_spin(&S.acc_full, ntc & 1u);
+                const long long tb = AS_CLK();
+                d_w0 += tb - tw;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (uint32_t ja = 0; ja < np; ++ja) {
                     const uint32_t nt = mem + (p0 + ja) * G;
                     const uint32_t bn = min(128u, P.npad[l] - nt * 128u);
                     if (l < 3) {
@@ -458,10 +532,6 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                 as_tmem_ld16_issue(tmem_base + ((q4 * 32u) << 16) + ja * 128u + col0 + sl * 16u, r[sl]);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                             d_acq += AS_CLK() - tl0;
-                            if (AS_EPI_TMA_STORE) {  // the previous TMA store of this warp must have read the staging tile
-                                if (tc_elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                                __syncwarp();
-                            }
                             const uint32_t srow = tc_smem_u32(stg) + lane * (AS_EPI_COLS * 2u);
                             const uint32_t bias_s = tc_smem_u32(bias + nt * 128u + col0);
                             const uint32_t sw = AS_EPI_CHUNKS == 8 ? (lane & 7u) : ((lane >> 1) & 3u);  // chunk swizzle of this row
@@ -487,129 +557,127 @@ __device__ void async_mlp_worker(const AzbLayout &L, const AzbAsyncParams &P, co
                                 as_sts128(srow + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
                                 as_sts128(srow + (((ch + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
                             }
+                            // the warp's [32 rows x AS_EPI_COLS columns] go out as contiguous row pieces: AS_EPI_CHUNKS lanes per
+                            // row (a store per thread and row touched 32 lines per instruction and held the epilogue to ~0.4 us
+                            // per 16-column slice on the LSU)
+                            __syncwarp();
+                            const uint32_t rr = lane / AS_EPI_CHUNKS, cc = lane % AS_EPI_CHUNKS;
+                            __nv_bfloat16 *dst0 = P.act[l] + (size_t)(grp * AS_TILE + q4 * 32u) * P.kpad[l + 1] + nt * 128u + col0 + cc * 8u;
+#pragma unroll
+                            for (uint32_t it = 0; it < AS_EPI_CHUNKS; ++it) {
+                                const uint32_t rw = it * (32u / AS_EPI_CHUNKS) + rr;
+                                const uint32_t sw2 = AS_EPI_CHUNKS == 8 ? (rw & 7u) : ((rw >> 1) & 3u);
+                                const uint4 v = as_lds128(tc_smem_u32(stg) + rw * (AS_EPI_COLS * 2u) + ((cc ^ sw2) << 4));
+                                if (!AS_DBG(1u)) *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * P.kpad[l + 1]) = v;
+                            }
+                            __syncwarp();
                         }
                     } else {
-                      // the Sigmoid head: f32 rows scattered to the owning trees' prior rows, 16 columns at a time
-                      for (uint32_t c0 = col0; c0 < min(bn, col0 + (uint32_t)AS_EPI_COLS); c0 += 16) {
-                        uint32_t r[16];
-                        const long long tl0 = AS_CLK();
-                        as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + ja * 128u + c0, r);
-                        d_acq += AS_CLK() - tl0;
-                        const uint32_t nb = nt * 128u + c0;
-                        float b[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4 *>(bias + nb + j);
-                            b[j] = b4.x;
-                            b[j + 1] = b4.y;
-                            b[j + 2] = b4.z;
-                            b[j + 3] = b4.w;
-                        }
-                        if (my_tree != AS_NONE) {
-                            float *dst = L.h + (size_t)my_tree * L.h_ld;
-                            const bool vec = (L.h_ld & 3u) == 0u;
+                        // the Sigmoid head: f32 rows scattered to the owning trees' prior rows, 16 columns at a time
+                        for (uint32_t c0 = col0; c0 < min(bn, col0 + (uint32_t)AS_EPI_COLS); c0 += 16) {
+                            uint32_t r[16];
+                            const long long tl0 = AS_CLK();
+                            as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + ja * 128u + c0, r);
+                            d_acq += AS_CLK() - tl0;
+                            const uint32_t nb = nt * 128u + c0;
+                            float b[16];
 #pragma unroll
                             for (int j = 0; j < 16; j += 4) {
-                                float o[4];
+                                const float4 b4 = *reinterpret_cast<const float4 *>(bias + nb + j);
+                                b[j] = b4.x;
+                                b[j + 1] = b4.y;
+                                b[j + 2] = b4.z;
+                                b[j + 3] = b4.w;
+                            }
+                            if (my_tree != AS_NONE) {
+                                float *dst = L.h + (size_t)my_tree * L.h_ld;
+                                const bool vec = (L.h_ld & 3u) == 0u;
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const float v = __uint_as_float(r[j + t]) + b[j + t];
-                                    o[t] = __fdividef(1.0f, 1.0f + __expf(-v));
-                                }
-                                const uint32_t n = nb + j;
-                                if (vec && n + 3u < L.A) {
-                                    *reinterpret_cast<float4 *>(dst + n) = make_float4(o[0], o[1], o[2], o[3]);
-                                } else {
+                                for (int j = 0; j < 16; j += 4) {
+                                    float o[4];
 #pragma unroll
-                                    for (int t = 0; t < 4; ++t)
-                                        if (n + t < L.A) dst[n + t] = o[t];
+                                    for (int t = 0; t < 4; ++t) {
+                                        const float v = __uint_as_float(r[j + t]) + b[j + t];
+                                        o[t] = __fdividef(1.0f, 1.0f + __expf(-v));
+                                    }
+                                    const uint32_t n = nb + j;
+                                    if (vec && n + 3u < L.A) {
+                                        *reinterpret_cast<float4 *>(dst + n) = make_float4(o[0], o[1], o[2], o[3]);
+                                    } else {
+#pragma unroll
+                                        for (int t = 0; t < 4; ++t)
+                                            if (n + t < L.A) dst[n + t] = o[t];
+                                    }
                                 }
                             }
                         }
-                      }
-                    }
-                    if (AS_EPI_TMA_STORE && l < 3 && col0 < bn) {
-                        // the staged [32 rows x 64 columns] is a SWIZZLE_128B box: one TMA store (no LSU work at all)
-                        as_fence_proxy_async();  // the staging writes, for the async proxy
-                        __syncwarp();
-                        if (tc_elect_one() && !AS_DBG(1u)) {
-                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&M.act_st[l]),
-                                         "r"(tc_smem_u32(stg)), "r"((int)(nt * 128u + col0)), "r"((int)(grp * AS_TILE + q4 * 32u))
-                                         : "memory");
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }
-                    } else if (l < 3 && col0 < bn) {
-                        // the warp's [32 rows x AS_EPI_COLS columns] go out as contiguous row pieces: AS_EPI_CHUNKS lanes per
-                        // row (a store per thread and row touched 32 lines per instruction and held the epilogue to ~0.4 us
-                        // per 16-column slice on the LSU)
-                        __syncwarp();
-                        const uint32_t rr = lane / AS_EPI_CHUNKS, cc = lane % AS_EPI_CHUNKS;
-                        __nv_bfloat16 *dst0 = P.act[l] + (size_t)(grp * AS_TILE + q4 * 32u) * P.kpad[l + 1] + nt * 128u + col0 + cc * 8u;
-#pragma unroll
-                        for (uint32_t it = 0; it < AS_EPI_CHUNKS; ++it) {
-                            const uint32_t rw = it * (32u / AS_EPI_CHUNKS) + rr;
-                            const uint32_t sw = AS_EPI_CHUNKS == 8 ? (rw & 7u) : ((rw >> 1) & 3u);
-                            const uint4 v = as_lds128(tc_smem_u32(stg) + rw * (AS_EPI_COLS * 2u) + ((cc ^ sw) << 4));
-                            if (!AS_DBG(1u)) *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * P.kpad[l + 1]) = v;
-                        }
-                        __syncwarp();
-                    }
-                  }
-                  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                  __syncwarp();
-                  if (lane == 0) as_mbar_arrive(&acc_empty);
-                  d_busy += AS_CLK() - tb;
-                }
-                // ---- layer boundary: this member's share of the layer is stored; tell the group
-                const long long tf0 = AS_CLK();
-                if (AS_EPI_TMA_STORE) {
-                    if (l < 3 && tc_elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's stores are done
-                    __syncwarp();
-                } else if (l < 3) {
-                    as_fence_proxy_async();  // the next layer reads these stores through TMA
-                }
-                __threadfence();
-                as_named_bar(2, AS_EPI_WARPS * 32);
-                if (threadIdx.x == 64u) {
-                    if (l < 3) {
-                        if (G == 1u) as_mbar_arrive(&layer_bar);
-                        else atomicAdd(&st->grp_layer[grp * 4 + l], 1u);
-                    } else if (atomicAdd(&st->grp_done[grp], 1u) + 1u == arrive_target) {
-                        s_epi_count = 1u;  // this member is the last of the group to finish the tile
-                    } else {
-                        s_epi_count = 0u;
                     }
                 }
-                d_w1 += AS_CLK() - tf0;
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) as_mbar_arrive(&S.acc_empty);
+                d_busy += AS_CLK() - tb;
             }
-            // the tile is answered once every member is done: the last one raises the owners' flags
+            // ---- layer boundary: this member's share of the layer is stored; tell the group
+            const long long tf0 = AS_CLK();
+            if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
+            __threadfence();
             as_named_bar(2, AS_EPI_WARPS * 32);
-            if (s_epi_count) {
-                __threadfence();
-                if (part == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
-                if (threadIdx.x == 64u) {
-                    atomicAdd(P.tile_retired + (q % P.NT), 1u);
-                    atomicAdd(&st->tiles_done, 1u);
+            if (et == 0u) {
+                if (l < 3) {
+                    if (G == 1u) as_mbar_arrive(&S.layer_bar);
+                    else atomicAdd(&st->grp_layer[grp * 4 + l], 1u);
+                } else if (atomicAdd(&st->grp_done[grp], 1u) + 1u == arrive_target) {
+                    S.epi_last = 1u;  // this member is the last of the group to finish the tile
+                } else {
+                    S.epi_last = 0u;
                 }
+            }
+            d_w1 += AS_CLK() - tf0;
+        }
+        // the tile is answered once every member is done: the last one raises the owners' flags
+        as_named_bar(2, AS_EPI_WARPS * 32);
+        if (S.epi_last) {
+            __threadfence();
+            if (part == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
+            if (et == 0u) {
+                atomicAdd(P.tile_retired + (q % P.NT), 1u);
+                atomicAdd(&st->tiles_done, 1u);
             }
         }
         seq += 1u;
-        as_named_bar(1, MLP_THREADS);
+        as_named_bar(1, AS_MLP_THREADS);
     }
-    if (P.dbg && lane == 0 && (warp <= 2)) {
-        unsigned long long *d = P.dbg + warp * 5;  // producer: acquire, wait empty, wait layer, tile busy, tiles
-        atomicAdd(d + 0, (unsigned long long)d_acq);   // MMA: -, wait full, wait acc_empty;  epilogue (warp 2): -, wait acc_full, -, busy
-        atomicAdd(d + 1, (unsigned long long)d_w0);
-        atomicAdd(d + 2, (unsigned long long)d_w1);
-        atomicAdd(d + 3, (unsigned long long)d_busy);
-        atomicAdd(d + 4, (unsigned long long)d_tiles);
+    if (P.dbg && et == 0u) {  // epilogue (first warp): TMEM reads, wait acc_full, layer boundary, busy
+        atomicAdd(P.dbg + 10, (unsigned long long)d_acq);
+        atomicAdd(P.dbg + 11, (unsigned long long)d_w0);
+        atomicAdd(P.dbg + 12, (unsigned long long)d_w1);
+        atomicAdd(P.dbg + 13, (unsigned long long)d_busy);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    as_named_bar(1, MLP_THREADS);
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    as_named_bar(1, AS_MLP_THREADS);
+}
+
+// Role dispatch of a model CTA (all 1024 threads enter): re-divide the registers, then run the role
+__device__ __forceinline__ void async_model_cta(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
+                                                const uint32_t worker, uint8_t *smem, AsWorkerShared &S) {
+    const uint32_t warp = threadIdx.x >> 5, wg = warp >> 2;
+    AsWorkerId id;
+    id.G = P.group;
+    id.grp = worker / P.group;
+    id.mem = worker % P.group;
+    if (wg >= 3u) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AS_REGS_IDLE));
+        return;
     }
+    if (wg == 0u) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AS_REGS_FRONT));
+        if (warp == 0u) async_worker_producer(L, P, M, id, smem, S);
+        else if (warp == 1u) async_worker_mma(P, id, smem, S);
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AS_REGS_EPI));
+    async_worker_epilogue(L, P, id, smem, S);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -639,8 +707,10 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     uint32_t my_steps = 0;                        // times this tree has been advanced
     long long my_run = 0, my_wait = 0, my_t0 = 0;  // cycles spent advancing this tree / waiting for its priors (P.dbg)
     const long long t_k0 = AS_CLK();
-    const unsigned long long t_start = as_now();
-    uint32_t err_tree = 0, idle = 0, naps = 0;
+    // start time for the watchdog: parked in two free words of the warp's counter block (only the idle path reads it)
+    if (lane == 0) *reinterpret_cast<unsigned long long *>(cx.ct + 28) = as_now();
+    __syncwarp();
+    uint32_t idle = 0, naps = 0;
     const uint32_t ring_rows = P.NT * AS_TILE;
     for (;;) {
         if (my_state == 1u && as_ld_volatile(P.h_flag + my_tree) >= my_sub) {
@@ -657,7 +727,8 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
             ++naps;
             if ((++idle & 31u) == 0u) {
                 if (as_ld_volatile(&st->abort)) break;
-                if ((idle & 2047u) == 0u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+                if ((idle & 2047u) == 0u && as_now() - *reinterpret_cast<const unsigned long long *>(cx.ct + 28) > P.timeout_ns)
+                    atomicExch(&st->abort, 1u);
             }
             continue;
         }
@@ -667,18 +738,21 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         const uint32_t tree = gw + (uint32_t)k * NW;
         const long long t_run0 = AS_CLK();
         naps = 0;
+#if AS_ACQUIRE
+        // the relaxed poll saw this tree's flag: one acquire load of it orders the prior row (read in add_actions) behind it
+        if (__shfl_sync(FULL, my_sub, k) != 0u) (void)as_ld_acquire(P.h_flag + tree);
+#endif
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
         ctx_bind_tree(L, cx, tree);
         uint32_t *gwk = L.walker + (size_t)tree * L.WS;
         for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gwk[i];
         __syncwarp();
-        if (cx.wk[WK_FLAGS] & 1u) tree_add_actions(L, cx, tree);
+        if (cx.wk[WK_FLAGS] & 1u) tree_add_actions<DEPTH == 5>(L, cx, tree);
         if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) tree_rollout<DEPTH>(L, cx, tree, 0u);
         uint32_t new_state = 0u;
         const bool pending = (cx.wk[WK_FLAGS] & 1u) != 0u, at_target = cx.wk[WK_STEP] >= P.target_step;
         if (cx.err) {
             new_state = 2u;
-            err_tree = tree;
         } else {
             // a new node needs priors: its state vector goes to the next ring row — or, on the last step of this launch,
             // to the tree's own row (the host runs one batched forward over those)
@@ -691,6 +765,9 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
                 // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
                 const uint32_t q = slot / AS_TILE;
                 while (as_ld_volatile(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
+#if AS_ACQUIRE
+                if (q >= P.NT) (void)as_ld_acquire(P.tile_retired + (q % P.NT));  // the row is overwritten after this
+#endif
                 pos = slot % ring_rows;
                 row = P.ring + (size_t)pos * P.ring_ld;
             }
@@ -723,7 +800,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (cx.err) {
             if (lane == 0) {
                 if (atomicCAS(&L.g->err, 0u, cx.err) == 0u) {
-                    L.g->err_tree = err_tree;
+                    L.g->err_tree = tree;
                     L.g->err_step = cx.wk[WK_STEP];
                 }
                 atomicExch(&st->abort, 2u);
@@ -733,10 +810,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         __syncwarp();
     }
     if (lane < 16) {
-        uint32_t v = COUNT ? cx.ct[lane] : 0u;
-        if (lane == CT_INS) v = cx.n_ins;
-        if (lane == CT_LIVE) v = cx.n_live;
-        if (lane == CT_NOOP) v = cx.n_noop;
+        const uint32_t v = (COUNT || lane == CT_INS || lane == CT_LIVE || lane == CT_NOOP) ? cx.ct[lane] : 0u;
         if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
     }
 #ifdef AZB_PROFILE
@@ -763,13 +837,10 @@ template <int DEPTH, bool COUNT>
 __global__ void __launch_bounds__(AS_THREADS, 1)
     azb_async_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
     extern __shared__ __align__(1024) uint8_t as_smem[];
-    if (P.split) {  // the model runs in its own kernel beside this one (the default): every CTA walks
-        async_tree_worker<DEPTH, COUNT>(L, P, blockIdx.x, gridDim.x, reinterpret_cast<uint32_t *>(as_smem));
-        return;
-    }
-    // One-kernel form (AZB_ASYNC_SPLIT=0; what a kernel-serialising profiler such as ncu can capture): the first CTA on
-    // each of n_workers SMs becomes that SM's MLP worker (compiled under this kernel's 64 registers: slower epilogue)
+    __shared__ __align__(8) AsWorkerShared s_worker;
     __shared__ uint32_t s_role, s_idx;
+    // the first CTA to arrive on each of n_workers SMs becomes that SM's model CTA; every other CTA walks trees.  The
+    // launch is cooperative with one CTA per SM, so every role is resident from the start.
     if (threadIdx.x == 0) {
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -787,20 +858,9 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
     }
     __syncthreads();
     if (s_role) {
-        if (threadIdx.x >= AS_MLP_THREADS) return;
         uint8_t *smem = (uint8_t *)(((uintptr_t)as_smem + 1023) & ~(uintptr_t)1023);
-        async_mlp_worker(L, P, M, s_idx, smem);
+        async_model_cta(L, P, M, s_idx, smem, s_worker);
     } else {
         async_tree_worker<DEPTH, COUNT>(L, P, s_idx, gridDim.x - P.n_workers, reinterpret_cast<uint32_t *>(as_smem));
     }
-}
-
-// The MLP workers are a kernel of their own, launched beside the tree kernel on a second stream, one CTA per worker SM
-// (their shared memory excludes a tree CTA from the SM).  The tree kernel then asks only for its own shared memory and
-// the workers are not held to its 64 registers per thread (the epilogue keeps four TMEM slices in flight).
-__global__ void __launch_bounds__(AS_MLP_THREADS, 1)
-    azb_worker_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
-    extern __shared__ __align__(1024) uint8_t as_wsmem[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)as_wsmem + 1023) & ~(uintptr_t)1023);
-    async_mlp_worker(L, P, M, blockIdx.x, smem);
 }

@@ -14,6 +14,7 @@
 //   inl    [B][cap_in]    8 B  in-arcs beyond the fourth of a node ((depth-4)+ slots reserved at creation)
 //   key    [B][cap_nodes][W]   ActionSet bit mask of the node (path/set.rs:5-8)
 //   hash   [B][cap_hash]  u32  open-addressing transposition table: (node index + 1) | fingerprint << 21
+//   casc   [B][2][cap_nodes] u32  continuation of the cascade's work lists beyond their shared-memory part
 //   cand   [cap_steps+1][B] 8 B  per-step argmin candidate of every tree (slot 0 = the roots)
 #pragma once
 #include <cuda_runtime.h>
@@ -71,6 +72,7 @@ struct AzbGlobals {  // one per handle, in device memory
     uint32_t n_behind;              // ... of the last finished launch
     uint32_t argmin_tree, argmin_node;
     uint32_t next_slot;             // first candidate slot the argmin pass has not consumed (device copy; single-step graph)
+    uint32_t casc_spills;           // cascade waves that outgrew the shared-memory work list (diagnostic)
     uint32_t argmin_state[16 + 61]; // parents packed (16 words) + permitted (61 words)
     AzbCounters counters;
     unsigned long long prof[16];    // -DAZB_PROFILE: lane-0 cycles per phase
@@ -92,6 +94,7 @@ struct AzbLayout {
     uint2 *inl;
     uint32_t *key;
     uint32_t *hash;
+    uint32_t *casc;       // [B][2][cap_nodes] continuation of the cascade's shared-memory work lists (rarely touched)
     uint2 *cand;
     unsigned long long *stepmin;
     float *sv;

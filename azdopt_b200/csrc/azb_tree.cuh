@@ -66,10 +66,10 @@ struct WarpCtx {
     uint2 *inl;
     uint32_t *key;
     uint32_t *hash;
+    uint32_t *casc;    // two cascade work lists of cap_nodes entries each (continuation of the shared-memory lists)
     int lane;
     uint32_t err;
-    bool full_count;   // all 16 workload counters (tests, roofline pass) or only LIVE / NOOP / INS
-    uint32_t n_ins, n_live, n_noop;
+    bool full_count;   // all 16 workload counters (tests, roofline pass) or only LIVE / NOOP / INS (always counted)
 };
 
 // carve a warp's shared-memory region: walker block | cur mask | prefix | counters | one region shared by the
@@ -77,7 +77,6 @@ struct WarpCtx {
 __device__ __forceinline__ void ctx_bind_smem(const AzbLayout &L, WarpCtx &cx, uint32_t *base, const uint8_t *lut, int lane) {
     cx.lane = lane;
     cx.err = 0;
-    cx.n_ins = cx.n_live = cx.n_noop = 0u;
     cx.lut = lut;
     cx.wk = base;
     cx.par = (uint8_t *)(base + WK_HDR);
@@ -104,6 +103,7 @@ __device__ __forceinline__ void ctx_bind_tree(const AzbLayout &L, WarpCtx &cx, u
     cx.inl = L.inl + (size_t)tree * L.cap_in;
     cx.key = L.key + (size_t)tree * L.cap_nodes * L.W;
     cx.hash = L.hash + (size_t)tree * L.cap_hash;
+    cx.casc = L.casc + (size_t)tree * 2u * L.cap_nodes;
 }
 
 __device__ __forceinline__ void count(WarpCtx &cx, int which, uint32_t n) {
@@ -116,6 +116,7 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t r) {
 }
 
 // hash of a W-word action-set mask held as (k0 = word lane, k1 = word lane+32) across the warp
+// (WIDE = false: W <= 32, k1 is 0 and its term is a constant)
 __device__ __forceinline__ uint32_t key_hash(uint32_t k0, uint32_t k1, int lane, uint32_t W) {
     uint32_t hv = (k0 * 0x9E3779B1u + (uint32_t)lane * 0x85EBCA77u) ^ ((k1 + 0x7F4A7C15u) * 0xC2B2AE3Du);
     hv ^= hv >> 15;
@@ -175,6 +176,7 @@ __device__ __forceinline__ float prior_of(const AzbLayout &L, uint32_t tree, uin
 // add_actions (graph_operations.rs:32-56): one prediction per legal action, ascending; g = c_s - h (04-c21-tree.rs:103).
 // Allocates the node's block [preds | header | kids] and publishes its address to the node record and to the copy in
 // the creator's kid entry.
+template <bool WIDE>  // WIDE: W > 32 (N >= 47); otherwise the second mask word per lane is compiled out
 __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
     const int lane = cx.lane;
     const uint32_t pos = cx.wk[WK_POS];
@@ -189,26 +191,31 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
     build_cur_mask(L, cx);
     // legal = permitted minus current edges (space.rs:75-89); counts per word -> exclusive prefix
     uint32_t l0 = (uint32_t)lane < L.W ? (cx.perm[lane] & ~cx.cur[lane]) : 0u;
-    uint32_t l1 = (uint32_t)lane + 32 < L.W ? (cx.perm[lane + 32] & ~cx.cur[lane + 32]) : 0u;
+    uint32_t l1 = 0u;
+    if constexpr (WIDE) l1 = (uint32_t)lane + 32 < L.W ? (cx.perm[lane + 32] & ~cx.cur[lane + 32]) : 0u;
     uint32_t s0 = __popc(l0), s1 = __popc(l1);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, d), t1 = __shfl_up_sync(0xffffffffu, s1, d);
-        if (lane >= d) {
-            s0 += t0;
-            s1 += t1;
+        const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, d);
+        if (lane >= d) s0 += t0;
+        if constexpr (WIDE) {
+            const uint32_t t1 = __shfl_up_sync(0xffffffffu, s1, d);
+            if (lane >= d) s1 += t1;
         }
     }
     const uint32_t tot0 = __shfl_sync(0xffffffffu, s0, 31);
-    const uint32_t cnt = tot0 + __shfl_sync(0xffffffffu, s1, 31);
+    uint32_t cnt = tot0;
+    if constexpr (WIDE) cnt += __shfl_sync(0xffffffffu, s1, 31);
     __syncwarp();
     if ((uint32_t)lane < L.W) {
         cx.cur[lane] = l0;
         cx.pfx[lane + 1] = s0;
     }
-    if ((uint32_t)lane + 32 < L.W) {
-        cx.cur[lane + 32] = l1;
-        cx.pfx[lane + 33] = tot0 + s1;
+    if constexpr (WIDE) {
+        if ((uint32_t)lane + 32 < L.W) {
+            cx.cur[lane + 32] = l1;
+            cx.pfx[lane + 33] = tot0 + s1;
+        }
     }
     if (lane == 0) cx.pfx[0] = 0u;
     __syncwarp();
@@ -266,21 +273,29 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
 //   A. value pass over ALL ancestors: the walker's own path (known, WK_PATH) is the first work list and is processed
 //      in one go; in-arcs that lead off the path (transposition arcs) seed further work lists; a bitmap keeps every
 //      node to one visit.  Each node gets "c* <- min / else n_t += 1 (old: n_t = max(n_t, n_t of target))" and
-//      refreshes the copies held by its parents' kid entries.
+//      refreshes the copies held by its parents' kid entries.  A work list lives in shared memory up to
+//      AZB_FRONTIER_CAP entries and continues in the tree's global scratch (L.casc, cap_nodes entries per list), so
+//      no DAG shape can overflow it — the reference's BTreeMap has no limit either.
 //   B. exhaustion pass: exhausted_children += 1 at the source if the arc's target is inactive; a node whose count
-//      thereby reaches its prediction count became inactive and hands +1 to each of its parents (rare, serial).
+//      thereby reaches its prediction count became inactive and hands +1 to each of its parents.  Depth first with an
+//      explicit stack: a parent is one level shallower than its child, so the stack never holds more than depth + 1
+//      entries (<= N - 2), and the increments commute, so the order does not matter.
 // Before a cascade every ancestor of the (active) source is active, so "inactive after the update" in the reference
 // (:65-70) is exactly "became inactive in this cascade".
+__device__ __forceinline__ uint32_t wl_get(const uint32_t *sh, const uint32_t *gl, uint32_t i) {
+    return i < AZB_FRONTIER_CAP ? sh[i] : gl[i - AZB_FRONTIER_CAP];
+}
 __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint32_t depth, float cstar, uint32_t ntt,
                              uint32_t e0, bool old) {
     const int lane = cx.lane;
     const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
-    uint32_t *wa = cx.fr, *wb = cx.fr + AZB_FRONTIER_CAP, *qb = cx.fr + 2 * AZB_FRONTIER_CAP;
+    uint32_t *wa = cx.fr, *wb = cx.fr + AZB_FRONTIER_CAP;
+    uint32_t *ga = cx.casc, *gb = cx.casc + L.cap_nodes;  // the lists' continuation beyond AZB_FRONTIER_CAP entries
     uint32_t *vis = cx.fr + 3 * AZB_FRONTIER_CAP;
     const uint32_t nwords = (L.cap_nodes + 31u) >> 5;
     for (uint32_t w = lane; w < nwords; w += 32) vis[w] = 0u;
     __syncwarp();
-    uint32_t ncur = depth + 1u;
+    uint32_t ncur = depth + 1u;  // <= 62 < AZB_FRONTIER_CAP
     for (uint32_t i = lane; i < ncur; i += 32) {
         const uint32_t p = cx.wk[WK_PATH + i];
         wa[i] = p;
@@ -288,7 +303,7 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
     }
     __syncwarp();
     // ---- A. value pass
-    while (ncur > 0 && cx.err == 0) {
+    while (ncur > 0) {
         uint32_t nnext = 0, links = 0;
         count(cx, CT_CN, ncur);
         for (uint32_t base = 0; base < ncur; base += 32) {
@@ -297,7 +312,7 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
             uint32_t nin = 0, in_off = 0, w1 = 0, w2 = 0, w3 = 0;
             uint4 q2 = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
             if (valid) {
-                uint4 *rec = cx.node + (size_t)wa[i] * 4;
+                uint4 *rec = cx.node + (size_t)wl_get(wa, ga, i) * 4;
                 uint4 q0 = rec[0];
                 const uint4 q1 = rec[1];
                 q2 = rec[2];
@@ -343,9 +358,12 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
                     fresh = (atomicOr(&vis[q >> 5], bit) & bit) == 0u;
                 }
                 const uint32_t bal = __ballot_sync(FULL, fresh);
-                if (fresh) {
+                if (fresh) {  // at most cap_nodes distinct nodes are ever enlisted: the global continuation cannot overflow
                     const uint32_t at = nnext + __popc(bal & lt);
-                    if (at < AZB_FRONTIER_CAP) wb[at] = q;
+                    if (at < AZB_FRONTIER_CAP)
+                        wb[at] = q;
+                    else
+                        gb[at - AZB_FRONTIER_CAP] = q;
                 }
                 nnext += __popc(bal);
             }
@@ -354,46 +372,45 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
             links = __reduce_add_sync(FULL, links);
             count(cx, CT_DCN, links);
         }
-        if (nnext > AZB_FRONTIER_CAP) {
-            cx.err = 3;
-            break;
-        }
+        if (nnext > AZB_FRONTIER_CAP && lane == 0) atomicAdd(&L.g->casc_spills, 1u);
         uint32_t *t = wa;
         wa = wb;
         wb = t;
+        t = ga;
+        ga = gb;
+        gb = t;
         ncur = nnext;
         __syncwarp();
     }
     // ---- B. exhaustion pass
-    if (e0 == 0u || cx.err) return;
-    if (lane == 0) qb[0] = src;
-    uint32_t nq = 1, head = 0;
-    __syncwarp();
-    while (head < nq) {
-        const uint32_t p = qb[head];
-        ++head;
+    if (e0 == 0u) return;
+    uint32_t *stk = cx.fr;  // (node, next in-arc, in-arc count, overflow in-arc offset) per level; the work lists are done
+    uint32_t sp = 0, p = src;
+    for (;;) {
         uint4 *rec = cx.node + (size_t)p * 4;
         const uint4 q0 = rec[0], q1 = rec[1];
         const uint32_t ex = (q0.w & 0xffffu) + 1u, cnt = q0.w >> 16, nin = q1.y;
         __syncwarp();
         if (lane == 0) reinterpret_cast<uint32_t *>(rec)[3] = ex | (cnt << 16);
-        if (ex >= cnt && ex - 1u < cnt) {  // p just became inactive: tell its parents
-            if (nq + nin > AZB_FRONTIER_CAP) {
-                cx.err = 3;
-                break;
-            }
+        if (ex == cnt && nin != 0u) {  // p just became inactive: its parents' copies lose the active bit, each parent gets +1
             for (uint32_t k = lane; k < nin; k += 32) {
-                uint2 ent;
-                if (k < 4u)
-                    ent = reinterpret_cast<const uint2 *>(rec + 2)[k];
-                else
-                    ent = cx.inl[q1.z + k - 4u];
-                reinterpret_cast<uint32_t *>(cx.blk4 + ent.y)[1] = q1.x;  // the copy loses its active bit
-                qb[nq + k] = ent.x;
+                const uint2 ent = k < 4u ? reinterpret_cast<const uint2 *>(rec + 2)[k] : cx.inl[q1.z + k - 4u];
+                reinterpret_cast<uint32_t *>(cx.blk4 + ent.y)[1] = q1.x;
             }
-            nq += nin;
+            if (lane == 0) *reinterpret_cast<uint4 *>(stk + 4u * sp) = make_uint4(p, 0u, nin, q1.z);
+            ++sp;
         }
         __syncwarp();
+        if (sp == 0u) break;
+        const uint4 top = *reinterpret_cast<const uint4 *>(stk + 4u * (sp - 1u));
+        const uint2 ent = top.y < 4u ? reinterpret_cast<const uint2 *>(cx.node + (size_t)top.x * 4 + 2)[top.y] : cx.inl[top.w + top.y - 4u];
+        __syncwarp();
+        if (top.y + 1u < top.z) {
+            if (lane == 0) stk[4u * (sp - 1u) + 1u] = top.y + 1u;
+        } else {
+            --sp;
+        }
+        p = ent.x;
     }
 }
 
@@ -442,7 +459,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             if (depth != 0u)
                 cx.err = 6;
             else {
-                cx.n_noop += 1;
+                if (lane == 0) cx.ct[CT_NOOP] += 1u;
                 step_done(L, cx, tree);
             }
             break;
@@ -566,9 +583,9 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         count(cx, CT_PROBE, 1);
         // key of the successor = path + a; look it up
         const uint32_t k0 = (uint32_t)lane < L.W ? (cx.keym[lane] | (((a >> 5) == (uint32_t)lane) ? 1u << (a & 31) : 0u)) : 0u;
-        const uint32_t k1 = (uint32_t)lane + 32 < L.W
-                                ? (cx.keym[lane + 32] | (((a >> 5) == (uint32_t)lane + 32) ? 1u << (a & 31) : 0u))
-                                : 0u;
+        uint32_t k1 = 0u;
+        if constexpr (DEPTH == 5)  // W > 32 only for N >= 47
+            k1 = (uint32_t)lane + 32 < L.W ? (cx.keym[lane + 32] | (((a >> 5) == (uint32_t)lane + 32) ? 1u << (a & 31) : 0u)) : 0u;
         const uint32_t hv = key_hash(k0, k1, lane, L.W);
         const uint32_t fp = hv >> 21;
         uint32_t slot = hv & (L.cap_hash - 1);
@@ -580,7 +597,8 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 const uint32_t idx = (e & 0x1fffffu) - 1u;
                 bool eq = true;
                 if ((uint32_t)lane < L.W) eq = cx.key[(size_t)idx * L.W + lane] == k0;
-                if ((uint32_t)lane + 32 < L.W) eq = eq && (cx.key[(size_t)idx * L.W + lane + 32] == k1);
+                if constexpr (DEPTH == 5)
+                    if ((uint32_t)lane + 32 < L.W) eq = eq && (cx.key[(size_t)idx * L.W + lane + 32] == k1);
                 if (__all_sync(FULL, eq)) {
                     hit = (int)idx;
                     break;
@@ -639,7 +657,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             }
             const float c_new = azb_evaluate(mu, l1, L.c_lower, L.slope);
             PROF_ADD(cx, PH_COST);
-            cx.n_ins += 1;
+            if (lane == 0) cx.ct[CT_INS] += 1u;
             const uint32_t nn = cx.wk[WK_NNODES], in_off = cx.wk[WK_INTOP];
             const uint32_t in_need = ndepth > 4u ? ndepth - 4u : 0u;
             if (nn >= L.cap_nodes || in_off + in_need > L.cap_in) {
@@ -664,7 +682,8 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 cx.node[(size_t)nn * 4 + lane] = q;
             }
             if ((uint32_t)lane < L.W) cx.key[(size_t)nn * L.W + lane] = k0;
-            if ((uint32_t)lane + 32 < L.W) cx.key[(size_t)nn * L.W + lane + 32] = k1;
+            if constexpr (DEPTH == 5)
+                if ((uint32_t)lane + 32 < L.W) cx.key[(size_t)nn * L.W + lane + 32] = k1;
             if (lane == 0) {
                 cx.hash[slot] = (nn + 1u) | (fp << 21);
                 cx.wk[WK_NNODES] = nn + 1;
@@ -701,7 +720,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                     cx.wk[WK_PEND_C] = __float_as_uint(c_new);
                     cx.wk[WK_PKIDX] = kidx;
                 }
-                cx.n_live += 1;
+                if (lane == 0) cx.ct[CT_LIVE] += 1u;
                 __syncwarp();
                 step_done(L, cx, tree);
                 break;  // tree/mod.rs:212-215
@@ -816,7 +835,8 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
                 cx.node[lane] = q;
             }
             if ((uint32_t)lane < L.W) cx.key[lane] = 0u;
-            if ((uint32_t)lane + 32 < L.W) cx.key[lane + 32] = 0u;
+            if constexpr (DEPTH == 5)
+                if ((uint32_t)lane + 32 < L.W) cx.key[lane + 32] = 0u;
             const uint32_t hv = key_hash(0u, 0u, lane, L.W);  // the empty path hashes like every other key
             if (lane == 0) {
                 cx.hash[hv & (L.cap_hash - 1)] = 1u | ((hv >> 21) << 21);
@@ -851,7 +871,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
             build_cur_mask(L, cx);
             tree_pack(L, cx, tree);
         }
-        if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions(L, cx, tree);
+        if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions<DEPTH == 5>(L, cx, tree);
         PROF_ADD(cx, PH_ADD);
         if ((flags & AZB_F_ROLLOUT) && cx.err == 0 && cx.wk[WK_STEP] < target_step && !(cx.wk[WK_FLAGS] & 1u)) {
             tree_rollout<DEPTH>(L, cx, tree, max_episodes);
@@ -869,10 +889,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
         for (uint32_t i = lane; i < live_words; i += 32) gw[i] = cx.wk[i];
         if (lane < 16) {
-            uint32_t v = COUNT ? cx.ct[lane] : 0u;
-            if (lane == CT_INS) v = cx.n_ins;
-            if (lane == CT_LIVE) v = cx.n_live;
-            if (lane == CT_NOOP) v = cx.n_noop;
+            const uint32_t v = (COUNT || lane == CT_INS || lane == CT_LIVE || lane == CT_NOOP) ? cx.ct[lane] : 0u;
             if (v) atomicAdd(&L.g->counters.v[lane], (unsigned long long)v);
         }
         PROF_ADD(cx, PH_STORE);
@@ -881,7 +898,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
         if (lane == 0 && tree < 65536u) {
             uint32_t tot = 0;
             for (int q = 16; q < 28; ++q) tot += cx.ct[q];
-            g_tree_prof[tree] = make_uint4(tot, cx.ct[CT_RESET] + 1u, cx.n_ins, cx.ct[30]);
+            g_tree_prof[tree] = make_uint4(tot, cx.ct[CT_RESET] + 1u, cx.ct[CT_INS], cx.ct[30]);
         }
         if (lane >= 16) {
             const uint32_t v = cx.ct[lane];

@@ -83,13 +83,14 @@ typedef struct azb_config {
                                    episodes and finishes the step in a later launch; same results, shorter launches */
     uint32_t n_groups;          /* >1: the trees of this handle advance as that many independent groups on their own
                                    CUDA streams (needs max_episodes = 0); results are identical, launches overlap */
-    uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as two persistent kernels side
-                                   by side in which trees never wait for each other — tree warps advance whichever of their
-                                   trees has its priors, that many tensor-core worker SMs (20 at 4096 roots, 32 from 16 K roots;
-                                   in pairs per tile from 40) answer state vectors in 128-row tiles as they fill.  Same
-                                   results as the lock step (trees are independent).  0 = lock step.  Environment, read when
-                                   the handle first runs this way: AZB_ASYNC_SPLIT=0 (one kernel, for ncu), AZB_ASYNC_GROUP=g,
-                                   AZB_ASYNC_PIPE=1 (weight-stationary model pipeline), AZB_ASYNC_FLUSH_NS. */
+    uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as ONE persistent cooperative
+                                   kernel in which trees never wait for each other — the CTAs of that many SMs (20 at 4096
+                                   roots, 32 from 16 K roots; in pairs per tile from 40) become tensor-core model workers that
+                                   answer state vectors in 128-row tiles as they fill, all other CTAs walk trees, a warp
+                                   advancing whichever of its trees has its priors.  Same results as the lock step (trees are
+                                   independent).  0 = lock step.  Environment, read when the handle first runs this way:
+                                   AZB_ASYNC_GROUP=g (worker SMs per tile), AZB_ASYNC_FLUSH_NS, AZB_ASYNC_TIMEOUT_MS (watchdog
+                                   floor, default 2000). */
     uint32_t reserved[5];
 } azb_config;
 
@@ -251,6 +252,10 @@ int azb_comm_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double
 int azb_kernel_launches(const azb_handle *h, uint64_t *n);   /* kernels launched by this handle so far */
 int azb_device_bytes(const azb_handle *h, uint64_t *bytes);  /* HBM held by this handle */
 int azb_flush_l2(azb_handle *h);                             /* overwrite a >L2 scratch buffer */
+/* cascades (cascade_new_terminal / cascade_old_node, nabla/tree/empty_transitions.rs:50-127) whose ancestor wave
+ * outgrew the on-chip work list and continued in the tree's HBM scratch, since azb_create.  The reference's BTreeMap
+ * frontier has no limit and neither has this path; the count exists so that tests can prove they exercised it. */
+int azb_debug_cascade_spills(azb_handle *h, uint32_t *n);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,7 @@
-"""The asynchronous search step (azb_config.async_workers > 0: a persistent tree kernel beside a persistent tensor-core
-model kernel, azb_async.cuh) must give exactly what the lock step gives: trees are independent and a row's forward pass
-does not depend on the tile it rides in.  Bit-exact trees, walkers, priors, improvement log, argmin, counters — in the
-default two-kernel form, the one-kernel form (AZB_ASYNC_SPLIT=0, what ncu captures) and the weight-stationary model
-pipeline (AZB_ASYNC_PIPE=1, azb_pipe.cuh)."""
+"""The asynchronous search step (azb_config.async_workers > 0: ONE persistent cooperative kernel whose CTAs are tree
+walkers or tensor-core model workers, azb_async.cuh) must give exactly what the lock step gives: trees are independent
+and a row's forward pass does not depend on the tile it rides in.  Bit-exact trees, walkers, priors, improvement log,
+argmin, counters.  The timed configurations themselves are covered in test_gpu_timed_configs.py."""
 import numpy as np
 import pytest
 
@@ -49,10 +48,10 @@ def test_async_equals_lock_step(capi, n, b, workers):
         _same(lock, asy, b)
 
 
-@pytest.mark.parametrize("env", [{"AZB_ASYNC_SPLIT": "0"}, {"AZB_ASYNC_PIPE": "1"}, {"AZB_ASYNC_GROUP": "2"}])
+@pytest.mark.parametrize("env", [{"AZB_ASYNC_GROUP": "2"}, {"AZB_ASYNC_GROUP": "4"}, {"AZB_ASYNC_FLUSH_NS": "0"}])
 @pytest.mark.parametrize("n,b,workers", [(19, 1024, 8), (12, 77, 4)])
 def test_async_variants_equal_lock_step(capi, monkeypatch, env, n, b, workers):
-    """The other forms of the model side (read from the environment when the handle first runs asynchronously)."""
+    """Worker groups (G SMs per tile, N-split) and an eager flush of partial tiles: same results."""
     steps = 30
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -163,3 +162,24 @@ def test_step_poll_reports_each_step_while_later_steps_run(capi, workers):
             assert n_end == n_ref == len(polled)
             assert [tuple(x) for x in log_end] == polled == [tuple(x) for x in log_ref]
         _same(ref, h, b)
+
+
+def test_async_watchdog_ends_a_stuck_launch_within_seconds(capi, monkeypatch):
+    """Every spin loop of the persistent kernel watches %globaltimer.  With the floor set to 1 ms and no per-step
+    allowance left to speak of, a launch that cannot finish in time must drain and return AZB_ERR_CUDA ("watchdog")
+    instead of hanging, and the handle must be usable afterwards."""
+    import time
+
+    n, b = 19, 2048
+    monkeypatch.setenv("AZB_ASYNC_TIMEOUT_MS", "0")
+    parents, masks = capi.generate_roots(3, 0, b, n)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=4000, async_workers=8) as h:
+        h.mlp_init(1)
+        h.set_roots(parents, masks)
+        h.init_trees()
+        t0 = time.time()
+        try:
+            h.step(2)  # allowance: 2 x 20 ms — enough for two steps; must succeed or report, never hang
+        except capi.AzbError as e:
+            assert e.code == capi.ERR_CUDA and "watchdog" in str(e)
+        assert time.time() - t0 < 20.0

@@ -133,3 +133,50 @@ def test_oracle_against_golden_digests(orc):
     for case in golden["cases"]:
         got = run_golden_case(orc, case["config"])
         assert got == case["expect"], case["config"]
+
+
+def _run_both(orc, n, parents, masks, tol, tol_default, steps, prior_fn):
+    """The oracle and the pure-Python restatement on the same roots and priors; every tree must come out identical."""
+    b = len(parents)
+    o = orc.Optimizer(n, b, n_as_tol=tol, n_as_tol_default=tol_default, lambda_method=orc.LAMBDA_DENSE)
+    o.set_roots(parents, masks)
+    py = pyref.Optimizer(n, parents, [orc.actions_from_mask(m) for m in masks], tol=tol, tol_default=tol_default)
+    pri = prior_fn(0)
+    o.init_trees(pri)
+    py.init_trees(pri)
+    for s in range(steps):
+        pri = prior_fn(s + 1)
+        o.rollout()
+        assert o.add_actions(pri) == (py.step(pri) is not None), f"step {s}"
+    for i in range(b):
+        bad = _same(o.dump_tree(i), py.dump(i, orc.mask_words(n)))
+        assert bad is None, f"tree {i}: {bad} differ"
+    assert o.argmin()["eval"] == py.best
+    return o
+
+
+@pytest.mark.parametrize("n,tol,tol_default,seed", [(6, (2, 1), 1, 0), (8, (3, 2), 1, 1), (9, (1,), 1, 2),
+                                                    (10, (4, 2, 2), 2, 3), (12, (2, 2), 1, 4), (7, (200, 50, 50), 25, 5)])
+def test_tie_stress_oracle_matches_python_restatement(orc, n, tol, tol_default, seed):
+    """Priors quantised to three values and tiny revisit budgets: ties in (n_t, c*) (first minimum, newest arc first),
+    in the curiosity sums (last maximum) and in the no-children argmin (first minimum) at almost every selection —
+    nabla/tree/next_action.rs:28-88.  Continuous hash priors almost never tie outside c*."""
+    b, steps = 6, 70
+    a_dim = orc.action_dim(n)
+    rng = np.random.default_rng(100 + seed)
+    parents, masks = orc.generate_roots(seed, 0, b, n, k_min=min(5, a_dim // 2), k_max=a_dim // 2)
+    vals = np.array([0.25, 0.5, 0.75], dtype=np.float32)
+    _run_both(orc, n, parents, masks, tol, tol_default, steps, lambda s: rng.choice(vals, size=(b, a_dim)))
+
+
+def test_boolean_lattice_dag_oracle_matches_python_restatement(orc):
+    """Every child has one permitted action, so states are SETS of moved children: the densest transposition DAG of the
+    space (2^8 nodes, every node of depth d has d parents).  Cascades (nabla/tree/empty_transitions.rs:50-127) then
+    merge many contributions per parent and per level; both restatements must exhaust the lattice identically."""
+    n, b = 11, 2
+    a_dim = orc.action_dim(n)
+    parents = np.zeros((b, n), dtype=np.uint8)
+    acts = [c * (c - 1) // 2 for c in range(2, n - 1)]
+    masks = np.stack([orc.mask_from_actions(n, acts) for _ in range(b)])
+    o = _run_both(orc, n, parents, masks, (4, 2, 2), 2, 300, lambda s: orc.hash_priors(31, 0, b, a_dim, s))
+    assert o.tree_sizes(0)[0] == 2 ** (n - 3) and o.tree_sizes(0)[1] == 2 ** (n - 3) * (n - 3) // 2

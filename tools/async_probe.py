@@ -38,16 +38,3 @@ for w in workers:
             print(f"      trees: kernel {d[18]/1965e3:.1f} ms; cycles advancing a tree: mean {d[16]/b/1965e3:.1f} ms, max {d[17]/1965e3:.1f} ms "
                   f"(per step: mean {d[16]/b/steps/1965:.1f} us, slowest tree {d[17]/steps/1965:.1f} us); waiting for priors per step: "
                   f"mean {d[19]/b/steps/1965:.1f} us, max tree {d[20]/steps/1965:.1f} us; max (run+wait) {d[21]/1965e3:.1f} ms", flush=True)
-            try:
-                L.azb_debug_pipe.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
-                e = (C.c_uint64 * 40)()
-                mem = (C.c_uint32 * 4)()
-                if L.azb_debug_pipe(h._h, e, mem) == 0:
-                    for l in range(4):
-                        t = max(e[l * 8 + 2] / max(mem[l], 1), 1)
-                        u = lambda c, div=1: c / div / t / 1965.0
-                        print(f"      pipe stage {l} ({mem[l]} SMs, {int(t)} tiles), us per tile: producer wait-input {u(e[l*8+0], mem[l]):6.2f} wait-empty {u(e[l*8+1], mem[l]):6.2f} | "
-                              f"MMA wait-acc {u(e[l*8+3], mem[l]):6.2f} wait-first {u(e[l*8+7], mem[l]):6.2f} wait-full {u(e[l*8+4], mem[l]):6.2f} issue {u(e[32+l], mem[l]):6.2f} | epilogue wait {u(e[l*8+5], mem[l]):6.2f} busy {u(e[l*8+6], mem[l]):6.2f}", flush=True)
-                    print(f"      epilogue leader, us per tile: stage0 fence {e[36]/2/t/1965:.2f} | stage1 slot-wait {e[37]/8/t/1965:.2f} fence {e[38]/8/t/1965:.2f} | stage2 fence {e[39]/8/t/1965:.2f}")
-            except AttributeError:
-                pass

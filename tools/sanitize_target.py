@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from azdopt_b200 import capi
 
 CASES = ((19, 24, 30, "tc"), (19, 9, 25, "hash"), (33, 6, 12, "fp32"), (19, 130, 6, "groups"), (19, 200, 10, "async"))
-if len(sys.argv) > 1:  # e.g. `sanitize_target.py async` (AZB_ASYNC_SPLIT / AZB_ASYNC_PIPE choose the form of the model side)
+if len(sys.argv) > 1:  # e.g. `sanitize_target.py async`
     CASES = tuple(c for c in CASES if c[3] in sys.argv[1:])
 for n, b, steps, mode in CASES:
     kw = dict(max_steps=steps + 4)

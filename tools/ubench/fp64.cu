@@ -1,6 +1,6 @@
 // FP64 pipe throughput on B200 vs the number of active lanes: cycles per DFMA warp-instruction with 32 warps per SM,
 // 8 independent accumulators per thread (throughput bound, not latency bound).
-// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/ubench/fp64 tools/ubench/fp64.cu
+// build: nvcc -O3 -cudart shared -gencode arch=compute_100a,code=sm_100a -o tools/ubench/fp64 tools/ubench/fp64.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k(double *out, int active, int iters, long long *cyc) {
