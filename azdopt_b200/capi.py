@@ -82,6 +82,7 @@ SIGNATURES = {
     "azb_rollout_host": (C.c_int, [C.c_void_p, f32p]),
     "azb_add_actions_host": (C.c_int, [C.c_void_p, f32p, C.POINTER(C.c_int)]),
     "azb_get_argmin": (C.c_int, [C.c_void_p, u8p, u32p, f64p, u32p, f32p]),
+    "azb_get_node_state": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, u8p, u32p]),
     "azb_get_walkers": (C.c_int, [C.c_void_p, u8p, u32p, u32p, u32p, u32p]),
     "azb_tree_sizes": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u32p, u32p]),
     "azb_dump_tree": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u32p, u32p, u32p]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "azb_comm_unique_id": (C.c_int, [u8p]),
     "azb_comm_init": (C.c_int, [C.c_void_p, u8p, C.c_int, C.c_int]),
     "azb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "azb_comm_allreduce_bench": (C.c_int, [C.c_void_p, C.c_uint32, f32p]),
     "azb_comm_argmin": (C.c_int, [C.c_void_p, u8p, u32p, f64p, u32p, f32p, C.POINTER(C.c_int)]),
     "azb_kernel_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "azb_device_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -449,6 +451,18 @@ class Handle:
         n = C.c_uint64()
         self._ck(self._L.azb_kernel_launches(self._h, C.byref(n)))
         return int(n.value)
+
+    def node_state(self, tree: int, node: int):
+        """(parents, permitted mask) of a node: the root with the node's action set replayed; does not wait for steps"""
+        parents = np.zeros(self.n, dtype=np.uint8)
+        permitted = np.zeros(self.w, dtype=np.uint32)
+        self._ck(self._L.azb_get_node_state(self._h, tree, node, _p(parents, C.c_uint8), _p(permitted, C.c_uint32)))
+        return parents, permitted
+
+    def comm_allreduce_bench(self, reps: int = 20) -> float:
+        ms = C.c_float()
+        self._ck(self._L.azb_comm_allreduce_bench(self._h, reps, C.byref(ms)))
+        return float(ms.value)
 
     def cascade_spills(self) -> int:
         n = C.c_uint32()

@@ -325,6 +325,9 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     L.tol_default = cfg.n_as_tol_default;
     L.prior_mode = cfg.prior_mode;
     L.log_cap = 4096;
+    L.frontier_cap = AZB_FRONTIER_CAP;
+    if (const char *e = getenv("AZB_TEST_FRONTIER_CAP"))  // tests: push ordinary cascades through the global continuation
+        L.frontier_cap = std::min<uint32_t>(AZB_FRONTIER_CAP, std::max(1, atoi(e)));
     L.first_root = cfg.first_root;
     L.prior_seed = cfg.prior_seed;
     CK(dmalloc(h, &L.walker, (size_t)B * L.WS));
@@ -1526,6 +1529,33 @@ extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {  // o
     return AZB_OK;
 }
 
+// State of one node = its tree's root with the node's action set replayed in ascending order (what
+// par_update_argmmim_data does for the winning node: optimizer/mod.rs:224-239).  Runs on the poll stream from device
+// data that never changes once written (root part of the walker block, the node's key), so a caller of azb_step_poll
+// can turn an improvement record into ArgminData while later steps are still running.
+extern "C" int azb_get_node_state(azb_handle *h, uint32_t tree, uint32_t node, uint8_t *parents, uint32_t *permitted) {
+    if (!h || !parents || !permitted || tree >= h->L.B || node >= h->L.cap_nodes) return AZB_ERR_INVALID;
+    if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->poll_stream) CK(cudaStreamCreateWithFlags(&h->poll_stream, cudaStreamNonBlocking));
+    const uint32_t W = h->W, PW = h->PW;
+    std::vector<uint32_t> root(PW + W), key(W);
+    const uint32_t *wk = h->L.walker + (size_t)tree * h->L.WS + WK_HDR + PW + 2 * W;  // root parents | root permitted
+    CK(cudaMemcpyAsync(root.data(), wk, (size_t)(PW + W) * 4, cudaMemcpyDeviceToHost, h->poll_stream));
+    CK(cudaMemcpyAsync(key.data(), h->L.key + ((size_t)tree * h->L.cap_nodes + node) * W, (size_t)W * 4, cudaMemcpyDeviceToHost,
+                       h->poll_stream));
+    CK(cudaStreamSynchronize(h->poll_stream));
+    memcpy(parents, root.data(), h->N);
+    memcpy(permitted, root.data() + PW, (size_t)W * 4);
+    for (uint32_t a = 0; a < h->A; ++a) {
+        if (!((key[a >> 5] >> (a & 31)) & 1u)) continue;
+        const uint32_t child = azb_action_child(a), first = azb_child_first_action(child);  // act: rooted_tree/space.rs:56-73
+        parents[child] = (uint8_t)(a - first);
+        for (uint32_t q = first; q < first + child; ++q) permitted[q >> 5] &= ~(1u << (q & 31));
+    }
+    return AZB_OK;
+}
+
 // cascade waves that outgrew the shared-memory work list and continued in global scratch since azb_create (diagnostic;
 // tests use it to prove that a dense transposition DAG really exercised that path)
 extern "C" int azb_debug_cascade_spills(azb_handle *h, uint32_t *out) {
@@ -1920,6 +1950,27 @@ int azb_comm_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double
     if (mu) *mu = m;
     if (eval) *eval = c;
     if (owner_rank) *owner_rank = best;
+    return AZB_OK;
+}
+
+// measurement helper: `reps` all-reduces of the gradient buffer (the 1 284 248 floats azb_update_model reduces once per
+// epoch) back to back between two events; *ms = time per all-reduce.  The buffer holds zeros between training steps.
+int azb_comm_allreduce_bench(azb_handle *h, uint32_t reps, float *ms) {
+    if (!h || !ms || reps == 0) return AZB_ERR_INVALID;
+    if (!h->nccl_comm) return fail(h, AZB_ERR_STATE, "azb_comm_init has not been called");
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = train_alloc(h);
+    if (rc) return rc;
+    rc = comm_allreduce(h, h->grad, h->n_params, AZB_NCCL_FLOAT32);  // warm-up (channel set-up)
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (uint32_t i = 0; i < reps && rc == AZB_OK; ++i) rc = comm_allreduce(h, h->grad, h->n_params, AZB_NCCL_FLOAT32);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+    *ms = t / (float)reps;
     return AZB_OK;
 }
 

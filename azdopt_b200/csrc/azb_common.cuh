@@ -86,6 +86,7 @@ struct AzbLayout {
     uint32_t tol[8];
     uint32_t tol_len, tol_default;
     uint32_t prior_mode, log_cap;
+    uint32_t frontier_cap;  // entries of a cascade work list kept in shared memory (<= AZB_FRONTIER_CAP)
     unsigned long long first_root, prior_seed;
     const uint8_t *lut;   // child vertex of every action (A bytes, padded to a multiple of 4)
     uint32_t *walker;

@@ -282,8 +282,14 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
 //      entries (<= N - 2), and the increments commute, so the order does not matter.
 // Before a cascade every ancestor of the (active) source is active, so "inactive after the update" in the reference
 // (:65-70) is exactly "became inactive in this cascade".
-__device__ __forceinline__ uint32_t wl_get(const uint32_t *sh, const uint32_t *gl, uint32_t i) {
-    return i < AZB_FRONTIER_CAP ? sh[i] : gl[i - AZB_FRONTIER_CAP];
+__device__ __forceinline__ uint32_t wl_get(const uint32_t *sh, const uint32_t *gl, uint32_t cap, uint32_t i) {
+    return i < cap ? sh[i] : gl[i - cap];
+}
+__device__ __forceinline__ void wl_put(uint32_t *sh, uint32_t *gl, uint32_t cap, uint32_t i, uint32_t v) {
+    if (i < cap)
+        sh[i] = v;
+    else
+        gl[i - cap] = v;
 }
 __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint32_t depth, float cstar, uint32_t ntt,
                              uint32_t e0, bool old) {
@@ -295,10 +301,11 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
     const uint32_t nwords = (L.cap_nodes + 31u) >> 5;
     for (uint32_t w = lane; w < nwords; w += 32) vis[w] = 0u;
     __syncwarp();
-    uint32_t ncur = depth + 1u;  // <= 62 < AZB_FRONTIER_CAP
+    const uint32_t fcap = L.frontier_cap;  // entries a list keeps in shared memory (AZB_FRONTIER_CAP; tests shrink it)
+    uint32_t ncur = depth + 1u;
     for (uint32_t i = lane; i < ncur; i += 32) {
         const uint32_t p = cx.wk[WK_PATH + i];
-        wa[i] = p;
+        wl_put(wa, ga, fcap, i, p);
         atomicOr(&vis[p >> 5], 1u << (p & 31));
     }
     __syncwarp();
@@ -312,7 +319,7 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
             uint32_t nin = 0, in_off = 0, w1 = 0, w2 = 0, w3 = 0;
             uint4 q2 = make_uint4(0, 0, 0, 0), q3 = make_uint4(0, 0, 0, 0);
             if (valid) {
-                uint4 *rec = cx.node + (size_t)wl_get(wa, ga, i) * 4;
+                uint4 *rec = cx.node + (size_t)wl_get(wa, ga, fcap, i) * 4;
                 uint4 q0 = rec[0];
                 const uint4 q1 = rec[1];
                 q2 = rec[2];
@@ -358,13 +365,8 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
                     fresh = (atomicOr(&vis[q >> 5], bit) & bit) == 0u;
                 }
                 const uint32_t bal = __ballot_sync(FULL, fresh);
-                if (fresh) {  // at most cap_nodes distinct nodes are ever enlisted: the global continuation cannot overflow
-                    const uint32_t at = nnext + __popc(bal & lt);
-                    if (at < AZB_FRONTIER_CAP)
-                        wb[at] = q;
-                    else
-                        gb[at - AZB_FRONTIER_CAP] = q;
-                }
+                // at most cap_nodes distinct nodes are ever enlisted: the global continuation cannot overflow
+                if (fresh) wl_put(wb, gb, fcap, nnext + __popc(bal & lt), q);
                 nnext += __popc(bal);
             }
         }
@@ -372,7 +374,7 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
             links = __reduce_add_sync(FULL, links);
             count(cx, CT_DCN, links);
         }
-        if (nnext > AZB_FRONTIER_CAP && lane == 0) atomicAdd(&L.g->casc_spills, 1u);
+        if (nnext > fcap && lane == 0) atomicAdd(&L.g->casc_spills, 1u);
         uint32_t *t = wa;
         wa = wb;
         wb = t;
@@ -418,9 +420,12 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
 __device__ __forceinline__ void step_done(const AzbLayout &L, WarpCtx &cx, uint32_t tree) {
     if (cx.lane == 0) {
         const uint32_t step = cx.wk[WK_STEP];
-        if (step < L.cap_steps)
-            L.cand[(size_t)(step + 1u) * L.B + tree] = make_uint2(cx.wk[WK_CAND_C], cx.wk[WK_CAND_NODE]);
-        else
+        if (step < L.cap_steps) {
+            // a release store: azb_step_poll reads this row from the host while the kernel runs, and whoever sees the
+            // entry must also see the node it names (its key and record were plain stores of this warp)
+            uint2 *dst = L.cand + (size_t)(step + 1u) * L.B + tree;
+            asm volatile("st.release.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(cx.wk[WK_CAND_C]), "r"(cx.wk[WK_CAND_NODE]) : "memory");
+        } else
             cx.err = 3;
         cx.wk[WK_STEP] = step + 1u;
         cx.wk[WK_CAND_C] = 0xffffffffu;

@@ -10,8 +10,12 @@ counted separately and excluded.  Workload at N GPUs: `--roots` (4096, BASELINE 
 N = 19, random-init MLP 304-512-1024-512-152, synthetic roots of the example's distribution (weak scaling; roots
 shard across ranks with no collective inside a step).
 
-torch is used here only for torch.distributed (barrier, max/sum over ranks; gloo on host scalars) and
-torch.cuda.synchronize — the product is libazb.so.
+torch is used here only for torch.distributed (NCCL process group: barrier, max/sum over ranks, the broadcast of the
+library's communicator id) and torch.cuda.synchronize — the product is libazb.so.
+
+Extra objects in the JSON line: `same_priors` (the GPU lock step on the CPU arm's hash priors:
+the two arms then build the same trees), `c4` (N = 64) at one GPU, `c3` (8192 roots per GPU) at eight, and at N > 1
+`epoch_boundary` (azb_comm_init + azb_update_model + azb_comm_argmin over NCCL, timed outside the step metric).
 The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference.
 """
 from __future__ import annotations
@@ -133,6 +137,28 @@ def cpu_reference_run(n, roots, steps, warmup, seed, threads, budget_s=None):
     return k["n_live"] / dt, dt, k
 
 
+def timed_config(capi, n, b, workers, steps, warmup, seed, rank, local_rank, prior_hash=False):
+    """K device-timed steps of another configuration on this rank's GPU (inputs resident, W warm-up steps first).
+    Returns (simulations, ms, cost evals, device bytes)."""
+    kw = dict(device=local_rank, first_root=rank * b, max_steps=warmup + steps + 8)
+    if prior_hash:
+        kw.update(prior_mode=capi.PRIOR_HASH, prior_seed=seed)
+    else:
+        kw.update(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, async_workers=workers)
+    parents, masks = capi.generate_roots(seed, rank * b, b, n)
+    with capi.Handle(capi.default_config(n, b, **kw)) as h:
+        if not prior_hash:
+            h.mlp_init(seed + 1)
+        h.set_roots(parents, masks)
+        h.init_trees()
+        h.step(warmup)
+        h.reset_counters()
+        h.set_counter_mode(False)
+        ms, _ = h.step_timed(steps)
+        k = h.counters()
+        return float(k["n_live"]), float(ms), float(k["n_ins"]), h.device_bytes()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -151,6 +177,7 @@ def main():
     ap.add_argument("--cpu-baseline-roots", type=int, default=4096)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0, help="time bound of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the same_priors / c3 / c4 objects")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -188,14 +215,21 @@ def main():
     import torch
     import torch.distributed as dist
 
+    backend = None
     if world > 1:
-        # roots shard across ranks with no collective inside a step; the only cross-rank traffic of this benchmark
-        # is the barrier and two scalar reductions, which go over gloo on host tensors (NCCL is reserved for the
-        # epoch-boundary collectives: azdopt_b200/shard.py)
+        # roots shard across ranks with no collective inside a step; the cross-rank traffic of this benchmark is the
+        # barrier, a few scalar reductions and the communicator id — over NCCL like everything else on this box
         import datetime
 
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=180))
+        try:
+            dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=180),
+                                    device_id=torch.device("cuda", local_rank))
+            backend = "nccl"
+        except Exception as e:  # pragma: no cover - the line says so
+            sys.stderr.write(f"bench: NCCL process group failed ({e}); using gloo for the scalars\n")
+            dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=180))
+            backend = "gloo"
     from azdopt_b200 import capi
 
     a = capi.action_dim(n)
@@ -230,10 +264,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    dev = torch.device("cuda", local_rank) if backend == "nccl" else torch.device("cpu")
+
     def allreduce(x, op):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=op)
         return float(t.item())
 
@@ -294,7 +330,7 @@ def main():
     achieved = bytes_per_launch / tree_launch_s / 1e9
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel (ncu --set full, profiles/)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)
         if tr.get("roots") == b and tr.get("vertices") == n and tr.get("kernel") == ("azb_async_kernel" if aw else "azb_tree_kernel"):
             traffic = tr["dram_bytes_per_launch"] * (prof_steps / tr.get("steps_per_launch", prof_steps) if aw else 1)
@@ -368,7 +404,65 @@ def main():
                                       "as soon as every tree has finished it, later steps still running) + azb_step(0)",
                               "d2h_bytes_per_step": 8 * b, "same_argmin": bool(am2["eval"] == am["eval"]),
                               "same_improvements": bool(n_pol == n_imp)}
+    # ---- epoch boundary over NCCL (N > 1): the library's own communicator (azb_comm_init), the sharded training step
+    #      (weight sum, 1 284 248-float gradient and loss all-reduced inside azb_update_model) and the all-gather of the
+    #      per-rank best (azb_comm_argmin).  Timed separately; none of it is inside the step metric.
+    epoch_boundary = None
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(uid, 0)
+        try:
+            h.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+            n_obs_tol = min(200, max(1, args.steps // 4))  # the example's 200 after a whole 800-step epoch
+            barrier()
+            u0 = time.perf_counter()
+            loss = h.update_model(n_obs_tol)
+            torch.cuda.synchronize()
+            u1 = time.perf_counter()
+            gbest = h.comm_argmin()
+            torch.cuda.synchronize()
+            u2 = time.perf_counter()
+            ar_ms = h.comm_allreduce_bench(20)
+            epoch_boundary = {
+                "collective": "NCCL (libazb's communicator: ncclAllReduce x3 in azb_update_model, ncclAllGather in azb_comm_argmin)",
+                "nccl_ranks": world, "update_model_ms": allreduce((u1 - u0) * 1e3, dist.ReduceOp.MAX),
+                "comm_argmin_ms": allreduce((u2 - u1) * 1e3, dist.ReduceOp.MAX),
+                "gradient_allreduce_ms": allreduce(ar_ms, dist.ReduceOp.MAX), "gradient_floats": h.mlp_num_params(),
+                "loss": float(loss), "global_best_eval": float(gbest[4]), "global_best_owner_rank": int(gbest[5]),
+                "n_obs_tol": n_obs_tol}
+        except capi.AzbError as e:
+            epoch_boundary = {"error": str(e), "nccl_ranks": world}
     h.close()
+
+    # ---- the other configurations BASELINE.json names, as objects beside the headline (same timing rules: W warm-up
+    #      steps, inputs resident, events on the library's stream, max over ranks)
+    extra = {}
+    xsteps = min(args.steps, 400)
+    if world == 1 and not args.no_extra:
+        # the GPU on the CPU arm's own priors (counter hash; lock step, no model): identical trees in both arms
+        sp_steps = min(args.steps, 200)
+        sims, ms, evals_sp, _ = timed_config(capi, n, b, 0, sp_steps, args.warmup, args.seed, rank, local_rank, prior_hash=True)
+        extra["same_priors"] = {"value": sims / (ms * 1e-3), "unit": UNIT, "steps": sp_steps, "ms_per_step": ms / sp_steps,
+                                "what": f"N={n}, {b} roots, hash priors (the reference arm's), lock-step launches, no model forward"}
+        # C4: 64-vertex trees (cost path dominated): 4096 roots, 32 model SMs
+        c4_roots, c4_steps = 4096, min(args.steps, 64)
+        try:
+            sims, ms, ev4, bytes4 = timed_config(capi, 64, c4_roots, 32, c4_steps, max(3, min(args.warmup, 8)), args.seed, rank, local_rank)
+            extra["c4"] = {"value": sims / (ms * 1e-3), "unit": UNIT, "vertices": 64, "roots": c4_roots, "steps": c4_steps,
+                           "ms_per_step": ms / c4_steps, "cost_evals_per_sec": ev4 / (ms * 1e-3), "device_bytes": bytes4,
+                           "what": "BASELINE configs[3]: N=64 (A=1952, MLP 3904-512-1024-512-1952), asynchronous kernel, 32 model SMs"}
+        except capi.AzbError as e:
+            extra["c4"] = {"error": str(e)}
+    if world == 8 and not args.no_extra:
+        # C3: 65 536 roots over the 8 GPUs = 8192 per GPU, 48 model SMs in pairs
+        sims, ms, ev3, _ = timed_config(capi, n, 8192, 48, xsteps, args.warmup, args.seed, rank, local_rank)
+        ms3 = allreduce(ms, dist.ReduceOp.MAX)
+        sims3 = allreduce(sims, dist.ReduceOp.SUM)
+        extra["c3"] = {"value": sims3 / (ms3 * 1e-3), "unit": UNIT, "roots_total": 8192 * world, "roots_per_gpu": 8192,
+                       "steps": xsteps, "ms_per_step": ms3 / xsteps,
+                       "what": "BASELINE configs[2]: 65 536 roots sharded over 8 GPUs, no collective inside a step"}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu = None
@@ -379,6 +473,9 @@ def main():
                "sample": f"{cb} roots x {kc['steps_run']} steps ({dt:.1f} s); restated reference (C++ oracle), tree+state+cost on "
                          "all host threads, hash priors, MLP forward excluded"}
 
+    if cpu and "same_priors" in extra:
+        extra["same_priors"]["cpu_value"] = cpu["value"]
+        extra["same_priors"]["ratio_vs_cpu"] = extra["same_priors"]["value"] / cpu["value"]
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -388,8 +485,8 @@ def main():
             "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",
                        "vertices": n, "roots_per_gpu": b, "roots_total": b * world, "mlp": mlp_note, "max_episodes_per_launch": args.max_episodes, "tree_groups": 1 if args.max_episodes else args.groups,
-                       "search": (f"asynchronous: persistent tree kernel ({148 - aw} SMs) beside a persistent tensor-core model "
-                                  f"kernel ({aw} SMs), one launch of each per azb_step call" if aw
+                       "search": (f"asynchronous: ONE persistent cooperative kernel per azb_step call — {148 - aw} SMs walk trees, "
+                                  f"{aw} SMs run the tensor-core model (setmaxnreg role split)" if aw
                                   else "lock step: one search launch + model forward per step"),
                        "l2": f"per-GPU arenas {dev_bytes / 1e6:.0f} MB > 126 MB L2; no flush between steps",
                        "simulations_in_timed_region": sims, "noop_root_steps": noops,
@@ -397,6 +494,9 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "argmin_eval": float(am["eval"]),
         }
+        line.update(extra)
+        if epoch_boundary is not None:
+            line["epoch_boundary"] = epoch_boundary
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -175,6 +175,10 @@ int azb_add_actions_host(azb_handle *h, const float *h_theta /*[B*A]*/, int *imp
 /* ArgminData{state, cost, eval} (log.rs:1-11; optimizer/mod.rs:361-363) */
 int azb_get_argmin(azb_handle *h, uint8_t *parents /*[N]*/, uint32_t *permitted /*[W]*/, double *lambda1,
                    uint32_t *mu, float *eval);
+/* The state of one node: its tree's root with the node's action set replayed in ascending order — the rebuild
+ * par_update_argmmim_data does for the winning node (optimizer/mod.rs:224-239).  Does not wait for enqueued steps, so
+ * an azb_step_poll record (tree, node) can be turned into ArgminData while later steps still run. */
+int azb_get_node_state(azb_handle *h, uint32_t tree, uint32_t node, uint8_t *parents /*[N]*/, uint32_t *permitted /*[W]*/);
 /* persistent walker state: states, paths, last_positions (optimizer/mod.rs:10-14) */
 int azb_get_walkers(azb_handle *h, uint8_t *parents, uint32_t *permitted, uint32_t *path, uint32_t *pos,
                     uint32_t *path_len);
@@ -247,6 +251,10 @@ int azb_comm_destroy(azb_handle *h);
  * azb_get_argmin plus the owning rank; the lowest rank wins ties */
 int azb_comm_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double *lambda1, uint32_t *mu, float *eval,
                     int *owner_rank);
+
+/* measurement helper: `reps` NCCL all-reduces of the gradient buffer (azb_mlp_num_params floats), timed with events on
+ * the library's stream; *ms = milliseconds per all-reduce */
+int azb_comm_allreduce_bench(azb_handle *h, uint32_t reps, float *ms);
 
 /* ---- measurement helpers ---- */
 int azb_kernel_launches(const azb_handle *h, uint64_t *n);   /* kernels launched by this handle so far */

@@ -46,6 +46,7 @@ def _worker(rank, world, id_path, out_dir):
         h.comm_init(uid, rank, world)
         loss = h.update_model(TOL)
         p, m, lam, mu, ev, owner = h.comm_argmin()
+        assert h.comm_allreduce_bench(3) > 0.0  # the gradient-sized all-reduce alone, timed with events
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), loss=loss, params=h.mlp_get_params(), parents=p, permitted=m,
                  lam=lam, mu=mu, ev=ev, owner=owner, local_ev=h.argmin()["eval"])
 

@@ -179,8 +179,14 @@ def lattice_roots(orc, n, b):
     return parents, masks
 
 
-def test_dense_transposition_dag_cascades_beyond_the_on_chip_work_list(capi, orc):
-    n, b, steps, seed = 14, 3, 2300, 31  # 11 movable children: 2048 lattice nodes, C(10,5) = 252 ancestors in one wave
+@pytest.mark.parametrize("frontier_cap", [None, 4])
+def test_dense_transposition_dag_and_the_cascade_continuation_lists(capi, orc, monkeypatch, frontier_cap):
+    """The cascade's work lists keep AZB_FRONTIER_CAP (128) entries on chip and continue in HBM, so no DAG shape can
+    overflow them.  With the on-chip part shrunk to 4 entries (AZB_TEST_FRONTIER_CAP, read by azb_create) almost every
+    cascade of the lattice runs through the continuation; both settings must reproduce the oracle bit for bit."""
+    n, b, steps, seed = 14, 3, 2300, 31  # 11 movable children: all 2048 lattice nodes get inserted and exhausted
+    if frontier_cap:
+        monkeypatch.setenv("AZB_TEST_FRONTIER_CAP", str(frontier_cap))
     a_dim = orc.action_dim(n)
     parents, masks = lattice_roots(orc, n, b)
     tol, tol_default = (4, 2, 2), 2
@@ -193,13 +199,56 @@ def test_dense_transposition_dag_cascades_beyond_the_on_chip_work_list(capi, orc
         h.set_roots(parents, masks)
         h.init_trees()
         h.step(steps)
-        assert h.cascade_spills() > 0, "the lattice did not push a cascade wave past the shared-memory work list"
+        if frontier_cap:
+            assert h.cascade_spills() > 1000, "the shrunken work list did not push cascades into the continuation"
         for i in range(b):
             d_o, d_g = o.dump_tree(i), h.dump_tree(i)
             for key in ("nodes", "keys", "preds", "arcs"):
                 assert np.array_equal(d_o[key], d_g[key]), (i, key)
         assert h.counters() == o.counters()
         assert int(h.tree_sizes(0)[0]) == 2 ** (n - 3)  # the whole lattice was inserted and exhausted
+
+
+def test_ordinary_trees_through_the_cascade_continuation(capi, orc, monkeypatch):
+    """The example's root distribution with a 2-entry on-chip list: the walker's own path already spills."""
+    monkeypatch.setenv("AZB_TEST_FRONTIER_CAP", "2")
+    n, b, steps, seed = 19, 24, 150, 8
+    parents, masks = orc.generate_roots(seed, 0, b, n)
+    o = orc.Optimizer(n, b, lambda_method=orc.LAMBDA_MULTISECTION, n_threads=4)
+    o.set_roots(parents, masks)
+    o.init_trees(orc.hash_priors(seed, 0, b, orc.action_dim(n), 0))
+    o.steps_hash(seed, 0, 1, steps)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_HASH, prior_seed=seed, max_steps=steps) as h:
+        h.set_roots(parents, masks)
+        h.init_trees()
+        h.step(steps)
+        assert h.cascade_spills() > 0
+        assert [digest(o.dump_tree(i)) for i in range(b)] == [digest(h.dump_tree(i)) for i in range(b)]
+        assert h.counters() == o.counters()
+
+
+def test_node_state_replays_the_action_set_on_the_root(capi, orc):
+    """azb_get_node_state = the root with the node's key replayed (optimizer/mod.rs:224-239); checked against the
+    oracle's act() for nodes of several trees, and against azb_get_argmin for the winning node."""
+    n, b, steps, seed = 19, 16, 60, 5
+    parents, masks = orc.generate_roots(seed, 0, b, n)
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_HASH, prior_seed=seed, max_steps=steps) as h:
+        h.set_roots(parents, masks)
+        h.init_trees()
+        n_imp, imps = h.step(steps, cap=256)
+        for t in (0, 7, 15):
+            d = h.dump_tree(t)
+            for node in range(0, len(d["nodes"]), 9):
+                p, m = parents[t].copy(), masks[t].copy()
+                for a in orc.actions_from_mask(d["keys"][node]):
+                    p, m = orc.act(p, m, a)
+                gp, gm = h.node_state(t, node)
+                assert np.array_equal(gp, p) and np.array_equal(gm, m), (t, node)
+        assert n_imp > 0
+        _, tree, node, ev = imps[-1]
+        am = h.argmin()
+        gp, gm = h.node_state(tree, node)
+        assert np.array_equal(gp, am["parents"]) and np.array_equal(gm, am["permitted"]) and am["eval"] == np.float32(ev)
 
 
 def test_update_model_without_observations_is_refused(capi):
