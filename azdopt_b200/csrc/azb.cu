@@ -744,6 +744,7 @@ static int async_create(azb_handle *h) {
     // tree warps per CTA: 32, fewer when a large N needs more shared memory per warp (at most ~160 KB per SM, the rest is L1)
     const size_t lut_bytes = (h->A + 15) & ~15u, per_warp = (size_t)h->smem_words_per_warp * 4;
     uint32_t tree_warps = (uint32_t)std::max<size_t>(4, std::min<size_t>(AS_WARPS, (160 * 1024 - lut_bytes) / per_warp));
+    if (azb_stack_depth(h->N) == 5) tree_warps = std::min<uint32_t>(tree_warps, AS_WIDE_TREE_WARPS);  // see azb_async_kernel
     if (const char *e = getenv("AZB_ASYNC_TREE_WARPS")) tree_warps = std::min<uint32_t>(tree_warps, std::max(1, atoi(e)));
     const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
     size_t bias_bytes = 0;

@@ -16,8 +16,9 @@
 //     registers with setmaxnreg: warpgroup 0 (TMA producer warp + tcgen05.mma issuer warp) shrinks to 56, warpgroups
 //     1-2 (eight epilogue warps) grow to 168 — four 16-column TMEM slices in flight per warp without spilling —, and
 //     warpgroups 3-7 shrink to 24 and leave.  A worker takes the next full tile and runs the four Linear layers on
-//     the tensor cores in A-stationary passes (per 64-deep k-block ONE activation tile and the weight tiles of up to
-//     four 128-column blocks feed four TMEM accumulators; adjacent blocks as one N = 256 MMA), hidden activations
+//     the tensor cores in passes of two 128-column blocks (per 64-deep k-block one activation tile and two weight
+//     tiles, issued as ONE N = 256 MMA per k-step; the 512 TMEM columns hold two passes, so the epilogue of one pass
+//     overlaps the MMAs of the next), hidden activations
 //     round-trip through an L2-resident scratch, the Sigmoid head scatters f32 rows to the owning trees' prior rows
 //     and the last writer raises their flags.  A tile that stays partial for `flush_ns` is topped up with dummy rows
 //     and run anyway (tail of the run, tiny batches).
@@ -46,8 +47,12 @@
 #define AS_REGS_FRONT 56
 #define AS_REGS_EPI 168
 #define AS_REGS_IDLE 24
-#define AS_STAGES 2
-#define AS_ACC 4          // 128-column blocks per pass: one A k-block is reused by up to four TMEM accumulators
+#define AS_WIDE_TREE_WARPS 16   // tree warps per CTA for N >= 47 (DEPTH == 5)
+#define AS_REGS_WIDE_TREE 104   // their register budget
+#define AS_STAGES 3
+#define AS_ACC 2          // 128-column blocks per pass (one N = 256 MMA per k-step).  The 512 TMEM columns hold TWO passes:
+                          // the epilogue drains one while the MMAs of the next run (4-block passes filled TMEM and
+                          // serialised the two: MMA 24 us + epilogue 25 us per tile)
 #define AS_TILE 128
 #define AS_NONE 0xffffffffu
 // one acquire load of a flag after the relaxed polls have seen it (PTX memory model: what the flag guards is read or
@@ -190,7 +195,7 @@ __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.pro
 // warps 4-11 epilogue (warpgroups 1-2, 168 registers).  Each role is its own function with its own copy of the loop
 // over tiles, so that no code is shared between register budgets; they meet at named barrier 1 (AS_MLP_THREADS).
 struct AsWorkerShared {
-    uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full, acc_empty, layer_bar;
+    uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full[2], acc_empty[2], layer_bar;
     uint32_t tmem_slot, tile, epi_last;
     uint32_t bias_off[4];  // first entry of layer l's biases in the shared-memory copy
     uint32_t rowtree[AS_TILE];
@@ -208,7 +213,7 @@ __device__ __forceinline__ uint32_t as_blocks_of_member(uint32_t npad, const AsW
     return n_tiles > id.mem ? (n_tiles - id.mem + id.G - 1u) / id.G : 0u;
 }
 #define AS_TILE_BYTES (AS_TILE * TC_BK * 2u)              // one 128 x 64 bf16 operand tile, 16 KB
-#define AS_STAGE_BYTES ((1u + AS_ACC) * AS_TILE_BYTES)    // [A | B0 | B1 | B2 | B3]
+#define AS_STAGE_BYTES ((1u + AS_ACC) * AS_TILE_BYTES)    // [A | B0 | B1]
 
 // ---- warp 0: takes tiles for the group, feeds the operand ring by TMA
 __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M, const AsWorkerId id,
@@ -220,8 +225,10 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
             tc_mbar_init(&S.full_bar[s], 1);
             tc_mbar_init(&S.empty_bar[s], 1);
         }
-        tc_mbar_init(&S.acc_full, 1);
-        tc_mbar_init(&S.acc_empty, AS_EPI_WARPS);
+        for (int a = 0; a < 2; ++a) {
+            tc_mbar_init(&S.acc_full[a], 1);
+            tc_mbar_init(&S.acc_empty[a], AS_EPI_WARPS);
+        }
         tc_mbar_init(&S.layer_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
@@ -403,8 +410,10 @@ __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const 
                 for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
                     const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                     long long tw = AS_CLK();
-                    as_mbar_spin(&S.acc_empty, (ntc & 1u) ^ 1u);  // the epilogue has drained the previous pass
+                    const uint32_t slot = ntc & 1u, acc_ph = (ntc >> 1) & 1u;  // TMEM half of this pass, phase of its barriers
+                    as_mbar_spin(&S.acc_empty[slot], acc_ph ^ 1u);  // the epilogue has drained the pass before last
                     d_w1 += AS_CLK() - tw;
+                    const uint32_t tmem_acc = tmem_base + slot * (AS_ACC * 128u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
@@ -425,7 +434,7 @@ __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const 
 #pragma unroll
                                     for (uint32_t k = 0; k < TC_BK / 16; ++k)
                                         if (!AS_DBG(8u))
-                                            tc_umma_f16(tmem_base + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
+                                            tc_umma_f16(tmem_acc + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
                                                         idesc, (kb | k) != 0u ? 1u : 0u);
                                 }
                             } else {
@@ -437,12 +446,12 @@ __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const 
 #pragma unroll
                                     for (uint32_t k = 0; k < TC_BK / 16; ++k)
                                         if (!AS_DBG(8u))  // timing experiment: loads only
-                                            tc_umma_f16(tmem_base + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
+                                            tc_umma_f16(tmem_acc + j * 128u, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u),
                                                         idesc, (kb | k) != 0u ? 1u : 0u);
                                 }
                             }
                             tc_umma_commit(&S.empty_bar[s]);
-                            if (kb + 1 == k_blocks) tc_umma_commit(&S.acc_full);
+                            if (kb + 1 == k_blocks) tc_umma_commit(&S.acc_full[slot]);
                         }
                         __syncwarp();
                     }
@@ -513,7 +522,9 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
             for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
                 const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                 const long long tw = AS_CLK();
-                as_mbar_spin(&S.acc_full, ntc & 1u);
+                const uint32_t slot = ntc & 1u, acc_ph = (ntc >> 1) & 1u;
+                as_mbar_spin(&S.acc_full[slot], acc_ph);
+                const uint32_t tmem_acc = tmem_base + slot * (AS_ACC * 128u);
                 const long long tb = AS_CLK();
                 d_w0 += tb - tw;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -529,7 +540,7 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
                             const long long tl0 = AS_CLK();
 #pragma unroll
                             for (uint32_t sl = 0; sl < AS_EPI_SLICES; ++sl)
-                                as_tmem_ld16_issue(tmem_base + ((q4 * 32u) << 16) + ja * 128u + col0 + sl * 16u, r[sl]);
+                                as_tmem_ld16_issue(tmem_acc + ((q4 * 32u) << 16) + ja * 128u + col0 + sl * 16u, r[sl]);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                             d_acq += AS_CLK() - tl0;
                             const uint32_t srow = tc_smem_u32(stg) + lane * (AS_EPI_COLS * 2u);
@@ -577,7 +588,7 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
                         for (uint32_t c0 = col0; c0 < min(bn, col0 + (uint32_t)AS_EPI_COLS); c0 += 16) {
                             uint32_t r[16];
                             const long long tl0 = AS_CLK();
-                            as_tmem_ld16(tmem_base + ((q4 * 32u) << 16) + ja * 128u + c0, r);
+                            as_tmem_ld16(tmem_acc + ((q4 * 32u) << 16) + ja * 128u + c0, r);
                             d_acq += AS_CLK() - tl0;
                             const uint32_t nb = nt * 128u + c0;
                             float b[16];
@@ -615,7 +626,7 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) as_mbar_arrive(&S.acc_empty);
+                if (lane == 0) as_mbar_arrive(&S.acc_empty[slot]);
                 d_busy += AS_CLK() - tb;
             }
             // ---- layer boundary: this member's share of the layer is stored; tell the group
@@ -689,9 +700,11 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     const uint32_t FULL = 0xffffffffu;
     AzbAsyncState *st = P.st;
     uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)P.tree_warps * P.smem_words_per_warp);
-    for (uint32_t a = threadIdx.x; 4u * a < L.A; a += blockDim.x)
+    // (for N >= 47 only the first AS_WIDE_TREE_WARPS warps of the CTA are here: the barrier counts the threads present)
+    const uint32_t n_thr = DEPTH == 5 ? AS_WIDE_TREE_WARPS * 32u : (uint32_t)AS_THREADS;
+    for (uint32_t a = threadIdx.x; 4u * a < L.A; a += n_thr)
         reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
-    __syncthreads();
+    as_named_bar(3, n_thr);
     if ((uint32_t)warp >= P.tree_warps) return;
     uint32_t *base = smem + (size_t)warp * P.smem_words_per_warp;
     WarpCtx cx;
@@ -819,6 +832,10 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (v) atomicAdd(&L.g->prof[lane - 16], (unsigned long long)v);
     }
 #endif
+#ifdef AZB_PROFILE
+    if (my_tree < L.B && my_tree < 65536u)  // per tree: K-cycles walking, K-cycles waiting for priors, advances, rows
+        g_tree_prof[my_tree] = make_uint4((uint32_t)(my_run >> 10), (uint32_t)(my_wait >> 10), my_steps, my_sub);
+#endif
     if (P.dbg && my_tree < L.B) {
         atomicAdd(P.dbg + 16, (unsigned long long)my_run);
         atomicMax(P.dbg + 17, (unsigned long long)my_run);
@@ -861,6 +878,16 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
         uint8_t *smem = (uint8_t *)(((uintptr_t)as_smem + 1023) & ~(uintptr_t)1023);
         async_model_cta(L, P, M, s_idx, smem, s_worker);
     } else {
+        if constexpr (DEPTH == 5) {
+            // N >= 47: a tree warp needs 6-10 KB of shared memory, so at most 16 of them fit (the host caps tree_warps
+            // at AS_WIDE_TREE_WARPS).  Warpgroups 4-7 hand their registers over and leave; the walkers grow to 104
+            // registers (128 x (4 x 104 + 4 x 24) = 65 536), which is what the Sturm-section stack program wants.
+            if ((threadIdx.x >> 7) >= AS_WIDE_TREE_WARPS / 4) {
+                asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AS_REGS_IDLE));
+                return;
+            }
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AS_REGS_WIDE_TREE));
+        }
         async_tree_worker<DEPTH, COUNT>(L, P, s_idx, gridDim.x - P.n_workers, reinterpret_cast<uint32_t *>(as_smem));
     }
 }

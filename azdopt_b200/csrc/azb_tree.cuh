@@ -313,6 +313,7 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
     while (ncur > 0) {
         uint32_t nnext = 0, links = 0;
         count(cx, CT_CN, ncur);
+        if (ncur > fcap && lane == 0) atomicAdd(&L.g->casc_spills, 1u);  // this wave continues in the global list
         for (uint32_t base = 0; base < ncur; base += 32) {
             const uint32_t i = base + lane;
             const bool valid = i < ncur;
@@ -374,7 +375,6 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
             links = __reduce_add_sync(FULL, links);
             count(cx, CT_DCN, links);
         }
-        if (nnext > fcap && lane == 0) atomicAdd(&L.g->casc_spills, 1u);
         uint32_t *t = wa;
         wa = wb;
         wb = t;

@@ -443,23 +443,23 @@ def main():
     if world == 1 and not args.no_extra:
         # the GPU on the CPU arm's own priors (counter hash; lock step, no model): identical trees in both arms
         sp_steps = min(args.steps, 200)
-        sims, ms, evals_sp, _ = timed_config(capi, n, b, 0, sp_steps, args.warmup, args.seed, rank, local_rank, prior_hash=True)
-        extra["same_priors"] = {"value": sims / (ms * 1e-3), "unit": UNIT, "steps": sp_steps, "ms_per_step": ms / sp_steps,
+        sp_sims, sp_ms, _, _ = timed_config(capi, n, b, 0, sp_steps, args.warmup, args.seed, rank, local_rank, prior_hash=True)
+        extra["same_priors"] = {"value": sp_sims / (sp_ms * 1e-3), "unit": UNIT, "steps": sp_steps, "ms_per_step": sp_ms / sp_steps,
                                 "what": f"N={n}, {b} roots, hash priors (the reference arm's), lock-step launches, no model forward"}
         # C4: 64-vertex trees (cost path dominated): 4096 roots, 32 model SMs
         c4_roots, c4_steps = 4096, min(args.steps, 64)
         try:
-            sims, ms, ev4, bytes4 = timed_config(capi, 64, c4_roots, 32, c4_steps, max(3, min(args.warmup, 8)), args.seed, rank, local_rank)
-            extra["c4"] = {"value": sims / (ms * 1e-3), "unit": UNIT, "vertices": 64, "roots": c4_roots, "steps": c4_steps,
-                           "ms_per_step": ms / c4_steps, "cost_evals_per_sec": ev4 / (ms * 1e-3), "device_bytes": bytes4,
+            c4_sims, c4_ms, ev4, bytes4 = timed_config(capi, 64, c4_roots, 32, c4_steps, max(3, min(args.warmup, 8)), args.seed, rank, local_rank)
+            extra["c4"] = {"value": c4_sims / (c4_ms * 1e-3), "unit": UNIT, "vertices": 64, "roots": c4_roots, "steps": c4_steps,
+                           "ms_per_step": c4_ms / c4_steps, "cost_evals_per_sec": ev4 / (c4_ms * 1e-3), "device_bytes": bytes4,
                            "what": "BASELINE configs[3]: N=64 (A=1952, MLP 3904-512-1024-512-1952), asynchronous kernel, 32 model SMs"}
         except capi.AzbError as e:
             extra["c4"] = {"error": str(e)}
     if world == 8 and not args.no_extra:
         # C3: 65 536 roots over the 8 GPUs = 8192 per GPU, 48 model SMs in pairs
-        sims, ms, ev3, _ = timed_config(capi, n, 8192, 48, xsteps, args.warmup, args.seed, rank, local_rank)
-        ms3 = allreduce(ms, dist.ReduceOp.MAX)
-        sims3 = allreduce(sims, dist.ReduceOp.SUM)
+        c3_sims, c3_ms, ev3, _ = timed_config(capi, n, 8192, 48, xsteps, args.warmup, args.seed, rank, local_rank)
+        ms3 = allreduce(c3_ms, dist.ReduceOp.MAX)
+        sims3 = allreduce(c3_sims, dist.ReduceOp.SUM)
         extra["c3"] = {"value": sims3 / (ms3 * 1e-3), "unit": UNIT, "roots_total": 8192 * world, "roots_per_gpu": 8192,
                        "steps": xsteps, "ms_per_step": ms3 / xsteps,
                        "what": "BASELINE configs[2]: 65 536 roots sharded over 8 GPUs, no collective inside a step"}
