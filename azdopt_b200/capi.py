@@ -15,7 +15,7 @@ from .build import lib_path
 NONE = 0xFFFFFFFF
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NAN, ERR_LAMBDA, ERR_UNREACHABLE, ERR_STATE = range(8)
 PRIOR_MLP, PRIOR_HASH, PRIOR_INJECTED = 0, 1, 2
-MLP_FP32, MLP_TC = 0, 1
+MLP_FP32, MLP_TC, MLP_TC3 = 0, 1, 2
 MAX_TOL = 8
 
 COUNTER_FIELDS = [

@@ -229,7 +229,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     azb_config cfg = *cfg_in;
     if (cfg.n_vertices < 5 || cfg.n_vertices > AZB_MAX_VERTICES || cfg.n_roots == 0) return AZB_ERR_INVALID;
     if (cfg.n_as_tol_len > AZB_MAX_TOL) return AZB_ERR_INVALID;
-    if (cfg.prior_mode > AZB_PRIOR_INJECTED || cfg.mlp_mode > AZB_MLP_TC) return AZB_ERR_INVALID;
+    if (cfg.prior_mode > AZB_PRIOR_INJECTED || cfg.mlp_mode > AZB_MLP_TC3) return AZB_ERR_INVALID;
     azb_handle *h = new azb_handle();
     memset((void *)h, 0, sizeof(*h));
     h->err[0] = 0;
@@ -365,12 +365,12 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
 
     CK(dmalloc(h, &h->params, h->n_params));
     for (int i = 0; i < 3; ++i) CK(dmalloc(h, &h->act[i], (size_t)B * h->dims[i + 1]));
-    if (cfg.mlp_mode == AZB_MLP_TC) {
-        const char *why = azb_mlp_tc_create(h->tc, B, h->dims, &h->dev_bytes);
+    if (cfg.mlp_mode == AZB_MLP_TC || cfg.mlp_mode == AZB_MLP_TC3) {
+        const char *why = azb_mlp_tc_create(h->tc, B, h->dims, &h->dev_bytes, cfg.mlp_mode == AZB_MLP_TC3);
         if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
         if (cfg.prior_mode == AZB_PRIOR_MLP) {  // write_vec feeds the first GEMM directly
             L.sv16 = reinterpret_cast<uint16_t *>(h->tc.act[0]);
-            L.sv16_ld = h->tc.kpad[0];
+            L.sv16_ld = (h->tc.split ? 2u : 1u) * h->tc.kpad[0];  // bf16x3: [hi | lo]; write_vec fills hi, lo stays zero
         }
     }
 
@@ -501,7 +501,7 @@ int azb_mlp_set_params(azb_handle *h, const float *params) {
     if (!h || !params) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaMemcpyAsync(h->params, params, h->n_params * 4, cudaMemcpyHostToDevice, h->stream));
-    if (h->cfg.mlp_mode == AZB_MLP_TC) {
+    if (h->tc.ready) {
         const char *why = azb_mlp_tc_load(h->tc, h->params, h->stream, &h->launches);
         if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
     }
@@ -540,7 +540,7 @@ int azb_mlp_get_params(azb_handle *h, float *params) {
 // ActionModel::forward (nabla/model/dfdx.rs:81-83) on device rows [row0, row0 + rows)
 static int mlp_forward(azb_handle *h, const float *x, uint32_t ldx, float *y, uint32_t ldy, uint32_t row0, uint32_t rows,
                        cudaStream_t stream) {
-    if (h->cfg.mlp_mode == AZB_MLP_TC) {
+    if (h->tc.ready) {
         const bool packed = h->L.sv16 != nullptr && x == h->L.sv;  // tree_pack already wrote the bf16 rows
         const char *why = azb_mlp_tc_forward(h->tc, packed ? nullptr : x, ldx, y, ldy, row0, rows, stream, &h->launches);
         if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
@@ -731,8 +731,8 @@ static int async_prepare_kernel(azb_handle *h, int *blocks_per_sm) {
 
 static int async_create(azb_handle *h) {
     if (h->async_ready) return AZB_OK;
-    if (h->cfg.prior_mode != AZB_PRIOR_MLP || h->cfg.mlp_mode != AZB_MLP_TC || !h->tc.ready)
-        return fail(h, AZB_ERR_INVALID, "async_workers needs AZB_PRIOR_MLP with AZB_MLP_TC");
+    if (h->cfg.prior_mode != AZB_PRIOR_MLP || !h->tc.ready)
+        return fail(h, AZB_ERR_INVALID, "async_workers needs AZB_PRIOR_MLP with AZB_MLP_TC or AZB_MLP_TC3");
     if (h->cfg.max_episodes || h->n_groups > 1) return fail(h, AZB_ERR_INVALID, "async_workers excludes max_episodes / n_groups");
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->cfg.device));
@@ -775,7 +775,8 @@ static int async_create(azb_handle *h) {
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
     P.smem_words_per_warp = h->smem_words_per_warp;
-    P.ring_ld = h->tc.kpad[0];
+    P.wide = h->tc.split ? 2u : 1u;
+    P.ring_ld = P.wide * h->tc.kpad[0];
     h->async_timeout_base_ns = 2ull * 1000000000ull;
     if (const char *e = getenv("AZB_ASYNC_TIMEOUT_MS")) h->async_timeout_base_ns = strtoull(e, nullptr, 10) * 1000000ull;
     P.timeout_ns = h->async_timeout_base_ns;
@@ -804,16 +805,16 @@ static int async_create(azb_handle *h) {
     CK(alloc((void **)&P.h_flag, (size_t)B * 4));
     CK(alloc((void **)&P.dbg, 64 * 8));
     CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
-    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * h->tc.kpad[l + 1] * 2));
+    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * P.wide * h->tc.kpad[l + 1] * 2));
     azb_encode_fn enc = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres) != cudaSuccess || !enc)
         return fail(h, AZB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
     const char *why = azb_tc_make_map(enc, &h->asM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
     for (int l = 0; l < 3 && !why; ++l)
-        why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, h->tc.kpad[l + 1], AS_TILE);
+        why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, P.wide * h->tc.kpad[l + 1], AS_TILE);
     for (int l = 0; l < 4 && !why; ++l)
-        why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, h->tc.kpad[l], 128);
+        why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, P.wide * h->tc.kpad[l], 128);
     if (why) return fail(h, AZB_ERR_CUDA, "async tensor maps: %s", why);
     CK(cudaStreamSynchronize(h->stream));
     h->async_ready = true;
@@ -918,7 +919,7 @@ static int enqueue_steps(azb_handle *h, uint32_t n_steps, uint32_t flags) {
                     cudaGraphDestroy(graph);
                     h->ggraph_key[g] = key;
                 }
-                const uint64_t per_step = 1 + (mlp ? (h->cfg.mlp_mode == AZB_MLP_TC ? 4 : 4) : 0);
+                const uint64_t per_step = 1 + (mlp ? 4 : 0);
                 while (left >= AZB_GRAPH_STEPS) {
                     CK(cudaGraphLaunch(h->ggraph[g], st));
                     h->launches += per_step * AZB_GRAPH_STEPS;
@@ -1778,7 +1779,7 @@ static int train_adam(azb_handle *h) {
     azb_adam_kernel<<<nblk, 256, 0, h->stream>>>(h->params, h->grad, h->adam_m, h->adam_v, h->n_params, cfg);
     h->launches += 1;
     CK(cudaGetLastError());
-    if (h->cfg.mlp_mode == AZB_MLP_TC) {
+    if (h->tc.ready) {
         const char *why = azb_mlp_tc_load(h->tc, h->params, h->stream, &h->launches);
         if (why) return fail(h, AZB_ERR_CUDA, "tensor-core MLP: %s", why);
     }

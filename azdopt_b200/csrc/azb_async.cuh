@@ -99,6 +99,7 @@ struct AzbAsyncParams {
     __nv_bfloat16 *act[3];
     const float *bias[4];
     uint32_t kpad[4], npad[4];
+    uint32_t wide;           // 1: bf16 operands; 2: bf16x3 (AZB_MLP_TC3) — rows hold [hi(kpad) | lo(kpad)], three k-segments
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
     unsigned long long timeout_ns, flush_ns;
@@ -311,8 +312,11 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
             d_tiles += 1;
             const uint64_t w_policy = as_policy_evict_last();
             as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
+            // bf16x3: a dot product runs over three k-segments, (A half, W half) = (hi,hi), (hi,lo), (lo,hi); the lo halves
+            // start k_blocks blocks into a row
+            const uint32_t nseg = P.wide == 2u ? 3u : 1u;
             for (uint32_t l = 0; l < 4; ++l) {
-                const uint32_t k_blocks = P.kpad[l] / TC_BK;
+                const uint32_t k_blocks = P.kpad[l] / TC_BK, kb_all = nseg * k_blocks;
                 // this member's blocks nt = mem, mem + G, ... in passes of up to AS_ACC: per k-block ONE A tile and the
                 // pass's B tiles, so a tile's activations are read once per pass instead of once per block
                 const uint32_t mine = as_blocks_of_member(P.npad[l], id);
@@ -348,11 +352,14 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
                 const int arow = (int)(l == 0 ? ring_row0 : grp * AS_TILE);
                 for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC) {
                     const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
-                    for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
+                    for (uint32_t kb = 0; kb < kb_all; ++kb, ++kbc) {
                         const uint32_t s = kbc % AS_STAGES, ph = (kbc / AS_STAGES) & 1u;
+                        const uint32_t seg = kb / k_blocks, kj = kb - seg * k_blocks;
+                        const int a_col = (int)(((seg == 2u ? k_blocks : 0u) + kj) * TC_BK);
+                        const int w_col = (int)(((seg == 1u ? k_blocks : 0u) + kj) * TC_BK);
                         uint8_t *a_dst = smem + (size_t)s * AS_STAGE_BYTES;
                         if (p0 == 0u && kb < pre) {  // stage claimed and its B tiles requested above: only the A tile is left
-                            tc_tma_load_2d(a_dst, ma, &S.full_bar[s], (int)(kb * TC_BK), arow);
+                            tc_tma_load_2d(a_dst, ma, &S.full_bar[s], a_col, arow);
                             continue;
                         }
                         const long long tw = AS_CLK();
@@ -363,9 +370,9 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
                             continue;
                         }
                         tc_mbar_expect_tx(&S.full_bar[s], (1u + np) * AS_TILE_BYTES);
-                        tc_tma_load_2d(a_dst, ma, &S.full_bar[s], (int)(kb * TC_BK), arow);
+                        tc_tma_load_2d(a_dst, ma, &S.full_bar[s], a_col, arow);
                         for (uint32_t j = 0; j < np; ++j)
-                            as_tma_load_2d_hint(a_dst + (1u + j) * AS_TILE_BYTES, &M.w[l], &S.full_bar[s], (int)(kb * TC_BK),
+                            as_tma_load_2d_hint(a_dst + (1u + j) * AS_TILE_BYTES, &M.w[l], &S.full_bar[s], w_col,
                                                 (int)((mem + (p0 + j) * G) * 128u), w_policy);
                     }
                 }
@@ -405,7 +412,7 @@ __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const 
         if (q == AS_NONE) break;
         if (!AS_DBG(16u))
             for (uint32_t l = 0; l < 4; ++l) {
-                const uint32_t k_blocks = P.kpad[l] / TC_BK;
+                const uint32_t k_blocks = (P.wide == 2u ? 3u : 1u) * (P.kpad[l] / TC_BK);  // all k-segments
                 const uint32_t mine = as_blocks_of_member(P.npad[l], id);
                 for (uint32_t p0 = 0; p0 < mine; p0 += AS_ACC, ++ntc) {
                     const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
@@ -546,42 +553,52 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
                             const uint32_t srow = tc_smem_u32(stg) + lane * (AS_EPI_COLS * 2u);
                             const uint32_t bias_s = tc_smem_u32(bias + nt * 128u + col0);
                             const uint32_t sw = AS_EPI_CHUNKS == 8 ? (lane & 7u) : ((lane >> 1) & 3u);  // chunk swizzle of this row
+                            const uint32_t act_ld = P.wide * P.kpad[l + 1];
+                            // half 0: the bf16 activations; half 1 (bf16x3 only): what bf16 lost, bf16(v - hi), stored
+                            // kpad columns further into the row
+                            for (uint32_t half = 0; half < P.wide; ++half) {
 #pragma unroll
-                            for (uint32_t sl = 0; sl < AS_EPI_SLICES; ++sl) {
-                                uint32_t pk[8];
+                                for (uint32_t sl = 0; sl < AS_EPI_SLICES; ++sl) {
+                                    uint32_t pk[8];
 #pragma unroll
-                                for (int t = 0; t < 8; t += 2) {
-                                    const uint4 b4 = as_lds128(bias_s + (sl * 16u + 2u * t) * 4u);
-                                    float v0 = __uint_as_float(r[sl][2 * t]) + __uint_as_float(b4.x);
-                                    float v1 = __uint_as_float(r[sl][2 * t + 1]) + __uint_as_float(b4.y);
-                                    float v2 = __uint_as_float(r[sl][2 * t + 2]) + __uint_as_float(b4.z);
-                                    float v3 = __uint_as_float(r[sl][2 * t + 3]) + __uint_as_float(b4.w);
-                                    v0 = fmaxf(v0, 0.f);
-                                    v1 = fmaxf(v1, 0.f);
-                                    v2 = fmaxf(v2, 0.f);
-                                    v3 = fmaxf(v3, 0.f);
-                                    __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
-                                    pk[t] = *reinterpret_cast<uint32_t *>(&h01);
-                                    pk[t + 1] = *reinterpret_cast<uint32_t *>(&h23);
+                                    for (int t = 0; t < 8; t += 2) {
+                                        const uint4 b4 = as_lds128(bias_s + (sl * 16u + 2u * t) * 4u);
+                                        float v0 = __uint_as_float(r[sl][2 * t]) + __uint_as_float(b4.x);
+                                        float v1 = __uint_as_float(r[sl][2 * t + 1]) + __uint_as_float(b4.y);
+                                        float v2 = __uint_as_float(r[sl][2 * t + 2]) + __uint_as_float(b4.z);
+                                        float v3 = __uint_as_float(r[sl][2 * t + 3]) + __uint_as_float(b4.w);
+                                        v0 = fmaxf(v0, 0.f);
+                                        v1 = fmaxf(v1, 0.f);
+                                        v2 = fmaxf(v2, 0.f);
+                                        v3 = fmaxf(v3, 0.f);
+                                        __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+                                        if (half) {
+                                            h01 = __floats2bfloat162_rn(v0 - __low2float(h01), v1 - __high2float(h01));
+                                            h23 = __floats2bfloat162_rn(v2 - __low2float(h23), v3 - __high2float(h23));
+                                        }
+                                        pk[t] = *reinterpret_cast<uint32_t *>(&h01);
+                                        pk[t + 1] = *reinterpret_cast<uint32_t *>(&h23);
+                                    }
+                                    const uint32_t ch = 2u * sl;  // this slice's two 16-byte chunks in the staged row
+                                    as_sts128(srow + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                                    as_sts128(srow + (((ch + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
                                 }
-                                const uint32_t ch = 2u * sl;  // this slice's two 16-byte chunks in the staged row
-                                as_sts128(srow + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-                                as_sts128(srow + (((ch + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
-                            }
-                            // the warp's [32 rows x AS_EPI_COLS columns] go out as contiguous row pieces: AS_EPI_CHUNKS lanes per
-                            // row (a store per thread and row touched 32 lines per instruction and held the epilogue to ~0.4 us
-                            // per 16-column slice on the LSU)
-                            __syncwarp();
-                            const uint32_t rr = lane / AS_EPI_CHUNKS, cc = lane % AS_EPI_CHUNKS;
-                            __nv_bfloat16 *dst0 = P.act[l] + (size_t)(grp * AS_TILE + q4 * 32u) * P.kpad[l + 1] + nt * 128u + col0 + cc * 8u;
+                                // the warp's [32 rows x AS_EPI_COLS columns] go out as contiguous row pieces: AS_EPI_CHUNKS lanes
+                                // per row (a store per thread and row touched 32 lines per instruction and held the epilogue to
+                                // ~0.4 us per 16-column slice on the LSU)
+                                __syncwarp();
+                                const uint32_t rr = lane / AS_EPI_CHUNKS, cc = lane % AS_EPI_CHUNKS;
+                                __nv_bfloat16 *dst0 = P.act[l] + (size_t)(grp * AS_TILE + q4 * 32u) * act_ld + half * P.kpad[l + 1] +
+                                                      nt * 128u + col0 + cc * 8u;
 #pragma unroll
-                            for (uint32_t it = 0; it < AS_EPI_CHUNKS; ++it) {
-                                const uint32_t rw = it * (32u / AS_EPI_CHUNKS) + rr;
-                                const uint32_t sw2 = AS_EPI_CHUNKS == 8 ? (rw & 7u) : ((rw >> 1) & 3u);
-                                const uint4 v = as_lds128(tc_smem_u32(stg) + rw * (AS_EPI_COLS * 2u) + ((cc ^ sw2) << 4));
-                                if (!AS_DBG(1u)) *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * P.kpad[l + 1]) = v;
+                                for (uint32_t it = 0; it < AS_EPI_CHUNKS; ++it) {
+                                    const uint32_t rw = it * (32u / AS_EPI_CHUNKS) + rr;
+                                    const uint32_t sw2 = AS_EPI_CHUNKS == 8 ? (rw & 7u) : ((rw >> 1) & 3u);
+                                    const uint4 v = as_lds128(tc_smem_u32(stg) + rw * (AS_EPI_COLS * 2u) + ((cc ^ sw2) << 4));
+                                    if (!AS_DBG(1u)) *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * act_ld) = v;
+                                }
+                                __syncwarp();
                             }
-                            __syncwarp();
                         }
                     } else {
                         // the Sigmoid head: f32 rows scattered to the owning trees' prior rows, 16 columns at a time

@@ -13,6 +13,13 @@
 //     bf16 activations for the next layer (or the f32 h_theta rows).
 // The input rows are exactly {0,1} (write_vec), so layer 1 loses nothing to bf16; weights and hidden activations are
 // rounded to bf16 (tests compare with the f32 forward at 2e-2 absolute on the sigmoid outputs).
+//
+// AZB_MLP_TC3 ("bf16x3"): the reference's forward is f32 (dfdx sgemm).  Every operand is split into two bf16 halves,
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), and a dot product becomes three tensor-core products accumulated in
+// the same fp32 TMEM accumulator: hi.hi + hi.lo + lo.hi (the dropped lo.lo term is 2^-16 relative).  In memory the
+// halves sit side by side — weights [N][hi(Kpad) | lo(Kpad)], activations [rows][hi(Kpad) | lo(Kpad)] — and the
+// kernels simply run 3 Kpad/64 k-blocks whose TMA coordinates pick (A half, W half) = (hi,hi), (hi,lo), (lo,hi); the
+// epilogue emits both halves of the next layer's input.  Outputs agree with the f32 forward to ~1e-6.
 // Roles per CTA (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
 #pragma once
 #include <cuda.h>
@@ -112,7 +119,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     azb_linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                          const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out_bf16,
                          float *__restrict__ out_f32, uint32_t ld_out, uint32_t row0, uint32_t rows_end, uint32_t n_valid,
-                         uint32_t k_blocks, uint32_t bn) {
+                         uint32_t k_blocks, uint32_t bn, uint32_t nseg, uint32_t lo_out) {
+    // k_blocks = k-blocks per segment; nseg = 1 (plain bf16) or 3 (bf16x3: segments (hi,hi), (hi,lo), (lo,hi); the lo
+    // halves start k_blocks * 64 columns into a row); lo_out = column offset of the lo half of the output rows
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_slot;
@@ -149,20 +158,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (warp == 0) {
         // ===== TMA producer =====
         if (tc_elect_one()) {
-            for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+            for (uint32_t kb = 0; kb < nseg * k_blocks; ++kb) {
                 const uint32_t s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1u;
+                const uint32_t seg = kb / k_blocks, j = kb - seg * k_blocks;
                 tc_mbar_wait(&empty_bar[s], ph ^ 1u);
                 uint8_t *a_dst = smem + (size_t)s * stage_bytes, *b_dst = a_dst + a_bytes;
                 tc_mbar_expect_tx(&full_bar[s], stage_bytes);
-                tc_tma_load_2d(a_dst, &map_x, &full_bar[s], (int)(kb * TC_BK), (int)m0);
-                tc_tma_load_2d(b_dst, &map_w, &full_bar[s], (int)(kb * TC_BK), (int)n0);
+                tc_tma_load_2d(a_dst, &map_x, &full_bar[s], (int)(((seg == 2u ? k_blocks : 0u) + j) * TC_BK), (int)m0);
+                tc_tma_load_2d(b_dst, &map_w, &full_bar[s], (int)(((seg == 1u ? k_blocks : 0u) + j) * TC_BK), (int)n0);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         // instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, N >> 3, M >> 4
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((TC_BM >> 4) << 24);
-        for (uint32_t kb = 0; kb < k_blocks; ++kb) {
+        const uint32_t kb_all = nseg * k_blocks;
+        for (uint32_t kb = 0; kb < kb_all; ++kb) {
             const uint32_t s = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1u;
             tc_mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     tc_umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0u ? 1u : 0u);
                 }
                 tc_umma_commit(&empty_bar[s]);                     // frees the ring slot when these MMAs retire
-                if (kb + 1 == k_blocks) tc_umma_commit(&accum_bar);  // accumulator complete
+                if (kb + 1 == kb_all) tc_umma_commit(&accum_bar);  // accumulator complete
             }
             __syncwarp();
         }
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     __nv_bfloat16 *dst = out_bf16 + (size_t)row * ld_out + n0 + c0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        uint32_t pk[4];
+                        uint32_t pk[4], pl[4];
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const uint32_t n = n0 + c0 + j + 2 * t;
@@ -202,8 +213,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                             v1 = v1 > 0.f ? v1 : 0.f;
                             __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
                             pk[t] = *reinterpret_cast<uint32_t *>(&h2);
+                            // the part bf16 lost, itself rounded to bf16 (x - hi is exact in f32)
+                            __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __low2float(h2), v1 - __high2float(h2));
+                            pl[t] = *reinterpret_cast<uint32_t *>(&l2);
                         }
                         *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (nseg == 3u) *reinterpret_cast<uint4 *>(dst + lo_out + j) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
             }
@@ -235,26 +250,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-// f32 rows -> bf16 rows padded to Kpad (zeros beyond K)
+// f32 rows -> bf16 rows padded to Kpad (zeros beyond K); split: the row is [hi(Kpad) | lo(Kpad)], lo = bf16(x - hi)
 __global__ void azb_rows_to_bf16_kernel(const float *__restrict__ x, uint32_t ldx, uint32_t K, __nv_bfloat16 *__restrict__ y,
-                                        uint32_t ldy, uint32_t rows) {
+                                        uint32_t ldy, uint32_t rows, uint32_t Kpad, uint32_t split) {
     const uint32_t r = blockIdx.x;
     if (r >= rows) return;
-    for (uint32_t k = threadIdx.x; k < ldy; k += blockDim.x)
-        y[(size_t)r * ldy + k] = __float2bfloat16(k < K ? x[(size_t)r * ldx + k] : 0.f);
+    for (uint32_t k = threadIdx.x; k < Kpad; k += blockDim.x) {
+        const float v = k < K ? x[(size_t)r * ldx + k] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        y[(size_t)r * ldy + k] = hi;
+        if (split) y[(size_t)r * ldy + Kpad + k] = __float2bfloat16(v - __bfloat162float(hi));
+    }
 }
 
-// dfdx parameter block (weight[out][in], bias[out]) -> bf16 weight [Npad x Kpad], f32 bias [Npad], zero padded
+// dfdx parameter block (weight[out][in], bias[out]) -> bf16 weight [Npad x Kpad] (split: [Npad x (hi(Kpad) | lo(Kpad))]),
+// f32 bias [Npad], zero padded
 __global__ void azb_params_to_bf16_kernel(const float *__restrict__ w, const float *__restrict__ b, uint32_t K, uint32_t N,
-                                          __nv_bfloat16 *__restrict__ wq, float *__restrict__ bq, uint32_t Kpad, uint32_t Npad) {
+                                          __nv_bfloat16 *__restrict__ wq, float *__restrict__ bq, uint32_t Kpad, uint32_t Npad,
+                                          uint32_t split) {
     const uint32_t n = blockIdx.x;
-    for (uint32_t k = threadIdx.x; k < Kpad; k += blockDim.x)
-        wq[(size_t)n * Kpad + k] = __float2bfloat16((n < N && k < K) ? w[(size_t)n * K + k] : 0.f);
+    const uint32_t ld = split ? 2u * Kpad : Kpad;
+    for (uint32_t k = threadIdx.x; k < Kpad; k += blockDim.x) {
+        const float v = (n < N && k < K) ? w[(size_t)n * K + k] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        wq[(size_t)n * ld + k] = hi;
+        if (split) wq[(size_t)n * ld + Kpad + k] = __float2bfloat16(v - __bfloat162float(hi));
+    }
     if (threadIdx.x == 0) bq[n] = n < N ? b[n] : 0.f;
 }
 
 struct AzbMlpTc {
     bool ready;
+    uint32_t split;         // 0: plain bf16; 1: bf16x3 (operands stored as [hi | lo], three products per dot product)
     uint32_t rows_pad, dims[5], kpad[4], npad[4], bn[4];
     __nv_bfloat16 *act[4];  // act[l] = input of layer l, [rows_pad x kpad[l]]
     __nv_bfloat16 *w[4];
@@ -290,8 +317,10 @@ static inline void azb_mlp_tc_destroy(AzbMlpTc &t) {
     t.ready = false;
 }
 
-static inline const char *azb_mlp_tc_create(AzbMlpTc &t, uint32_t rows, const uint32_t *dims, uint64_t *dev_bytes) {
+static inline const char *azb_mlp_tc_create(AzbMlpTc &t, uint32_t rows, const uint32_t *dims, uint64_t *dev_bytes,
+                                            bool split = false) {
     memset(&t, 0, sizeof(t));
+    t.split = split ? 1u : 0u;
     azb_encode_fn enc = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres) != cudaSuccess || !enc)
@@ -311,16 +340,17 @@ static inline const char *azb_mlp_tc_create(AzbMlpTc &t, uint32_t rows, const ui
     }
     for (int l = 0; l < 4; ++l) {
         // weight rows are padded (zeros) to a multiple of 128 so that a 128-row TMA box never leaves the tensor
-        const size_t abytes = (size_t)t.rows_pad * t.kpad[l] * 2, wbytes = (size_t)((t.npad[l] + 127u) / 128u * 128u) * t.kpad[l] * 2;
+        const uint32_t kw = (t.split ? 2u : 1u) * t.kpad[l];  // row width in elements: [hi | lo] when split
+        const size_t abytes = (size_t)t.rows_pad * kw * 2, wbytes = (size_t)((t.npad[l] + 127u) / 128u * 128u) * kw * 2;
         if (cudaMalloc((void **)&t.act[l], abytes) != cudaSuccess) return "cudaMalloc (activations) failed";
         if (cudaMalloc((void **)&t.w[l], wbytes) != cudaSuccess) return "cudaMalloc (weights) failed";
         if (cudaMalloc((void **)&t.bias[l], (size_t)t.npad[l] * 4) != cudaSuccess) return "cudaMalloc (bias) failed";
         cudaMemset(t.act[l], 0, abytes);
         cudaMemset(t.w[l], 0, wbytes);
         if (dev_bytes) *dev_bytes += abytes + wbytes + (size_t)t.npad[l] * 4;
-        const char *why = azb_tc_make_map(enc, &t.map_x[l], t.act[l], t.rows_pad, t.kpad[l], TC_BM);
+        const char *why = azb_tc_make_map(enc, &t.map_x[l], t.act[l], t.rows_pad, kw, TC_BM);
         if (why) return why;
-        why = azb_tc_make_map(enc, &t.map_w[l], t.w[l], t.npad[l], t.kpad[l], t.bn[l]);
+        why = azb_tc_make_map(enc, &t.map_w[l], t.w[l], t.npad[l], kw, t.bn[l]);
         if (why) return why;
         t.smem_bytes[l] = (size_t)TC_STAGES * (TC_BM + t.bn[l]) * TC_BK * 2 + 1024;
     }
@@ -337,7 +367,7 @@ static inline const char *azb_mlp_tc_load(AzbMlpTc &t, const float *params, cuda
     for (int l = 0; l < 4; ++l) {
         const uint32_t K = t.dims[l], N = t.dims[l + 1];
         azb_params_to_bf16_kernel<<<t.npad[l], 128, 0, stream>>>(p, p + (size_t)K * N, K, N, t.w[l], t.bias[l], t.kpad[l],
-                                                                 t.npad[l]);
+                                                                 t.npad[l], t.split);
         if (launches) *launches += 1;
         p += (size_t)K * N + N;
     }
@@ -349,9 +379,11 @@ static inline const char *azb_mlp_tc_load(AzbMlpTc &t, const float *params, cuda
 static inline const char *azb_mlp_tc_forward(AzbMlpTc &t, const float *x, uint32_t ldx, float *y, uint32_t ldy,
                                              uint32_t row0, uint32_t rows, cudaStream_t stream, uint64_t *launches) {
     if (!t.ready) return "not created";
+    const uint32_t wide = t.split ? 2u : 1u;
     if (x) {
         azb_rows_to_bf16_kernel<<<rows, 128, 0, stream>>>(x + (size_t)row0 * ldx, ldx, t.dims[0],
-                                                          t.act[0] + (size_t)row0 * t.kpad[0], t.kpad[0], rows);
+                                                          t.act[0] + (size_t)row0 * wide * t.kpad[0], wide * t.kpad[0], rows,
+                                                          t.kpad[0], t.split);
         if (launches) *launches += 1;
     }
     for (int l = 0; l < 4; ++l) {
@@ -359,8 +391,15 @@ static inline const char *azb_mlp_tc_forward(AzbMlpTc &t, const float *x, uint32
         const bool head = l == 3;
         azb_linear_tc_kernel<<<grid, TC_THREADS, t.smem_bytes[l], stream>>>(
             t.map_x[l], t.map_w[l], t.bias[l], head ? nullptr : t.act[l + 1], head ? y : nullptr,
-            head ? ldy : t.kpad[l + 1], row0, row0 + rows, t.dims[l + 1], t.kpad[l] / TC_BK, t.bn[l]);
+            head ? ldy : wide * t.kpad[l + 1], row0, row0 + rows, t.dims[l + 1], t.kpad[l] / TC_BK, t.bn[l], t.split ? 3u : 1u,
+            head ? 0u : t.kpad[l + 1]);
         if (launches) *launches += 1;
+    }
+    if (x && t.split) {
+        // the search kernels' write_vec only ever writes the hi half of a layer-0 row (its entries are exactly 0 or 1):
+        // leave the lo half of the rows just used as zero as it found them
+        cudaMemset2DAsync(t.act[0] + (size_t)row0 * 2u * t.kpad[0] + t.kpad[0], (size_t)2u * t.kpad[0] * 2, 0, (size_t)t.kpad[0] * 2,
+                          rows, stream);
     }
     return cudaGetLastError() == cudaSuccess ? nullptr : "tensor-core forward launch failed";
 }

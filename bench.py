@@ -137,14 +137,14 @@ def cpu_reference_run(n, roots, steps, warmup, seed, threads, budget_s=None):
     return k["n_live"] / dt, dt, k
 
 
-def timed_config(capi, n, b, workers, steps, warmup, seed, rank, local_rank, prior_hash=False):
+def timed_config(capi, n, b, workers, steps, warmup, seed, rank, local_rank, prior_hash=False, mlp_mode=None):
     """K device-timed steps of another configuration on this rank's GPU (inputs resident, W warm-up steps first).
     Returns (simulations, ms, cost evals, device bytes)."""
     kw = dict(device=local_rank, first_root=rank * b, max_steps=warmup + steps + 8)
     if prior_hash:
         kw.update(prior_mode=capi.PRIOR_HASH, prior_seed=seed)
     else:
-        kw.update(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, async_workers=workers)
+        kw.update(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC if mlp_mode is None else mlp_mode, async_workers=workers)
     parents, masks = capi.generate_roots(seed, rank * b, b, n)
     with capi.Handle(capi.default_config(n, b, **kw)) as h:
         if not prior_hash:
@@ -167,7 +167,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--roots", type=int, default=4096, help="roots per GPU (BASELINE configs[1])")
     ap.add_argument("--vertices", type=int, default=19)
-    ap.add_argument("--mlp", default=os.environ.get("AZB_MLP", "tc"), choices=["fp32", "tc"])
+    ap.add_argument("--mlp", default=os.environ.get("AZB_MLP", "tc"), choices=["fp32", "tc", "tc3"],
+                    help="tc: bf16 tensor cores (default); tc3: bf16x3 tensor cores at f32 accuracy; fp32: CUDA cores")
     ap.add_argument("--max-episodes", type=int, default=int(os.environ.get("AZB_MAX_EPISODES", "0")))
     ap.add_argument("--groups", type=int, default=int(os.environ.get("AZB_GROUPS", "1")),
                     help="concurrent tree groups per GPU (own CUDA stream each); needs --max-episodes 0")
@@ -238,10 +239,10 @@ def main():
     aw = args.async_workers
     if aw < 0:  # auto: 20 of the 148 SMs answer state vectors (128 x 32 warps walk: one tree per warp at 4096 roots);
         # 48 SMs in pairs up to 16 K roots, 32 single SMs beyond (profiles/README.md, worker sweeps)
-        ok = args.mlp == "tc" and not args.max_episodes and args.groups == 1 and 1024 <= b <= 100000
+        ok = args.mlp in ("tc", "tc3") and not args.max_episodes and args.groups == 1 and 1024 <= b <= 100000
         aw = (40 if b < 4096 else 20 if b == 4096 else 48 if b < 16384 else 32) if ok else 0
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
-                              mlp_mode=capi.MLP_TC if args.mlp == "tc" else capi.MLP_FP32,
+                              mlp_mode={"tc": capi.MLP_TC, "tc3": capi.MLP_TC3, "fp32": capi.MLP_FP32}[args.mlp],
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
                               n_groups=1 if args.max_episodes else args.groups, async_workers=aw)
     parents, masks = capi.generate_roots(args.seed, rank * b, b, n)
@@ -249,7 +250,7 @@ def main():
     try:
         h = capi.Handle(cfg)
     except capi.AzbError as e:  # e.g. no tensor-map driver entry point: still a CUDA path, and the line says so
-        if args.mlp != "tc":
+        if args.mlp == "fp32":
             raise
         cfg.mlp_mode = capi.MLP_FP32
         cfg.async_workers = aw = 0
@@ -446,6 +447,14 @@ def main():
         sp_sims, sp_ms, _, _ = timed_config(capi, n, b, 0, sp_steps, args.warmup, args.seed, rank, local_rank, prior_hash=True)
         extra["same_priors"] = {"value": sp_sims / (sp_ms * 1e-3), "unit": UNIT, "steps": sp_steps, "ms_per_step": sp_ms / sp_steps,
                                 "what": f"N={n}, {b} roots, hash priors (the reference arm's), lock-step launches, no model forward"}
+        # the f32-accurate tensor-core model (AZB_MLP_TC3: bf16 hi + lo operands, three products per dot product): what the
+        # reference's f32 forward costs on the tensor cores; the default stays bf16 because it is the faster step
+        if args.mlp == "tc" and aw:
+            t3_steps = min(args.steps, 200)
+            t3_sims, t3_ms, _, _ = timed_config(capi, n, b, aw, t3_steps, args.warmup, args.seed, rank, local_rank, mlp_mode=capi.MLP_TC3)
+            extra["f32_accurate_model"] = {"value": t3_sims / (t3_ms * 1e-3), "unit": UNIT, "steps": t3_steps, "ms_per_step": t3_ms / t3_steps,
+                                           "what": "same workload with mlp_mode = AZB_MLP_TC3 (priors within 1e-5 relative of the f32 forward; "
+                                                   "tests/test_gpu_parity.py) instead of bf16 (2e-2 absolute)"}
         # C4: 64-vertex trees (cost path dominated): 4096 roots, 32 model SMs
         c4_roots, c4_steps = 4096, min(args.steps, 64)
         try:
@@ -480,7 +489,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 search + f64 lambda_1 + " + ("bf16 tensor-core MLP" if args.mlp == "tc" else "f32 MLP"),
+            "vs_baseline": None, "dtype": "f32 search + f64 lambda_1 + " + {"tc": "bf16 tensor-core MLP", "tc3": "bf16x3 tensor-core MLP (f32 accuracy)", "fp32": "f32 MLP"}[args.mlp],
             "data": "synthetic",
             "config": {"workload": f"06-c21 (snapshot: 04-c21-tree.rs) N={n}, {b} roots per GPU x {world} GPU, "
                                    f"random-init MLP {2 * a}-512-1024-512-{a}, n_as_tol=[200,50,50]->25",

@@ -56,7 +56,10 @@ enum {
 /* MLP arithmetic */
 enum {
     AZB_MLP_FP32 = 0,     /* fp32 CUDA-core GEMM: what cuBLAS sgemm gives the reference */
-    AZB_MLP_TC = 1        /* tcgen05 tensor cores */
+    AZB_MLP_TC = 1,       /* tcgen05 tensor cores, bf16 weights and hidden activations, fp32 accumulate */
+    AZB_MLP_TC3 = 2       /* tcgen05 tensor cores at f32 accuracy: every operand as bf16 hi + lo, three products per dot
+                             product (hi.hi + hi.lo + lo.hi), fp32 accumulate — within ~1e-6 of the f32 forward the
+                             reference runs (nabla/model/dfdx.rs:69-84), at about three times the tensor work */
 };
 
 typedef struct azb_config {

@@ -23,6 +23,7 @@ pub const AZB_PRIOR_INJECTED: u32 = 2;
 
 pub const AZB_MLP_FP32: u32 = 0;
 pub const AZB_MLP_TC: u32 = 1;
+pub const AZB_MLP_TC3: u32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]

@@ -471,3 +471,54 @@ def test_concurrent_tree_groups_give_identical_results(capi, orc, n_groups, mlp)
         o.init_trees(orc.hash_priors(6, 0, b, orc.action_dim(n), 0))
         o.steps_hash(6, 0, 1, steps)
         assert [digest(o.dump_tree(i)) for i in range(b)] == outs[1][0]
+
+
+def test_mlp_tc3_is_f32_accurate_on_the_tensor_cores(capi, orc):
+    """AZB_MLP_TC3: bf16 hi + lo operands, three tcgen05 products per dot product, fp32 accumulate.  The reference's
+    forward is f32 (nabla/model/dfdx.rs:69-84); this mode must agree with the f32 CPU forward to 1e-5 relative — on the
+    0/1 state vectors of the space and on arbitrary f32 inputs (NablaModel::write_predictions takes any &[f32])."""
+    n, b = 19, 300
+    a_dim = orc.action_dim(n)
+    rng = np.random.default_rng(3)
+    dims = [2 * a_dim, 512, 1024, 512, a_dim]
+    with _mk(capi, n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC3) as h:
+        h.mlp_init(42)
+        params = h.mlp_get_params()
+        for x in ((rng.random((b, 2 * a_dim)) < 0.2).astype(np.float32),
+                  rng.standard_normal((b, 2 * a_dim)).astype(np.float32) * 0.7):
+            y = h.model_write_predictions(x)
+            want = orc.mlp_forward(params, dims, x, n_threads=4)
+            rel = np.abs(y - want) / np.abs(want)
+            assert rel.max() < 1e-5, rel.max()  # tolerance: 1e-5 relative (north_star), against 2e-2 absolute for AZB_MLP_TC
+        # the 0/1 rows again after the general ones: the lo half of the input rows must be back to zero
+        x = (rng.random((b, 2 * a_dim)) < 0.3).astype(np.float32)
+        assert np.array_equal(h.model_write_predictions(x[:7]), h.model_write_predictions(x)[:7])
+
+
+def test_tc3_fused_loop_matches_oracle_and_the_async_kernel(capi, orc):
+    """The f32-accurate tensor-core model in the fused loop: lock step == oracle fed with the device's priors, and the
+    asynchronous kernel == lock step, bit for bit."""
+    n, b, steps = 19, 300, 24
+    parents, masks = orc.generate_roots(8, 0, b, n)
+    idx = list(range(0, b, 10))
+    o = orc.Optimizer(n, len(idx), lambda_method=orc.LAMBDA_MULTISECTION)
+    o.set_roots(parents[idx], masks[idx])
+    kw = dict(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC3, max_steps=steps + 2)
+    with _mk(capi, n, b, **kw) as lock, _mk(capi, n, b, async_workers=4, **kw) as asy:
+        for h in (lock, asy):
+            h.mlp_init(9)
+            h.set_roots(parents, masks)
+            h.init_trees()
+        o.init_trees(np.ascontiguousarray(lock.priors()[idx]))
+        asy.step(steps)
+        for s in range(steps):
+            lock.step(1)
+            o.rollout()
+            o.add_actions(np.ascontiguousarray(lock.priors()[idx]))
+        for j, i in enumerate(idx):
+            assert digest(o.dump_tree(j)) == digest(lock.dump_tree(i)), i
+        assert [digest(lock.dump_tree(i)) for i in range(b)] == [digest(asy.dump_tree(i)) for i in range(b)]
+        live = lock.walkers()["path_len"] > 0
+        assert np.array_equal(lock.priors()[live], asy.priors()[live])
+        want = orc.mlp_forward(lock.mlp_get_params(), [2 * orc.action_dim(n), 512, 1024, 512, orc.action_dim(n)], lock.state_vecs(), n_threads=4)
+        assert (np.abs(lock.priors() - want) / np.abs(want)).max() < 1e-5
