@@ -383,6 +383,7 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
         seq += 1u;
         as_named_bar(1, AS_MLP_THREADS);
     }
+#ifdef AZB_PROFILE
     if (P.dbg && lane == 0) {  // producer: acquire, wait empty, wait layer, tile busy, tiles
         atomicAdd(P.dbg + 0, (unsigned long long)d_acq);
         atomicAdd(P.dbg + 1, (unsigned long long)d_w0);
@@ -390,12 +391,14 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
         atomicAdd(P.dbg + 3, (unsigned long long)d_busy);
         atomicAdd(P.dbg + 4, (unsigned long long)d_tiles);
     }
+#endif
     as_named_bar(1, AS_MLP_THREADS);
 }
 
 // ---- warp 1: owns TMEM, issues tcgen05.mma
 __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const AsWorkerId id, uint8_t *smem, AsWorkerShared &S) {
     const uint32_t lane = threadIdx.x & 31;
+    (void)lane;
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&S.tmem_slot)), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -466,10 +469,12 @@ __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const 
             }
         as_named_bar(1, AS_MLP_THREADS);
     }
+#ifdef AZB_PROFILE
     if (P.dbg && lane == 0) {  // MMA: -, wait full, wait acc_empty
         atomicAdd(P.dbg + 5 + 1, (unsigned long long)d_w0);
         atomicAdd(P.dbg + 5 + 2, (unsigned long long)d_w1);
     }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     as_named_bar(1, AS_MLP_THREADS);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -676,12 +681,14 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
         seq += 1u;
         as_named_bar(1, AS_MLP_THREADS);
     }
+#ifdef AZB_PROFILE
     if (P.dbg && et == 0u) {  // epilogue (first warp): TMEM reads, wait acc_full, layer boundary, busy
         atomicAdd(P.dbg + 10, (unsigned long long)d_acq);
         atomicAdd(P.dbg + 11, (unsigned long long)d_w0);
         atomicAdd(P.dbg + 12, (unsigned long long)d_w1);
         atomicAdd(P.dbg + 13, (unsigned long long)d_busy);
     }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     as_named_bar(1, AS_MLP_THREADS);
 }
@@ -737,6 +744,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     uint32_t my_steps = 0;                        // times this tree has been advanced
     long long my_run = 0, my_wait = 0, my_t0 = 0;  // cycles spent advancing this tree / waiting for its priors (P.dbg)
     const long long t_k0 = AS_CLK();
+    (void)t_k0;
     // start time for the watchdog: parked in two free words of the warp's counter block (only the idle path reads it)
     if (lane == 0) *reinterpret_cast<unsigned long long *>(cx.ct + 28) = as_now();
     __syncwarp();
@@ -775,6 +783,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
         ctx_bind_tree(L, cx, tree);
         uint32_t *gwk = L.walker + (size_t)tree * L.WS;
+#pragma unroll 4
         for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gwk[i];
         __syncwarp();
         if (cx.wk[WK_FLAGS] & 1u) tree_add_actions<DEPTH == 5>(L, cx, tree);
@@ -801,7 +810,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
                 pos = slot % ring_rows;
                 row = P.ring + (size_t)pos * P.ring_ld;
             }
-            if (pending) tree_pack(L, cx, tree, row);
+            if (pending) tree_pack<true>(L, cx, tree, row);
             if (to_ring) {
                 if (lane == 0) P.slot_tree[pos] = tree;
                 __threadfence();
@@ -815,6 +824,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         }
         __syncwarp();
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
+#pragma unroll 1
         for (uint32_t i = lane; i < live_words; i += 32) gwk[i] = cx.wk[i];
         if (lane == k) {
             my_state = new_state;
@@ -853,6 +863,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     if (my_tree < L.B && my_tree < 65536u)  // per tree: K-cycles walking, K-cycles waiting for priors, advances, rows
         g_tree_prof[my_tree] = make_uint4((uint32_t)(my_run >> 10), (uint32_t)(my_wait >> 10), my_steps, my_sub);
 #endif
+#ifdef AZB_PROFILE
     if (P.dbg && my_tree < L.B) {
         atomicAdd(P.dbg + 16, (unsigned long long)my_run);
         atomicMax(P.dbg + 17, (unsigned long long)my_run);
@@ -861,6 +872,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         atomicMax(P.dbg + 21, (unsigned long long)(my_wait + my_run));
         if (my_tree == 0) P.dbg[18] = (unsigned long long)(AS_CLK() - t_k0);
     }
+#endif
     {
         const uint32_t rows = warp_sum_u32(my_sub);
         if (lane == 0 && rows) atomicAdd(&st->rows_real, rows);

@@ -268,6 +268,7 @@ struct __align__(16) PolyScratch {  // per-warp shared memory, lives in the same
     uint32_t B[AZB_POLY_NV][AZB_POLY_KMAX + 1];
     uint32_t cnt[32];
     uint32_t w2[32];
+    double cf[AZB_POLY_KMAX + 1];  // signed coefficients of p(y), highest power first
 };
 
 __device__ __forceinline__ void azb_two_sum(double a, double b, double &s, double &e) {
@@ -306,6 +307,7 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         // sibling array w2 is taken, so reuse A[p][1] directly below
         if (lf && (__ffs(m) - 1) == lane) nleaf = (uint32_t)__popc(m);
     }
+#pragma unroll 1
     for (uint32_t i = lane; i < n * (KM + 1); i += 32) {
         const uint32_t one = (i % (KM + 1)) == 0u ? 1u : 0u;
         (&ps->A[0][0])[i] = one;
@@ -353,19 +355,19 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
     const uint32_t nz = __ballot_sync(FULL, mk != 0u);
     const uint32_t K = 31u - __clz(nz);
     *mu_out = K;
-    // ---- coefficients: position j of a fixed 12-term Horner holds m_(j - sh), sh = KM - K leading zeros, so the
-    //      fixed-length Horner IS the K-term Horner; m_k <= 6435, two per register; sign (-1)^(j - sh)
+    // ---- coefficients: position j of a fixed 12-term Horner holds (-1)^(j - sh) m_(j - sh), sh = KM - K leading zeros, so
+    //      the fixed-length Horner IS the K-term Horner.  m_k <= 6435 is exact in f64.  The signed values sit in shared
+    //      memory, one per lane, and the Horner loops below are ROLLED: a dozen instructions instead of 5 KB of unrolled
+    //      unpack-convert-fma code in the hottest loop of the walkers (instruction fetch is their largest stall).  A zero
+    //      leading coefficient keeps the sign its position gives it (-0.0 or +0.0), as the oracle's mirror does.
     const int sh = KM - (int)K;
-    uint32_t pk[(KM + 1) / 2];
-#pragma unroll
-    for (int j = 0; j <= KM; j += 2) {
-        const uint32_t lo16 = j >= sh ? ps->A[0][j - sh] : 0u;
-        const uint32_t hi16 = j + 1 >= sh ? ps->A[0][j + 1 - sh] : 0u;
-        pk[j / 2] = lo16 | (hi16 << 16);
+    if (k <= KM) {
+        const uint32_t u = k >= sh ? ps->A[0][k - sh] : 0u;
+        const bool neg = ((k & 1) != 0) != ((sh & 1) != 0);
+        ps->cf[k] = neg ? -(double)u : (double)u;
     }
-    const bool shodd = (sh & 1) != 0;
-#define AZB_COEF(j) ((((j) & 1) != 0) != shodd ? -(double)((pk[(j) / 2] >> (((j) & 1) * 16)) & 0xffffu) \
-                                                : (double)((pk[(j) / 2] >> (((j) & 1) * 16)) & 0xffffu))
+    __syncwarp();
+    const double *cf = ps->cf;
     CPROF(2);
     // ---- 2. Laguerre from the right (plain Horner for p, p', p''/2): for a real-rooted polynomial the iterates
     //         decrease monotonically onto the largest root, cubically
@@ -373,16 +375,12 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
     const double nn = (double)K, nm1 = (double)(K - 1u);
 #pragma unroll 1
     for (int it = 0; it < 40; ++it) {
-        // keep the coefficients packed across iterations: without this the int->f64 conversions are hoisted out of
-        // the loop and cost 24 registers for the whole kernel
-#pragma unroll
-        for (int q = 0; q < (KM + 1) / 2; ++q) asm volatile("" : "+r"(pk[q]));
-        double s = AZB_COEF(0), d = 0.0, h = 0.0;
-#pragma unroll
+        double s = cf[0], d = 0.0, h = 0.0;
+#pragma unroll 1
         for (int j = 1; j <= KM; ++j) {
             h = __fma_rn(h, y, d);
             d = __fma_rn(d, y, s);
-            s = __fma_rn(s, y, AZB_COEF(j));
+            s = __fma_rn(s, y, cf[j]);
         }
         const double dd = __dmul_rn(2.0, h);
         double disc = __dmul_rn(nm1, __dsub_rn(__dmul_rn(nm1, __dmul_rn(d, d)), __dmul_rn(nn, __dmul_rn(s, dd))));
@@ -399,12 +397,10 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
     // ---- 3. polish: compensated Horner for p ----
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-#pragma unroll
-        for (int q = 0; q < (KM + 1) / 2; ++q) asm volatile("" : "+r"(pk[q]));
-        double s = AZB_COEF(0), e = 0.0, t = s, d = 0.0;
-#pragma unroll
+        double s = cf[0], e = 0.0, t = s, d = 0.0;
+#pragma unroll 1
         for (int j = 1; j <= KM; ++j) {
-            const double cj = AZB_COEF(j);
+            const double cj = cf[j];
             d = __fma_rn(d, y, t);
             t = __fma_rn(t, y, cj);
             const double pr = __dmul_rn(s, y);
@@ -417,7 +413,6 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         if (!(d > 0.0)) break;
         y = __dsub_rn(y, __ddiv_rn(pv, d));
     }
-#undef AZB_COEF
     CPROF(4);
     __syncwarp();
     return __dsqrt_rn(y);

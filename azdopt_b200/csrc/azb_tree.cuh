@@ -131,8 +131,10 @@ __device__ __forceinline__ uint32_t key_hash(uint32_t k0, uint32_t k1, int lane,
 
 // current-edge mask of the walker state into cx.cur (rooted_tree/mod.rs:60-72)
 __device__ __forceinline__ void build_cur_mask(const AzbLayout &L, WarpCtx &cx) {
+#pragma unroll 1
     for (uint32_t w = cx.lane; w < L.W; w += 32) cx.cur[w] = 0u;
     __syncwarp();
+#pragma unroll 1
     for (uint32_t c = 2 + cx.lane; c + 1 < L.N; c += 32) {
         uint32_t e = azb_action_index(cx.par[c], c);
         atomicOr(&cx.cur[e >> 5], 1u << (e & 31));
@@ -146,6 +148,7 @@ __device__ __forceinline__ void walker_act(const AzbLayout &L, WarpCtx &cx, uint
     const uint32_t first = azb_child_first_action(child);
     const uint32_t last = first + child;  // exclusive
     if (cx.lane == 0) cx.par[child] = (uint8_t)(a - first);
+#pragma unroll 1
     for (uint32_t w = cx.lane; w < L.W; w += 32) {
         const uint32_t b0 = w * 32, b1 = b0 + 32;
         const uint32_t s = max(first, b0), e = min(last, b1);
@@ -160,7 +163,9 @@ __device__ __forceinline__ void walker_act(const AzbLayout &L, WarpCtx &cx, uint
 }
 
 __device__ __forceinline__ void walker_reset(const AzbLayout &L, WarpCtx &cx) {  // tree/mod.rs:176-178
+#pragma unroll 1
     for (uint32_t i = cx.lane; i < L.PW; i += 32) ((uint32_t *)cx.par)[i] = ((const uint32_t *)cx.rpar)[i];
+#pragma unroll 1
     for (uint32_t w = cx.lane; w < L.W; w += 32) {
         cx.perm[w] = cx.rperm[w];
         cx.keym[w] = 0u;
@@ -186,6 +191,7 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
     const bool hashed = L.prior_mode == 1;
     if (!hashed) {
         const float *hrow = L.h + (size_t)tree * L.h_ld;
+#pragma unroll 4
         for (uint32_t a = lane; a < L.A; a += 32) cx.lbuf[a] = __ldcg(hrow + a);  // written by other SMs in the async kernel
     }
     build_cur_mask(L, cx);
@@ -232,6 +238,7 @@ __device__ void tree_add_actions(const AzbLayout &L, WarpCtx &cx, uint32_t tree)
         return;
     }
     const uint32_t lo2 = lo >> 1;
+#pragma unroll 1
     for (uint32_t j = lane; j < cnt; j += 32) {
         // word holding the j-th legal action: largest w with pfx[w] <= j
         uint32_t a0 = 0, a1 = L.W;  // invariant pfx[a0] <= j < pfx[a1]
@@ -299,10 +306,12 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
     uint32_t *ga = cx.casc, *gb = cx.casc + L.cap_nodes;  // the lists' continuation beyond AZB_FRONTIER_CAP entries
     uint32_t *vis = cx.fr + 3 * AZB_FRONTIER_CAP;
     const uint32_t nwords = (L.cap_nodes + 31u) >> 5;
+#pragma unroll 1
     for (uint32_t w = lane; w < nwords; w += 32) vis[w] = 0u;
     __syncwarp();
     const uint32_t fcap = L.frontier_cap;  // entries a list keeps in shared memory (AZB_FRONTIER_CAP; tests shrink it)
     uint32_t ncur = depth + 1u;
+#pragma unroll 1
     for (uint32_t i = lane; i < ncur; i += 32) {
         const uint32_t p = cx.wk[WK_PATH + i];
         wl_put(wa, ga, fcap, i, p);
@@ -395,6 +404,7 @@ __device__ void tree_cascade(const AzbLayout &L, WarpCtx &cx, uint32_t src, uint
         __syncwarp();
         if (lane == 0) reinterpret_cast<uint32_t *>(rec)[3] = ex | (cnt << 16);
         if (ex == cnt && nin != 0u) {  // p just became inactive: its parents' copies lose the active bit, each parent gets +1
+#pragma unroll 1
             for (uint32_t k = lane; k < nin; k += 32) {
                 const uint2 ent = k < 4u ? reinterpret_cast<const uint2 *>(rec + 2)[k] : cx.inl[q1.z + k - 4u];
                 reinterpret_cast<uint32_t *>(cx.blk4 + ent.y)[1] = q1.x;
@@ -672,6 +682,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             // is_terminal (nabla/space/mod.rs:27-29)
             build_cur_mask(L, cx);
             bool any = false;
+#pragma unroll 1
             for (uint32_t w = lane; w < L.W; w += 32) any = any || ((cx.perm[w] & ~cx.cur[w]) != 0u);
             any = __any_sync(FULL, any);
             if (lane < 4) {  // StateWeight::new (state_weight.rs:13-21) + the creating arc as in-arc 0
@@ -759,8 +770,10 @@ __device__ __forceinline__ uint32_t pack_bit(const AzbLayout &L, const WarpCtx &
     const uint32_t word = i < L.A ? cx.cur[j >> 5] : cx.perm[j >> 5];
     return (word >> (j & 31)) & 1u;
 }
+// BF16_ONLY: the caller knows the rows go out as bf16 (the asynchronous kernel): the f32 path is compiled out
+template <bool BF16_ONLY = false>
 __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint16_t *row_override = nullptr) {
-    if (L.sv16) {
+    if (BF16_ONLY || L.sv16) {
         // tensor-core MLP: the row goes out as bf16 (1.0 = 0x3F80), eight entries per 128-bit store; the row pitch is
         // a multiple of 64 entries and the tail beyond 2A stays zero
         uint16_t *row = row_override ? row_override : L.sv16 + (size_t)tree * L.sv16_ld;
@@ -788,6 +801,7 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
         }
         return;
     }
+    if constexpr (BF16_ONLY) return;
     float *row = L.sv + (size_t)tree * L.sv_ld;
     if ((L.A & 1u) == 0u && (L.sv_ld & 3u) == 0u) {  // rows are 16-byte aligned: one 128-bit store per four entries
         for (uint32_t i = 4u * cx.lane; i < 2 * L.A; i += 128)
@@ -795,6 +809,7 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
                 make_float4(pack_bit(L, cx, i) ? 1.f : 0.f, pack_bit(L, cx, i + 1) ? 1.f : 0.f,
                             pack_bit(L, cx, i + 2) ? 1.f : 0.f, pack_bit(L, cx, i + 3) ? 1.f : 0.f);
     } else {
+#pragma unroll 1
         for (uint32_t i = cx.lane; i < 2 * L.A; i += 32) row[i] = pack_bit(L, cx, i) ? 1.f : 0.f;
     }
 }
@@ -822,6 +837,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
         uint32_t *gw = L.walker + (size_t)tree * L.WS;
         PROF_T0();
         cx.ct[lane] = 0u;
+#pragma unroll 4
         for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gw[i];
         __syncwarp();
         PROF_ADD(cx, PH_LOAD);
@@ -892,6 +908,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
         __syncwarp();
         // publish: walker block (without the root part), counters, errors, distance to the target
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
+#pragma unroll 1
         for (uint32_t i = lane; i < live_words; i += 32) gw[i] = cx.wk[i];
         if (lane < 16) {
             const uint32_t v = (COUNT || lane == CT_INS || lane == CT_LIVE || lane == CT_NOOP) ? cx.ct[lane] : 0u;
@@ -968,7 +985,9 @@ __device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, con
     cx.perm = scratch + WK_HDR + L.PW;
     cx.keym = cx.perm + L.W;
     const uint32_t *src = L.walker + (size_t)tree * L.WS;
+#pragma unroll 1
     for (uint32_t i = lane; i < L.PW; i += 32) ((uint32_t *)cx.par)[i] = src[WK_HDR + L.PW + 2 * L.W + i];
+#pragma unroll 1
     for (uint32_t w = lane; w < L.W; w += 32) {
         cx.perm[w] = src[WK_HDR + 2 * L.PW + 2 * L.W + w];
         cx.keym[w] = 0u;
@@ -983,7 +1002,9 @@ __device__ void finalize_argmin_state(const AzbLayout &L, uint32_t *scratch, con
             walker_act(L, cx, w * 32 + b);
         }
     }
+#pragma unroll 1
     for (uint32_t i = lane; i < 16; i += 32) L.g->argmin_state[i] = i < L.PW ? ((uint32_t *)cx.par)[i] : 0u;
+#pragma unroll 1
     for (uint32_t w = lane; w < 61; w += 32) L.g->argmin_state[16 + w] = w < L.W ? cx.perm[w] : 0u;
 }
 
@@ -993,6 +1014,7 @@ __global__ void __launch_bounds__(32) azb_argmin_kernel(const AzbLayout L, const
     __shared__ uint32_t scratch[WK_HDR + 16 + 2 * 61 + 8];
     __shared__ uint8_t lut[2048];
     const int lane = threadIdx.x;
+#pragma unroll 1
     for (uint32_t a = lane; a < L.A; a += 32) lut[a] = (uint8_t)azb_action_child(a);
     __syncwarp();
     AzbGlobals *g = L.g;
@@ -1096,6 +1118,7 @@ __global__ void __launch_bounds__(128) azb_observe_kernel(const AzbLayout L, con
     const uint32_t tree = blockIdx.x * 4 + warp;
     if (tree >= L.B) return;
     float *o = obs + (size_t)tree * L.A, *w = wts + (size_t)tree * L.A;
+#pragma unroll 1
     for (uint32_t a = lane; a < L.A; a += 32) {
         o[a] = 0.f;
         w[a] = 0.f;
@@ -1106,6 +1129,7 @@ __global__ void __launch_bounds__(128) azb_observe_kernel(const AzbLayout L, con
     if (lo2 != AZB_LO_NONE) {
         const uint4 *blk4 = reinterpret_cast<const uint4 *>(L.blk + (size_t)tree * L.cap_blk);
         const uint32_t n_out = blk4[lo2].y & 0xffffu;
+#pragma unroll 1
         for (uint32_t t = lane; t < n_out; t += 32) {
             const uint4 kd = blk4[lo2 + 1u + t];
             if (!(kd.y >> 31) || kd.z >= n_obs_tol) {
@@ -1119,6 +1143,7 @@ __global__ void __launch_bounds__(128) azb_observe_kernel(const AzbLayout L, con
         const uint8_t *rpar = (const uint8_t *)(wk + WK_HDR + L.PW + 2 * L.W);
         const uint32_t *rperm = wk + WK_HDR + 2 * L.PW + 2 * L.W;
         float *row = root_vecs + (size_t)tree * L.sv_ld;
+#pragma unroll 1
         for (uint32_t i = lane; i < 2 * L.A; i += 32) {
             bool one;
             if (i < L.A) {
@@ -1161,8 +1186,10 @@ __global__ void __launch_bounds__(128) azb_modify_roots_kernel(const AzbLayout L
     uint16_t *perm = s_perm[warp];
     uint32_t *mask = s_mask[warp];
     uint8_t *par = s_par[warp];
+#pragma unroll 1
     for (uint32_t i = lane; i < L.PW; i += 32) reinterpret_cast<uint32_t *>(par)[i] = g_rpar[i];
     uint32_t kcur = 0;
+#pragma unroll 1
     for (uint32_t w = lane; w < L.W; w += 32) kcur += __popc(g_rperm[w]);
     kcur = warp_sum_u32(kcur);
     __syncwarp();
@@ -1224,6 +1251,7 @@ __global__ void __launch_bounds__(128) azb_modify_roots_kernel(const AzbLayout L
             }
             // p.actions_taken().for_each(|a| space.act(state, a)): only the parents survive the re-draw below
             const uint32_t *key = L.key + ((size_t)tree * L.cap_nodes + chosen) * L.W;
+#pragma unroll 1
             for (uint32_t w = lane; w < L.W; w += 32) {
                 uint32_t word = key[w];
                 while (word) {
@@ -1238,7 +1266,9 @@ __global__ void __launch_bounds__(128) azb_modify_roots_kernel(const AzbLayout L
     }
     __syncwarp();
     // choose_multiple(rng, num) over 0..A as a partial Fisher-Yates (the host generator's algorithm)
+#pragma unroll 1
     for (uint32_t i = lane; i < L.A; i += 32) perm[i] = (uint16_t)i;
+#pragma unroll 1
     for (uint32_t w = lane; w < 64; w += 32) mask[w] = 0u;
     __syncwarp();
     if (err == 0) {
@@ -1252,7 +1282,9 @@ __global__ void __launch_bounds__(128) azb_modify_roots_kernel(const AzbLayout L
             }
         }
         __syncwarp();
+#pragma unroll 1
         for (uint32_t i = lane; i < L.PW; i += 32) g_rpar[i] = reinterpret_cast<uint32_t *>(par)[i];
+#pragma unroll 1
         for (uint32_t w = lane; w < L.W; w += 32) g_rperm[w] = mask[w];
     } else if (lane == 0) {
         if (atomicCAS(&L.g->err, 0u, err) == 0u) {
