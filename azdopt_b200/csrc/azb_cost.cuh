@@ -271,6 +271,10 @@ struct __align__(16) PolyScratch {  // per-warp shared memory, lives in the same
     double cf[AZB_POLY_KMAX + 1];  // signed coefficients of p(y), highest power first
 };
 
+// (tried as __noinline__ single copies to shrink the walkers' hot code: the calls cost more than the 0.9 KB saved)
+__device__ __forceinline__ double azb_dsqrt(double x) { return __dsqrt_rn(x); }
+__device__ __forceinline__ double azb_ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
 __device__ __forceinline__ void azb_two_sum(double a, double b, double &s, double &e) {
     s = __dadd_rn(a, b);
     const double bb = __dsub_rn(s, a);
@@ -334,6 +338,7 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         // branch-free product loop: lanes beyond the useful range read clamped slots and multiply by zero (lanes above
         // KM read a few words past their row, still inside the scratch, and are never stored)
         const uint32_t *Ap = ps->A[p], *Bp = ps->B[p];
+#pragma unroll 1
         for (int i = 0; i <= dav; ++i) {
             const uint32_t ac = __shfl_sync(FULL, av, i), bc = __shfl_sync(FULL, bv, i);
             const int j = k - i;
@@ -385,9 +390,9 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         const double dd = __dmul_rn(2.0, h);
         double disc = __dmul_rn(nm1, __dsub_rn(__dmul_rn(nm1, __dmul_rn(d, d)), __dmul_rn(nn, __dmul_rn(s, dd))));
         if (!(disc >= 0.0)) disc = 0.0;
-        const double den = __dadd_rn(d, __dsqrt_rn(disc));
+        const double den = __dadd_rn(d, azb_dsqrt(disc));
         if (!(den > 0.0)) break;
-        const double yn = __dsub_rn(y, __ddiv_rn(__dmul_rn(nn, s), den));
+        const double yn = __dsub_rn(y, azb_ddiv(__dmul_rn(nn, s), den));
         if (!(yn < y)) break;
         const bool close = __dsub_rn(y, yn) < __dmul_rn(1e-5, yn);  // the two polishing steps finish from here
         y = yn;
@@ -411,11 +416,11 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         }
         const double pv = __dadd_rn(s, e);
         if (!(d > 0.0)) break;
-        y = __dsub_rn(y, __ddiv_rn(pv, d));
+        y = __dsub_rn(y, azb_ddiv(pv, d));
     }
     CPROF(4);
     __syncwarp();
-    return __dsqrt_rn(y);
+    return azb_dsqrt(y);
 }
 
 // cost of the tree in `par`: picks the method by size; every lane gets (lambda_1, mu)

@@ -111,6 +111,7 @@ __device__ __forceinline__ void count(WarpCtx &cx, int which, uint32_t n) {
 }
 
 __device__ __forceinline__ uint32_t nth_set_bit(uint32_t mask, uint32_t r) {
+#pragma unroll 1
     for (uint32_t i = 0; i < r; ++i) mask &= mask - 1;
     return __ffs(mask) - 1;
 }
