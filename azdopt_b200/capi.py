@@ -17,6 +17,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NAN, ERR_LAMBDA, ERR_UNREACHABLE, E
 PRIOR_MLP, PRIOR_HASH, PRIOR_INJECTED = 0, 1, 2
 MLP_FP32, MLP_TC, MLP_TC3 = 0, 1, 2
 MAX_TOL = 8
+ASYNC_AUTO = 0xFFFFFFFF
 
 COUNTER_FIELDS = [
     "n_sel", "d_sel", "n_cur", "n_cand", "n_probe", "n_ins", "n_term", "n_hit", "n_arc", "n_pred",

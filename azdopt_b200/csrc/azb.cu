@@ -265,6 +265,19 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     // arena growth measured with the oracle on the example's root distribution: at most ~1.9 nodes,
     // ~A/7 predictions (A/4 in the first steps) and ~N in-arc slots per step per tree; sized with >= 1.5x head-room,
     // overflow is reported as AZB_ERR_CAPACITY, never dropped
+    if (cfg.async_workers == AZB_ASYNC_AUTO) {
+        // measured on one B200 (profiles/README.md, round 2 worker sweeps): the model side needs ~2.3 M rows/s of capacity
+        // per SM it gets, the tree side one warp per tree up to 4096 roots
+        const bool applies = cfg.prior_mode == AZB_PRIOR_MLP && (cfg.mlp_mode == AZB_MLP_TC || cfg.mlp_mode == AZB_MLP_TC3) &&
+                             cfg.max_episodes == 0 && cfg.n_groups <= 1 && cfg.n_roots >= 1024;
+        if (!applies) cfg.async_workers = 0;
+        else if (cfg.n_vertices >= 47) cfg.async_workers = 32;
+        else if (cfg.n_roots < 4096) cfg.async_workers = 40;
+        else if (cfg.n_roots == 4096) cfg.async_workers = 20;
+        else if (cfg.n_roots <= 8192) cfg.async_workers = 28;
+        else if (cfg.n_roots <= 32768) cfg.async_workers = 36;
+        else cfg.async_workers = 40;
+    }
     if (cfg.cap_nodes == 0) cfg.cap_nodes = 3 * cfg.max_steps + 64;
     if (cfg.cap_preds == 0) cfg.cap_preds = 2 * A + cfg.max_steps * ((2 * A + 6) / 7);
     if (cfg.cap_parents == 0) cfg.cap_parents = cfg.cap_nodes * (N > 8 ? N - 7 : 1);  // in-arcs beyond the 4 inline ones
@@ -770,8 +783,8 @@ static int async_create(azb_handle *h) {
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
     P.n_workers = W;  // model CTAs (whole SMs)
     P.tree_warps = tree_warps;
-    // worker SMs per tile: one when few SMs serve the model (every tree keeps its own warp at 4096 roots), pairs otherwise
-    P.group = W < 40 ? 1 : 2;
+    // worker SMs per tile
+    P.group = B < 4096 ? 2 : 1;  // pairs answer a tile faster; from 4096 roots on the model's throughput matters more
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
     if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
     P.smem_words_per_warp = h->smem_words_per_warp;

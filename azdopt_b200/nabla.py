@@ -90,10 +90,8 @@ class NablaOptimizer:
         else:
             prior, mlp, hidden = capi.PRIOR_INJECTED, capi.MLP_FP32, (512, 1024, 512)
         if async_workers is None:
-            # the asynchronous search kernel (same results) wherever it applies: the tensor-core device model and
-            # enough roots to fill tiles; 20 worker SMs keep one warp per tree at 4096 roots
-            ok = mlp == capi.MLP_TC and prior == capi.PRIOR_MLP and 1024 <= batch <= 100000
-            async_workers = (40 if batch < 4096 else 20 if batch == 4096 else 48 if batch < 16384 else 32) if ok else 0
+            # the asynchronous search kernel (same results) wherever it applies; the library picks the model SMs
+            async_workers = capi.ASYNC_AUTO
         cfg = capi.default_config(space.n, batch, device=device, first_root=first_root, c_lower=space.c_lower,
                                   c_upper=space.c_upper, n_as_tol=n_as_tol, n_as_tol_default=n_as_tol_default,
                                   prior_mode=prior, mlp_mode=mlp, mlp_hidden=hidden, max_steps=max_steps,

@@ -237,10 +237,8 @@ def main():
     total_steps = args.warmup + args.steps
     prof_steps = min(args.steps, 100)
     aw = args.async_workers
-    if aw < 0:  # auto: 20 of the 148 SMs answer state vectors (128 x 32 warps walk: one tree per warp at 4096 roots);
-        # 48 SMs in pairs up to 16 K roots, 32 single SMs beyond (profiles/README.md, worker sweeps)
-        ok = args.mlp in ("tc", "tc3") and not args.max_episodes and args.groups == 1 and 1024 <= b <= 100000
-        aw = (40 if b < 4096 else 20 if b == 4096 else 48 if b < 16384 else 32) if ok else 0
+    if aw < 0:  # auto: the library's choice for this root count (AZB_ASYNC_AUTO; include/azb.h)
+        aw = capi.ASYNC_AUTO if not args.max_episodes and args.groups == 1 else 0
     cfg = capi.default_config(n, b, device=local_rank, first_root=rank * b, prior_mode=capi.PRIOR_MLP,
                               mlp_mode={"tc": capi.MLP_TC, "tc3": capi.MLP_TC3, "fp32": capi.MLP_FP32}[args.mlp],
                               max_steps=total_steps + prof_steps + 8, max_episodes=args.max_episodes,
@@ -257,6 +255,7 @@ def main():
         h = capi.Handle(cfg)
         mlp_note = f"fp32 (tensor-core path unavailable: {e})"
         args.mlp = "fp32"
+    aw = cfg.async_workers = int(h.cfg.async_workers)  # the resolved choice
     h.mlp_init(args.seed + 1)  # same seed on every rank: replicated weights
 
     def barrier():
@@ -458,7 +457,7 @@ def main():
         # C4: 64-vertex trees (cost path dominated): 4096 roots, 32 model SMs
         c4_roots, c4_steps = 4096, min(args.steps, 64)
         try:
-            c4_sims, c4_ms, ev4, bytes4 = timed_config(capi, 64, c4_roots, 32, c4_steps, max(3, min(args.warmup, 8)), args.seed, rank, local_rank)
+            c4_sims, c4_ms, ev4, bytes4 = timed_config(capi, 64, c4_roots, capi.ASYNC_AUTO, c4_steps, max(3, min(args.warmup, 8)), args.seed, rank, local_rank)
             extra["c4"] = {"value": c4_sims / (c4_ms * 1e-3), "unit": UNIT, "vertices": 64, "roots": c4_roots, "steps": c4_steps,
                            "ms_per_step": c4_ms / c4_steps, "cost_evals_per_sec": ev4 / (c4_ms * 1e-3), "device_bytes": bytes4,
                            "what": "BASELINE configs[3]: N=64 (A=1952, MLP 3904-512-1024-512-1952), asynchronous kernel, 32 model SMs"}
@@ -466,7 +465,7 @@ def main():
             extra["c4"] = {"error": str(e)}
     if world == 8 and not args.no_extra:
         # C3: 65 536 roots over the 8 GPUs = 8192 per GPU, 48 model SMs in pairs
-        c3_sims, c3_ms, ev3, _ = timed_config(capi, n, 8192, 48, xsteps, args.warmup, args.seed, rank, local_rank)
+        c3_sims, c3_ms, ev3, _ = timed_config(capi, n, 8192, capi.ASYNC_AUTO, xsteps, args.warmup, args.seed, rank, local_rank)
         ms3 = allreduce(c3_ms, dist.ReduceOp.MAX)
         sims3 = allreduce(c3_sims, dist.ReduceOp.SUM)
         extra["c3"] = {"value": sims3 / (ms3 * 1e-3), "unit": UNIT, "roots_total": 8192 * world, "roots_per_gpu": 8192,

@@ -13,6 +13,8 @@ int main(int argc, char **argv) {
     const bool per_step = argc > 3 && atoi(argv[3]) != 0;  // the example's loop shape: one result per step, as it completes
     azb_config cfg;
     if (azb_config_default(&cfg, n, batch) != AZB_OK) return 1;
+    cfg.mlp_mode = AZB_MLP_TC;             // the built-in model on the tensor cores ...
+    cfg.async_workers = AZB_ASYNC_AUTO;    // ... and the asynchronous search kernel wherever the batch is large enough
     const uint32_t a = (n - 1) * (n - 2) / 2 - 1, w = (a + 31) / 32;
     std::vector<uint8_t> parents((size_t)batch * n);
     std::vector<uint32_t> permitted((size_t)batch * w);

@@ -34,6 +34,7 @@ extern "C" {
 #define AZB_NONE 0xFFFFFFFFu
 #define AZB_MAX_VERTICES 64
 #define AZB_MAX_TOL 8
+#define AZB_ASYNC_AUTO 0xFFFFFFFFu  /* azb_config.async_workers: let the library pick the model SMs from the root count */
 
 enum {
     AZB_OK = 0,
@@ -91,7 +92,11 @@ typedef struct azb_config {
                                    roots, 32 from 16 K roots; in pairs per tile from 40) become tensor-core model workers that
                                    answer state vectors in 128-row tiles as they fill, all other CTAs walk trees, a warp
                                    advancing whichever of its trees has its priors.  Same results as the lock step (trees are
-                                   independent).  0 = lock step.  Environment, read when the handle first runs this way:
+                                   independent).  0 = lock step.  AZB_ASYNC_AUTO = the measured best layout for the root count
+                                   (40 SMs in pairs below 4096 roots, 20 at 4096, 28 up to 8192, 36 up to
+                                   32 768, 40 beyond; 32 for N >= 47), or the lock step where the asynchronous kernel does not
+                                   apply (no tensor-core model, fewer than 1024 roots, max_episodes or n_groups set); azb_get_config
+                                   shows the choice.  Environment, read when the handle first runs this way:
                                    AZB_ASYNC_GROUP=g (worker SMs per tile), AZB_ASYNC_FLUSH_NS, AZB_ASYNC_TIMEOUT_MS (watchdog
                                    floor, default 2000). */
     uint32_t reserved[5];

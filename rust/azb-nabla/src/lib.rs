@@ -187,18 +187,8 @@ impl<const N: usize, M: NablaModel> B200Optimizer<N, M> {
             Model::Device { params, tensor_cores } => {
                 cfg.prior_mode = sys::AZB_PRIOR_MLP;
                 cfg.mlp_mode = if tensor_cores { sys::AZB_MLP_TC } else { sys::AZB_MLP_FP32 };
-                // the asynchronous kernel's model SMs (include/azb.h: 20 at 4096 roots, 32 from 16 K roots, pairs from 40)
-                cfg.async_workers = if !tensor_cores || batch < 1024 {
-                    0
-                } else if batch < 4096 {
-                    40
-                } else if batch == 4096 {
-                    20
-                } else if batch < 16384 {
-                    48
-                } else {
-                    32
-                };
+                // the asynchronous kernel wherever it applies; the library picks the model SMs for the root count
+                cfg.async_workers = if tensor_cores { sys::AZB_ASYNC_AUTO } else { 0 };
                 (None, Some(params))
             }
         };

@@ -7,6 +7,7 @@ pub const AZB_VERSION: c_int = 100;
 pub const AZB_NONE: u32 = 0xFFFF_FFFF;
 pub const AZB_MAX_VERTICES: u32 = 64;
 pub const AZB_MAX_TOL: usize = 8;
+pub const AZB_ASYNC_AUTO: u32 = 0xFFFF_FFFF;
 
 pub const AZB_OK: c_int = 0;
 pub const AZB_ERR_INVALID: c_int = 1;
