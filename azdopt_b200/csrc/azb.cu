@@ -765,6 +765,8 @@ static int async_create(azb_handle *h) {
     const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + 1024 + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
     // every CTA of the one cooperative launch asks for the larger of the two roles' shared memory
     h->async_smem = std::max(tree_smem, mlp_smem);
+    if (const char *e = getenv("AZB_ASYNC_SMEM_PAD_KB"))  // experiment: shrink the L1 the walkers see
+        h->async_smem = std::min<size_t>(224 * 1024, h->async_smem + (size_t)atoi(e) * 1024);
     int nb = 0, nb2 = 0, rc;
     switch (azb_stack_depth(h->N)) {
         case 3: rc = async_prepare_kernel<3, false>(h, &nb); if (!rc) rc = async_prepare_kernel<3, true>(h, &nb2); break;
@@ -783,6 +785,8 @@ static int async_create(azb_handle *h) {
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
     P.n_workers = W;  // model CTAs (whole SMs)
     P.tree_warps = tree_warps;
+    P.early = B <= NW ? 1u : 0u;  // one tree per warp: the tree's own latency chain is the bound (azb_async.cuh)
+    if (const char *e = getenv("AZB_ASYNC_EARLY")) P.early = atoi(e) != 0;
     // worker SMs per tile
     P.group = B < 4096 ? 2 : 1;  // pairs answer a tile faster; from 4096 roots on the model's throughput matters more
     if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);

@@ -102,6 +102,7 @@ struct AzbAsyncParams {
     uint32_t wide;           // 1: bf16 operands; 2: bf16x3 (AZB_MLP_TC3) — rows hold [hi(kpad) | lo(kpad)], three k-segments
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
+    uint32_t early;          // 1: the state vector is handed to the model from inside the walk (before the cost evaluation)
     unsigned long long timeout_ns, flush_ns;
     uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
     unsigned long long *dbg;  // optional [16] cycle counters of the MLP workers (tools/async_probe.py); null = off
@@ -787,15 +788,13 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         for (uint32_t i = lane; i < L.WS; i += 32) cx.wk[i] = gwk[i];
         __syncwarp();
         if (cx.wk[WK_FLAGS] & 1u) tree_add_actions<DEPTH == 5>(L, cx, tree);
-        if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) tree_rollout<DEPTH>(L, cx, tree, 0u);
-        uint32_t new_state = 0u;
-        const bool pending = (cx.wk[WK_FLAGS] & 1u) != 0u, at_target = cx.wk[WK_STEP] >= P.target_step;
-        if (cx.err) {
-            new_state = 2u;
-        } else {
-            // a new node needs priors: its state vector goes to the next ring row — or, on the last step of this launch,
-            // to the tree's own row (the host runs one batched forward over those)
-            const bool to_ring = pending && !at_target;
+        // A new node needs priors: its state vector goes to the next ring row — or, on the last step of this launch, to
+        // the tree's own row (the host runs one batched forward over those).  Called from inside the walk as soon as
+        // the new node is known to be non-terminal, so the model's round trip overlaps the cost evaluation and the insert.
+        bool submitted = false, to_ring = false, in_walk = true;
+        auto submit = [&](WarpCtx &c) {
+            // inside the walk the step that owns this row is still open: WK_STEP advances when it completes
+            to_ring = c.wk[WK_STEP] + (in_walk ? 1u : 0u) < P.target_step;
             uint32_t slot = 0, pos = 0;
             uint16_t *row = nullptr;
             if (to_ring) {
@@ -810,17 +809,38 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
                 pos = slot % ring_rows;
                 row = P.ring + (size_t)pos * P.ring_ld;
             }
-            if (pending) tree_pack<true>(L, cx, tree, row);
+            tree_pack<true>(L, c, tree, row);
             if (to_ring) {
                 if (lane == 0) P.slot_tree[pos] = tree;
                 __threadfence();
                 as_fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
-                new_state = 1u;
-            } else if (at_target) {
-                new_state = 2u;
             }
+            submitted = true;
+        };
+        if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) {
+            // Early hand-over pays where a tree's own chain (walk -> model -> walk) is the bound, i.e. while warps own one
+            // tree each; with several trees per warp it only lengthens the hot loop (32 768 roots: -11 %), so those
+            // launches take the instantiation that submits after the walk.
+            if (P.early)
+                tree_rollout<DEPTH>(L, cx, tree, 0u, submit);
+            else
+                tree_rollout<DEPTH>(L, cx, tree, 0u);
+        }
+        in_walk = false;
+        uint32_t new_state = 0u;
+        const bool pending = (cx.wk[WK_FLAGS] & 1u) != 0u, at_target = cx.wk[WK_STEP] >= P.target_step;
+        if (cx.err) {
+            new_state = 2u;
+        } else {
+            // (a tree that entered this advance with its target already reached still holds a node that awaits priors: its
+            // row goes to the tree's own slot like every last step's)
+            if (pending && !submitted) submit(cx);
+            if (submitted && to_ring)
+                new_state = 1u;
+            else if (at_target)
+                new_state = 2u;
         }
         __syncwarp();
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;

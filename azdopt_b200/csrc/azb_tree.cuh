@@ -445,8 +445,15 @@ __device__ __forceinline__ void step_done(const AzbLayout &L, WarpCtx &cx, uint3
     cx.err = __reduce_or_sync(0xffffffffu, cx.err);
 }
 
-template <int DEPTH>
-__device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint32_t max_episodes) {
+// `early(cx)` is called as soon as the step's new node is known to be non-terminal — BEFORE its cost is evaluated and the
+// node is inserted: the walker's state is final from that point on, so the asynchronous kernel hands the state vector to
+// the model there and the cost evaluation (~5 us) and the insert overlap the model's round trip.  The lock step passes a
+// no-op and packs after the walk (cx.cur still holds the current-edge mask then).
+struct TreeNoEarly {
+    __device__ __forceinline__ void operator()(WarpCtx &) const {}
+};
+template <int DEPTH, class Early = TreeNoEarly>
+__device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uint32_t max_episodes, Early early = Early()) {
     const int lane = cx.lane;
     const uint32_t FULL = 0xffffffffu;
     uint32_t pos = cx.wk[WK_POS], depth = cx.wk[WK_DEPTH], lo2 = cx.wk[WK_CURLO];
@@ -665,6 +672,13 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             // ---- new node (tree/mod.rs:181-216)
             walker_act(L, cx, a);
             const uint32_t ndepth = depth + 1;
+            // is_terminal (nabla/space/mod.rs:27-29) first: it only needs the state
+            build_cur_mask(L, cx);
+            bool any = false;
+#pragma unroll 1
+            for (uint32_t w = lane; w < L.W; w += 32) any = any || ((cx.perm[w] & ~cx.cur[w]) != 0u);
+            any = __any_sync(FULL, any);
+            if (any) early(cx);
             uint32_t mu = 0;
             const double l1 = azb_cost_warp<DEPTH>(L.N, cx.par, cx.cs, lane, &mu);
             if (!(l1 >= 1.4)) {  // ordered_edge.rs:79
@@ -680,12 +694,6 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
                 cx.err = 3;
                 break;
             }
-            // is_terminal (nabla/space/mod.rs:27-29)
-            build_cur_mask(L, cx);
-            bool any = false;
-#pragma unroll 1
-            for (uint32_t w = lane; w < L.W; w += 32) any = any || ((cx.perm[w] & ~cx.cur[w]) != 0u);
-            any = __any_sync(FULL, any);
             if (lane < 4) {  // StateWeight::new (state_weight.rs:13-21) + the creating arc as in-arc 0
                 uint4 q;
                 if (lane == 0)
