@@ -18,6 +18,7 @@ PRIOR_MLP, PRIOR_HASH, PRIOR_INJECTED = 0, 1, 2
 MLP_FP32, MLP_TC, MLP_TC3 = 0, 1, 2
 MAX_TOL = 8
 ASYNC_AUTO = 0xFFFFFFFF
+ASYNC_SHARED = 0xFFFFFFFE  # every SM walks trees and serves the model with its last warpgroup (include/azb.h)
 
 COUNTER_FIELDS = [
     "n_sel", "d_sel", "n_cur", "n_cand", "n_probe", "n_ins", "n_term", "n_hit", "n_arc", "n_pred",

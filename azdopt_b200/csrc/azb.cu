@@ -65,7 +65,7 @@ struct azb_handle {
     AzbAsyncParams asP;
     AzbAsyncMaps asM;
     int async_grid;
-    size_t async_smem;
+    size_t async_smem, async_zero_bytes;
     unsigned long long async_timeout_base_ns;
     // azb_step_poll: per-step results of enqueued steps while they still run (copies on their own stream)
     cudaStream_t poll_stream;
@@ -96,6 +96,11 @@ struct azb_handle {
     cudaGraphExec_t step_graph;   // one step incl. the argmin pass and the read-back of the globals (azb_step(h, 1, ...))
     uint32_t step_graph_key;
     AzbGlobals *pin_g;            // pinned host copy of the globals' head, written by the step graph
+    uint32_t *roots_pin, *roots_dev;  // azb_set_roots: pinned staging of the packed root blocks and their device copy
+    cudaEvent_t roots_ev;             // the staging buffer is free again once this has passed
+    AzbGlobals *pin_rg;               // pinned landing zone of read_globals / azb_get_argmin
+    uint32_t *pin_abort;
+    uint32_t *pin_cost;               // pinned: lambda_1 (8 bytes), mu, eval, error word of azb_get_argmin's cost evaluation
     azb_improvement *pin_log;
     char err[512];
 };
@@ -212,6 +217,12 @@ int azb_destroy(azb_handle *h) {
     if (h->fork_event) cudaEventDestroy(h->fork_event);
     if (h->pin_g) cudaFreeHost(h->pin_g);
     if (h->poll_pin) cudaFreeHost(h->poll_pin);
+    if (h->roots_pin) cudaFreeHost(h->roots_pin);
+    if (h->roots_dev) cudaFree(h->roots_dev);
+    if (h->roots_ev) cudaEventDestroy(h->roots_ev);
+    if (h->pin_rg) cudaFreeHost(h->pin_rg);
+    if (h->pin_abort) cudaFreeHost(h->pin_abort);
+    if (h->pin_cost) cudaFreeHost(h->pin_cost);
     if (h->poll_word) cudaFreeHost(h->poll_word);
     if (h->poll_stream) cudaStreamDestroy(h->poll_stream);
     if (h->pin_log) cudaFreeHost(h->pin_log);
@@ -457,34 +468,51 @@ int azb_generate_roots(uint64_t seed, uint64_t first_root, uint32_t count, uint3
     return AZB_OK;
 }
 
-static int check_roots(azb_handle *h, const uint8_t *parents, const uint32_t *permitted) {
-    const uint32_t N = h->N, A = h->A, W = h->W, B = h->L.B;
+// root blocks [B][PW + W] (packed parents | permitted mask) -> the root part of every walker block
+__global__ void azb_scatter_roots_kernel(uint32_t *__restrict__ walker, const uint32_t *__restrict__ src, uint32_t n_words,
+                                         uint32_t per_root, uint32_t WS, uint32_t off) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint32_t r = i / per_root, j = i - r * per_root;
+    walker[(size_t)r * WS + off + j] = src[i];
+}
+
+int azb_set_roots(azb_handle *h, const uint8_t *parents, const uint32_t *permitted) {
+    if (!h || !parents || !permitted) return AZB_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const uint32_t N = h->N, A = h->A, W = h->W, PW = h->PW, WS = h->WS, B = h->L.B, per = PW + W;
+    const size_t bytes = (size_t)B * per * 4;
+    // One pass over the caller's arrays validates them and packs the root part of each walker block
+    // [hdr | state parents, permitted, path | ROOT parents, permitted] into a pinned staging buffer; one contiguous copy
+    // and a scatter kernel put it in place (a strided copy out of pageable memory cost 0.8 ms per 4096 roots — a quarter
+    // of a 20-step epoch).  The caller's buffers are free on return; nothing waits for the device here.
+    if (!h->roots_pin) {
+        CK(cudaMallocHost((void **)&h->roots_pin, bytes));
+        CK(cudaMalloc((void **)&h->roots_dev, bytes));
+        h->dev_bytes += bytes;
+        CK(cudaEventCreateWithFlags(&h->roots_ev, cudaEventDisableTiming));
+    } else {
+        CK(cudaEventSynchronize(h->roots_ev));  // the previous call's copy has left the staging buffer
+    }
+    const uint32_t tail_bits = A % 32;
     for (uint32_t i = 0; i < B; ++i) {
         const uint8_t *p = parents + (size_t)i * N;
         for (uint32_t v = 1; v < N; ++v)
             if (p[v] >= v) return fail(h, AZB_ERR_INVALID, "root %u: parents[%u] = %u is not < %u", i, v, p[v], v);
         const uint32_t *m = permitted + (size_t)i * W;
-        if (A % 32 && (m[W - 1] >> (A % 32))) return fail(h, AZB_ERR_INVALID, "root %u: permitted bit >= ACTION_DIM", i);
+        if (tail_bits && (m[W - 1] >> tail_bits)) return fail(h, AZB_ERR_INVALID, "root %u: permitted bit >= ACTION_DIM", i);
+        uint32_t *dst = h->roots_pin + (size_t)i * per;
+        dst[PW - 1] = 0u;
+        memcpy(dst, p, N);
+        memcpy(dst + PW, m, (size_t)W * 4);
     }
-    return AZB_OK;
-}
-
-int azb_set_roots(azb_handle *h, const uint8_t *parents, const uint32_t *permitted) {
-    if (!h || !parents || !permitted) return AZB_ERR_INVALID;
-    int rc = check_roots(h, parents, permitted);
-    if (rc) return rc;
-    CK(cudaSetDevice(h->cfg.device));
-    const uint32_t N = h->N, W = h->W, PW = h->PW, WS = h->WS, B = h->L.B;
-    // the root part of each walker block: [hdr | state parents, permitted, path | ROOT parents, permitted]
-    std::vector<uint32_t> blk((size_t)B * (PW + W), 0u);
-    for (uint32_t i = 0; i < B; ++i) {
-        uint32_t *dst = blk.data() + (size_t)i * (PW + W);
-        memcpy(dst, parents + (size_t)i * N, N);
-        memcpy(dst + PW, permitted + (size_t)i * W, (size_t)W * 4);
-    }
-    CK(cudaMemcpy2DAsync(h->L.walker + WK_HDR + PW + 2 * W, (size_t)WS * 4, blk.data(), (size_t)(PW + W) * 4,
-                         (size_t)(PW + W) * 4, B, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(h->roots_dev, h->roots_pin, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->roots_ev, h->stream));
+    const uint32_t n_words = B * per;
+    azb_scatter_roots_kernel<<<(n_words + 255u) / 256u, 256, 0, h->stream>>>(h->L.walker, h->roots_dev, n_words, per, WS,
+                                                                             WK_HDR + PW + 2 * W);
+    CK(cudaGetLastError());
+    h->launches += 1;
     h->roots_set = true;
     h->trees_init = false;
     return AZB_OK;
@@ -644,10 +672,17 @@ static int launch_tree(azb_handle *h, uint32_t flags, uint32_t target_step, int 
 }
 
 static int read_globals(azb_handle *h, AzbGlobals *g) {
-    CK(cudaMemcpyAsync(g, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
-    uint32_t as_abort = 0;
-    if (h->async_ran) CK(cudaMemcpyAsync(&as_abort, &h->asP.st->abort, 4, cudaMemcpyDeviceToHost, h->stream));
+    // pinned landing zones: a copy into pageable memory is staged and synchronised by the driver, once per call
+    if (!h->pin_rg) {
+        CK(cudaMallocHost((void **)&h->pin_rg, sizeof(AzbGlobals)));
+        CK(cudaMallocHost((void **)&h->pin_abort, 16));
+    }
+    CK(cudaMemcpyAsync(h->pin_rg, h->L.g, offsetof(AzbGlobals, argmin_state), cudaMemcpyDeviceToHost, h->stream));
+    h->pin_abort[0] = 0u;
+    if (h->async_ran) CK(cudaMemcpyAsync(h->pin_abort, &h->asP.st->abort, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    memcpy(g, h->pin_rg, offsetof(AzbGlobals, argmin_state));
+    const uint32_t as_abort = h->pin_abort[0];
     h->async_ran = false;
     if (as_abort == 1u) return fail(h, AZB_ERR_CUDA, "async search kernel: watchdog expired (no progress)");
     if (g->err)
@@ -754,17 +789,44 @@ static int async_create(azb_handle *h) {
     if (!coop) return fail(h, AZB_ERR_CUDA, "cooperative launch not supported");
     uint32_t W = h->cfg.async_workers;
     const uint32_t B = h->L.B;
+    // shared-SM form (azb_async.cuh): no SM is taken from the trees, the last warpgroup of every CTA is a model group member
+    bool shared_sm = W == AZB_ASYNC_SHARED;
+    if (const char *e = getenv("AZB_ASYNC_SHARED_SM")) shared_sm = atoi(e) != 0;
+    if (shared_sm && azb_stack_depth(h->N) == 5)
+        return fail(h, AZB_ERR_INVALID, "AZB_ASYNC_SHARED needs N <= 46 (larger trees take the whole SM's shared memory)");
+    uint32_t group = shared_sm ? 8u : (B < 4096 ? 2u : 1u);  // pairs answer a tile faster; from 4096 roots on the model's throughput matters more
+    if (const char *e = getenv("AZB_ASYNC_GROUP")) group = (uint32_t)strtoul(e, nullptr, 10);
+    if (group == 0) return fail(h, AZB_ERR_INVALID, "AZB_ASYNC_GROUP must be positive");
+    if (shared_sm) W = 0;
     // tree warps per CTA: 32, fewer when a large N needs more shared memory per warp (at most ~160 KB per SM, the rest is L1)
     const size_t lut_bytes = (h->A + 15) & ~15u, per_warp = (size_t)h->smem_words_per_warp * 4;
     uint32_t tree_warps = (uint32_t)std::max<size_t>(4, std::min<size_t>(AS_WARPS, (160 * 1024 - lut_bytes) / per_warp));
     if (azb_stack_depth(h->N) == 5) tree_warps = std::min<uint32_t>(tree_warps, AS_WIDE_TREE_WARPS);  // see azb_async_kernel
     if (const char *e = getenv("AZB_ASYNC_TREE_WARPS")) tree_warps = std::min<uint32_t>(tree_warps, std::max(1, atoi(e)));
+    if (shared_sm) tree_warps = SH_TREE_WARPS;
     const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
     const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + 1024 + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
     // every CTA of the one cooperative launch asks for the larger of the two roles' shared memory
     h->async_smem = std::max(tree_smem, mlp_smem);
+    uint32_t cw[4] = {0, 0, 0, 0}, sh_stages = 0;
+    if (shared_sm) {
+        // a member's column slice of every layer: ceil(npad / G) rounded up to the MMA's N granularity
+        uint32_t cwmax = 0, cwsum = 0;
+        for (int l = 0; l < 4; ++l) {
+            cw[l] = ((h->tc.npad[l] + group - 1u) / group + 15u) & ~15u;
+            if (cw[l] > 256u) return fail(h, AZB_ERR_INVALID, "AZB_ASYNC_SHARED: %u columns per member exceed one 256-column MMA (raise AZB_ASYNC_GROUP)", cw[l]);
+            cwmax = std::max(cwmax, cw[l]);
+            cwsum += cw[l];
+        }
+        const size_t stage = (size_t)AS_TILE * TC_BK * 2 + (size_t)cwmax * TC_BK * 2;
+        // trees | (1 KB alignment) operand ring | bias slices | (1 KB alignment) one staging tile per model warp
+        sh_stages = SH_MAX_STAGES;
+        auto need = [&](uint32_t st) { return tree_smem + 1024 + (size_t)st * stage + (size_t)cwsum * 4 + 1024 + 4u * SH_STG_BYTES; };
+        while (sh_stages > 2u && need(sh_stages) > (size_t)prop.sharedMemPerBlockOptin - 2048) --sh_stages;
+        h->async_smem = need(sh_stages);
+    }
     if (const char *e = getenv("AZB_ASYNC_SMEM_PAD_KB"))  // experiment: shrink the L1 the walkers see
         h->async_smem = std::min<size_t>(224 * 1024, h->async_smem + (size_t)atoi(e) * 1024);
     int nb = 0, nb2 = 0, rc;
@@ -778,19 +840,24 @@ static int async_create(azb_handle *h) {
     if (nb < 1) return fail(h, AZB_ERR_CUDA, "the async kernel does not fit on an SM (%zu bytes of shared memory)", h->async_smem);
     h->async_grid = nb * prop.multiProcessorCount;
     if ((int)W >= prop.multiProcessorCount || (int)W >= h->async_grid) return fail(h, AZB_ERR_INVALID, "async_workers >= SM count");
+    const uint32_t n_model_groups = shared_sm ? (uint32_t)h->async_grid / group : W / group;
+    if (shared_sm && (nb != 1 || n_model_groups == 0)) return fail(h, AZB_ERR_INVALID, "AZB_ASYNC_SHARED needs one CTA per SM and at least %u SMs", group);
     const uint32_t NW = (uint32_t)(h->async_grid - (int)W) * tree_warps;
     if (B > 32u * NW) return fail(h, AZB_ERR_INVALID, "async mode holds at most %u trees per GPU", 32u * NW);
     AzbAsyncParams &P = h->asP;
     memset(&P, 0, sizeof(P));
-    P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * W + 8;
+    P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * (shared_sm ? n_model_groups : W) + 8;
     P.n_workers = W;  // model CTAs (whole SMs)
+    P.shared_sm = shared_sm ? 1u : 0u;
+    for (int l = 0; l < 4; ++l) P.cw[l] = cw[l];
+    P.sh_stages = sh_stages;
     P.tree_warps = tree_warps;
     P.early = B <= NW ? 1u : 0u;  // one tree per warp: the tree's own latency chain is the bound (azb_async.cuh)
     if (const char *e = getenv("AZB_ASYNC_EARLY")) P.early = atoi(e) != 0;
     // worker SMs per tile
-    P.group = B < 4096 ? 2 : 1;  // pairs answer a tile faster; from 4096 roots on the model's throughput matters more
-    if (const char *e = getenv("AZB_ASYNC_GROUP")) P.group = (uint32_t)strtoul(e, nullptr, 10);
-    if (P.group == 0 || W % P.group || W / P.group > 64) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
+    P.group = group;
+    if (W % P.group) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);
+    if (n_model_groups > AS_MAX_GROUPS) return fail(h, AZB_ERR_INVALID, "more than %u model groups", (unsigned)AS_MAX_GROUPS);
     P.smem_words_per_warp = h->smem_words_per_warp;
     P.wide = h->tc.split ? 2u : 1u;
     P.ring_ld = P.wide * h->tc.kpad[0];
@@ -815,23 +882,35 @@ static int async_create(azb_handle *h) {
         }
         return e;
     };
-    CK(alloc((void **)&P.st, sizeof(AzbAsyncState)));
-    CK(alloc((void **)&P.tile_count, (size_t)P.NT * 4));
-    CK(alloc((void **)&P.tile_retired, (size_t)P.NT * 4));
+    // everything a launch starts from zero sits in ONE slab (one memset per launch): state | tile counters | answer flags | debug
+    {
+        auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        const size_t o_cnt = up(sizeof(AzbAsyncState)), o_ret = o_cnt + up((size_t)P.NT * 4), o_flag = o_ret + up((size_t)P.NT * 4),
+                     o_dbg = o_flag + up((size_t)B * 4);
+        h->async_zero_bytes = o_dbg + 64 * 8;
+        uint8_t *slab = nullptr;
+        CK(alloc((void **)&slab, h->async_zero_bytes));
+        P.st = reinterpret_cast<AzbAsyncState *>(slab);
+        P.tile_count = reinterpret_cast<uint32_t *>(slab + o_cnt);
+        P.tile_retired = reinterpret_cast<uint32_t *>(slab + o_ret);
+        P.h_flag = reinterpret_cast<uint32_t *>(slab + o_flag);
+        P.dbg = reinterpret_cast<unsigned long long *>(slab + o_dbg);
+    }
     CK(alloc((void **)&P.slot_tree, (size_t)P.NT * AS_TILE * 4));
-    CK(alloc((void **)&P.h_flag, (size_t)B * 4));
-    CK(alloc((void **)&P.dbg, 64 * 8));
     CK(alloc((void **)&P.ring, (size_t)P.NT * AS_TILE * P.ring_ld * 2));
-    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)W * AS_TILE * P.wide * h->tc.kpad[l + 1] * 2));
+    const uint32_t scratch_tiles = shared_sm ? n_model_groups : W;  // one 128-row scratch tile per group (whole-SM form: per worker)
+    for (int l = 0; l < 3; ++l) CK(alloc((void **)&P.act[l], (size_t)scratch_tiles * AS_TILE * P.wide * h->tc.kpad[l + 1] * 2));
     azb_encode_fn enc = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&enc, cudaEnableDefault, &qres) != cudaSuccess || !enc)
         return fail(h, AZB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
     const char *why = azb_tc_make_map(enc, &h->asM.ring, P.ring, (uint64_t)P.NT * AS_TILE, P.ring_ld, AS_TILE);
     for (int l = 0; l < 3 && !why; ++l)
-        why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)W * AS_TILE, P.wide * h->tc.kpad[l + 1], AS_TILE);
+        why = azb_tc_make_map(enc, &h->asM.act[l], P.act[l], (uint64_t)scratch_tiles * AS_TILE, P.wide * h->tc.kpad[l + 1], AS_TILE);
     for (int l = 0; l < 4 && !why; ++l)
         why = azb_tc_make_map(enc, &h->asM.w[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, P.wide * h->tc.kpad[l], 128);
+    for (int l = 0; l < 4 && !why && shared_sm; ++l)  // the same weights, fetched one member's column slice at a time
+        why = azb_tc_make_map(enc, &h->asM.ws[l], h->tc.w[l], (uint64_t)(h->tc.npad[l] + 127u) / 128u * 128u, P.wide * h->tc.kpad[l], cw[l]);
     if (why) return fail(h, AZB_ERR_CUDA, "async tensor maps: %s", why);
     CK(cudaStreamSynchronize(h->stream));
     h->async_ready = true;
@@ -851,11 +930,7 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     int rc = async_create(h);
     if (rc) return rc;
     AzbAsyncParams &P = h->asP;
-    CK(cudaMemsetAsync(P.st, 0, sizeof(AzbAsyncState), h->stream));
-    CK(cudaMemsetAsync(P.tile_count, 0, (size_t)P.NT * 4, h->stream));
-    CK(cudaMemsetAsync(P.tile_retired, 0, (size_t)P.NT * 4, h->stream));
-    CK(cudaMemsetAsync(P.h_flag, 0, (size_t)h->L.B * 4, h->stream));
-    CK(cudaMemsetAsync(P.dbg, 0, 64 * 8, h->stream));
+    CK(cudaMemsetAsync(P.st, 0, h->async_zero_bytes, h->stream));
     P.target_step = h->steps_done + n_steps;
     // watchdog, measured from the start of the launch: a step takes 0.1-1.2 ms at the supported sizes, so 2 s plus
     // 20 ms per step never fires on a healthy run, profiler replays included, and a stuck launch ends within seconds
@@ -872,8 +947,7 @@ static int run_async(azb_handle *h, uint32_t n_steps) {
     if (ce != cudaSuccess) return fail(h, AZB_ERR_CUDA, "async kernel launch: %s", cudaGetErrorString(ce));
     h->launches += 1;
     h->async_ran = true;
-    rc = mlp_forward(h, h->L.sv, h->L.sv_ld, h->L.h, h->L.h_ld, 0, h->L.B, h->stream);
-    if (rc) return rc;
+    // (the rows of the last step are answered inside the kernel too: no batched forward behind it)
     h->steps_done = P.target_step;
     h->pending_add = true;
     return AZB_OK;
@@ -1248,8 +1322,7 @@ int azb_add_actions_host(azb_handle *h, const float *h_theta, int *improved) {
 }
 
 // ---- stand-alone cost kernel ----
-static int eval_costs_dev(azb_handle *h, const uint8_t *parents, uint32_t m, double *lambda1, uint32_t *mu, float *c,
-                          float *ms) {
+static int cost_buffers(azb_handle *h, uint32_t m) {
     if (m > h->cost_cap) {
         void *old[] = {h->cost_par, h->cost_l1, h->cost_mu, h->cost_c};
         for (void *p : old)
@@ -1265,16 +1338,27 @@ static int eval_costs_dev(azb_handle *h, const uint8_t *parents, uint32_t m, dou
         h->cost_cap = m;
     }
     if (!h->cost_err) CK(dmalloc(h, &h->cost_err, 1));
-    CK(cudaMemcpyAsync(h->cost_par, parents, (size_t)m * h->N, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemsetAsync(h->cost_err, 0, 4, h->stream));
+    return AZB_OK;
+}
+
+static void launch_cost_kernel(azb_handle *h, const uint8_t *dev_parents, uint32_t m) {
     const uint32_t threads = 256, blocks = (m + 7) / 8;
-    CK(cudaEventRecord(h->ev0, h->stream));
     switch (azb_stack_depth(h->N)) {
-        case 3: azb_cost_kernel<3><<<blocks, threads, 0, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
-        case 4: azb_cost_kernel<4><<<blocks, threads, 0, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
-        default: azb_cost_kernel<5><<<blocks, threads, 0, h->stream>>>(h->cost_par, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
+        case 3: azb_cost_kernel<3><<<blocks, threads, 0, h->stream>>>(dev_parents, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
+        case 4: azb_cost_kernel<4><<<blocks, threads, 0, h->stream>>>(dev_parents, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
+        default: azb_cost_kernel<5><<<blocks, threads, 0, h->stream>>>(dev_parents, m, h->N, h->L.c_lower, h->L.slope, h->cost_l1, h->cost_mu, h->cost_c, h->cost_err); break;
     }
     h->launches += 1;
+}
+
+static int eval_costs_dev(azb_handle *h, const uint8_t *parents, uint32_t m, double *lambda1, uint32_t *mu, float *c,
+                          float *ms) {
+    int rc0 = cost_buffers(h, m);
+    if (rc0) return rc0;
+    CK(cudaMemcpyAsync(h->cost_par, parents, (size_t)m * h->N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->cost_err, 0, 4, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    launch_cost_kernel(h, h->cost_par, m);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     uint32_t err = 0;
@@ -1354,22 +1438,31 @@ int azb_get_argmin(azb_handle *h, uint8_t *parents, uint32_t *permitted, double 
     if (!h) return AZB_ERR_INVALID;
     if (!h->trees_init) return fail(h, AZB_ERR_STATE, "azb_init_trees has not been called");
     CK(cudaSetDevice(h->cfg.device));
-    AzbGlobals g;
-    CK(cudaMemcpyAsync(&g, h->L.g, sizeof(g), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    uint8_t par[AZB_MAX_VERTICES];
-    memcpy(par, g.argmin_state, h->N);
-    if (parents) memcpy(parents, par, h->N);
-    if (permitted) memcpy(permitted, g.argmin_state + 16, (size_t)h->W * 4);
-    // *cost = space.cost(state); *eval = space.evaluate(cost)  (optimizer/mod.rs:240-241)
-    double l1 = 0;
-    uint32_t m = 0;
-    float c = 0;
-    int rc = eval_costs_dev(h, par, 1, &l1, &m, &c, nullptr);
+    int rc = cost_buffers(h, 1);
     if (rc) return rc;
-    if (lambda1) *lambda1 = l1;
-    if (mu) *mu = m;
-    if (eval) *eval = c;
+    if (!h->pin_rg) {
+        CK(cudaMallocHost((void **)&h->pin_rg, sizeof(AzbGlobals)));
+        CK(cudaMallocHost((void **)&h->pin_abort, 16));
+    }
+    // *cost = space.cost(state); *eval = space.evaluate(cost)  (optimizer/mod.rs:240-241): the cost kernel reads the argmin
+    // state where the argmin pass left it, and everything comes back behind ONE synchronisation into pinned memory
+    CK(cudaMemsetAsync(h->cost_err, 0, 4, h->stream));
+    launch_cost_kernel(h, reinterpret_cast<const uint8_t *>(h->L.g->argmin_state), 1);
+    CK(cudaGetLastError());
+    if (!h->pin_cost) CK(cudaMallocHost((void **)&h->pin_cost, 32));
+    CK(cudaMemcpyAsync(h->pin_rg, h->L.g, sizeof(AzbGlobals), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin_cost, h->cost_l1, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin_cost + 2, h->cost_mu, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin_cost + 3, h->cost_c, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->pin_cost + 4, h->cost_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const AzbGlobals &g = *h->pin_rg;
+    if (parents) memcpy(parents, g.argmin_state, h->N);
+    if (permitted) memcpy(permitted, g.argmin_state + 16, (size_t)h->W * 4);
+    if (h->pin_cost[4]) return fail(h, (int)h->pin_cost[4], "%s", azb_strerror((int)h->pin_cost[4]));
+    if (lambda1) memcpy(lambda1, h->pin_cost, 8);
+    if (mu) *mu = h->pin_cost[2];
+    if (eval) memcpy(eval, h->pin_cost + 3, 4);
     return AZB_OK;
 }
 

@@ -55,6 +55,7 @@
                           // serialised the two: MMA 24 us + epilogue 25 us per tile)
 #define AS_TILE 128
 #define AS_NONE 0xffffffffu
+#define AS_MAX_GROUPS 128
 // one acquire load of a flag after the relaxed polls have seen it (PTX memory model: what the flag guards is read or
 // overwritten afterwards).  It costs one L1 invalidation (CCTL.IVALL) per tree-step; -DAS_ACQUIRE=0 measures without.
 #ifndef AS_ACQUIRE
@@ -79,14 +80,20 @@ struct AzbAsyncState {  // device memory, zeroed before every launch
     uint32_t tiles_done;
     uint32_t done_trees;
     uint32_t rows_real, rows_dummy;
-    // worker groups (AS_MAX_GROUPS): the leader's tile mailbox and the group's monotonic barriers
-    uint32_t grp_seq[64], grp_tile[64], grp_done[64], grp_layer[64 * 4];
+    // worker groups: the leader's tile mailbox and the group's monotonic barriers, one 128-byte line per group (the
+    // members of a group spin on their own line only)
+    struct Group {
+        uint32_t seq, tile, done, pad0;
+        uint32_t layer[4];
+        uint32_t pad1[24];
+    } grp[AS_MAX_GROUPS];
 };
 
 struct AzbAsyncMaps {
     CUtensorMap ring;    // layer-0 input: [NT*128 rows][kpad0] bf16
     CUtensorMap act[3];  // hidden activations of the workers: [n_workers*128 rows][kpad[l+1]]
     CUtensorMap w[4];    // weights [rows padded to 128][kpad[l]], box 64 x 128
+    CUtensorMap ws[4];   // the same weights with a box of 64 x cw[l]: one member's column slice (shared-SM form)
 };
 
 struct AzbAsyncParams {
@@ -103,6 +110,9 @@ struct AzbAsyncParams {
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
     uint32_t early;          // 1: the state vector is handed to the model from inside the walk (before the cost evaluation)
+    uint32_t shared_sm;      // 1: shared-SM form — every CTA walks trees with 28 warps and serves the model with its last warpgroup
+    uint32_t sh_stages;      // shared-SM form: stages of a member's operand ring
+    uint32_t cw[4];          // shared-SM form: output columns of layer l per group member (a multiple of 16, <= 256)
     unsigned long long timeout_ns, flush_ns;
     uint32_t dbg_flags;       // timing experiments only (AZB_ASYNC_DBG): 1 skip activation stores, 2 skip the TMEM reads
     unsigned long long *dbg;  // optional [16] cycle counters of the MLP workers (tools/async_probe.py); null = off
@@ -217,6 +227,79 @@ __device__ __forceinline__ uint32_t as_blocks_of_member(uint32_t npad, const AsW
 #define AS_TILE_BYTES (AS_TILE * TC_BK * 2u)              // one 128 x 64 bf16 operand tile, 16 KB
 #define AS_STAGE_BYTES ((1u + AS_ACC) * AS_TILE_BYTES)    // [A | B0 | B1]
 
+// Lane 0 of a group's first warp: the tile the group answers next (AS_NONE: leave).  The leader (member 0) waits until
+// every member has finished the previous tile (its scratch is reused), takes the next ticket, waits until that tile is
+// full — topping a stale partial tile up with dummy rows after flush_ns —, and posts it to the group's mailbox; the other
+// members wait for the mailbox (member_nap_ns > 0: with a nanosleep between polls, for members that share their SM with
+// walking trees).
+__device__ __forceinline__ uint32_t as_group_next_tile(const AzbLayout &L, const AzbAsyncParams &P, const AsWorkerId id, const uint32_t seq,
+                                                       const unsigned long long t_start, const uint32_t member_nap_ns) {
+    AzbAsyncState *st = P.st;
+    const uint32_t G = id.G, grp = id.grp, mem = id.mem;
+    uint32_t q;
+    if (mem == 0) {
+        // ---- the previous tile must be finished by every member before its scratch is reused
+        while (as_ld_volatile(&st->grp[grp].done) < G * seq && !as_ld_volatile(&st->abort)) {}
+        // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
+        q = atomicAdd(&st->tile_head, 1u);
+        const uint32_t *cnt_p = P.tile_count + (q % P.NT);
+        const uint32_t want = AS_TILE * (q / P.NT + 1u);
+        unsigned long long t_partial = 0;
+        bool flushed = false;
+        for (uint32_t spins = 0;; ++spins) {
+            if (as_ld_volatile(cnt_p) >= want) break;
+            if (as_ld_volatile(&st->abort)) {
+                q = AS_NONE;
+                break;
+            }
+            // every tree has finished the launch: its last row is already published (the rows of the last step are answered
+            // in here too — no batched forward behind the kernel), so a tile no row has reached will stay empty
+            const bool all_done = as_ld_volatile(&st->done_trees) >= L.B;
+            const uint32_t tail = as_ld_volatile(&st->row_tail);
+            if (all_done && tail <= q * AS_TILE) {
+                q = AS_NONE;
+                break;
+            }
+            if (!flushed && tail > q * AS_TILE && tail < (q + 1u) * AS_TILE) {
+                const unsigned long long now = as_now();
+                if (t_partial == 0) t_partial = now;
+                if (all_done || now - t_partial > P.flush_ns) {
+                    const uint32_t k = (q + 1u) * AS_TILE - tail;
+                    const uint32_t old = atomicAdd(&st->row_tail, k);
+                    for (uint32_t i = 0; i < k; ++i) P.slot_tree[(old + i) % (P.NT * AS_TILE)] = AS_NONE;
+                    __threadfence();
+                    for (uint32_t i = 0; i < k; ++i) atomicAdd(P.tile_count + (((old + i) / AS_TILE) % P.NT), 1u);
+                    atomicAdd(&st->rows_dummy, k);
+                    flushed = true;
+                }
+            }
+            __nanosleep(100);
+            if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
+                atomicExch(&st->abort, 1u);
+                q = AS_NONE;
+                break;
+            }
+        }
+#if AS_ACQUIRE
+        if (q != AS_NONE) (void)as_ld_acquire(cnt_p);  // the tile's rows and owners are read after this
+#endif
+        st->grp[grp].tile = q;
+        __threadfence();
+        atomicAdd(&st->grp[grp].seq, 1u);
+    } else {
+        for (uint32_t spins = 0; as_ld_volatile(&st->grp[grp].seq) <= seq; ++spins) {
+            if (member_nap_ns) __nanosleep(member_nap_ns);
+            if ((spins & 4095u) == 4095u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+            if (as_ld_volatile(&st->abort)) break;
+        }
+#if AS_ACQUIRE
+        (void)as_ld_acquire(&st->grp[grp].seq);
+#endif
+        q = as_ld_volatile(&st->abort) ? AS_NONE : as_ld_volatile(&st->grp[grp].tile);
+    }
+    return q;
+}
+
 // ---- warp 0: takes tiles for the group, feeds the operand ring by TMA
 __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M, const AsWorkerId id,
                                       uint8_t *smem, AsWorkerShared &S) {
@@ -246,59 +329,7 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
     for (;;) {
         if (lane == 0) {
             const long long tq0 = AS_CLK();
-            uint32_t q;
-            if (mem == 0) {
-                // ---- the previous tile must be finished by every member before its scratch is reused
-                while (as_ld_volatile(&st->grp_done[grp]) < G * seq && !as_ld_volatile(&st->abort)) {}
-                // ---- take the next tile; wait until it is full, flush it when it stays partial, leave when all trees are done
-                q = atomicAdd(&st->tile_head, 1u);
-                const uint32_t *cnt_p = P.tile_count + (q % P.NT);
-                const uint32_t want = AS_TILE * (q / P.NT + 1u);
-                unsigned long long t_partial = 0;
-                bool flushed = false;
-                for (uint32_t spins = 0;; ++spins) {
-                    if (as_ld_volatile(cnt_p) >= want) break;
-                    if (as_ld_volatile(&st->abort) || as_ld_volatile(&st->done_trees) >= L.B) {
-                        q = AS_NONE;
-                        break;
-                    }
-                    const uint32_t tail = as_ld_volatile(&st->row_tail);
-                    if (!flushed && tail > q * AS_TILE && tail < (q + 1u) * AS_TILE) {
-                        const unsigned long long now = as_now();
-                        if (t_partial == 0) t_partial = now;
-                        if (now - t_partial > P.flush_ns) {
-                            const uint32_t k = (q + 1u) * AS_TILE - tail;
-                            const uint32_t old = atomicAdd(&st->row_tail, k);
-                            for (uint32_t i = 0; i < k; ++i) P.slot_tree[(old + i) % (P.NT * AS_TILE)] = AS_NONE;
-                            __threadfence();
-                            for (uint32_t i = 0; i < k; ++i) atomicAdd(P.tile_count + (((old + i) / AS_TILE) % P.NT), 1u);
-                            atomicAdd(&st->rows_dummy, k);
-                            flushed = true;
-                        }
-                    }
-                    __nanosleep(100);
-                    if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
-                        atomicExch(&st->abort, 1u);
-                        q = AS_NONE;
-                        break;
-                    }
-                }
-#if AS_ACQUIRE
-                if (q != AS_NONE) (void)as_ld_acquire(cnt_p);  // the tile's rows and owners are read after this
-#endif
-                st->grp_tile[grp] = q;
-                __threadfence();
-                atomicAdd(&st->grp_seq[grp], 1u);
-            } else {
-                for (uint32_t spins = 0; as_ld_volatile(&st->grp_seq[grp]) <= seq; ++spins) {
-                    if ((spins & 4095u) == 4095u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
-                    if (as_ld_volatile(&st->abort)) break;
-                }
-#if AS_ACQUIRE
-                (void)as_ld_acquire(&st->grp_seq[grp]);
-#endif
-                q = as_ld_volatile(&st->abort) ? AS_NONE : as_ld_volatile(&st->grp_tile[grp]);
-            }
+            const uint32_t q = as_group_next_tile(L, P, id, seq, t_start, 0u);
             S.tile = q;
             d_acq += AS_CLK() - tq0;
         }
@@ -341,9 +372,9 @@ __device__ __forceinline__ void async_worker_producer(const AzbLayout &L, const 
                         as_mbar_spin(&S.layer_bar, lbc & 1u);
                         ++lbc;
                     } else {
-                        while (as_ld_volatile(&st->grp_layer[grp * 4 + l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
+                        while (as_ld_volatile(&st->grp[grp].layer[l - 1]) < arrive_target && !as_ld_volatile(&st->abort)) {}
 #if AS_ACQUIRE
-                        (void)as_ld_acquire(&st->grp_layer[grp * 4 + l - 1]);
+                        (void)as_ld_acquire(&st->grp[grp].layer[l - 1]);
 #endif
                     }
                     d_w1 += AS_CLK() - tw;
@@ -520,7 +551,7 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
             }
             if (et == 0u) {
                 if (mem == 0) atomicAdd(P.tile_retired + (q % P.NT), 1u);
-                atomicAdd(&st->grp_done[grp], 1u);
+                atomicAdd(&st->grp[grp].done, 1u);
             }
             seq += 1u;
             as_named_bar(1, AS_MLP_THREADS);
@@ -660,8 +691,8 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
             if (et == 0u) {
                 if (l < 3) {
                     if (G == 1u) as_mbar_arrive(&S.layer_bar);
-                    else atomicAdd(&st->grp_layer[grp * 4 + l], 1u);
-                } else if (atomicAdd(&st->grp_done[grp], 1u) + 1u == arrive_target) {
+                    else atomicAdd(&st->grp[grp].layer[l], 1u);
+                } else if (atomicAdd(&st->grp[grp].done, 1u) + 1u == arrive_target) {
                     S.epi_last = 1u;  // this member is the last of the group to finish the tile
                 } else {
                     S.epi_last = 0u;
@@ -717,16 +748,393 @@ __device__ __forceinline__ void async_model_cta(const AzbLayout &L, const AzbAsy
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Shared-SM form (P.shared_sm; azb_config.async_workers = AZB_ASYNC_SHARED).  No SM is taken from the trees: every CTA
+// walks trees with its first SH_TREE_WARPS warps, and its last warpgroup (4 warps, the kernel's 64 registers) is one
+// MEMBER of a model group.  G members on G different SMs answer a 128-row tile together: member m computes the columns
+// [m cw_l, (m + 1) cw_l) of every layer, so only 1/G of the weights streams through each SM's 64 B/clk L2 port — the
+// port is what bounds a tile on one SM (3.9 MB per tile: 31 us) —, the hidden activations meet in the group's L2-resident
+// scratch, and the members synchronise at the three layer boundaries through the group's counter line.  With G = 8 a tile
+// moves 0.95 MB through each member and 18 groups are in flight on 148 SMs, which is far more model throughput than
+// 4096 trees can ask for: the round trip a tree waits for shrinks while all 148 SMs keep walking.
+// Roles inside the warpgroup: warp 0's elected lane takes the tile (group leader) or reads the mailbox and issues the TMA
+// loads, warp 1's elected lane issues tcgen05.mma (accumulator [128 x cw_l] fp32 in TMEM, single-buffered: the next
+// layer cannot start before the group barrier anyway); then all four warps drain their TMEM lane quadrant (bias, ReLU,
+// bf16 through a swizzled staging tile into the scratch; the Sigmoid head scatters f32 to the owners' prior rows).
+// Waits on mbarriers suspend (try_wait) and the mailbox poll naps, so an idle member costs its SM's walkers next to nothing.
+#define SH_TREE_WARPS 28
+#define SH_THREADS 128
+#define SH_MAX_STAGES AS_STAGES  // operand ring stages (P.sh_stages <= this; fewer when a wide slice fills shared memory)
+#define SH_STG_BYTES (32u * 128u)  // per-warp staging tile: 32 rows x 64 bf16
+#define SH_TMEM_COLS 256u
+
+__device__ __forceinline__ uint32_t sh_stage_bytes(const AzbAsyncParams &P) {
+    const uint32_t cwmax = max(max(P.cw[0], P.cw[1]), max(P.cw[2], P.cw[3]));
+    return AS_TILE_BYTES + cwmax * (TC_BK * 2u);
+}
+
+// shared-space addresses (u32) all the way in the member's issue loops: one lane runs them beside 28 walking warps, and
+// every instruction on that lane's path costs ~10 cycles there
+__device__ __forceinline__ void sh_mbar_wait(uint32_t bar_s, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SH_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni SH_WAIT_DONE;\n"
+        "bra.uni SH_WAIT_LOOP;\n"
+        "SH_WAIT_DONE:\n"
+        "}\n" ::"r"(bar_s),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void sh_mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sh_tma_load_2d(uint32_t dst_s, const CUtensorMap *map, uint32_t bar_s, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_s),
+                 "l"(map), "r"(bar_s), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void sh_tma_load_2d_hint(uint32_t dst_s, const CUtensorMap *map, uint32_t bar_s, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst_s),
+        "l"(map), "r"(bar_s), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void sh_umma_commit(uint32_t bar_s) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void sh_tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) { as_tmem_ld16_issue(taddr, r); }
+
+// bias + ReLU + bf16 of one 16-column TMEM slice into two 16-byte chunks of the warp's staged row
+__device__ __forceinline__ void sh_relu_pack_store(const uint32_t (&r)[16], uint32_t bias_s, uint32_t half, uint32_t srow, uint32_t ch, uint32_t sw) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int t = 0; t < 8; t += 2) {
+        const uint4 b4 = as_lds128(bias_s + 2u * t * 4u);
+        float v0 = __uint_as_float(r[2 * t]) + __uint_as_float(b4.x);
+        float v1 = __uint_as_float(r[2 * t + 1]) + __uint_as_float(b4.y);
+        float v2 = __uint_as_float(r[2 * t + 2]) + __uint_as_float(b4.z);
+        float v3 = __uint_as_float(r[2 * t + 3]) + __uint_as_float(b4.w);
+        v0 = fmaxf(v0, 0.f);
+        v1 = fmaxf(v1, 0.f);
+        v2 = fmaxf(v2, 0.f);
+        v3 = fmaxf(v3, 0.f);
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(v0, v1), h23 = __floats2bfloat162_rn(v2, v3);
+        if (half) {  // bf16x3: what bf16 lost, itself rounded to bf16
+            h01 = __floats2bfloat162_rn(v0 - __low2float(h01), v1 - __high2float(h01));
+            h23 = __floats2bfloat162_rn(v2 - __low2float(h23), v3 - __high2float(h23));
+        }
+        pk[t] = *reinterpret_cast<uint32_t *>(&h01);
+        pk[t + 1] = *reinterpret_cast<uint32_t *>(&h23);
+    }
+    as_sts128(srow + ((ch ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+    as_sts128(srow + (((ch + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+}
+
+__device__ void shared_model_warpgroup(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M, const uint32_t member,
+                                       uint8_t *smem, AsWorkerShared &S) {
+    const uint32_t mt = threadIdx.x - SH_TREE_WARPS * 32u, warp = mt >> 5, lane = mt & 31u;
+    AzbAsyncState *st = P.st;
+    AsWorkerId id;
+    id.G = P.group;
+    id.grp = member / P.group;
+    id.mem = member % P.group;
+    const uint32_t G = id.G, grp = id.grp, mem = id.mem;
+#ifdef SH_CONST_STAGES
+    const uint32_t stage_bytes = sh_stage_bytes(P), n_stages = SH_CONST_STAGES;
+#else
+    const uint32_t stage_bytes = sh_stage_bytes(P), n_stages = P.sh_stages;
+#endif
+    // this member's bias slices behind the operand ring, then one staging tile per warp
+    float *s_bias = reinterpret_cast<float *>(smem + (size_t)n_stages * stage_bytes);
+    uint32_t bias_end = 0;
+    for (uint32_t l = 0; l < 4; ++l) {
+        if (mt == 0u) S.bias_off[l] = bias_end;
+        for (uint32_t i = mt; i < P.cw[l]; i += SH_THREADS) {
+            const uint32_t n = mem * P.cw[l] + i;
+            s_bias[bias_end + i] = n < P.npad[l] ? P.bias[l][n] : 0.f;
+        }
+        bias_end += P.cw[l];
+    }
+    uint8_t *stg = reinterpret_cast<uint8_t *>(s_bias + bias_end);
+    stg = (uint8_t *)(((uintptr_t)stg + 1023) & ~(uintptr_t)1023) + warp * SH_STG_BYTES;
+    if (mt == 0u) {
+        for (uint32_t s = 0; s < n_stages; ++s) {
+            tc_mbar_init(&S.full_bar[s], 1);
+            tc_mbar_init(&S.empty_bar[s], 1);
+        }
+        tc_mbar_init(&S.acc_full[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
+        for (int l = 0; l < 4; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ws[l]) : "memory");
+        for (int l = 0; l < 3; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.act[l]) : "memory");
+    }
+    if (warp == 1u) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&S.tmem_slot)), "r"(SH_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, SH_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_slot;
+    const unsigned long long t_start = as_now();
+    const uint32_t nseg = P.wide == 2u ? 3u : 1u;
+    const uint32_t ring_s = tc_smem_u32(smem), full_s = tc_smem_u32(&S.full_bar[0]), empty_s = tc_smem_u32(&S.empty_bar[0]),
+                   acc_s = tc_smem_u32(&S.acc_full[0]);
+    // ring cursor of the issuing lanes (warps 0 and 1 walk the same k-block sequence): stage and phase, no divisions
+    uint32_t rs = 0, rph = 0;
+    uint32_t accc = 0, seq = 0;  // accumulators completed, tiles answered (uniform over the warpgroup)
+    long long d_acq = 0, d_busy = 0, d_w1 = 0, d_tiles = 0, d_pe = 0, d_mf = 0, d_acc = 0, d_epi = 0, d_bar = 0;
+    for (;;) {
+        if (mt == 0u) {
+            const long long tq0 = AS_CLK();
+            S.tile = as_group_next_tile(L, P, id, seq, t_start, 200u);
+            d_acq += AS_CLK() - tq0;
+        }
+        as_named_bar(1, SH_THREADS);
+        const uint32_t q = S.tile;
+        if (q == AS_NONE) break;
+        const long long tt0 = AS_CLK();
+        const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
+        const uint32_t arrive_target = G * (seq + 1u);
+        const uint32_t my_tree = __ldcg(P.slot_tree + ring_row0 + mt);  // owner of this thread's row (128 threads, 128 rows)
+        for (uint32_t l = 0; l < 4; ++l) {
+            const uint32_t k_blocks = P.kpad[l] / TC_BK;
+            const uint32_t n0 = mem * P.cw[l];
+            const uint32_t bn = n0 < P.npad[l] ? min(P.cw[l], P.npad[l] - n0) : 0u;  // this member's columns of the layer
+            if (warp == 0u) {
+                // ===== TMA producer (one elected lane)
+                if (tc_elect_one()) {
+                    const uint32_t tx_bytes = AS_TILE_BYTES + P.cw[l] * (TC_BK * 2u);  // the weight box is always cw[l] rows
+                    const uint64_t w_policy = as_policy_evict_last();
+                    const CUtensorMap *mw = &M.ws[l];
+                    uint32_t pre = 0;
+                    if (l == 0u) {
+                        as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
+                    } else {
+                        // the weights do not depend on the previous layer: the first stages' B tiles go out before the
+                        // group's layer barrier opens, only their A tiles wait for it
+                        uint32_t ps = rs, pph = rph;
+                        for (; bn && pre < min(n_stages, k_blocks); ++pre) {
+                            sh_mbar_wait(empty_s + 8u * ps, pph ^ 1u);
+                            sh_mbar_expect_tx(full_s + 8u * ps, tx_bytes);
+                            sh_tma_load_2d_hint(ring_s + ps * stage_bytes + AS_TILE_BYTES, mw, full_s + 8u * ps, (int)(pre * TC_BK), (int)n0, w_policy);
+                            if (++ps == n_stages) {
+                                ps = 0;
+                                pph ^= 1u;
+                            }
+                        }
+                        const long long tw = AS_CLK();
+                        const uint32_t *lp = &st->grp[grp].layer[l - 1];
+                        while (as_ld_volatile(lp) < arrive_target && !as_ld_volatile(&st->abort)) {}
+#if AS_ACQUIRE
+                        (void)as_ld_acquire(lp);
+#endif
+                        d_w1 += AS_CLK() - tw;
+                        as_fence_proxy_async();
+                    }
+                    const CUtensorMap *ma = l == 0u ? &M.ring : &M.act[l - 1];
+                    const int arow = (int)(l == 0u ? ring_row0 : grp * AS_TILE);
+                    if (bn) {
+                        uint32_t kb = 0;
+                        for (uint32_t seg = 0; seg < nseg; ++seg) {
+                            // bf16x3: (A half, W half) = (hi,hi), (hi,lo), (lo,hi); the lo halves start k_blocks blocks into a row
+                            int a_col = (int)((seg == 2u ? k_blocks : 0u) * TC_BK), w_col = (int)((seg == 1u ? k_blocks : 0u) * TC_BK);
+                            for (uint32_t kj = 0; kj < k_blocks; ++kj, ++kb, a_col += TC_BK, w_col += TC_BK) {
+                                const uint32_t fb = full_s + 8u * rs, dst = ring_s + rs * stage_bytes;
+                                if (kb >= pre) {  // (else: stage claimed and its B tile requested above)
+                                    const long long te = AS_CLK();
+                                    sh_mbar_wait(empty_s + 8u * rs, rph ^ 1u);
+                                    d_pe += AS_CLK() - te;
+                                    sh_mbar_expect_tx(fb, tx_bytes);
+                                    sh_tma_load_2d_hint(dst + AS_TILE_BYTES, mw, fb, w_col, (int)n0, w_policy);
+                                }
+                                sh_tma_load_2d(dst, ma, fb, a_col, arow);
+                                if (++rs == n_stages) {
+                                    rs = 0;
+                                    rph ^= 1u;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 1u && bn) {
+                // ===== MMA issuer (one elected lane): D[128 x bn] (+)= A[128 x 64] B[bn x 64]^T per k-block, four K = 16 steps
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tc_elect_one()) {
+                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((AS_TILE >> 4) << 24);
+                    const uint32_t kb_all = nseg * k_blocks;
+                    for (uint32_t kb = 0; kb < kb_all; ++kb) {
+                        const long long tf = AS_CLK();
+                        sh_mbar_wait(full_s + 8u * rs, rph);
+                        d_mf += AS_CLK() - tf;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_addr = ring_s + rs * stage_bytes;
+                        const uint64_t adesc = tc_smem_desc(a_addr), bdesc = tc_smem_desc(a_addr + AS_TILE_BYTES);
+#pragma unroll
+                        for (uint32_t k = 0; k < TC_BK / 16; ++k)  // 32 bytes further along K: +2 in the descriptor's address field
+                            tc_umma_f16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0u ? 1u : 0u);
+                        sh_umma_commit(empty_s + 8u * rs);
+                        if (kb + 1u == kb_all) sh_umma_commit(acc_s);
+                        if (++rs == n_stages) {
+                            rs = 0;
+                            rph ^= 1u;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (bn) {
+                // ===== epilogue: every warp drains its TMEM lane quadrant (rows 32 warp .. of the tile)
+                const long long ta = AS_CLK();
+                sh_mbar_wait(acc_s, accc & 1u);
+                ++accc;
+                const long long tb = AS_CLK();
+                d_acc += tb - ta;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t bias_s = tc_smem_u32(s_bias + S.bias_off[l]);
+                const uint32_t tq = tmem_base + ((warp * 32u) << 16);
+                if (l < 3u) {
+                    const uint32_t act_ld = P.wide * P.kpad[l + 1];
+                    const uint32_t stg_s = tc_smem_u32(stg), srow = stg_s + lane * 128u, sw = lane & 7u;
+                    for (uint32_t c0 = 0; c0 < bn; c0 += 64u) {
+                        const uint32_t ncols = min(64u, bn - c0), chunks = ncols >> 3;
+                        for (uint32_t half = 0; half < P.wide; ++half) {
+                            // 16-column slices in pairs: two TMEM loads in flight, one wait
+#pragma unroll 1
+                            for (uint32_t sl = 0; sl < (ncols >> 4); sl += 2u) {
+                                uint32_t r0[16], r1[16];
+                                const bool two = sl + 1u < (ncols >> 4);
+                                sh_tmem_ld16_issue(tq + c0 + sl * 16u, r0);
+                                if (two) sh_tmem_ld16_issue(tq + c0 + sl * 16u + 16u, r1);
+                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                                sh_relu_pack_store(r0, bias_s + (c0 + sl * 16u) * 4u, half, srow, 2u * sl, sw);
+                                if (two) sh_relu_pack_store(r1, bias_s + (c0 + sl * 16u + 16u) * 4u, half, srow, 2u * sl + 2u, sw);
+                            }
+                            __syncwarp();
+                            // the warp's [32 rows x ncols] leave as contiguous row pieces, `chunks` lanes per row
+                            __nv_bfloat16 *dst0 = P.act[l] + (size_t)(grp * AS_TILE + warp * 32u) * act_ld + half * P.kpad[l + 1] + n0 + c0;
+                            if (chunks == 8u) {
+                                const uint32_t rr = lane >> 3, cc = lane & 7u;
+#pragma unroll
+                                for (uint32_t it = 0; it < 8u; ++it) {
+                                    const uint32_t rw = it * 4u + rr;
+                                    const uint4 v = as_lds128(stg_s + rw * 128u + ((cc ^ (rw & 7u)) << 4));
+                                    *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * act_ld + cc * 8u) = v;
+                                }
+                            } else {
+#pragma unroll 1
+                                for (uint32_t idx = lane; idx < 32u * chunks; idx += 32u) {
+                                    const uint32_t rw = idx / chunks, cc = idx - rw * chunks;
+                                    const uint4 v = as_lds128(stg_s + rw * 128u + ((cc ^ (rw & 7u)) << 4));
+                                    *reinterpret_cast<uint4 *>(dst0 + (size_t)rw * act_ld + cc * 8u) = v;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                } else {
+                    // the Sigmoid head: f32 rows scattered to the owning trees' prior rows, 16 columns at a time
+                    float *dst = L.h + (size_t)(my_tree != AS_NONE ? my_tree : 0u) * L.h_ld;
+                    const bool vec = (L.h_ld & 3u) == 0u;
+#pragma unroll 1
+                    for (uint32_t c0 = 0; c0 < bn; c0 += 16u) {
+                        uint32_t r[16];
+                        as_tmem_ld16(tq + c0, r);
+                        if (my_tree != AS_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const uint4 b4 = as_lds128(bias_s + (c0 + j) * 4u);
+                                float o[4];
+                                o[0] = __uint_as_float(r[j]) + __uint_as_float(b4.x);
+                                o[1] = __uint_as_float(r[j + 1]) + __uint_as_float(b4.y);
+                                o[2] = __uint_as_float(r[j + 2]) + __uint_as_float(b4.z);
+                                o[3] = __uint_as_float(r[j + 3]) + __uint_as_float(b4.w);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) o[t] = __fdividef(1.0f, 1.0f + __expf(-o[t]));
+                                const uint32_t n = n0 + c0 + j;
+                                if (vec && n + 3u < L.A) {
+                                    *reinterpret_cast<float4 *>(dst + n) = make_float4(o[0], o[1], o[2], o[3]);
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t)
+                                        if (n + t < L.A) dst[n + t] = o[t];
+                                }
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                d_epi += AS_CLK() - tb;
+            }
+            // ---- layer boundary: this member's share of the layer is stored; tell the group.  The barrier orders the 128
+            // threads' stores before thread 0's fence, and the fence is cumulative: ONE L1 invalidation per boundary on an
+            // SM whose other 28 warps are walking trees
+            const long long tz = AS_CLK();
+            if (l < 3u) as_fence_proxy_async();  // the next layer reads these stores through TMA
+            as_named_bar(2, SH_THREADS);
+            if (mt == 0u) {
+                __threadfence();
+                if (l < 3u)
+                    atomicAdd(&st->grp[grp].layer[l], 1u);
+                else
+                    S.epi_last = atomicAdd(&st->grp[grp].done, 1u) + 1u == arrive_target ? 1u : 0u;
+            }
+            d_bar += AS_CLK() - tz;
+        }
+        // the tile is answered once every member is done: the last one raises the owners' flags
+        as_named_bar(2, SH_THREADS);
+        if (S.epi_last) {
+            if (mt == 0u) __threadfence();  // behind the last arrival: every member's prior rows are visible before the flags
+            as_named_bar(2, SH_THREADS);
+            if (my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
+            if (mt == 0u) {
+                atomicAdd(P.tile_retired + (q % P.NT), 1u);
+                atomicAdd(&st->tiles_done, 1u);
+            }
+        }
+        seq += 1u;
+        d_tiles += 1;
+        d_busy += AS_CLK() - tt0;
+    }
+#ifdef AZB_PROFILE
+    if (P.dbg && mt == 0u) {  // acquire, producer wait-empty, wait layer, tile busy, tiles (the slots of the whole-SM producer)
+        atomicAdd(P.dbg + 0, (unsigned long long)d_acq);
+        atomicAdd(P.dbg + 1, (unsigned long long)d_pe);
+        atomicAdd(P.dbg + 2, (unsigned long long)d_w1);
+        atomicAdd(P.dbg + 3, (unsigned long long)d_busy);
+        atomicAdd(P.dbg + 4, (unsigned long long)d_tiles);
+    }
+    if (P.dbg && mt == 32u) atomicAdd(P.dbg + 6, (unsigned long long)d_mf);
+    if (P.dbg && mt == 64u) {  // a warp that only waits and drains: accumulator wait, epilogue, fence + barrier
+        atomicAdd(P.dbg + 11, (unsigned long long)d_acc);
+        atomicAdd(P.dbg + 13, (unsigned long long)d_epi);
+        atomicAdd(P.dbg + 12, (unsigned long long)d_bar);
+    }
+#endif
+    (void)d_acq; (void)d_busy; (void)d_w1; (void)d_tiles; (void)d_pe; (void)d_mf; (void)d_acc; (void)d_epi; (void)d_bar;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, SH_THREADS);
+    if (warp == 1u) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(SH_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Tree worker warp: owns trees gw, gw + NW, gw + 2 NW, ... (at most 32: lane k keeps the bookkeeping of tree k).
 template <int DEPTH, bool COUNT>
 __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, const uint32_t tree_cta,
-                                  const uint32_t n_tree_ctas, uint32_t *smem) {
+                                  const uint32_t n_tree_ctas, uint32_t *smem, const uint32_t n_thr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t FULL = 0xffffffffu;
     AzbAsyncState *st = P.st;
     uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)P.tree_warps * P.smem_words_per_warp);
-    // (for N >= 47 only the first AS_WIDE_TREE_WARPS warps of the CTA are here: the barrier counts the threads present)
-    const uint32_t n_thr = DEPTH == 5 ? AS_WIDE_TREE_WARPS * 32u : (uint32_t)AS_THREADS;
+    // n_thr = the threads of the CTA that are here (the barrier counts them): all 1024, the first AS_WIDE_TREE_WARPS warps
+    // for N >= 47, the first SH_TREE_WARPS warps in the shared-SM form
     for (uint32_t a = threadIdx.x; 4u * a < L.A; a += n_thr)
         reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
     as_named_bar(3, n_thr);
@@ -791,32 +1199,30 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         // A new node needs priors: its state vector goes to the next ring row — or, on the last step of this launch, to
         // the tree's own row (the host runs one batched forward over those).  Called from inside the walk as soon as
         // the new node is known to be non-terminal, so the model's round trip overlaps the cost evaluation and the insert.
-        bool submitted = false, to_ring = false, in_walk = true;
+        bool submitted = false, last = false, in_walk = true;
         auto submit = [&](WarpCtx &c) {
             // inside the walk the step that owns this row is still open: WK_STEP advances when it completes
-            to_ring = c.wk[WK_STEP] + (in_walk ? 1u : 0u) < P.target_step;
-            uint32_t slot = 0, pos = 0;
-            uint16_t *row = nullptr;
-            if (to_ring) {
-                if (lane == 0) slot = atomicAdd(&st->row_tail, 1u);
-                slot = __shfl_sync(FULL, slot, 0);
-                // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
-                const uint32_t q = slot / AS_TILE;
-                while (as_ld_volatile(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
+            last = c.wk[WK_STEP] + (in_walk ? 1u : 0u) >= P.target_step;
+            uint32_t slot = 0;
+            if (lane == 0) slot = atomicAdd(&st->row_tail, 1u);
+            slot = __shfl_sync(FULL, slot, 0);
+            // never lap a tile the workers have not retired yet (the ring is sized so that this does not spin)
+            const uint32_t q = slot / AS_TILE;
+            while (as_ld_volatile(P.tile_retired + (q % P.NT)) < q / P.NT && !as_ld_volatile(&st->abort)) __nanosleep(100);
 #if AS_ACQUIRE
-                if (q >= P.NT) (void)as_ld_acquire(P.tile_retired + (q % P.NT));  // the row is overwritten after this
+            if (q >= P.NT) (void)as_ld_acquire(P.tile_retired + (q % P.NT));  // the row is overwritten after this
 #endif
-                pos = slot % ring_rows;
-                row = P.ring + (size_t)pos * P.ring_ld;
-            }
-            tree_pack<true>(L, c, tree, row);
-            if (to_ring) {
-                if (lane == 0) P.slot_tree[pos] = tree;
-                __threadfence();
-                as_fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
-            }
+            const uint32_t pos = slot % ring_rows;
+            tree_pack<true>(L, c, tree, P.ring + (size_t)pos * P.ring_ld);
+            // the row of the launch's last step is answered in here like every other (the tree does not wait for it: its
+            // priors are in place when the next launch begins); it also goes to the tree's own slot, where
+            // azb_get_state_vecs and the host-model calls look for it
+            if (last) tree_pack<true>(L, c, tree, nullptr);
+            if (lane == 0) P.slot_tree[pos] = tree;
+            __threadfence();
+            as_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
             submitted = true;
         };
         if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) {
@@ -834,10 +1240,8 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         if (cx.err) {
             new_state = 2u;
         } else {
-            // (a tree that entered this advance with its target already reached still holds a node that awaits priors: its
-            // row goes to the tree's own slot like every last step's)
             if (pending && !submitted) submit(cx);
-            if (submitted && to_ring)
+            if (submitted && !last)
                 new_state = 1u;
             else if (at_target)
                 new_state = 2u;
@@ -848,7 +1252,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         for (uint32_t i = lane; i < live_words; i += 32) gwk[i] = cx.wk[i];
         if (lane == k) {
             my_state = new_state;
-            if (new_state == 1u) my_sub += 1u;
+            if (submitted) my_sub += 1u;
             my_steps += 1u;
             my_t0 = AS_CLK();
             my_run += my_t0 - t_run0;
@@ -907,7 +1311,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
     __shared__ uint32_t s_role, s_idx;
     // the first CTA to arrive on each of n_workers SMs becomes that SM's model CTA; every other CTA walks trees.  The
     // launch is cooperative with one CTA per SM, so every role is resident from the start.
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !P.shared_sm) {
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         uint32_t role = 0, idx = 0;
@@ -923,9 +1327,28 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
         s_idx = idx;
     }
     __syncthreads();
-    if (s_role) {
+    // one call site for the tree role of both forms (a second one turns the walker into a called function with spills)
+    uint32_t tree_cta = s_idx, n_tree_ctas = gridDim.x - P.n_workers, n_thr = DEPTH == 5 ? AS_WIDE_TREE_WARPS * 32u : (uint32_t)AS_THREADS;
+    if (P.shared_sm) {
+        // shared-SM form: every CTA walks trees; its last warpgroup is one member of a model group (CTAs beyond the last
+        // whole group have no model role)
+        if constexpr (DEPTH != 5) {
+            if ((threadIdx.x >> 5) >= SH_TREE_WARPS) {
+                const size_t tree_bytes = (size_t)SH_TREE_WARPS * P.smem_words_per_warp * 4 + ((L.A + 15u) & ~15u);
+                uint8_t *smem = (uint8_t *)(((uintptr_t)(as_smem + tree_bytes) + 1023) & ~(uintptr_t)1023);
+                if (blockIdx.x < (gridDim.x / P.group) * P.group) shared_model_warpgroup(L, P, M, blockIdx.x, smem, s_worker);
+                return;
+            }
+            tree_cta = blockIdx.x;
+            n_tree_ctas = gridDim.x;
+            n_thr = SH_TREE_WARPS * 32u;
+        } else {
+            return;
+        }
+    } else if (s_role) {
         uint8_t *smem = (uint8_t *)(((uintptr_t)as_smem + 1023) & ~(uintptr_t)1023);
         async_model_cta(L, P, M, s_idx, smem, s_worker);
+        return;
     } else {
         if constexpr (DEPTH == 5) {
             // N >= 47: a tree warp needs 6-10 KB of shared memory, so at most 16 of them fit (the host caps tree_warps
@@ -937,6 +1360,6 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
             }
             asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AS_REGS_WIDE_TREE));
         }
-        async_tree_worker<DEPTH, COUNT>(L, P, s_idx, gridDim.x - P.n_workers, reinterpret_cast<uint32_t *>(as_smem));
     }
+    async_tree_worker<DEPTH, COUNT>(L, P, tree_cta, n_tree_ctas, reinterpret_cast<uint32_t *>(as_smem), n_thr);
 }

@@ -35,6 +35,8 @@ extern "C" {
 #define AZB_MAX_VERTICES 64
 #define AZB_MAX_TOL 8
 #define AZB_ASYNC_AUTO 0xFFFFFFFFu  /* azb_config.async_workers: let the library pick the model SMs from the root count */
+#define AZB_ASYNC_SHARED 0xFFFFFFFEu /* azb_config.async_workers: no SM is taken from the trees — every SM walks trees with 28 warps and
+                                       its last warpgroup is one of 8 members of a model group (N <= 46) */
 
 enum {
     AZB_OK = 0,

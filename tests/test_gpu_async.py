@@ -183,3 +183,28 @@ def test_async_watchdog_ends_a_stuck_launch_within_seconds(capi, monkeypatch):
         except capi.AzbError as e:
             assert e.code == capi.ERR_CUDA and "watchdog" in str(e)
         assert time.time() - t0 < 20.0
+
+
+@pytest.mark.parametrize("env", [{}, {"AZB_ASYNC_GROUP": "4"}, {"AZB_ASYNC_GROUP": "16"}, {"AZB_ASYNC_FLUSH_NS": "0"}])
+@pytest.mark.parametrize("n,b,mlp", [(19, 1024, "tc"), (19, 300, "tc"), (12, 77, "tc"), (33, 160, "tc"), (19, 200, "tc3")])
+def test_shared_sm_form_equals_lock_step(capi, monkeypatch, env, n, b, mlp):
+    """AZB_ASYNC_SHARED: every SM walks trees with 28 warps and its last warpgroup is one of G members of a model group
+    (column slices of every layer, layer barriers through the group's counter line).  Same results as the lock step."""
+    steps = 30
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    parents, masks = capi.generate_roots(9, 0, b, n)
+    kw = dict(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC3 if mlp == "tc3" else capi.MLP_TC, max_steps=2 * steps + 2)
+    with _mk(capi, n, b, **kw) as lock, _mk(capi, n, b, async_workers=capi.ASYNC_SHARED, **kw) as asy:
+        for h in (lock, asy):
+            h.mlp_init(4)
+            h.set_roots(parents, masks)
+            h.init_trees()
+        n1, log1 = lock.step(steps, cap=256)
+        n2, log2 = asy.step(steps, cap=256)
+        assert n1 == n2 and [tuple(x) for x in log1] == [tuple(x) for x in log2]
+        _same(lock, asy, b)
+        for h in (lock, asy):
+            h.step(1)
+            h.step(steps)
+        _same(lock, asy, b)
