@@ -26,6 +26,8 @@
 // pass does not depend on which tile it rides in (same K order per dot product).  Per-tree step clocks and the
 // cand[step][tree] table make the argmin pass indifferent to the interleaving.
 // Every spin loop has a watchdog on %globaltimer; on expiry the kernel sets `abort` and drains.
+// AZB_ASYNC_PAIR=1 selects the CTA-PAIR form of the model CTAs (template parameter PAIR, launched in clusters of two):
+// two CTAs of one TPC answer two tiles with ONE tcgen05.mma.cta_group::2 stream, see "CTA pairs" below.
 //
 // Round 1 also had a two-kernel form (tree kernel + model kernel on two streams, spinning on each other) and a
 // weight-stationary model pipeline kernel.  Both are gone: separately launched kernels that wait for each other are
@@ -49,7 +51,9 @@
 #define AS_REGS_IDLE 24
 #define AS_WIDE_TREE_WARPS 16   // tree warps per CTA for N >= 47 (DEPTH == 5)
 #define AS_REGS_WIDE_TREE 104   // their register budget
+#ifndef AS_STAGES
 #define AS_STAGES 3
+#endif
 #define AS_ACC 2          // 128-column blocks per pass (one N = 256 MMA per k-step).  The 512 TMEM columns hold TWO passes:
                           // the epilogue drains one while the MMAs of the next run (4-block passes filled TMEM and
                           // serialised the two: MMA 24 us + epilogue 25 us per tile)
@@ -70,9 +74,17 @@
 #define AS_DBG(bit) false
 #endif
 
+// progress markers of the model CTAs (-DAS_MARKS; AZB_ASYNC_PEEK=1 prints them from the host while the kernel runs)
+#ifdef AS_MARKS
+#define AS_MARK(worker, role, v) do { if ((threadIdx.x & 31) == 0 && (worker) < 4u) *reinterpret_cast<volatile unsigned long long *>(P.dbg + 32 + (worker) * 8 + (role)) = (unsigned long long)(v); } while (0)
+#else
+#define AS_MARK(worker, role, v) do { } while (0)
+#endif
+
 struct AzbAsyncState {  // device memory, zeroed before every launch
     uint32_t abort;       // 1 watchdog, 2 tree error.  Polled by every waiting warp: alone in its 128-byte line, away
-    uint32_t pad0[31];    // from the counters the atomics below keep invalidating
+    uint32_t stuck;       // from the counters the atomics below keep invalidating.  stuck: the first barrier wait that
+    uint32_t pad0[30];    // expired (code << 16 | CTA), 0 = none
     uint32_t sm_flag[1024];  // first CTA to arrive on each SM (indexed by %smid)
     uint32_t mlp_claims, tree_claims;
     uint32_t row_tail;    // ring slots handed out
@@ -110,6 +122,8 @@ struct AzbAsyncParams {
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
     uint32_t early;          // 1: the state vector is handed to the model from inside the walk (before the cost evaluation)
+    uint32_t nap_count, nap_long_ns, nap_short_ns;  // a warp whose trees all wait: that many long sleeps, then short ones between polls
+    uint32_t pair;           // 1: model CTAs work as CTA pairs of one cluster (tcgen05.mma.cta_group::2): two 128-row tiles share every weight tile
     uint32_t shared_sm;      // 1: shared-SM form — every CTA walks trees with 28 warps and serves the model with its last warpgroup
     uint32_t sh_stages;      // shared-SM form: stages of a member's operand ring
     uint32_t cw[4];          // shared-SM form: output columns of layer l per group member (a multiple of 16, <= 256)
@@ -140,6 +154,19 @@ __device__ __forceinline__ uint32_t as_ld_acquire(const uint32_t *p) {
 __device__ __forceinline__ void as_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
+// CTA pairs (clusters of two): the same shared-memory offset in the pair's FIRST CTA — bit 24 of a shared::cluster address
+// is the CTA's rank within its pair
+#define AS_PEER_BIT_MASK 0xFEFFFFFFu
+__device__ __forceinline__ void as_mbar_arrive_leader(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_smem_u32(bar) & AS_PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void as_mbar_arrive_peer(uint64_t *bar) {  // the same barrier in the OTHER CTA of the pair
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tc_smem_u32(bar) ^ ~AS_PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void as_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // spin on test_wait (no suspend): the worker owns its SM, and try_wait's suspend/wake-up costs more than the
 // wait itself at this granularity (one barrier round trip per 64-deep k-block)
 __device__ __forceinline__ void as_mbar_spin(uint64_t *bar, uint32_t parity) {
@@ -155,6 +182,36 @@ __device__ __forceinline__ void as_mbar_spin(uint64_t *bar, uint32_t parity) {
             : "r"(tc_smem_u32(bar)), "r"(parity)
             : "memory");
     } while (!done);
+}
+// The same with a watchdog, for the warps of a CTA pair (their barriers are fed from the peer CTA): a barrier of this
+// kernel completes within microseconds, so 2^26 polls (a second or more) mean a broken protocol.  The wait then records
+// which barrier it was, raises `abort` and RETURNS — every later wait of the launch returns after 2^16 polls once `abort`
+// is up, so the kernel drains (with garbage in the tiles in flight) and the host reports the watchdog instead of hanging.
+__device__ __noinline__ void as_mbar_stuck(AzbAsyncState *st, uint32_t code) {
+    atomicCAS(&st->stuck, 0u, (code << 16) | (blockIdx.x & 0xffffu));
+    atomicExch(&st->abort, 1u);
+}
+__device__ __forceinline__ void as_mbar_spin_wd(uint64_t *bar, uint32_t parity, AzbAsyncState *st, uint32_t code) {
+    uint32_t done, spins = 0;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(tc_smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((++spins & 0xffffu) == 0u) {
+            if (*reinterpret_cast<volatile uint32_t *>(&st->abort)) return;
+            if (spins >= (1u << 26)) {
+                as_mbar_stuck(st, code);
+                return;
+            }
+        }
+    }
 }
 __device__ __forceinline__ void as_named_bar(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -206,9 +263,12 @@ __device__ __forceinline__ void as_fence_proxy_async() { asm volatile("fence.pro
 // Model CTA.  Roles: warp 0 TMA producer and tile taker, warp 1 MMA issuer and TMEM owner (warpgroup 0, 56 registers),
 // warps 4-11 epilogue (warpgroups 1-2, 168 registers).  Each role is its own function with its own copy of the loop
 // over tiles, so that no code is shared between register budgets; they meet at named barrier 1 (AS_MLP_THREADS).
+#define AS_PAIR_STAGES 4   // operand ring of a CTA pair: [A | half of B] per stage (see "CTA pairs" below)
+#define AS_MAX_STAGES (AS_STAGES > AS_PAIR_STAGES ? AS_STAGES : AS_PAIR_STAGES)
 struct AsWorkerShared {
-    uint64_t full_bar[AS_STAGES], empty_bar[AS_STAGES], acc_full[2], acc_empty[2], layer_bar;
+    uint64_t full_bar[AS_MAX_STAGES], empty_bar[AS_MAX_STAGES], acc_full[2], acc_empty[2], layer_bar, exit_bar;
     uint32_t tmem_slot, tile, epi_last;
+    uint32_t stored;  // pair form: (epilogue warp, pass) pairs of hidden layers whose activations are stored (monotonic over the launch)
     uint32_t bias_off[4];  // first entry of layer l's biases in the shared-memory copy
     uint32_t rowtree[AS_TILE];
 };
@@ -513,7 +573,298 @@ __device__ __forceinline__ void async_worker_mma(const AzbAsyncParams &P, const 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA pairs (P.pair).  A model SM moves ~87 GB/s through TMA whatever the schedule, and 2.75 of the 4.0 MB a 128-row tile
+// needs are weights.  Two model CTAs of one cluster (one TPC) therefore answer two tiles TOGETHER: every 256-column
+// weight tile is fetched once per pair — each CTA loads its own activation tile and HALF of the weight tile —, and ONE
+// tcgen05.mma.cta_group::2 (M = 256: rows 0-127 in the first CTA's TMEM, 128-255 in the second's) reads both halves
+// through the pair's shared memory.  Per CTA and k-block 16 + 16 KB arrive instead of 16 + 32; the ring has four stages.
+//  * full barriers live in the first CTA: both CTAs' TMA loads complete their bytes there (cta_group::2 loads, peer bit
+//    of the barrier address cleared), the first CTA's producer posts the expected bytes of both;
+//  * the first CTA's MMA warp issues; tcgen05.commit multicasts to the empty / accumulator-full barriers of both CTAs;
+//  * the epilogue warps of both CTAs arrive on the first CTA's accumulator-empty barriers;
+//  * each CTA runs its own epilogue, layer boundaries and answer flags for its own 128 rows (the code of a single worker).
+// A ticket is a double tile: ring tiles 2q and 2q + 1.
+#define AS_PAIR_STAGE_BYTES (2u * AS_TILE_BYTES)  // [A | B half]
+
+__device__ __forceinline__ void as_tma_load_2d_pair(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            tc_smem_u32(dst)),
+        "l"(map), "r"(tc_smem_u32(bar) & AS_PEER_BIT_MASK), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t as_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void as_umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void as_umma_commit_pair(uint64_t *bar) {  // arrives on this barrier in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+// The double tile the pair answers next (AS_NONE: leave).  Lane 0 of the producer warp of each CTA; `rank` = CTA in the pair.
+__device__ __forceinline__ uint32_t as_pair_next_ticket(const AzbLayout &L, const AzbAsyncParams &P, const uint32_t worker, const uint32_t rank,
+                                                        const uint32_t seq, const unsigned long long t_start) {
+    AzbAsyncState *st = P.st;
+    AzbAsyncState::Group &box = st->grp[worker & ~1u];  // the pair's mailbox: the line of its first CTA
+    uint32_t q;
+    if (rank == 0) {
+        q = atomicAdd(&st->tile_head, 1u);  // tickets count double tiles here
+        const uint32_t t0 = 2u * q, t1 = t0 + 1u;  // NT is even: both tiles are in the same generation of the ring
+        const uint32_t *c0 = P.tile_count + (t0 % P.NT), *c1 = P.tile_count + (t1 % P.NT);
+        const uint32_t want = AS_TILE * (t0 / P.NT + 1u);
+        const uint32_t row_lo = t0 * AS_TILE, row_hi = row_lo + 2u * AS_TILE;
+        unsigned long long t_partial = 0;
+        bool flushed = false;
+        for (uint32_t spins = 0;; ++spins) {
+            if (as_ld_volatile(c0) >= want && as_ld_volatile(c1) >= want) break;
+            if (as_ld_volatile(&st->abort)) {
+                q = AS_NONE;
+                break;
+            }
+            const bool all_done = as_ld_volatile(&st->done_trees) >= L.B;
+            const uint32_t tail = as_ld_volatile(&st->row_tail);
+            if (all_done && tail <= row_lo) {  // every tree has finished and no row has reached this double tile
+                q = AS_NONE;
+                break;
+            }
+            if (!flushed && tail > row_lo && tail < row_hi) {
+                const unsigned long long now = as_now();
+                if (t_partial == 0) t_partial = now;
+                if (all_done || now - t_partial > P.flush_ns) {  // top the stale double tile up with dummy rows
+                    const uint32_t k = row_hi - tail;
+                    const uint32_t old = atomicAdd(&st->row_tail, k);
+                    for (uint32_t i = 0; i < k; ++i) P.slot_tree[(old + i) % (P.NT * AS_TILE)] = AS_NONE;
+                    __threadfence();
+                    for (uint32_t r = old; r < old + k;) {  // one add per ring tile the dummies fall into
+                        const uint32_t t = r / AS_TILE, n = min(old + k, (t + 1u) * AS_TILE) - r;
+                        atomicAdd(P.tile_count + (t % P.NT), n);
+                        r += n;
+                    }
+                    atomicAdd(&st->rows_dummy, k);
+                    flushed = true;
+                }
+            }
+            __nanosleep(100);
+            if ((spins & 255u) == 255u && as_now() - t_start > P.timeout_ns) {
+                atomicExch(&st->abort, 1u);
+                q = AS_NONE;
+                break;
+            }
+        }
+#if AS_ACQUIRE
+        if (q != AS_NONE) {  // the tiles' rows and owners are read after this
+            (void)as_ld_acquire(c0);
+            (void)as_ld_acquire(c1);
+        }
+#endif
+        box.tile = q;
+        __threadfence();
+        atomicAdd(&box.seq, 1u);
+    } else {
+        for (uint32_t spins = 0; as_ld_volatile(&box.seq) <= seq; ++spins) {
+            if ((spins & 4095u) == 4095u && as_now() - t_start > P.timeout_ns) atomicExch(&st->abort, 1u);
+            if (as_ld_volatile(&st->abort)) break;
+        }
+#if AS_ACQUIRE
+        (void)as_ld_acquire(&box.seq);
+#endif
+        q = as_ld_volatile(&st->abort) ? AS_NONE : as_ld_volatile(&box.tile);
+    }
+    return q;
+}
+
+// ---- warp 0 of each CTA of a pair: feeds its own activation tile and its half of the weight tile
+__device__ __forceinline__ void pair_worker_producer(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M, const uint32_t worker,
+                                                     const uint32_t rank, uint8_t *smem, AsWorkerShared &S) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&M.ring) : "memory");
+        for (int l = 0; l < 4; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.w[l]) : "memory");
+        for (int l = 0; l < 3; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(&M.act[l]) : "memory");
+    }
+    __syncwarp();
+    AS_MARK(worker, 0, 2);
+    as_named_bar(1, AS_MLP_THREADS);
+    AS_MARK(worker, 0, 3);
+    const unsigned long long t_start = as_now();
+    uint32_t kbc = 0, seq = 0, lbc = 0, seen = 0;  // lbc: stored passes before the current layer's input
+    long long d_acq = 0, d_w0 = 0, d_w1 = 0, d_busy = 0, d_tiles = 0;
+    for (;;) {
+        if (lane == 0) {
+            const long long tq0 = AS_CLK();
+            const uint32_t q = as_pair_next_ticket(L, P, worker, rank, seq, t_start);
+            S.tile = q == AS_NONE ? AS_NONE : 2u * q + rank;  // this CTA's own 128-row ring tile
+            d_acq += AS_CLK() - tq0;
+        }
+        __syncwarp();
+        AS_MARK(worker, 0, 4u | (S.tile << 8));
+        as_named_bar(1, AS_MLP_THREADS);
+        const uint32_t q = S.tile;
+        if (q == AS_NONE) break;
+        const uint32_t ring_row0 = (q % P.NT) * AS_TILE;
+        if (tc_elect_one()) {
+            const long long tt0 = AS_CLK();
+            d_tiles += 1;
+            const uint64_t w_policy = as_policy_evict_last(), a_policy = as_policy_evict_first();
+            as_fence_proxy_async();  // the tile's rows were written by tree warps through the generic proxy
+            const uint32_t nseg = P.wide == 2u ? 3u : 1u;
+            for (uint32_t l = 0; l < 4; ++l) {
+                const uint32_t k_blocks = P.kpad[l] / TC_BK, kb_all = nseg * k_blocks;
+                const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
+                // a k-block of layer l > 0 reads 64 columns of the previous layer's output: it goes out once this CTA's own
+                // epilogue has stored the pass those columns belong to (AS_ACC * 128 columns per pass, AS_EPI_WARPS counts each)
+                const uint32_t in_passes = l > 0 ? ((P.npad[l - 1] + 127u) / 128u + AS_ACC - 1u) / AS_ACC : 0u;
+                const CUtensorMap *ma = l == 0 ? &M.ring : &M.act[l - 1];
+                const int arow = (int)(l == 0 ? ring_row0 : worker * AS_TILE);
+                for (uint32_t p0 = 0; p0 < n_tiles; p0 += AS_ACC) {
+                    // the pass's columns [128 p0, 128 p0 + w): this CTA holds the w / 2 weight rows 128 p0 + rank w / 2 ..
+                    // (the box is always 128 rows; with w = 128 its upper half is not read)
+                    const uint32_t w = min((uint32_t)AS_ACC, n_tiles - p0) * 128u;
+                    const int brow = (int)(p0 * 128u + rank * (w >> 1));
+                    for (uint32_t kb = 0; kb < kb_all; ++kb, ++kbc) {
+                        const uint32_t s = kbc % AS_PAIR_STAGES, ph = (kbc / AS_PAIR_STAGES) & 1u;
+                        const uint32_t seg = kb / k_blocks, kj = kb - seg * k_blocks;
+                        const int a_col = (int)(((seg == 2u ? k_blocks : 0u) + kj) * TC_BK);
+                        const int w_col = (int)(((seg == 1u ? k_blocks : 0u) + kj) * TC_BK);
+                        uint8_t *a_dst = smem + (size_t)s * AS_PAIR_STAGE_BYTES;
+                        if (l > 0) {
+                            const uint32_t need = AS_EPI_WARPS * (lbc + min(in_passes, kj / (AS_ACC * 128u / TC_BK) + 1u));
+                            if (seen < need) {
+                                const long long tw1 = AS_CLK();
+                                for (uint32_t spins = 0; (seen = *reinterpret_cast<volatile uint32_t *>(&S.stored)) < need;)
+                                    if ((++spins & 0xffffu) == 0u && (as_ld_volatile(&P.st->abort) || spins >= (1u << 26))) {
+                                        if (spins >= (1u << 26)) as_mbar_stuck(P.st, 1u);
+                                        break;
+                                    }
+                                d_w1 += AS_CLK() - tw1;
+                                asm volatile("fence.acq_rel.cta;" ::: "memory");
+                                as_fence_proxy_async();
+                            }
+                        }
+                        const long long tw = AS_CLK();
+                        as_mbar_spin_wd(&S.empty_bar[s], ph ^ 1u, P.st, 2u);
+                        d_w0 += AS_CLK() - tw;
+                        // the full barrier of the stage is the first CTA's: it expects the bytes of both CTAs
+                        if (rank == 0) tc_mbar_expect_tx(&S.full_bar[s], 2u * AS_PAIR_STAGE_BYTES);
+                        as_tma_load_2d_pair(a_dst, ma, &S.full_bar[s], a_col, arow, a_policy);
+                        as_tma_load_2d_pair(a_dst + AS_TILE_BYTES, &M.w[l], &S.full_bar[s], w_col, brow, w_policy);
+                    }
+                }
+                lbc += in_passes;  // passes of hidden layers this CTA's epilogue has stored once layer l's input is complete
+            }
+            d_busy += AS_CLK() - tt0;
+        }
+        __syncwarp();
+        seq += 1u;
+        AS_MARK(worker, 0, 5u | (seq << 8));
+        as_named_bar(1, AS_MLP_THREADS);
+        AS_MARK(worker, 0, 6u | (seq << 8));
+    }
+#ifdef AZB_PROFILE
+    if (P.dbg && lane == 0) {
+        atomicAdd(P.dbg + 0, (unsigned long long)d_acq);
+        atomicAdd(P.dbg + 1, (unsigned long long)d_w0);
+        atomicAdd(P.dbg + 2, (unsigned long long)d_w1);
+        atomicAdd(P.dbg + 3, (unsigned long long)d_busy);
+        atomicAdd(P.dbg + 4, (unsigned long long)d_tiles);
+    }
+#endif
+    (void)d_acq; (void)d_w0; (void)d_w1; (void)d_busy; (void)d_tiles;
+    as_named_bar(1, AS_MLP_THREADS);
+}
+
+// ---- warp 1: TMEM of the pair (allocated by both CTAs together); the first CTA's warp issues the MMAs of both
+__device__ __forceinline__ void pair_worker_mma(const AzbAsyncParams &P, const uint32_t worker, const uint32_t rank, uint8_t *smem,
+                                                AsWorkerShared &S) {
+    AS_MARK(worker, 1, 2);
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&S.tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    AS_MARK(worker, 1, 3);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, AS_MLP_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_slot;
+    uint32_t kbc = 0, ntc = 0;
+    long long d_w0 = 0, d_w1 = 0;
+    const uint32_t nseg = P.wide == 2u ? 3u : 1u;
+    for (;;) {
+        as_named_bar(1, AS_MLP_THREADS);
+        const uint32_t q = S.tile;
+        AS_MARK(worker, 1, 4u | (q << 8));
+        if (q == AS_NONE) break;
+        if (rank == 0)
+            for (uint32_t l = 0; l < 4; ++l) {
+                const uint32_t k_blocks = nseg * (P.kpad[l] / TC_BK);
+                const uint32_t n_tiles = (P.npad[l] + 127u) / 128u;
+                for (uint32_t p0 = 0; p0 < n_tiles; p0 += AS_ACC, ++ntc) {
+                    const uint32_t w = min((uint32_t)AS_ACC, n_tiles - p0) * 128u;
+                    long long tw = AS_CLK();
+                    const uint32_t slot = ntc & 1u, acc_ph = (ntc >> 1) & 1u;
+                    as_mbar_spin_wd(&S.acc_empty[slot], acc_ph ^ 1u, P.st, 3u);  // both CTAs' epilogues have drained the pass before last
+                    d_w1 += AS_CLK() - tw;
+                    const uint32_t tmem_acc = tmem_base + slot * (AS_ACC * 128u);
+                    // D[256 x w] (rows 128 r .. in CTA r), A[256 x 64] (one tile per CTA), B[w x 64] (w / 2 rows per CTA)
+                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((w >> 3) << 17) | ((256u >> 4) << 24);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (uint32_t kb = 0; kb < k_blocks; ++kb, ++kbc) {
+                        const uint32_t s = kbc % AS_PAIR_STAGES, ph = (kbc / AS_PAIR_STAGES) & 1u;
+                        tw = AS_CLK();
+                        as_mbar_spin_wd(&S.full_bar[s], ph, P.st, 4u);
+                        d_w0 += AS_CLK() - tw;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (tc_elect_one()) {
+                            const uint32_t a_addr = tc_smem_u32(smem + (size_t)s * AS_PAIR_STAGE_BYTES), b_addr = a_addr + AS_TILE_BYTES;
+#pragma unroll
+                            for (uint32_t k = 0; k < TC_BK / 16; ++k)
+                                as_umma_f16_pair(tmem_acc, tc_smem_desc(a_addr + k * 32u), tc_smem_desc(b_addr + k * 32u), idesc,
+                                                 (kb | k) != 0u ? 1u : 0u);
+                            as_umma_commit_pair(&S.empty_bar[s]);
+                            if (kb + 1 == k_blocks) as_umma_commit_pair(&S.acc_full[slot]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        as_named_bar(1, AS_MLP_THREADS);
+    }
+#ifdef AZB_PROFILE
+    if (P.dbg && (threadIdx.x & 31) == 0 && rank == 0) {
+        atomicAdd(P.dbg + 5 + 1, (unsigned long long)d_w0);
+        atomicAdd(P.dbg + 5 + 2, (unsigned long long)d_w1);
+    }
+#endif
+    (void)d_w0; (void)d_w1;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    as_named_bar(1, AS_MLP_THREADS);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    AS_MARK(worker, 1, 7);
+    // Neither CTA may leave while the other can still reach into it (the peer's epilogue warps arrive on the first CTA's
+    // accumulator barriers, tcgen05.commit signals the second CTA's): the two MMA warps shake hands through their exit
+    // barriers.  (A cluster barrier here — with the CTA's other warps exiting instead of arriving — never completed.)
+    if ((threadIdx.x & 31) == 0) as_mbar_arrive_peer(&S.exit_bar);
+    as_mbar_spin_wd(&S.exit_bar, 0u, P.st, 6u);
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    AS_MARK(worker, 1, 9);
+}
+
 // ---- warps 4-11: TMEM -> registers -> bias + activation -> scratch / prior rows
+template <bool PAIR>
 __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const AzbAsyncParams &P, const AsWorkerId id, uint8_t *smem,
                                       AsWorkerShared &S) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -557,6 +908,7 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
             as_named_bar(1, AS_MLP_THREADS);
             continue;
         }
+        if (warp == AS_EPI_WARP0) AS_MARK(id.grp, 2, 4u | (q << 8));
         if (et < AS_TILE) S.rowtree[et] = __ldcg(P.slot_tree + ring_row0 + et);
         as_named_bar(2, AS_EPI_WARPS * 32);
         const uint32_t my_tree = S.rowtree[row];
@@ -567,7 +919,8 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
                 const uint32_t np = min((uint32_t)AS_ACC, mine - p0);
                 const long long tw = AS_CLK();
                 const uint32_t slot = ntc & 1u, acc_ph = (ntc >> 1) & 1u;
-                as_mbar_spin(&S.acc_full[slot], acc_ph);
+                if (PAIR) as_mbar_spin_wd(&S.acc_full[slot], acc_ph, st, 5u);
+                else as_mbar_spin(&S.acc_full[slot], acc_ph);
                 const uint32_t tmem_acc = tmem_base + slot * (AS_ACC * 128u);
                 const long long tb = AS_CLK();
                 d_w0 += tb - tw;
@@ -680,10 +1033,25 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) as_mbar_arrive(&S.acc_empty[slot]);
+                if (lane == 0) {
+                    if (PAIR) as_mbar_arrive_leader(&S.acc_empty[slot]);  // the MMA issuer sits in the pair's first CTA
+                    else as_mbar_arrive(&S.acc_empty[slot]);
+                }
+                if (PAIR && l < 3u) {
+                    // pair form: the next layer starts on the columns this pass has stored (its k-blocks wait for S.stored,
+                    // not for the whole layer): this warp's rows of the pass are visible to TMA, count them
+                    // (writer and reader sit in one CTA: the cross-proxy fence plus a CTA-scope release is what the memory
+                    // model asks for; a GPU-scope fence here waits for every store's acknowledgement, once per pass)
+                    as_fence_proxy_async();
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&S.stored, 1u);
+                }
                 d_busy += AS_CLK() - tb;
             }
+            if (PAIR && l < 3u) continue;  // (no layer barrier in the pair form)
             // ---- layer boundary: this member's share of the layer is stored; tell the group
+            if (warp == AS_EPI_WARP0) AS_MARK(id.grp, 2, 5u | (l << 4) | (q << 8));
             const long long tf0 = AS_CLK();
             if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
             __threadfence();
@@ -726,6 +1094,7 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
 }
 
 // Role dispatch of a model CTA (all 1024 threads enter): re-divide the registers, then run the role
+template <bool PAIR>
 __device__ __forceinline__ void async_model_cta(const AzbLayout &L, const AzbAsyncParams &P, const AzbAsyncMaps &M,
                                                 const uint32_t worker, uint8_t *smem, AsWorkerShared &S) {
     const uint32_t warp = threadIdx.x >> 5, wg = warp >> 2;
@@ -733,18 +1102,45 @@ __device__ __forceinline__ void async_model_cta(const AzbLayout &L, const AzbAsy
     id.G = P.group;
     id.grp = worker / P.group;
     id.mem = worker % P.group;
+    const uint32_t rank = worker & 1u;  // pair form: this CTA's rank in its cluster of two (workers 2c and 2c + 1)
+    if constexpr (PAIR) {
+        // the pair's barriers: the full and accumulator-empty barriers that count are the first CTA's (both CTAs initialise
+        // theirs the same way); nobody may arrive on a peer's barrier before it exists, hence the cluster barrier
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < AS_PAIR_STAGES; ++s) {
+                tc_mbar_init(&S.full_bar[s], 1);   // the first CTA's producer (arrive.expect_tx for the bytes of both CTAs)
+                tc_mbar_init(&S.empty_bar[s], 1);  // tcgen05.commit, multicast to both CTAs
+            }
+            for (int a = 0; a < 2; ++a) {
+                tc_mbar_init(&S.acc_full[a], 1);                  // tcgen05.commit, multicast
+                tc_mbar_init(&S.acc_empty[a], 2 * AS_EPI_WARPS);  // the epilogue warps of both CTAs
+            }
+            tc_mbar_init(&S.layer_bar, 1);
+            S.stored = 0u;
+            tc_mbar_init(&S.exit_bar, 1);  // the peer's MMA warp, once nothing of the peer touches this CTA any more
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 2u) AS_MARK(worker, 7, 1);
+        as_cluster_sync();
+        if (warp == 2u) AS_MARK(worker, 7, 2);
+    }
     if (wg >= 3u) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AS_REGS_IDLE));
         return;
     }
     if (wg == 0u) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AS_REGS_FRONT));
-        if (warp == 0u) async_worker_producer(L, P, M, id, smem, S);
-        else if (warp == 1u) async_worker_mma(P, id, smem, S);
+        if constexpr (PAIR) {
+            if (warp == 0u) pair_worker_producer(L, P, M, worker, rank, smem, S);
+            else if (warp == 1u) pair_worker_mma(P, worker, rank, smem, S);
+        } else {
+            if (warp == 0u) async_worker_producer(L, P, M, id, smem, S);
+            else if (warp == 1u) async_worker_mma(P, id, smem, S);
+        }
         return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AS_REGS_EPI));
-    async_worker_epilogue(L, P, id, smem, S);
+    async_worker_epilogue<PAIR>(L, P, id, smem, S);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1170,7 +1566,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
             // every tree of this warp waits for its priors.  The round trip is tens of microseconds, so the first sleeps
             // after a walk are long and only then does the warp poll every microsecond: waiting warps would otherwise
             // take issue slots and LSU bandwidth from the walking ones (phase cycles 91 K -> 74 K per tree-step)
-            __nanosleep(naps < 6u ? 5000u : 1000u);
+            __nanosleep(naps < P.nap_count ? P.nap_long_ns : P.nap_short_ns);
             ++naps;
             if ((++idle & 31u) == 0u) {
                 if (as_ld_volatile(&st->abort)) break;
@@ -1303,7 +1699,10 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     }
 }
 
-template <int DEPTH, bool COUNT>
+// PAIR: the CTA-pair form of the model CTAs (its own instantiation: a kernel that contains cta_group::2 code can only be
+// launched in clusters — the driver refuses anything else as a "cluster misconfiguration" — and a cooperative launch in
+// clusters fails under ncu, so the default form stays free of it and keeps its plain cooperative launch)
+template <int DEPTH, bool COUNT, bool PAIR>
 __global__ void __launch_bounds__(AS_THREADS, 1)
     azb_async_kernel(const AzbLayout L, const AzbAsyncParams P, const __grid_constant__ AzbAsyncMaps M) {
     extern __shared__ __align__(1024) uint8_t as_smem[];
@@ -1311,7 +1710,12 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
     __shared__ uint32_t s_role, s_idx;
     // the first CTA to arrive on each of n_workers SMs becomes that SM's model CTA; every other CTA walks trees.  The
     // launch is cooperative with one CTA per SM, so every role is resident from the start.
-    if (threadIdx.x == 0 && !P.shared_sm) {
+    if (threadIdx.x == 0 && PAIR) {
+        // CTA pairs: the launch is clustered (CTAs 2c and 2c + 1 share a TPC), so roles go by cluster — the first
+        // n_workers / 2 clusters serve the model
+        s_role = blockIdx.x < P.n_workers ? 1u : 0u;
+        s_idx = blockIdx.x < P.n_workers ? blockIdx.x : blockIdx.x - P.n_workers;
+    } else if (threadIdx.x == 0 && !P.shared_sm) {
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         uint32_t role = 0, idx = 0;
@@ -1347,7 +1751,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
         }
     } else if (s_role) {
         uint8_t *smem = (uint8_t *)(((uintptr_t)as_smem + 1023) & ~(uintptr_t)1023);
-        async_model_cta(L, P, M, s_idx, smem, s_worker);
+        async_model_cta<PAIR>(L, P, M, s_idx, smem, s_worker);
         return;
     } else {
         if constexpr (DEPTH == 5) {
