@@ -284,11 +284,10 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
                              cfg.max_episodes == 0 && cfg.n_groups <= 1 && cfg.n_roots >= 1024;
         if (!applies) cfg.async_workers = 0;
         else if (cfg.n_vertices >= 47) cfg.async_workers = 32;
-        else if (cfg.n_roots < 4096) cfg.async_workers = 40;
-        else if (cfg.n_roots == 4096) cfg.async_workers = 20;
-        else if (cfg.n_roots <= 8192) cfg.async_workers = 28;
-        else if (cfg.n_roots <= 32768) cfg.async_workers = 36;
-        else cfg.async_workers = 40;
+        // (session 3, `profiles/r02_dyn_*`: with free warps taking over any runnable tree of their CTA the tree side no
+        // longer needs a whole number of trees per warp, and one layout serves every batch beyond 4096 roots)
+        else if (cfg.n_roots <= 4096) cfg.async_workers = 20;
+        else cfg.async_workers = 36;
     }
     if (cfg.cap_nodes == 0) cfg.cap_nodes = 3 * cfg.max_steps + 64;
     if (cfg.cap_preds == 0) cfg.cap_preds = 2 * A + cfg.max_steps * ((2 * A + 6) / 7);
@@ -816,7 +815,11 @@ static int async_create(azb_handle *h) {
     if (azb_stack_depth(h->N) == 5) tree_warps = std::min<uint32_t>(tree_warps, AS_WIDE_TREE_WARPS);  // see azb_async_kernel
     if (const char *e = getenv("AZB_ASYNC_TREE_WARPS")) tree_warps = std::min<uint32_t>(tree_warps, std::max(1, atoi(e)));
     if (shared_sm) tree_warps = SH_TREE_WARPS;
-    const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes;
+    // a tree CTA's scheduling table (azb_async.cuh): one entry per tree it owns
+    const uint32_t n_tree_ctas_est = (uint32_t)prop.multiProcessorCount - (shared_sm ? 0u : W);
+    if (!shared_sm && (int)W >= prop.multiProcessorCount) return fail(h, AZB_ERR_INVALID, "async_workers >= SM count");
+    const uint32_t tab_slots = ((B + n_tree_ctas_est - 1u) / n_tree_ctas_est + 31u) & ~31u;
+    const size_t tree_smem = (size_t)tree_warps * per_warp + lut_bytes + as_table_bytes(tab_slots);
     size_t bias_bytes = 0;
     for (int l = 0; l < 4; ++l) bias_bytes += (size_t)((h->tc.npad[l] + 31u) & ~31u) * 4;
     const size_t mlp_smem = (size_t)AS_STAGES * (1 + AS_ACC) * AS_TILE * TC_BK * 2 + 1024 + bias_bytes + 1024 + (size_t)AS_EPI_WARPS * AS_EPI_STG_BYTES;
@@ -855,7 +858,8 @@ static int async_create(azb_handle *h) {
     const uint32_t n_model_groups = shared_sm ? (uint32_t)h->async_grid / group : W / group;
     if (shared_sm && (nb != 1 || n_model_groups == 0)) return fail(h, AZB_ERR_INVALID, "AZB_ASYNC_SHARED needs one CTA per SM and at least %u SMs", group);
     const uint32_t NW = (uint32_t)(h->async_grid - (int)W) * tree_warps;
-    if (B > 32u * NW) return fail(h, AZB_ERR_INVALID, "async mode holds at most %u trees per GPU", 32u * NW);
+    if ((uint32_t)(h->async_grid - (int)W) != n_tree_ctas_est)
+        return fail(h, AZB_ERR_CUDA, "async kernel: %d CTAs where one per SM was expected", h->async_grid);
     AzbAsyncParams &P = h->asP;
     memset(&P, 0, sizeof(P));
     P.NT = 2 * ((B + AS_TILE - 1) / AS_TILE) + 2 * (shared_sm ? n_model_groups : W) + 8;
@@ -864,8 +868,13 @@ static int async_create(azb_handle *h) {
     for (int l = 0; l < 4; ++l) P.cw[l] = cw[l];
     P.sh_stages = sh_stages;
     P.tree_warps = tree_warps;
+    P.tab_slots = tab_slots;
     P.early = B <= NW ? 1u : 0u;  // one tree per warp: the tree's own latency chain is the bound (azb_async.cuh)
     if (const char *e = getenv("AZB_ASYNC_EARLY")) P.early = atoi(e) != 0;
+    P.steal = B > NW ? 1u : 0u;  // more trees than warps: free warps take over any runnable tree of their CTA (azb_async.cuh)
+    if (const char *e = getenv("AZB_ASYNC_STEAL")) P.steal = atoi(e) != 0;
+    P.sweep_gap = AS_SWEEP_GAP;
+    if (const char *e = getenv("AZB_ASYNC_SWEEP_GAP")) P.sweep_gap = (uint32_t)strtoul(e, nullptr, 10);
     // worker SMs per tile
     P.group = group;
     if (W % P.group) return fail(h, AZB_ERR_INVALID, "async_workers must be a multiple of the group size %u", P.group);

@@ -57,6 +57,7 @@
 #define AS_ACC 2          // 128-column blocks per pass (one N = 256 MMA per k-step).  The 512 TMEM columns hold TWO passes:
                           // the epilogue drains one while the MMAs of the next run (4-block passes filled TMEM and
                           // serialised the two: MMA 24 us + epilogue 25 us per tile)
+#define AS_SWEEP_GAP 1000u  // cycles between two sweeps of a tree CTA's answer flags
 #define AS_TILE 128
 #define AS_NONE 0xffffffffu
 #define AS_MAX_GROUPS 128
@@ -121,6 +122,9 @@ struct AzbAsyncParams {
     uint32_t wide;           // 1: bf16 operands; 2: bf16x3 (AZB_MLP_TC3) — rows hold [hi(kpad) | lo(kpad)], three k-segments
     uint32_t NT, n_workers, group, target_step, smem_words_per_warp, ring_ld;  // group = worker SMs per tile
     uint32_t tree_warps;     // tree warps per CTA (32 unless the per-warp shared memory of a large N does not fit)
+    uint32_t tab_slots;      // entries of a tree CTA's scheduling table: the most trees any CTA owns
+    uint32_t steal;          // 1: a free warp advances ANY runnable tree of its CTA (more trees than warps); 0: only its own
+    uint32_t sweep_gap;      // cycles between two sweeps of a tree CTA's answer flags (steal)
     uint32_t early;          // 1: the state vector is handed to the model from inside the walk (before the cost evaluation)
     uint32_t nap_count, nap_long_ns, nap_short_ns;  // a warp whose trees all wait: that many long sleeps, then short ones between polls
     uint32_t pair;           // 1: model CTAs work as CTA pairs of one cluster (tcgen05.mma.cta_group::2): two 128-row tiles share every weight tile
@@ -1521,7 +1525,35 @@ __device__ void shared_model_warpgroup(const AzbLayout &L, const AzbAsyncParams 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Tree worker warp: owns trees gw, gw + NW, gw + 2 NW, ... (at most 32: lane k keeps the bookkeeping of tree k).
+// Tree CTA.  A CTA owns a contiguous block of the batch's trees (slot i = tree0 + i), so a tree's arena is only ever seen through one
+// SM's L1 — but WITHIN the CTA any free warp advances any runnable tree.  (Round 1 and the first half of round 2 gave every
+// warp a fixed set of trees, warp + k * n_warps: with 8192 roots on 120 tree SMs some warps owned three trees and the
+// others two, and a warp whose tree waited for its priors idled beside a neighbour with two runnable trees.)
+// The CTA's scheduling table lives in shared memory, one entry per slot:
+//   state  0 runnable, 1 waiting for its priors, 2 done with this launch, 3 being advanced by a warp
+//   sub    rows this tree has handed to the model since the launch began (the answer flag it waits for)
+//   steps  times it has been advanced (the warp takes the runnable tree that is furthest behind)
+// A warp that finds nothing runnable takes the CTA's sweep token and polls the answer flags of ALL waiting slots (32 per
+// ld.volatile round trip), marks the answered ones runnable behind ONE gpu-scope fence — the acquire side of the model CTAs'
+// fence + atomicAdd; every tree-step used to pay its own acquire load and with it an invalidation of the SM's L1 — and
+// rescans.  Warps without the token nap and rescan shared memory only, so an SM polls L2 with one warp at a time however
+// many of its warps wait.
+#ifdef AZB_PROFILE
+#define AS_TAB_ARRAYS 6u
+#else
+#define AS_TAB_ARRAYS 3u
+#endif
+__host__ __device__ __forceinline__ size_t as_table_bytes(uint32_t slots) { return ((size_t)AS_TAB_ARRAYS * slots + 16u) * 4u; }
+struct AsTreeTable {
+    uint32_t *state, *sub, *steps;
+    uint32_t *ctl;  // [0] slots done, [1] sweep token, [3] clock of the last sweep, [4] runnable slots (a hint)
+#ifdef AZB_PROFILE
+    uint32_t *run, *wait, *t0;  // 16-cycle units: cycles advancing the tree, cycles between hand-over and pick-up, time of the hand-over
+#endif
+};
+__device__ __forceinline__ uint32_t as_lds_volatile(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void as_sts_volatile(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
 template <int DEPTH, bool COUNT>
 __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, const uint32_t tree_cta,
                                   const uint32_t n_tree_ctas, uint32_t *smem, const uint32_t n_thr) {
@@ -1533,6 +1565,29 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     // for N >= 47, the first SH_TREE_WARPS warps in the shared-SM form
     for (uint32_t a = threadIdx.x; 4u * a < L.A; a += n_thr)
         reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
+    // this CTA's trees: a contiguous block of the batch, tree0 .. tree0 + n_local - 1 (<= P.tab_slots; the first B mod n CTAs
+    // own one tree more)
+    const uint32_t q_trees = L.B / n_tree_ctas, r_trees = L.B % n_tree_ctas;
+    const uint32_t n_local = q_trees + (tree_cta < r_trees ? 1u : 0u), tree0 = tree_cta * q_trees + min(tree_cta, r_trees);
+    AsTreeTable T;
+    T.state = reinterpret_cast<uint32_t *>(lut + ((L.A + 15u) & ~15u));
+    T.sub = T.state + P.tab_slots;
+    T.steps = T.sub + P.tab_slots;
+    T.ctl = T.steps + P.tab_slots;
+#ifdef AZB_PROFILE
+    T.run = T.ctl + 16;
+    T.wait = T.run + P.tab_slots;
+    T.t0 = T.wait + P.tab_slots;
+#endif
+    for (uint32_t i = threadIdx.x; i < P.tab_slots; i += n_thr) {
+        T.state[i] = i < n_local ? 0u : 2u;
+        T.sub[i] = 0u;
+        T.steps[i] = 0u;
+#ifdef AZB_PROFILE
+        T.run[i] = T.wait[i] = T.t0[i] = 0u;
+#endif
+    }
+    if (threadIdx.x < 16) T.ctl[threadIdx.x] = threadIdx.x == 4 ? n_local : 0u;  // [4]: runnable slots (a hint)
     as_named_bar(3, n_thr);
     if ((uint32_t)warp >= P.tree_warps) return;
     uint32_t *base = smem + (size_t)warp * P.smem_words_per_warp;
@@ -1542,12 +1597,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     cx.ct[lane] = 0u;
     __syncwarp();
 
-    const uint32_t NW = n_tree_ctas * P.tree_warps, gw = tree_cta * P.tree_warps + warp;
-    const uint32_t my_tree = gw + (uint32_t)lane * NW;
-    uint32_t my_state = my_tree < L.B ? 0u : 2u;  // 0 runnable, 1 waiting for priors, 2 done
-    uint32_t my_sub = 0;                          // rows this tree has submitted
-    uint32_t my_steps = 0;                        // times this tree has been advanced
-    long long my_run = 0, my_wait = 0, my_t0 = 0;  // cycles spent advancing this tree / waiting for its priors (P.dbg)
+    uint32_t my_rows = 0;  // rows this warp has handed to the model (lane 0)
     const long long t_k0 = AS_CLK();
     (void)t_k0;
     // start time for the watchdog: parked in two free words of the warp's counter block (only the idle path reads it)
@@ -1555,35 +1605,125 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     __syncwarp();
     uint32_t idle = 0, naps = 0;
     const uint32_t ring_rows = P.NT * AS_TILE;
+    // A warp for every tree (P.steal == 0): lane k keeps the bookkeeping of the warp's k-th own slot in registers and the
+    // table is not used — a waiting warp's wake-up is one flag load, which matters: twenty idle warps per SM that run a
+    // hundred instructions per microsecond each slow the walking ones by 10 % (4096 roots: 101 against 91 us per step).
+    const uint32_t my_slot = (uint32_t)warp + (uint32_t)lane * P.tree_warps;
+    uint32_t my_state = my_slot < n_local ? 0u : 2u;  // 0 runnable, 1 waiting for priors, 2 done
+    uint32_t my_sub = 0, my_steps = 0;
     for (;;) {
-        if (my_state == 1u && as_ld_volatile(P.h_flag + my_tree) >= my_sub) {
-            my_state = 0u;
-            my_wait += AS_CLK() - my_t0;
-        }
-        const uint32_t runnable = __ballot_sync(FULL, my_state == 0u);
-        if (__ballot_sync(FULL, my_state != 2u) == 0u) break;
-        if (runnable == 0u) {
-            // every tree of this warp waits for its priors.  The round trip is tens of microseconds, so the first sleeps
-            // after a walk are long and only then does the warp poll every microsecond: waiting warps would otherwise
-            // take issue slots and LSU bandwidth from the walking ones (phase cycles 91 K -> 74 K per tree-step)
-            __nanosleep(naps < P.nap_count ? P.nap_long_ns : P.nap_short_ns);
-            ++naps;
-            if ((++idle & 31u) == 0u) {
-                if (as_ld_volatile(&st->abort)) break;
-                if ((idle & 2047u) == 0u && as_now() - *reinterpret_cast<const unsigned long long *>(cx.ct + 28) > P.timeout_ns)
-                    atomicExch(&st->abort, 1u);
+        int pick;
+        if (!P.steal) {
+            if (my_state == 1u && as_ld_volatile(P.h_flag + tree0 + my_slot) >= my_sub) my_state = 0u;
+            const uint32_t runnable = __ballot_sync(FULL, my_state == 0u);
+            if (__ballot_sync(FULL, my_state != 2u) == 0u) break;
+            if (runnable == 0u) {
+                // every tree of this warp waits for its priors.  The round trip is tens of microseconds, so the first sleeps
+                // after a walk are long and only then does the warp poll every microsecond
+                __nanosleep(naps < P.nap_count ? P.nap_long_ns : P.nap_short_ns);
+                ++naps;
+                if ((++idle & 31u) == 0u) {
+                    if (as_ld_volatile(&st->abort)) break;
+                    if ((idle & 2047u) == 0u && as_now() - *reinterpret_cast<const unsigned long long *>(cx.ct + 28) > P.timeout_ns)
+                        atomicExch(&st->abort, 1u);
+                }
+                continue;
             }
-            continue;
-        }
-        // among this warp's runnable trees take the one that is furthest behind: the run ends when its slowest tree does
-        const uint32_t behind = __reduce_min_sync(FULL, my_state == 0u ? my_steps : 0xffffffffu);
-        const int k = __ffs(__ballot_sync(FULL, my_state == 0u && my_steps == behind)) - 1;
-        const uint32_t tree = gw + (uint32_t)k * NW;
-        const long long t_run0 = AS_CLK();
-        naps = 0;
+            // among this warp's runnable trees take the one that is furthest behind: the run ends when its slowest tree does
+            const uint32_t behind = __reduce_min_sync(FULL, my_state == 0u ? my_steps : 0xffffffffu);
+            const int k = __ffs(__ballot_sync(FULL, my_state == 0u && my_steps == behind)) - 1;
+            pick = warp + k * (int)P.tree_warps;
+            naps = 0;
 #if AS_ACQUIRE
-        // the relaxed poll saw this tree's flag: one acquire load of it orders the prior row (read in add_actions) behind it
-        if (__shfl_sync(FULL, my_sub, k) != 0u) (void)as_ld_acquire(P.h_flag + tree);
+            // the relaxed poll saw this tree's flag: one acquire load of it orders the prior row (read in add_actions) behind it
+            if (__shfl_sync(FULL, my_sub, k) != 0u) (void)as_ld_acquire(P.h_flag + tree0 + (uint32_t)pick);
+#endif
+        } else {
+            // ---- a runnable slot: first among this warp's HOME slots (i = warp mod tree_warps: disjoint between warps, so
+            // a loaded CTA behaves like static ownership and nobody fights over a slot), the one that is furthest behind —
+            // the run ends when its slowest tree does
+            pick = -1;
+            uint32_t behind = 0xffffffffu;
+            for (uint32_t b0 = (uint32_t)warp; b0 < n_local; b0 += 32u * P.tree_warps) {
+                const uint32_t i = b0 + (uint32_t)lane * P.tree_warps;
+                const uint32_t st_i = i < n_local ? as_lds_volatile(T.state + i) : 2u;
+                const uint32_t key = st_i == 0u ? as_lds_volatile(T.steps + i) : 0xffffffffu;
+                const uint32_t m = __reduce_min_sync(FULL, key);
+                if (m < behind) {
+                    behind = m;
+                    pick = (int)(b0 + (uint32_t)(__ffs(__ballot_sync(FULL, key == m)) - 1) * P.tree_warps);
+                }
+            }
+            // ---- none at home: take over somebody else's (the counter of runnable slots is a hint that saves the scan)
+            if (pick < 0 && (int)as_lds_volatile(T.ctl + 4) > 0) {
+                const uint32_t n_chunks = (n_local + 31u) / 32u;
+                for (uint32_t c = 0; c < n_chunks && pick < 0; ++c) {
+                    const uint32_t i = ((c + (uint32_t)warp) % n_chunks) * 32u + lane;
+                    const uint32_t ok = __ballot_sync(FULL, i < n_local && as_lds_volatile(T.state + i) == 0u);
+                    if (ok) pick = (int)(i - lane) + __ffs(ok) - 1;
+                }
+            }
+            if (pick < 0) {
+                if (as_lds_volatile(T.ctl + 0) >= n_local) break;  // every tree of this CTA has finished the launch
+                // ---- nothing runnable: look at the answer flags of waiting slots
+                uint32_t found = 0;
+                // more trees than warps: ONE warp at a time sweeps ALL waiting slots of the CTA (32 flags per ld.volatile
+                // round trip), at most once per sweep_gap cycles; the others nap and rescan shared memory only
+                uint32_t got = 0;
+                if (lane == 0 && (uint32_t)clock64() - as_lds_volatile(T.ctl + 3) >= P.sweep_gap)
+                    got = atomicCAS(T.ctl + 1, 0u, 1u) == 0u ? 1u : 0u;
+                got = __shfl_sync(FULL, got, 0);
+                if (got) {
+                    for (uint32_t b0 = 0; b0 < n_local; b0 += 32) {
+                        const uint32_t i = b0 + lane;
+                        const bool ready = i < n_local && as_lds_volatile(T.state + i) == 1u &&
+                                           as_ld_volatile(P.h_flag + tree0 + i) >= as_lds_volatile(T.sub + i);
+                        const uint32_t rb = __ballot_sync(FULL, ready);
+                        if (rb) {
+                            // acquire side of the model CTA's (fence, atomicAdd): the prior rows of these trees are read after
+                            // it (ONE acquire load per answered tree, as before — not per poll: it invalidates the SM's L1)
+                            if (ready) {
+                                (void)as_ld_acquire(P.h_flag + tree0 + i);
+                                as_sts_volatile(T.state + i, 0u);
+                            }
+                            found += __popc(rb);
+                        }
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (found) atomicAdd(T.ctl + 4, found);
+                        as_sts_volatile(T.ctl + 3, (uint32_t)clock64());
+                        as_sts_volatile(T.ctl + 1, 0u);
+                    }
+                }
+                if (found) {
+                    idle = 0;
+                    continue;
+                }
+                // Every wake-up costs issue slots next to the walking warps, and an answer is tens of microseconds away.  With
+                // take-overs the CTA's idle warps wake at different times, so long naps still bring a sweep round every
+                // microsecond or so; a warp that polls for itself sleeps long at first and then polls every microsecond.
+                __nanosleep(P.nap_long_ns);
+                if ((++idle & 7u) == 0u) {
+                    if (as_ld_volatile(&st->abort)) break;
+                    if ((idle & 511u) == 0u && as_now() - *reinterpret_cast<const unsigned long long *>(cx.ct + 28) > P.timeout_ns)
+                        atomicExch(&st->abort, 1u);
+                }
+                continue;
+            }
+            // ---- claim it
+            uint32_t ok = 0;
+            if (lane == 0) ok = atomicCAS(T.state + pick, 0u, 3u) == 0u ? 1u : 0u;
+            if (!__shfl_sync(FULL, ok, 0)) continue;
+            if (lane == 0) atomicSub(T.ctl + 4, 1u);
+            __threadfence_block();  // (behind the sweeper's store of the state)
+            idle = 0;
+        }
+        const uint32_t tree = tree0 + (uint32_t)pick;
+        const long long t_run0 = AS_CLK();
+#ifdef AZB_PROFILE
+        if (lane == 0 && T.t0[pick]) T.wait[pick] += (uint32_t)(t_run0 >> 4) - T.t0[pick];
 #endif
         // ---- one step of `tree` (the body of azb_tree_kernel, minus the batch barrier)
         ctx_bind_tree(L, cx, tree);
@@ -1622,9 +1762,9 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
             submitted = true;
         };
         if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) {
-            // Early hand-over pays where a tree's own chain (walk -> model -> walk) is the bound, i.e. while warps own one
-            // tree each; with several trees per warp it only lengthens the hot loop (32 768 roots: -11 %), so those
-            // launches take the instantiation that submits after the walk.
+            // Early hand-over pays where a tree's own chain (walk -> model -> walk) is the bound, i.e. while there is a
+            // warp for every tree; with several trees per warp it only lengthens the hot loop (32 768 roots: -11 %), so
+            // those launches take the instantiation that submits after the walk.
             if (P.early)
                 tree_rollout<DEPTH>(L, cx, tree, 0u, submit);
             else
@@ -1646,16 +1786,47 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         const uint32_t live_words = WK_HDR + L.PW + 2 * L.W;
 #pragma unroll 1
         for (uint32_t i = lane; i < live_words; i += 32) gwk[i] = cx.wk[i];
-        if (lane == k) {
-            my_state = new_state;
-            if (submitted) my_sub += 1u;
-            my_steps += 1u;
-            my_t0 = AS_CLK();
-            my_run += my_t0 - t_run0;
-        }
-        if (new_state == 2u && lane == 0) {
-            __threadfence();
-            atomicAdd(&st->done_trees, 1u);
+        __syncwarp();
+        if (!P.steal) {
+            if (my_slot == (uint32_t)pick) {
+                my_state = new_state;
+                if (submitted) my_sub += 1u;
+                my_steps += 1u;
+            }
+            if (lane == 0) {
+                if (submitted) my_rows += 1u;
+#ifdef AZB_PROFILE
+                T.sub[pick] = T.sub[pick] + (submitted ? 1u : 0u);
+                T.steps[pick] += 1u;
+                const long long t_end = AS_CLK();
+                T.run[pick] += (uint32_t)((t_end - t_run0) >> 4);
+                T.t0[pick] = (uint32_t)(t_end >> 4) | 1u;
+#endif
+                if (new_state == 2u) {
+                    __threadfence();
+                    atomicAdd(&st->done_trees, 1u);
+                }
+            }
+        } else if (lane == 0) {
+            // the next warp to advance this tree reads its walker block and arena through this SM's L1: CTA scope is enough
+            if (submitted) {
+                T.sub[pick] += 1u;
+                my_rows += 1u;
+            }
+            T.steps[pick] += 1u;
+#ifdef AZB_PROFILE
+            const long long t_end = AS_CLK();
+            T.run[pick] += (uint32_t)((t_end - t_run0) >> 4);
+            T.t0[pick] = (uint32_t)(t_end >> 4) | 1u;
+#endif
+            __threadfence_block();
+            as_sts_volatile(T.state + pick, new_state);
+            if (new_state == 0u) atomicAdd(T.ctl + 4, 1u);
+            if (new_state == 2u) {
+                atomicAdd(T.ctl + 0, 1u);
+                __threadfence();
+                atomicAdd(&st->done_trees, 1u);
+            }
         }
         if (cx.err) {
             if (lane == 0) {
@@ -1678,25 +1849,29 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         const uint32_t v = cx.ct[lane];
         if (v) atomicAdd(&L.g->prof[lane - 16], (unsigned long long)v);
     }
-#endif
-#ifdef AZB_PROFILE
-    if (my_tree < L.B && my_tree < 65536u)  // per tree: K-cycles walking, K-cycles waiting for priors, advances, rows
-        g_tree_prof[my_tree] = make_uint4((uint32_t)(my_run >> 10), (uint32_t)(my_wait >> 10), my_steps, my_sub);
-#endif
-#ifdef AZB_PROFILE
-    if (P.dbg && my_tree < L.B) {
-        atomicAdd(P.dbg + 16, (unsigned long long)my_run);
-        atomicMax(P.dbg + 17, (unsigned long long)my_run);
-        atomicAdd(P.dbg + 19, (unsigned long long)my_wait);
-        atomicMax(P.dbg + 20, (unsigned long long)my_wait);
-        atomicMax(P.dbg + 21, (unsigned long long)(my_wait + my_run));
-        if (my_tree == 0) P.dbg[18] = (unsigned long long)(AS_CLK() - t_k0);
+    // per tree: K-cycles walking, K-cycles waiting for priors, advances, rows — written by the last warp to leave the CTA
+    __syncwarp();
+    uint32_t left = 0;
+    if (lane == 0) left = atomicAdd(T.ctl + 2, 1u) + 1u;
+    left = __shfl_sync(FULL, left, 0);
+    if (left == P.tree_warps) {
+        __threadfence_block();
+        for (uint32_t i = lane; i < n_local; i += 32) {
+            const uint32_t tree = tree0 + i;
+            const unsigned long long run = (unsigned long long)T.run[i] << 4, wait = (unsigned long long)T.wait[i] << 4;
+            if (tree < 65536u) g_tree_prof[tree] = make_uint4((uint32_t)(run >> 10), (uint32_t)(wait >> 10), T.steps[i], T.sub[i]);
+            if (P.dbg) {
+                atomicAdd(P.dbg + 16, run);
+                atomicMax(P.dbg + 17, run);
+                atomicAdd(P.dbg + 19, wait);
+                atomicMax(P.dbg + 20, wait);
+                atomicMax(P.dbg + 21, wait + run);
+            }
+        }
+        if (P.dbg && tree_cta == 0 && lane == 0) P.dbg[18] = (unsigned long long)(AS_CLK() - t_k0);
     }
 #endif
-    {
-        const uint32_t rows = warp_sum_u32(my_sub);
-        if (lane == 0 && rows) atomicAdd(&st->rows_real, rows);
-    }
+    if (lane == 0 && my_rows) atomicAdd(&st->rows_real, my_rows);
 }
 
 // PAIR: the CTA-pair form of the model CTAs (its own instantiation: a kernel that contains cta_group::2 code can only be
@@ -1738,7 +1913,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
         // whole group have no model role)
         if constexpr (DEPTH != 5) {
             if ((threadIdx.x >> 5) >= SH_TREE_WARPS) {
-                const size_t tree_bytes = (size_t)SH_TREE_WARPS * P.smem_words_per_warp * 4 + ((L.A + 15u) & ~15u);
+                const size_t tree_bytes = (size_t)SH_TREE_WARPS * P.smem_words_per_warp * 4 + ((L.A + 15u) & ~15u) + as_table_bytes(P.tab_slots);
                 uint8_t *smem = (uint8_t *)(((uintptr_t)(as_smem + tree_bytes) + 1023) & ~(uintptr_t)1023);
                 if (blockIdx.x < (gridDim.x / P.group) * P.group) shared_model_warpgroup(L, P, M, blockIdx.x, smem, s_worker);
                 return;

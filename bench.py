@@ -373,6 +373,8 @@ def main():
                    "azb_step(K steps, per-step improvement log D2H) + azb_get_argmin(D2H); wall clock, max over ranks"}
     # the same epoch driven one step per call, like the reference's loop body (04-c21-tree.rs:143): every call
     # synchronises and reads the step's improvement record back
+    for _ in range(3):  # warm-up of the single-step path (its CUDA graph and lazily loaded kernels are first used here)
+        h2.step(1, cap=4)
     barrier()
     p0 = time.perf_counter()
     h2.set_roots(parents, masks)

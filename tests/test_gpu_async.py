@@ -105,6 +105,31 @@ def test_cta_pair_form_needs_an_even_worker_count(capi, monkeypatch):
         assert e.value.code == capi.ERR_INVALID
 
 
+@pytest.mark.parametrize("steal", ["0", "1"])
+@pytest.mark.parametrize("n,b,workers", [(19, 300, 4), (19, 5000, 20), (12, 77, 4), (33, 160, 4), (64, 96, 4)])
+def test_tree_scheduling_forms_equal_lock_step(capi, monkeypatch, steal, n, b, workers):
+    """Inside a tree CTA either every warp advances only its own trees (AZB_ASYNC_STEAL=0: bookkeeping in registers, the
+    default while there is a warp for every tree) or any free warp takes over any runnable tree of the CTA through the
+    scheduling table in shared memory (1: the default beyond that).  Who advances a tree does not change the tree."""
+    steps = 30
+    monkeypatch.setenv("AZB_ASYNC_STEAL", steal)
+    parents, masks = capi.generate_roots(12, 0, b, n)
+    kw = dict(prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=2 * steps + 2)
+    with _mk(capi, n, b, **kw) as lock, _mk(capi, n, b, async_workers=workers, **kw) as asy:
+        for h in (lock, asy):
+            h.mlp_init(7)
+            h.set_roots(parents, masks)
+            h.init_trees()
+        n1, log1 = lock.step(steps, cap=256)
+        n2, log2 = asy.step(steps, cap=256)
+        assert n1 == n2 and [tuple(x) for x in log1] == [tuple(x) for x in log2]
+        _same(lock, asy, b)
+        for h in (lock, asy):
+            h.step(1)
+            h.step(steps)
+        _same(lock, asy, b)
+
+
 def test_async_then_training_and_reset(capi):
     """An epoch on the asynchronous kernel followed by the epoch boundary (update_model, reset_trees) and a second
     epoch: identical to the lock step all the way."""
