@@ -283,7 +283,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
         const bool applies = cfg.prior_mode == AZB_PRIOR_MLP && (cfg.mlp_mode == AZB_MLP_TC || cfg.mlp_mode == AZB_MLP_TC3) &&
                              cfg.max_episodes == 0 && cfg.n_groups <= 1 && cfg.n_roots >= 1024;
         if (!applies) cfg.async_workers = 0;
-        else if (cfg.n_vertices >= 47) cfg.async_workers = 32;
+        else if (cfg.n_vertices >= 47) cfg.async_workers = 16;  // N = 64, 4096 roots: 8 / 16 / 24 / 32 model SMs -> 6.4 / 8.8 / 8.3 / 7.8 M
         // (session 3, `profiles/r02_dyn_*`: with free warps taking over any runnable tree of their CTA the tree side no
         // longer needs a whole number of trees per warp, and one layout serves every batch beyond 4096 roots)
         else if (cfg.n_roots <= 4096) cfg.async_workers = 20;

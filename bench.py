@@ -464,17 +464,18 @@ def main():
             extra["f32_accurate_model"] = {"value": t3_sims / (t3_ms * 1e-3), "unit": UNIT, "steps": t3_steps, "ms_per_step": t3_ms / t3_steps,
                                            "what": "same workload with mlp_mode = AZB_MLP_TC3 (priors within 1e-5 relative of the f32 forward; "
                                                    "tests/test_gpu_parity.py) instead of bf16 (2e-2 absolute)"}
-        # C4: 64-vertex trees (cost path dominated): 4096 roots, 32 model SMs
+        # C4: 64-vertex trees (cost path dominated): 4096 roots, the library's layout for N >= 47 (16 model SMs)
         c4_roots, c4_steps = 4096, min(args.steps, 64)
         try:
             c4_sims, c4_ms, ev4, bytes4 = timed_config(capi, 64, c4_roots, capi.ASYNC_AUTO, c4_steps, max(3, min(args.warmup, 8)), args.seed, rank, local_rank)
             extra["c4"] = {"value": c4_sims / (c4_ms * 1e-3), "unit": UNIT, "vertices": 64, "roots": c4_roots, "steps": c4_steps,
                            "ms_per_step": c4_ms / c4_steps, "cost_evals_per_sec": ev4 / (c4_ms * 1e-3), "device_bytes": bytes4,
-                           "what": "BASELINE configs[3]: N=64 (A=1952, MLP 3904-512-1024-512-1952), asynchronous kernel, 32 model SMs"}
+                           "what": "BASELINE configs[3]: N=64 (A=1952, MLP 3904-512-1024-512-1952), asynchronous kernel, 16 model SMs "
+                                   "(AZB_ASYNC_AUTO), 16 tree warps per SM taking over each other's runnable trees"}
         except capi.AzbError as e:
             extra["c4"] = {"error": str(e)}
     if world == 8 and not args.no_extra:
-        # C3: 65 536 roots over the 8 GPUs = 8192 per GPU, 48 model SMs in pairs
+        # C3: 65 536 roots over the 8 GPUs = 8192 per GPU, the library's layout (36 model SMs)
         c3_sims, c3_ms, ev3, _ = timed_config(capi, n, 8192, capi.ASYNC_AUTO, xsteps, args.warmup, args.seed, rank, local_rank)
         ms3 = allreduce(c3_ms, dist.ReduceOp.MAX)
         sims3 = allreduce(c3_sims, dist.ReduceOp.SUM)

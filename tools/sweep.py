@@ -9,7 +9,7 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 200
 mode = sys.argv[4] if len(sys.argv) > 4 else "async"  # "async" (bench.py's default search kernel) or "lock"
 out = []
 for b in sizes:
-    aw = 0 if mode == "lock" or b < 1024 or b > 100000 else (40 if b < 4096 else 20 if b == 4096 else 48 if b < 16384 else 32)
+    aw = 0 if mode == "lock" or b < 1024 else capi.ASYNC_AUTO  # the library's layout for the root count
     cfg = capi.default_config(n, b, prior_mode=capi.PRIOR_MLP, mlp_mode=capi.MLP_TC, max_steps=steps + 24, async_workers=aw)
     p, m = capi.generate_roots(0, 0, b, n)
     with capi.Handle(cfg) as h:
@@ -21,7 +21,7 @@ for b in sizes:
         h.reset_counters()
         ms, _ = h.step_timed(steps)
         k = h.counters()
-        rec = dict(n=n, roots=b, steps=steps, async_workers=aw, us_per_step=ms / steps * 1e3, sims_per_s=k["n_live"] / (ms * 1e-3),
+        rec = dict(n=n, roots=b, steps=steps, async_workers=int(h.cfg.async_workers), us_per_step=ms / steps * 1e3, sims_per_s=k["n_live"] / (ms * 1e-3),
                    cost_evals_per_s=k["n_ins"] / (ms * 1e-3), hbm_mb=h.device_bytes() / 1e6)
         out.append(rec)
         print(json.dumps(rec), flush=True)
