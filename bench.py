@@ -342,12 +342,25 @@ def main():
             traffic = tr["dram_bytes_per_launch"] * (prof_steps / tr.get("steps_per_launch", prof_steps) if aw else 1)
     except Exception:
         pass
+    # what actually bounds the search kernel: instruction issue and single-warp latency, not bytes.  The
+    # warp-instruction count per launch is ncu's (same capture as `traffic`); the duration is this run's
+    issue = None
+    try:
+        if traffic is not None and tr.get("warp_instructions_per_launch"):
+            n_sm, sm_hz = torch.cuda.get_device_properties(local_rank).multi_processor_count, 1.965e9
+            wi = tr["warp_instructions_per_launch"] * (prof_steps / tr.get("steps_per_launch", prof_steps) if aw else 1)
+            issue = {"warp_instructions_per_launch": wi, "achieved_ginst_per_s": wi / tree_launch_s / 1e9,
+                     "peak_ginst_per_s": n_sm * 4 * sm_hz / 1e9, "frac": wi / tree_launch_s / (n_sm * 4 * sm_hz),
+                     "what": "warp instructions per launch (ncu smsp__inst_executed.sum, profiles/r02_traffic.json) / this run's launch "
+                             "duration, against 4 issue slots per SM per clock at 1965 MHz"}
+    except Exception:
+        issue = None
     roofline = {"bound": "hbm", "kernel": "azb_async_kernel" if aw else "azb_tree_kernel", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch, "launch_us": tree_launch_s * 1e6,
                 "steps_per_launch": prof_steps if aw else 1,
                 "mlp_us_per_step": None if aw else mlp_ms * 1e3 / prof_steps,
-                "tree_share_of_step": None if aw else tree_ms / max(tree_ms + mlp_ms, 1e-9)}
+                "tree_share_of_step": None if aw else tree_ms / max(tree_ms + mlp_ms, 1e-9), "issue": issue}
     dev_bytes = h.device_bytes()
 
     # ---- e2e: a whole epoch through the C ABI with HOST buffers: roots H2D (set_roots), init, K per-step calls each
