@@ -1722,6 +1722,7 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         }
         const uint32_t tree = tree0 + (uint32_t)pick;
         const long long t_run0 = AS_CLK();
+        (void)t_run0;
 #ifdef AZB_PROFILE
         if (lane == 0 && T.t0[pick]) T.wait[pick] += (uint32_t)(t_run0 >> 4) - T.t0[pick];
 #endif

@@ -90,17 +90,19 @@ typedef struct azb_config {
     uint32_t n_groups;          /* >1: the trees of this handle advance as that many independent groups on their own
                                    CUDA streams (needs max_episodes = 0); results are identical, launches overlap */
     uint32_t async_workers;     /* > 0 (needs AZB_PRIOR_MLP + AZB_MLP_TC): azb_step(h, n >= 2) runs as ONE persistent cooperative
-                                   kernel in which trees never wait for each other — the CTAs of that many SMs (20 at 4096
-                                   roots, 32 from 16 K roots; in pairs per tile from 40) become tensor-core model workers that
-                                   answer state vectors in 128-row tiles as they fill, all other CTAs walk trees, a warp
-                                   advancing whichever of its trees has its priors.  Same results as the lock step (trees are
-                                   independent).  0 = lock step.  AZB_ASYNC_AUTO = the measured best layout for the root count
-                                   (40 SMs in pairs below 4096 roots, 20 at 4096, 28 up to 8192, 36 up to
-                                   32 768, 40 beyond; 32 for N >= 47), or the lock step where the asynchronous kernel does not
-                                   apply (no tensor-core model, fewer than 1024 roots, max_episodes or n_groups set); azb_get_config
-                                   shows the choice.  Environment, read when the handle first runs this way:
-                                   AZB_ASYNC_GROUP=g (worker SMs per tile), AZB_ASYNC_FLUSH_NS, AZB_ASYNC_TIMEOUT_MS (watchdog
-                                   floor, default 2000). */
+                                   kernel in which trees never wait for each other — the CTAs of that many SMs become
+                                   tensor-core model workers that answer state vectors in 128-row tiles as they fill, all
+                                   other CTAs walk trees: a CTA owns a block of the batch's trees, each warp its own while there
+                                   is a warp for every tree, any free warp any runnable tree of its CTA beyond that.  Same
+                                   results as the lock step (trees are independent).  0 = lock step.  AZB_ASYNC_AUTO = the
+                                   measured best layout for the root count (20 model SMs up to 4096 roots — in
+                                   pairs per tile below 4096 —, 36 beyond; 16 for N >= 47), or the lock step where the
+                                   asynchronous kernel does not apply (no tensor-core model, fewer than 1024 roots,
+                                   max_episodes or n_groups set); azb_get_config shows the choice.  Environment, read when the
+                                   handle first runs this way: AZB_ASYNC_GROUP=g (worker SMs per tile), AZB_ASYNC_PAIR=1 (model
+                                   CTAs as CTA pairs of one cluster: tcgen05.mma.cta_group::2, even async_workers),
+                                   AZB_ASYNC_STEAL=0/1 (tree scheduling inside a CTA), AZB_ASYNC_FLUSH_NS,
+                                   AZB_ASYNC_TIMEOUT_MS (watchdog floor, default 2000). */
     uint32_t reserved[5];
 } azb_config;
 
