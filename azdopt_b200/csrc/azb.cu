@@ -869,10 +869,15 @@ static int async_create(azb_handle *h) {
     P.sh_stages = sh_stages;
     P.tree_warps = tree_warps;
     P.tab_slots = tab_slots;
-    P.early = B <= NW ? 1u : 0u;  // one tree per warp: the tree's own latency chain is the bound (azb_async.cuh)
-    if (const char *e = getenv("AZB_ASYNC_EARLY")) P.early = atoi(e) != 0;
-    P.steal = B > NW ? 1u : 0u;  // more trees than warps: free warps take over any runnable tree of their CTA (azb_async.cuh)
+    // Inside a tree CTA (azb_async.cuh): up to two trees per warp a warp's own trees keep it busy exactly while the model
+    // answers (walk A, walk B, A's priors are back), so static ownership loses nothing and its cheap wake-ups and the early
+    // hand-over of the state vector win (6144 roots: 115 us per step against 125-133 with take-overs); beyond that — and
+    // from one tree per warp on where the walk itself dominates the step (N >= 47: 16 tree warps per SM, 100+ us walks) —
+    // free warps take over any runnable tree of their CTA
+    P.steal = (B > 2u * NW || (azb_stack_depth(h->N) == 5 && B > NW)) ? 1u : 0u;
     if (const char *e = getenv("AZB_ASYNC_STEAL")) P.steal = atoi(e) != 0;
+    P.early = P.steal ? 0u : 1u;  // the tree's own latency chain is the bound: hand the state vector over before the cost evaluation
+    if (const char *e = getenv("AZB_ASYNC_EARLY")) P.early = atoi(e) != 0;
     P.sweep_gap = AS_SWEEP_GAP;
     if (const char *e = getenv("AZB_ASYNC_SWEEP_GAP")) P.sweep_gap = (uint32_t)strtoul(e, nullptr, 10);
     // worker SMs per tile
@@ -1696,11 +1701,11 @@ extern "C" int azb_debug_tree_prof(azb_handle *h, uint32_t *out4, uint32_t ntree
 
 // cycle counters of the async kernel's MLP workers (last launch) + its row statistics: out[0..14] counters,
 // out[15] = real rows << 32 | dummy rows
-extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {  // out: 24 entries
+extern "C" int azb_debug_async(azb_handle *h, unsigned long long *out16) {  // out: 32 entries
     if (!h || !out16 || !h->async_ready) return AZB_ERR_INVALID;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(out16, h->asP.dbg, 24 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out16, h->asP.dbg, 32 * 8, cudaMemcpyDeviceToHost));
     AzbAsyncState st;
     CK(cudaMemcpy(&st, h->asP.st, sizeof(st), cudaMemcpyDeviceToHost));
     out16[15] = ((unsigned long long)st.rows_real << 32) | st.rows_dummy;

@@ -1076,6 +1076,9 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
         as_named_bar(2, AS_EPI_WARPS * 32);
         if (S.epi_last) {
             __threadfence();
+#ifdef AZB_PROFILE
+            if (part == 0u && my_tree != AS_NONE && my_tree < 65536u) g_flag_time[my_tree] = as_now();
+#endif
             if (part == 0u && my_tree != AS_NONE) atomicAdd(P.h_flag + my_tree, 1u);
             if (et == 0u) {
                 atomicAdd(P.tile_retired + (q % P.NT), 1u);
@@ -1723,6 +1726,19 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
         const uint32_t tree = tree0 + (uint32_t)pick;
         const long long t_run0 = AS_CLK();
         (void)t_run0;
+#ifdef AZB_PROFILE
+        // pick-up latency: from the model raising the answer flag (its %globaltimer) to this warp starting the step
+        if (lane == 0 && P.dbg && tree < 65536u) {
+            const unsigned long long tf = *reinterpret_cast<volatile unsigned long long *>(g_flag_time + tree);
+            if (tf) {
+                const unsigned long long now = as_now(), dt = now > tf ? now - tf : 0ull;
+                atomicAdd(P.dbg + 24, dt);
+                atomicMax(P.dbg + 25, dt);
+                atomicAdd(P.dbg + 26, 1ull);
+                *reinterpret_cast<volatile unsigned long long *>(g_flag_time + tree) = 0ull;
+            }
+        }
+#endif
 #ifdef AZB_PROFILE
         if (lane == 0 && T.t0[pick]) T.wait[pick] += (uint32_t)(t_run0 >> 4) - T.t0[pick];
 #endif

@@ -41,6 +41,7 @@ enum { AZB_F_ADD = 1, AZB_F_ROLLOUT = 2, AZB_F_INIT = 4, AZB_F_FIRST = 8 };
 #define PROF_ADD(cx, ph) do {} while (0)
 #endif
 #ifdef AZB_PROFILE
+__device__ unsigned long long g_flag_time[65536];  // %globaltimer when the model last raised the tree's answer flag (pick-up latency)
 __device__ uint4 g_tree_prof[65536];  // per tree, last launch: cycles, episodes(resets)+1, cost evals, sqrt terms
 #endif
 enum { PH_SEL = 0, PH_CUR, PH_PROBE, PH_ARC, PH_CASCADE, PH_COST, PH_INSERT, PH_RESET, PH_ADD, PH_PACK, PH_LOAD, PH_STORE };

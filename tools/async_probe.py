@@ -28,7 +28,7 @@ for w in workers:
         if w and os.environ.get("PROBE_PROF"):
             L = capi.lib()
             L.azb_debug_async.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-            d = (C.c_uint64 * 24)()
+            d = (C.c_uint64 * 32)()
             L.azb_debug_async(h._h, d)
             tiles = max(d[4], 1)
             us = lambda c: c / tiles / 1965.0
@@ -37,4 +37,5 @@ for w in workers:
                   f"tiles {d[4]} rows real {d[15] >> 32} dummy {d[15] & 0xffffffff}", flush=True)
             print(f"      trees: kernel {d[18]/1965e3:.1f} ms; cycles advancing a tree: mean {d[16]/b/1965e3:.1f} ms, max {d[17]/1965e3:.1f} ms "
                   f"(per step: mean {d[16]/b/steps/1965:.1f} us, slowest tree {d[17]/steps/1965:.1f} us); waiting for priors per step: "
-                  f"mean {d[19]/b/steps/1965:.1f} us, max tree {d[20]/steps/1965:.1f} us; max (run+wait) {d[21]/1965e3:.1f} ms", flush=True)
+                  f"mean {d[19]/b/steps/1965:.1f} us, max tree {d[20]/steps/1965:.1f} us; max (run+wait) {d[21]/1965e3:.1f} ms; "
+                  f"pick-up latency (answer flag -> step starts): mean {d[24]/max(d[26],1)/1e3:.2f} us, max {d[25]/1e3:.1f} us over {d[26]} pick-ups", flush=True)

@@ -30,7 +30,7 @@ for mode in modes:
         if os.environ.get("PROBE_PROF"):
             L = capi.lib()
             L.azb_debug_async.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
-            d = (C.c_uint64 * 24)()
+            d = (C.c_uint64 * 32)()
             L.azb_debug_async(h._h, d)
             tiles = max(d[4], 1)
             us = lambda c: c / tiles / 1965.0
