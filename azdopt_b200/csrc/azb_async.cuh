@@ -1058,7 +1058,10 @@ __device__ __forceinline__ void async_worker_epilogue(const AzbLayout &L, const 
             if (warp == AS_EPI_WARP0) AS_MARK(id.grp, 2, 5u | (l << 4) | (q << 8));
             const long long tf0 = AS_CLK();
             if (l < 3) as_fence_proxy_async();  // the next layer reads these stores through TMA
-            __threadfence();
+            // a single worker hands its hidden activations to its OWN producer warp: the cross-proxy fence, the CTA barrier
+            // and the mbarrier's release/acquire are what the memory model asks for.  A GPU-scope fence is needed where
+            // another SM reads them (G > 1) and before the answer flags (l == 3; it waits for every store's acknowledgement)
+            if (G > 1u || l == 3u) __threadfence();
             as_named_bar(2, AS_EPI_WARPS * 32);
             if (et == 0u) {
                 if (l < 3) {
