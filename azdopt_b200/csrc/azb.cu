@@ -403,7 +403,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
     {
         // one region for: children's c* (selection) | cascade work lists + visited bitmap | cost scratch
         const uint32_t cascade_words = 3u * AZB_FRONTIER_CAP + ((L.cap_nodes + 31u) >> 5);
-        const uint32_t shared_region = (std::max(std::max(h->lcap, cascade_words), AZB_COST_SCRATCH_WORDS) + 3u) & ~3u;
+        const uint32_t shared_region = (std::max(std::max(h->lcap, cascade_words), azb_cost_scratch_words(h->N)) + 3u) & ~3u;
         h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 32 + shared_region;
     }
     h->smem_words_per_warp = (h->smem_words_per_warp + 3u) & ~3u;

@@ -23,14 +23,31 @@
 
 #define AZB_SECTION_ROUNDS 11
 
+#ifdef AZB_PROFILE
+__device__ unsigned long long g_cost_prof[8];
+#define CPROF_T0() long long cprof_t = clock64()
+#define CPROF(i)                                                            \
+    do {                                                                    \
+        long long t1_ = clock64();                                          \
+        if (lane == 0) atomicAdd(&g_cost_prof[i], (unsigned long long)(t1_ - cprof_t)); \
+        cprof_t = t1_;                                                      \
+    } while (0)
+#else
+#define CPROF_T0() do {} while (0)
+#define CPROF(i) do {} while (0)
+#endif
+
 enum { OP_END = 0, OP_L0 = 1, OP_L = 2, OP_T = 3, OP_PUSH = 4, OP_POPF = 5 };
 
+#define AZB_SECTION_MAX_DEPTH 5
 struct __align__(16) CostScratch {  // per-warp shared memory
     uint32_t cnt[64];               // number of children
     uint32_t w2[64];                // sum of the children's degrees
     uint8_t su[64], s1[64], s2[64], heavy[64], len[64], start[64], cur[64];
-    uint8_t ops[112];
-    uint32_t prog[12];
+    uint8_t ops[128];  // the program, one op per byte (at most ~2 n ops), read eight at a time
+    // saved (Q, S) pairs of the section evaluation: [level][Q | S][lane].  LAST: a tree of n vertices uses
+    // azb_stack_depth(n) - 1 levels, and the host sizes the scratch accordingly (azb_cost_scratch_words)
+    double stk[(AZB_SECTION_MAX_DEPTH - 1) * 2 * 32];
 };
 
 
@@ -89,13 +106,22 @@ __device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *
     hi = __dmul_rn(__dsqrt_rn((double)maxw2), 1.0 + 9.313225746154785e-10);
 
     if (lane == 0) {
-        // pass 1 (leaves first): slots needed by each internal vertex; heaviest internal child of each vertex
+        // pass 1 (leaves first; the children of v have larger indices, so v's own entries are final when v comes up):
+        // slots needed by each internal vertex, heaviest internal child of each vertex, program length of every subtree.
+        // A child contributes 1 op (leaf), len + 1 (the heaviest internal child: OP_T) or len + 2 (PUSH ... POPF); which
+        // child is the heaviest is only known once all children are in, so every internal child is entered as len + 2 and
+        // the vertex takes the 1 back when its own turn comes.
 #pragma unroll 1
         for (uint32_t v = n - 1; v >= 1; --v) {
-            if (cs->cnt[v] == 0u) continue;
+            const uint32_t p = par[v];
+            if (cs->cnt[v] == 0u) {
+                cs->len[p] = (uint8_t)(cs->len[p] + 1u);
+                continue;
+            }
+            const uint32_t lenv = cs->len[v] - (cs->heavy[v] != 0xff ? 1u : 0u);
+            cs->len[v] = (uint8_t)lenv;
             const uint32_t suv = max((uint32_t)cs->s1[v], 1u + cs->s2[v]);
             cs->su[v] = (uint8_t)suv;
-            const uint32_t p = par[v];
             if (suv > cs->s1[p]) {
                 cs->s2[p] = cs->s1[p];
                 cs->s1[p] = (uint8_t)suv;
@@ -103,14 +129,9 @@ __device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *
             } else if (suv > cs->s2[p]) {
                 cs->s2[p] = (uint8_t)suv;
             }
+            cs->len[p] = (uint8_t)(cs->len[p] + lenv + 2u);
         }
-        // pass 2 (leaves first): program length of every subtree
-#pragma unroll 1
-        for (uint32_t v = n - 1; v >= 1; --v) {
-            const uint32_t p = par[v];
-            const uint32_t sl = cs->cnt[v] == 0u ? 1u : cs->len[v] + (cs->heavy[p] == v ? 1u : 2u);
-            cs->len[p] = (uint8_t)(cs->len[p] + sl);
-        }
+        if (cs->heavy[0] != 0xff) cs->len[0] = (uint8_t)(cs->len[0] - 1u);
         // pass 3 (root first): slot offsets; every vertex writes its own op(s)
         cs->start[0] = 0;
         cs->cur[0] = cs->heavy[0] != 0xff ? (uint8_t)(cs->len[cs->heavy[0]] + 1u) : 0;
@@ -144,76 +165,75 @@ __device__ __forceinline__ uint32_t azb_cost_prepare(uint32_t n, const uint8_t *
         cs->ops[cs->len[0]] = OP_END;
     }
     __syncwarp();
-    const uint32_t nops = (uint32_t)cs->len[0] + 1u;
-    if (lane < 12) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-            const uint32_t i = lane * 10 + j;
-            if (i < nops) w |= (uint32_t)cs->ops[i] << (3 * j);
-        }
-        cs->prog[lane] = w;
-    }
-    __syncwarp();
-    return nops;
+    return (uint32_t)cs->len[0] + 1u;
 }
 
-// run the stack program at x: true iff P_v(x) > 0 for every vertex v
+// run the stack program at x: true iff P_v(x) > 0 for every vertex v.
+// The pair on top of the stack lives in registers, the saved pairs below it in the warp's shared memory ([level][Q | S]
+// [lane]: conflict-free), so PUSH and POPF are one store / load of a pair.  (The first version kept all DEPTH pairs in
+// registers and shifted them on every PUSH / POPF, and decoded 3-bit ops from packed words: ~40 dependent instructions per
+// op, 283 K cycles per evaluation at N = 64 — 86 % of a tree-step.)  The IEEE operations and their order per grid point
+// are unchanged, so lambda_1 stays bit-identical to the oracle's lambda1_multisection.
 template <int DEPTH>
-__device__ __forceinline__ bool azb_section_positive(const uint32_t *prog, double x) {
-    double Q0 = 0., S0 = 0., Q1 = 0., S1 = 0., Q2 = 0., S2 = 0., Q3 = 0., S3 = 0., Q4 = 0., S4 = 0.;
+__device__ __forceinline__ bool azb_section_positive(CostScratch *cs, int lane, double x) {
+    double Q0 = 0., S0 = 0.;
     bool ok = true;
-    uint32_t word = 0;
+    const uint2 *ops8 = reinterpret_cast<const uint2 *>(cs->ops);
+    double *sp = cs->stk + lane;
+    uint2 next_word = ops8[0];
 #pragma unroll 1
-    for (uint32_t i = 0;; ++i) {
-        const uint32_t r = i % 10u;
-        if (r == 0u) word = prog[i / 10u];
-        const uint32_t op = word & 7u;
-        word >>= 3;
-        if (op == OP_L) {  // fold a leaf child (P = x, Q = 1)
-            S0 = __fma_rn(S0, x, Q0);
-            Q0 = __dmul_rn(Q0, x);
-        } else if (op == OP_L0) {  // first child is a leaf
-            Q0 = x;
-            S0 = 1.0;
-        } else if (op == OP_T) {  // the slot held the heaviest child; it becomes the parent's pair
-            const double P = __fma_rn(x, Q0, -S0);
-            ok = ok && (P > 0.0);
-            S0 = Q0;
-            Q0 = P;
-        } else if (op == OP_PUSH) {
-            if (DEPTH > 4) { Q4 = Q3; S4 = S3; }
-            if (DEPTH > 3) { Q3 = Q2; S3 = S2; }
-            Q2 = Q1; S2 = S1;
-            Q1 = Q0; S1 = S0;
-        } else if (op == OP_POPF) {  // finish the vertex on top, fold it into the pair below
-            const double P = __fma_rn(x, Q0, -S0);
-            ok = ok && (P > 0.0);
-            const double t = __dmul_rn(Q1, Q0);
-            S0 = __fma_rn(S1, P, t);
-            Q0 = __dmul_rn(Q1, P);
-            Q1 = Q2; S1 = S2;
-            if (DEPTH > 3) { Q2 = Q3; S2 = S3; }
-            if (DEPTH > 4) { Q3 = Q4; S3 = S4; }
-        } else {  // OP_END: the root
-            const double P = __fma_rn(x, Q0, -S0);
-            ok = ok && (P > 0.0);
-            break;
+    for (uint32_t w = 1;; ++w) {
+        // eight ops per shared-memory load, the next eight requested while these run; the eight are decoded by constant
+        // byte extracts in an unrolled body (the walkers of N >= 23 are issue-bound in this loop: 16 warps per SM interpret
+        // the same kind of program, so what counts is instructions per op)
+        const uint2 word = next_word;
+        next_word = ops8[w];  // (ops[] is 128 bytes for at most ~113 ops: the look-ahead stays inside it)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t op = ((k < 4 ? word.x : word.y) >> (8 * (k & 3))) & 0xffu;
+            if (op == OP_L) {  // fold a leaf child (P = x, Q = 1)
+                S0 = __fma_rn(S0, x, Q0);
+                Q0 = __dmul_rn(Q0, x);
+            } else if (op == OP_POPF) {  // finish the vertex on top, fold it into the pair below
+                const double P = __fma_rn(x, Q0, -S0);
+                ok = ok && (P > 0.0);
+                sp -= 64;
+                const double Q1 = sp[0], S1 = sp[32];
+                const double t = __dmul_rn(Q1, Q0);
+                S0 = __fma_rn(S1, P, t);
+                Q0 = __dmul_rn(Q1, P);
+            } else if (op == OP_PUSH) {  // (the pair on top is dead until the pushed subtree's first leaf sets it)
+                sp[0] = Q0;
+                sp[32] = S0;
+                sp += 64;
+            } else if (op == OP_T) {  // the slot held the heaviest child; it becomes the parent's pair
+                const double P = __fma_rn(x, Q0, -S0);
+                ok = ok && (P > 0.0);
+                S0 = Q0;
+                Q0 = P;
+            } else if (op == OP_L0) {  // first child is a leaf
+                Q0 = x;
+                S0 = 1.0;
+            } else {  // OP_END: the root
+                const double P = __fma_rn(x, Q0, -S0);
+                return ok && (P > 0.0);
+            }
         }
     }
-    return ok;
 }
 
 // A whole warp on one tree.  par: n bytes of shared memory.  Warp-collective; every lane returns lambda_1.
 template <int DEPTH>
 __device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *par, CostScratch *cs, int lane) {
     double lo, hi;
+    CPROF_T0();
     azb_cost_prepare(n, par, cs, lane, lo, hi);
+    CPROF(0);
 #pragma unroll 1
     for (int round = 0; round < AZB_SECTION_ROUNDS; ++round) {
         const double w = __dmul_rn(__dsub_rn(hi, lo), 0.03125);
         const double x = __dadd_rn(lo, __dmul_rn((double)(lane + 1), w));
-        const bool pos = azb_section_positive<DEPTH>(cs->prog, x);
+        const bool pos = azb_section_positive<DEPTH>(cs, lane, x);
         const uint32_t bal = __ballot_sync(0xffffffffu, pos);  // bit l <-> grid point l+1 (bit 31 is never used)
         int L = 0, H = 32;
 #pragma unroll
@@ -230,6 +250,7 @@ __device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *pa
         hi = nhi;
     }
     __syncwarp();
+    CPROF(1);
     return __dmul_rn(0.5, __dadd_rn(lo, hi));
 }
 
@@ -249,19 +270,6 @@ __device__ __forceinline__ double azb_lambda1_warp(uint32_t n, const uint8_t *pa
 #define AZB_POLY_KMAX 11
 #define AZB_POLY_NV 22
 
-#ifdef AZB_PROFILE
-__device__ unsigned long long g_cost_prof[8];
-#define CPROF_T0() long long cprof_t = clock64()
-#define CPROF(i)                                                            \
-    do {                                                                    \
-        long long t1_ = clock64();                                          \
-        if (lane == 0) atomicAdd(&g_cost_prof[i], (unsigned long long)(t1_ - cprof_t)); \
-        cprof_t = t1_;                                                      \
-    } while (0)
-#else
-#define CPROF_T0() do {} while (0)
-#define CPROF(i) do {} while (0)
-#endif
 
 struct __align__(16) PolyScratch {  // per-warp shared memory, lives in the same bytes as CostScratch
     uint32_t A[AZB_POLY_NV][AZB_POLY_KMAX + 1];
@@ -466,6 +474,11 @@ __device__ __forceinline__ float azb_evaluate(uint32_t mu, double lambda1, float
 
 #define AZB_COST_SCRATCH_BYTES (sizeof(CostScratch) > sizeof(PolyScratch) ? sizeof(CostScratch) : sizeof(PolyScratch))
 #define AZB_COST_SCRATCH_WORDS ((uint32_t)(AZB_COST_SCRATCH_BYTES / 4))
+// what a tree of n vertices needs: the matching-polynomial scratch up to 22 vertices, the section scratch beyond
+__host__ __device__ __forceinline__ uint32_t azb_cost_scratch_words(uint32_t n) {
+    return (uint32_t)((n <= 22 ? sizeof(PolyScratch)
+                               : offsetof(CostScratch, stk) + (size_t)(azb_stack_depth(n) - 1) * 2 * 32 * sizeof(double)) / 4);
+}
 
 // Stand-alone batched cost kernel (azb_eval_costs): one warp per tree, 8 trees per block; the parent arrays of a
 // block are one contiguous, coalesced read; outputs are SoA.
