@@ -155,6 +155,10 @@ __device__ __forceinline__ uint32_t as_ld_acquire(const uint32_t *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// increment with release semantics at GPU scope (MEMBAR.ALL.GPU + RED: no L1 invalidation, unlike a full fence)
+__device__ __forceinline__ void as_red_release_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void as_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
@@ -1775,10 +1779,13 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
             // azb_get_state_vecs and the host-model calls look for it
             if (last) tree_pack<true>(L, c, tree, nullptr);
             if (lane == 0) P.slot_tree[pos] = tree;
-            __threadfence();
+            // publish: every lane's part of the row crosses to the async proxy (fence.proxy.async carries a GPU-scope
+            // MEMBAR), the warp barrier orders the lanes' stores before lane 0's RELEASE increment of the tile counter.
+            // Not __threadfence(): that is MEMBAR.SC + CCTL.IVALL — an invalidation of the SM's whole L1, which the 32
+            // walkers of the SM live on, for a fence that only has to release
             as_fence_proxy_async();
             __syncwarp();
-            if (lane == 0) atomicAdd(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
+            if (lane == 0) as_red_release_add(P.tile_count + ((slot / AS_TILE) % P.NT), 1u);
             submitted = true;
         };
         if (cx.err == 0 && cx.wk[WK_STEP] < P.target_step && !(cx.wk[WK_FLAGS] & 1u)) {
