@@ -1040,6 +1040,16 @@ static int enqueue_steps(azb_handle *h, uint32_t n_steps, uint32_t flags) {
         return fail(h, AZB_ERR_CAPACITY, "%u steps since azb_init_trees exceed max_steps", h->steps_done + n_steps);
     const uint32_t target = h->steps_done + n_steps;
     if (h->cfg.async_workers && n_steps >= 2 && flags == (AZB_F_ADD | AZB_F_ROLLOUT)) return run_async(h, n_steps);
+    if (h->cfg.prior_mode == AZB_PRIOR_HASH && h->cfg.max_episodes == 0 && h->n_groups <= 1 && n_steps >= 2 &&
+        flags == (AZB_F_ADD | AZB_F_ROLLOUT) && !getenv("AZB_HASH_LOCKSTEP")) {
+        // counter-hash priors need no model call, so nothing ties the trees together: ONE launch in which every warp takes
+        // its tree through all n_steps steps (per-tree step clocks and cand[step][tree] as in the asynchronous kernel)
+        int rc = launch_tree(h, flags | AZB_F_MULTI, target);
+        if (rc) return rc;
+        h->steps_done = target;
+        h->pending_add = true;
+        return AZB_OK;
+    }
     if (h->cfg.max_episodes == 0 && n_steps) {
         // Lock-step launches (every tree advances exactly one step per launch).  Groups of trees advance on their own
         // streams: a group's launch only waits for its own slowest tree and its model forward overlaps the other

@@ -25,7 +25,7 @@
 #include "azb_common.cuh"
 #include "azb_cost.cuh"
 
-enum { AZB_F_ADD = 1, AZB_F_ROLLOUT = 2, AZB_F_INIT = 4, AZB_F_FIRST = 8 };
+enum { AZB_F_ADD = 1, AZB_F_ROLLOUT = 2, AZB_F_INIT = 4, AZB_F_FIRST = 8, AZB_F_MULTI = 16 };
 
 // optional phase timing (-DAZB_PROFILE): cycles of lane 0 per phase, summed into AzbGlobals::prof
 #ifdef AZB_PROFILE
@@ -902,15 +902,23 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
             build_cur_mask(L, cx);
             tree_pack(L, cx, tree);
         }
-        if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions<DEPTH == 5>(L, cx, tree);
-        PROF_ADD(cx, PH_ADD);
-        if ((flags & AZB_F_ROLLOUT) && cx.err == 0 && cx.wk[WK_STEP] < target_step && !(cx.wk[WK_FLAGS] & 1u)) {
-            tree_rollout<DEPTH>(L, cx, tree, max_episodes);
+        // AZB_F_MULTI (counter-hash priors only: they are computed in add_actions, so a tree never waits for anybody): the
+        // warp takes its tree all the way to target_step in this one launch — the lock step without its barrier
+#pragma unroll 1
+        for (;;) {
+            if ((flags & AZB_F_ADD) && (cx.wk[WK_FLAGS] & 1u)) tree_add_actions<DEPTH == 5>(L, cx, tree);
+            PROF_ADD(cx, PH_ADD);
+            if ((flags & AZB_F_ROLLOUT) && cx.err == 0 && cx.wk[WK_STEP] < target_step && !(cx.wk[WK_FLAGS] & 1u)) {
+                tree_rollout<DEPTH>(L, cx, tree, max_episodes);
 #ifdef AZB_PROFILE
-            prof_t0 = clock64();
+                prof_t0 = clock64();
 #endif
-            if (cx.err == 0 && (cx.wk[WK_FLAGS] & 1u)) tree_pack(L, cx, tree);  // optimizer/mod.rs:171-173
-            PROF_ADD(cx, PH_PACK);
+                // optimizer/mod.rs:171-173 (every step, also in a multi-step launch: a tree whose later steps are no-ops
+                // keeps the vector of its last live step, exactly as in the lock step)
+                if (cx.err == 0 && (cx.wk[WK_FLAGS] & 1u)) tree_pack(L, cx, tree);
+                PROF_ADD(cx, PH_PACK);
+            }
+            if (!(flags & AZB_F_MULTI) || cx.err != 0 || cx.wk[WK_STEP] >= target_step) break;
         }
 #ifdef AZB_PROFILE
         prof_t0 = clock64();

@@ -468,7 +468,10 @@ def main():
         sp_steps = min(args.steps, 200)
         sp_sims, sp_ms, _, _ = timed_config(capi, n, b, 0, sp_steps, args.warmup, args.seed, rank, local_rank, prior_hash=True)
         extra["same_priors"] = {"value": sp_sims / (sp_ms * 1e-3), "unit": UNIT, "steps": sp_steps, "ms_per_step": sp_ms / sp_steps,
-                                "what": f"N={n}, {b} roots, hash priors (the reference arm's), lock-step launches, no model forward"}
+                                "what": f"N={n}, {b} roots, hash priors (the reference arm's), no model forward: the search (tree + state + cost) "
+                                        "kernel ALONE, one launch for all the steps (every warp takes its tree through them; hash priors "
+                                        "are computed in add_actions, so no tree waits for anybody)",
+                                "hbm_frac_algorithmic": (sp_sims / (sp_ms * 1e-3)) * (algorithmic_bytes(kp, n) / max(kp["n_live"], 1)) / 1e9 / hbm_peak}
         # the f32-accurate tensor-core model (AZB_MLP_TC3: bf16 hi + lo operands, three products per dot product): what the
         # reference's f32 forward costs on the tensor cores; the default stays bf16 because it is the faster step
         if args.mlp == "tc" and aw:
