@@ -824,8 +824,11 @@ __device__ __forceinline__ void tree_pack(const AzbLayout &L, WarpCtx &cx, uint3
     }
 }
 
+#ifndef AZB_TREE_MIN_BLOCKS
+#define AZB_TREE_MIN_BLOCKS 7
+#endif
 template <int DEPTH, bool COUNT>
-__global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, 7)
+__global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, AZB_TREE_MIN_BLOCKS)
     azb_tree_kernel(const AzbLayout L, const uint32_t flags, const uint32_t smem_words_per_warp, const uint32_t lcap,
                     const uint32_t target_step, const uint32_t max_episodes, const uint32_t tree0,
                     const uint32_t tree_end) {
