@@ -472,6 +472,14 @@ def main():
                                         "kernel ALONE, one launch for all the steps (every warp takes its tree through them; hash priors "
                                         "are computed in add_actions, so no tree waits for anybody)",
                                 "hbm_frac_algorithmic": (sp_sims / (sp_ms * 1e-3)) * (algorithmic_bytes(kp, n) / max(kp["n_live"], 1)) / 1e9 / hbm_peak}
+        try:  # the issue roofline of the search kernel alone: ncu's warp instructions per tree-step x this run's tree-steps/s
+            wi_step = tr["tree_kernel_alone"]["warp_instructions_per_tree_step"]
+            n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            extra["same_priors"]["issue_frac"] = (b * sp_steps / (sp_ms * 1e-3)) * wi_step / (n_sm * 4 * 1.965e9)
+            extra["same_priors"]["issue_note"] = ("warp instructions per tree-step from profiles/r02_traffic.json (ncu of this kernel at 65 536 "
+                                                  "roots: issue slots 69.5 % busy) x tree-steps/s of this run / (SMs x 4 x 1965 MHz)")
+        except Exception:
+            pass
         # the f32-accurate tensor-core model (AZB_MLP_TC3: bf16 hi + lo operands, three products per dot product): what the
         # reference's f32 forward costs on the tensor cores; the default stays bf16 because it is the faster step
         if args.mlp == "tc" and aw:
