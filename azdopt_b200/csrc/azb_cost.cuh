@@ -384,13 +384,16 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
     CPROF(2);
     // ---- 2. Laguerre from the right (plain Horner for p, p', p''/2): for a real-rooted polynomial the iterates
     //         decrease monotonically onto the largest root, cubically
+    // (the Horner loops start at the first non-zero coefficient, position sh: through the leading zeros the fixed-length
+    // form only carries signed zeros, and a signed zero added to the first non-zero term leaves it exact — s, d, h and
+    // with them every iterate are bit for bit what the 12-term form gives, for 40 % fewer Horner steps at K = 6 … 7)
     double y = (double)maxw2;
     const double nn = (double)K, nm1 = (double)(K - 1u);
 #pragma unroll 1
     for (int it = 0; it < 40; ++it) {
-        double s = cf[0], d = 0.0, h = 0.0;
+        double s = cf[sh], d = 0.0, h = 0.0;
 #pragma unroll 1
-        for (int j = 1; j <= KM; ++j) {
+        for (int j = sh + 1; j <= KM; ++j) {
             h = __fma_rn(h, y, d);
             d = __fma_rn(d, y, s);
             s = __fma_rn(s, y, cf[j]);
@@ -410,9 +413,9 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
     // ---- 3. polish: compensated Horner for p ----
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
-        double s = cf[0], e = 0.0, t = s, d = 0.0;
+        double s = cf[sh], e = 0.0, t = s, d = 0.0;
 #pragma unroll 1
-        for (int j = 1; j <= KM; ++j) {
+        for (int j = sh + 1; j <= KM; ++j) {
             const double cj = cf[j];
             d = __fma_rn(d, y, t);
             t = __fma_rn(t, y, cj);
