@@ -343,17 +343,20 @@ __device__ __forceinline__ double azb_lambda1_poly(uint32_t n, const uint8_t *pa
         // the child's polynomials sit one coefficient per lane; their degree bounds the product loop
         const uint32_t av = k <= KM ? ps->A[v][k] : 0u, bv = k <= KM ? ps->B[v][k] : 0u;
         const int dav = 31 - __clz(__ballot_sync(FULL, av != 0u));
-        // branch-free product loop: lanes beyond the useful range read clamped slots and multiply by zero (lanes above
-        // KM read a few words past their row, still inside the scratch, and are never stored)
-        const uint32_t *Ap = ps->A[p], *Bp = ps->B[p];
+        // product loop in registers: lane k holds the parent's A_k and B_k; SA / SB are those polynomials shifted up by
+        // i lanes (zero-filled from lane 0: one shuffle per iteration instead of clamped shared-memory reads), so
+        //   nb_k = sum_i a_i B_(k-i),   na_k = sum_i a_i A_(k-i) + b_i B_(k-i-1)
+        // (exact u32 arithmetic: the order of the terms does not matter)
+        uint32_t SA = k <= KM ? ps->A[p][k] : 0u, SB = k <= KM ? ps->B[p][k] : 0u;
 #pragma unroll 1
         for (int i = 0; i <= dav; ++i) {
             const uint32_t ac = __shfl_sync(FULL, av, i), bc = __shfl_sync(FULL, bv, i);
-            const int j = k - i;
-            const uint32_t acm = j >= 0 ? ac : 0u, bcm = j >= 1 ? bc : 0u;
-            const int j0 = j >= 0 ? j : 0, j1 = j >= 1 ? j - 1 : 0;
-            nb += acm * Bp[j0];
-            na += acm * Ap[j0] + bcm * Bp[j1];
+            const uint32_t ta = __shfl_up_sync(FULL, SA, 1), tb = __shfl_up_sync(FULL, SB, 1);
+            const uint32_t SB1 = k == 0 ? 0u : tb;  // B shifted by i + 1
+            nb += ac * SB;
+            na += ac * SA + bc * SB1;
+            SA = k == 0 ? 0u : ta;
+            SB = SB1;
         }
         __syncwarp();
         if (k <= KM) {
