@@ -407,7 +407,7 @@ int azb_create(const azb_config *cfg_in, azb_handle **out) {
         h->smem_words_per_warp = ((L.WS + 3) & ~3u) + 64 + 64 + 32 + shared_region;
     }
     h->smem_words_per_warp = (h->smem_words_per_warp + 3u) & ~3u;
-    h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4 + ((A + 15) & ~15u);  // + action->child LUT
+    h->smem_bytes = (size_t)AZB_WARPS_PER_BLOCK * h->smem_words_per_warp * 4 + azb_tables_bytes(A, N, h->W);  // + action->child LUT, child->action-mask table
     {
         const int sb = (int)h->smem_bytes;
         const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
@@ -810,7 +810,7 @@ static int async_create(azb_handle *h) {
     if (group == 0) return fail(h, AZB_ERR_INVALID, "AZB_ASYNC_GROUP must be positive");
     if (shared_sm) W = 0;
     // tree warps per CTA: 32, fewer when a large N needs more shared memory per warp (at most ~160 KB per SM, the rest is L1)
-    const size_t lut_bytes = (h->A + 15) & ~15u, per_warp = (size_t)h->smem_words_per_warp * 4;
+    const size_t lut_bytes = azb_tables_bytes(h->A, h->N, h->W), per_warp = (size_t)h->smem_words_per_warp * 4;
     uint32_t tree_warps = (uint32_t)std::max<size_t>(4, std::min<size_t>(AS_WARPS, (160 * 1024 - lut_bytes) / per_warp));
     if (azb_stack_depth(h->N) == 5) tree_warps = std::min<uint32_t>(tree_warps, AS_WIDE_TREE_WARPS);  // see azb_async_kernel
     if (const char *e = getenv("AZB_ASYNC_TREE_WARPS")) tree_warps = std::min<uint32_t>(tree_warps, std::max(1, atoi(e)));

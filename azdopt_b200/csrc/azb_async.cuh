@@ -1573,14 +1573,13 @@ __device__ void async_tree_worker(const AzbLayout &L, const AzbAsyncParams &P, c
     uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)P.tree_warps * P.smem_words_per_warp);
     // n_thr = the threads of the CTA that are here (the barrier counts them): all 1024, the first AS_WIDE_TREE_WARPS warps
     // for N >= 47, the first SH_TREE_WARPS warps in the shared-SM form
-    for (uint32_t a = threadIdx.x; 4u * a < L.A; a += n_thr)
-        reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
+    tree_tables_fill(L, lut, threadIdx.x, n_thr);
     // this CTA's trees: a contiguous block of the batch, tree0 .. tree0 + n_local - 1 (<= P.tab_slots; the first B mod n CTAs
     // own one tree more)
     const uint32_t q_trees = L.B / n_tree_ctas, r_trees = L.B % n_tree_ctas;
     const uint32_t n_local = q_trees + (tree_cta < r_trees ? 1u : 0u), tree0 = tree_cta * q_trees + min(tree_cta, r_trees);
     AsTreeTable T;
-    T.state = reinterpret_cast<uint32_t *>(lut + ((L.A + 15u) & ~15u));
+    T.state = reinterpret_cast<uint32_t *>(lut + azb_tables_bytes(L.A, L.N, L.W));
     T.sub = T.state + P.tab_slots;
     T.steps = T.sub + P.tab_slots;
     T.ctl = T.steps + P.tab_slots;
@@ -1940,7 +1939,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1)
         // whole group have no model role)
         if constexpr (DEPTH != 5) {
             if ((threadIdx.x >> 5) >= SH_TREE_WARPS) {
-                const size_t tree_bytes = (size_t)SH_TREE_WARPS * P.smem_words_per_warp * 4 + ((L.A + 15u) & ~15u) + as_table_bytes(P.tab_slots);
+                const size_t tree_bytes = (size_t)SH_TREE_WARPS * P.smem_words_per_warp * 4 + azb_tables_bytes(L.A, L.N, L.W) + as_table_bytes(P.tab_slots);
                 uint8_t *smem = (uint8_t *)(((uintptr_t)(as_smem + tree_bytes) + 1023) & ~(uintptr_t)1023);
                 if (blockIdx.x < (gridDim.x / P.group) * P.group) shared_model_warpgroup(L, P, M, blockIdx.x, smem, s_worker);
                 return;

@@ -146,6 +146,14 @@ __host__ __device__ __forceinline__ float azb_ord2f(uint32_t o) {
 // A.1 indexing (simple_graph/edge.rs:48-65, rooted_tree/ordered_edge.rs:35-42): action a <-> edge at colex
 // position a+1; the actions of child v are the contiguous range [v(v-1)/2 - 1, v(v-1)/2 + v - 2].
 __host__ __device__ __forceinline__ uint32_t azb_child_first_action(uint32_t v) { return v * (v - 1) / 2 - 1; }
+// Block-shared lookup tables of the tree kernels, behind the per-warp regions: the child vertex of every action (A bytes,
+// padded to 16) and — while a mask word per lane suffices (W <= 32) — for every child vertex the W-word mask of ITS actions
+// (what `act` clears from the permitted set): N x W words
+__host__ __device__ __forceinline__ uint32_t azb_lut_bytes(uint32_t A) { return (A + 15u) & ~15u; }
+__host__ __device__ __forceinline__ uint32_t azb_amask_bytes(uint32_t N, uint32_t W) { return W <= 32u ? ((N * W * 4u + 15u) & ~15u) : 0u; }
+__host__ __device__ __forceinline__ uint32_t azb_tables_bytes(uint32_t A, uint32_t N, uint32_t W) {
+    return azb_lut_bytes(A) + azb_amask_bytes(N, W);
+}
 __host__ __device__ __forceinline__ uint32_t azb_action_index(uint32_t parent, uint32_t child) {
     return child * (child - 1) / 2 + parent - 1;
 }

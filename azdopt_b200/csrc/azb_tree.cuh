@@ -59,7 +59,8 @@ struct WarpCtx {
     uint32_t *fr;      // frontier buffers [4][FRONTIER_CAP]
     uint32_t *ct;      // workload counters [16]
     CostScratch *cs;   // lambda_1 program scratch
-    const uint8_t *lut;  // child vertex of every action (block-shared)
+    const uint8_t *lut;  // child vertex of every action (block-shared); behind it, while W <= 32, the [N][W] action masks
+                         // of the child vertices (tree_tables_fill)
     // per-tree slabs
     uint4 *node;       // 4 x uint4 per node
     uint2 *blk;        // 8-byte units
@@ -145,9 +146,38 @@ __device__ __forceinline__ void build_cur_mask(const AzbLayout &L, WarpCtx &cx) 
 }
 
 // act (rooted_tree/space.rs:56-73): set the parent, drop every action of that child, extend the path set
+// fill the block-shared tables (all `n_thr` threads of the block, before the barrier that precedes their first use)
+__device__ __forceinline__ void tree_tables_fill(const AzbLayout &L, uint8_t *lut, uint32_t tid, uint32_t n_thr) {
+    for (uint32_t a = tid; 4u * a < L.A; a += n_thr) reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
+    if (L.W <= 32u) {
+        uint32_t *am = reinterpret_cast<uint32_t *>(lut + azb_lut_bytes(L.A));
+        for (uint32_t i = tid; i < L.N * L.W; i += n_thr) {
+            const uint32_t child = i / L.W, w = i - child * L.W;
+            uint32_t m = 0u;
+            if (child >= 2u) {  // the actions of `child` are first .. first + child - 1 (simple_graph/edge.rs:48-65)
+                const uint32_t first = azb_child_first_action(child), last = first + child, b0 = w * 32u;
+                const uint32_t s = max(first, b0), e = min(last, b0 + 32u);
+                if (s < e) m = (e - s == 32u ? 0xffffffffu : ((1u << (e - s)) - 1u)) << (s - b0);
+            }
+            am[i] = m;
+        }
+    }
+}
+
+// TABLE: cx.lut is the block's table pair and W <= 32 (the tree kernels for N <= 46)
+template <bool TABLE = false>
 __device__ __forceinline__ void walker_act(const AzbLayout &L, WarpCtx &cx, uint32_t a) {
     const uint32_t child = cx.lut[a];
     const uint32_t first = azb_child_first_action(child);
+    if constexpr (TABLE) {  // one mask word per lane: the child's action mask comes from the block's table
+        const uint32_t w = (uint32_t)cx.lane;
+        const uint32_t *amask = reinterpret_cast<const uint32_t *>(cx.lut + azb_lut_bytes(L.A));
+        if (w == 0u) cx.par[child] = (uint8_t)(a - first);
+        if (w < L.W) cx.perm[w] &= ~amask[child * L.W + w];
+        if (w == (a >> 5)) cx.keym[w] |= 1u << (a & 31);
+        __syncwarp();
+        return;
+    }
     const uint32_t last = first + child;  // exclusive
     if (cx.lane == 0) cx.par[child] = (uint8_t)(a - first);
 #pragma unroll 1
@@ -594,7 +624,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         }
         if (visit) {  // tree/mod.rs:139-159
             count(cx, CT_VISIT, 1);
-            walker_act(L, cx, best_w0 >> 20);
+            walker_act<DEPTH != 5>(L, cx, best_w0 >> 20);
             pos = best_w0 & 0xfffffu;
             lo2 = best_w1 & 0x7fffffffu;
             depth += 1;
@@ -671,7 +701,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             reset = true;
         } else {
             // ---- new node (tree/mod.rs:181-216)
-            walker_act(L, cx, a);
+            walker_act<DEPTH != 5>(L, cx, a);
             const uint32_t ndepth = depth + 1;
             // is_terminal (nabla/space/mod.rs:27-29) first: it only needs the state
             build_cur_mask(L, cx);
@@ -837,8 +867,7 @@ __global__ void __launch_bounds__(AZB_WARPS_PER_BLOCK * 32, AZB_TREE_MIN_BLOCKS)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tree = tree0 + blockIdx.x * AZB_WARPS_PER_BLOCK + warp;
     uint8_t *lut = reinterpret_cast<uint8_t *>(smem + (size_t)AZB_WARPS_PER_BLOCK * smem_words_per_warp);
-    for (uint32_t a = threadIdx.x; 4u * a < L.A; a += blockDim.x)
-        reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
+    tree_tables_fill(L, lut, threadIdx.x, blockDim.x);
     __syncthreads();
     uint32_t *base = smem + (size_t)warp * smem_words_per_warp;
     if (tree < tree_end) {
