@@ -151,10 +151,11 @@ __device__ __forceinline__ void tree_tables_fill(const AzbLayout &L, uint8_t *lu
     for (uint32_t a = tid; 4u * a < L.A; a += n_thr) reinterpret_cast<uint32_t *>(lut)[a] = reinterpret_cast<const uint32_t *>(L.lut)[a];
     if (L.W <= 32u) {
         uint32_t *am = reinterpret_cast<uint32_t *>(lut + azb_lut_bytes(L.A));
-        for (uint32_t i = tid; i < L.N * L.W; i += n_thr) {
-            const uint32_t child = i / L.W, w = i - child * L.W;
+        const uint32_t stride = azb_amask_stride(L.W);
+        for (uint32_t i = tid; i < L.N * stride; i += n_thr) {
+            const uint32_t child = i / stride, w = i - child * stride;
             uint32_t m = 0u;
-            if (child >= 2u) {  // the actions of `child` are first .. first + child - 1 (simple_graph/edge.rs:48-65)
+            if (child >= 2u && w < L.W) {  // the actions of `child` are first .. first + child - 1 (simple_graph/edge.rs:48-65)
                 const uint32_t first = azb_child_first_action(child), last = first + child, b0 = w * 32u;
                 const uint32_t s = max(first, b0), e = min(last, b0 + 32u);
                 if (s < e) m = (e - s == 32u ? 0xffffffffu : ((1u << (e - s)) - 1u)) << (s - b0);
@@ -164,16 +165,16 @@ __device__ __forceinline__ void tree_tables_fill(const AzbLayout &L, uint8_t *lu
     }
 }
 
-// TABLE: cx.lut is the block's table pair and W <= 32 (the tree kernels for N <= 46)
-template <bool TABLE = false>
+// STRIDE > 0: cx.lut is the block's table pair with rows of STRIDE words (the tree kernels for N <= 22: 8, N <= 46: 32)
+template <int STRIDE = 0>
 __device__ __forceinline__ void walker_act(const AzbLayout &L, WarpCtx &cx, uint32_t a) {
     const uint32_t child = cx.lut[a];
     const uint32_t first = azb_child_first_action(child);
-    if constexpr (TABLE) {  // one mask word per lane: the child's action mask comes from the block's table
+    if constexpr (STRIDE > 0) {  // one mask word per lane: the child's action mask comes from the block's table
         const uint32_t w = (uint32_t)cx.lane;
         const uint32_t *amask = reinterpret_cast<const uint32_t *>(cx.lut + azb_lut_bytes(L.A));
         if (w == 0u) cx.par[child] = (uint8_t)(a - first);
-        if (w < L.W) cx.perm[w] &= ~amask[child * L.W + w];
+        if (w < L.W) cx.perm[w] &= ~amask[child * STRIDE + w];
         if (w == (a >> 5)) cx.keym[w] |= 1u << (a & 31);
         __syncwarp();
         return;
@@ -624,7 +625,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         }
         if (visit) {  // tree/mod.rs:139-159
             count(cx, CT_VISIT, 1);
-            walker_act<DEPTH != 5>(L, cx, best_w0 >> 20);
+            walker_act<(DEPTH == 3 ? 8 : DEPTH == 4 ? 32 : 0)>(L, cx, best_w0 >> 20);
             pos = best_w0 & 0xfffffu;
             lo2 = best_w1 & 0x7fffffffu;
             depth += 1;
@@ -701,7 +702,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             reset = true;
         } else {
             // ---- new node (tree/mod.rs:181-216)
-            walker_act<DEPTH != 5>(L, cx, a);
+            walker_act<(DEPTH == 3 ? 8 : DEPTH == 4 ? 32 : 0)>(L, cx, a);
             const uint32_t ndepth = depth + 1;
             // is_terminal (nabla/space/mod.rs:27-29) first: it only needs the state
             build_cur_mask(L, cx);
