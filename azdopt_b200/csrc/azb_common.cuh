@@ -148,11 +148,11 @@ __host__ __device__ __forceinline__ float azb_ord2f(uint32_t o) {
 __host__ __device__ __forceinline__ uint32_t azb_child_first_action(uint32_t v) { return v * (v - 1) / 2 - 1; }
 // Block-shared lookup tables of the tree kernels, behind the per-warp regions: the child vertex of every action (A bytes,
 // padded to 16) and — while a mask word per lane suffices (W <= 32) — for every child vertex the W-word mask of ITS actions
-// (what `act` clears from the permitted set): N rows of 8 (W <= 8) or 32 words
+// (what `act` clears from the permitted set): N rows of 8 (W <= 8) or W words
 __host__ __device__ __forceinline__ uint32_t azb_lut_bytes(uint32_t A) { return (A + 15u) & ~15u; }
-// (rows of 8 or 32 words — a shift, not a multiplication by W, on the walkers' path)
-__host__ __device__ __forceinline__ uint32_t azb_amask_stride(uint32_t W) { return W <= 8u ? 8u : 32u; }
-__host__ __device__ __forceinline__ uint32_t azb_amask_bytes(uint32_t N, uint32_t W) { return W <= 32u ? N * azb_amask_stride(W) * 4u : 0u; }
+// (rows of 8 words up to N = 22 — a shift on the walkers' path —, of W words beyond)
+__host__ __device__ __forceinline__ uint32_t azb_amask_stride(uint32_t W) { return W <= 8u ? 8u : W; }
+__host__ __device__ __forceinline__ uint32_t azb_amask_bytes(uint32_t N, uint32_t W) { return W <= 32u ? ((N * azb_amask_stride(W) * 4u + 15u) & ~15u) : 0u; }
 __host__ __device__ __forceinline__ uint32_t azb_tables_bytes(uint32_t A, uint32_t N, uint32_t W) {
     return azb_lut_bytes(A) + azb_amask_bytes(N, W);
 }

@@ -165,16 +165,17 @@ __device__ __forceinline__ void tree_tables_fill(const AzbLayout &L, uint8_t *lu
     }
 }
 
-// STRIDE > 0: cx.lut is the block's table pair with rows of STRIDE words (the tree kernels for N <= 22: 8, N <= 46: 32)
+// STRIDE != 0: cx.lut is the block's table pair; rows of 8 words (STRIDE 8: the tree kernels for N <= 22) or of W words
+// (STRIDE -1: N <= 46)
 template <int STRIDE = 0>
 __device__ __forceinline__ void walker_act(const AzbLayout &L, WarpCtx &cx, uint32_t a) {
     const uint32_t child = cx.lut[a];
     const uint32_t first = azb_child_first_action(child);
-    if constexpr (STRIDE > 0) {  // one mask word per lane: the child's action mask comes from the block's table
+    if constexpr (STRIDE != 0) {  // one mask word per lane: the child's action mask comes from the block's table
         const uint32_t w = (uint32_t)cx.lane;
         const uint32_t *amask = reinterpret_cast<const uint32_t *>(cx.lut + azb_lut_bytes(L.A));
         if (w == 0u) cx.par[child] = (uint8_t)(a - first);
-        if (w < L.W) cx.perm[w] &= ~amask[child * STRIDE + w];
+        if (w < L.W) cx.perm[w] &= ~amask[child * (STRIDE > 0 ? (uint32_t)STRIDE : L.W) + w];
         if (w == (a >> 5)) cx.keym[w] |= 1u << (a & 31);
         __syncwarp();
         return;
@@ -625,7 +626,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
         }
         if (visit) {  // tree/mod.rs:139-159
             count(cx, CT_VISIT, 1);
-            walker_act<(DEPTH == 3 ? 8 : DEPTH == 4 ? 32 : 0)>(L, cx, best_w0 >> 20);
+            walker_act<(DEPTH == 3 ? 8 : DEPTH == 4 ? -1 : 0)>(L, cx, best_w0 >> 20);
             pos = best_w0 & 0xfffffu;
             lo2 = best_w1 & 0x7fffffffu;
             depth += 1;
@@ -702,7 +703,7 @@ __device__ void tree_rollout(const AzbLayout &L, WarpCtx &cx, uint32_t tree, uin
             reset = true;
         } else {
             // ---- new node (tree/mod.rs:181-216)
-            walker_act<(DEPTH == 3 ? 8 : DEPTH == 4 ? 32 : 0)>(L, cx, a);
+            walker_act<(DEPTH == 3 ? 8 : DEPTH == 4 ? -1 : 0)>(L, cx, a);
             const uint32_t ndepth = depth + 1;
             // is_terminal (nabla/space/mod.rs:27-29) first: it only needs the state
             build_cur_mask(L, cx);
